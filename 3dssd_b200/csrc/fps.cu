@@ -1,0 +1,570 @@
+// fps.cu -- farthest point sampling for sm_100a.
+//
+// Replaces the reference kernels farthestpointsamplingKernel / farthestpointsamplingwithdistKernel
+// (/root/reference/lib/utils/tf_ops/sampling/tf_sampling_g.cu:124-178, :181-230).
+//
+// Design (DESIGN.md "FPS"): FPS is a chain of m-1 dependent rounds, so the kernel is built to
+// minimise the latency of ONE round instead of streaming bandwidth:
+//   * one thread-block CLUSTER per scene (CL CTAs x 256 threads); every thread keeps its P points
+//     and their running min-distance in REGISTERS for the whole kernel -- no global/shared traffic
+//     for the distance update (the reference re-reads xyz and read-modify-writes `temp` in global
+//     memory every round);
+//   * per-round arg-max = two redux.sync per warp -> one 32-byte packet per warp in shared memory
+//     -> one packet per CTA pushed to every peer with st.async (DSMEM store + mbarrier complete_tx,
+//     a one-way message, no cluster barrier) -> every warp reduces the CL packets redundantly;
+//   * the winner's coordinates travel inside the packet, so the next round starts immediately.
+//
+// Bit-exactness: the reference's result is the arg-max under the order
+//     (value desc, k mod 1024 asc, k asc)            [1024-thread strided scan + left-biased tree]
+// which is reproduced by reducing the pair (value bits, key) with key = (k mod 1024, k div 1024).
+// Distances use the reference's contracted arithmetic: d = fma(dz,dz, fma(dy,dy, dx*dx)).
+#include "common.cuh"
+
+namespace ssd3d {
+
+constexpr int FPS_T = 256;  // threads per CTA
+constexpr int FPS_NW = FPS_T / 32;
+constexpr uint32_t KEY_INVALID = 0x7FFFFFFFu;
+
+__device__ __forceinline__ uint32_t fps_key(int k) { return ((uint32_t)(k & 1023) << 21) | (uint32_t)(k >> 10); }
+__device__ __forceinline__ int fps_key_to_k(uint32_t key) { return (int)(((key & 0x1FFFFFu) << 10) | (key >> 21)); }
+
+// Ownership map: slot i of global thread g (g = cta_rank*256 + tid, TT = CL*256 threads per scene).
+// Each thread owns points of one residue class mod 1024 (or 1024/TT classes when TT < 1024), visited
+// in ascending key order, so "first strictly greater" inside a thread == smallest key among its maxima.
+template <int TT, int P>
+struct FpsMap {
+    static constexpr int S = TT >= 1024 ? TT / 1024 : 1;  // threads sharing one residue class
+    static constexpr int R = TT >= 1024 ? 1 : 1024 / TT;  // residue classes per thread
+    static constexpr int J = P / R;
+    static_assert(P % R == 0 && J >= 1, "P must be a multiple of the residue classes per thread");
+    __device__ static __forceinline__ int k_of(int g, int i)
+    {
+        const int a = i / J, jj = i % J;
+        return (g & 1023) + a * TT + 1024 * ((g >> 10) + S * jj);
+    }
+    // inverse: (global thread, slot) that own point k
+    __device__ static __forceinline__ void owner_of(int k, int &g, int &i)
+    {
+        const int r = k & 1023, q = k >> 10;
+        if (TT >= 1024) { g = r + 1024 * (q % S); i = q / S; }
+        else { g = r % TT; i = (r / TT) * J + q; }
+    }
+};
+
+struct __align__(16) FpsPacket {
+    uint32_t val;  // bits of the (non-negative) candidate distance
+    uint32_t key;  // fps_key(k); smaller wins ties
+    float x, y, z; // coordinates of the candidate (c==3 kernel only)
+    uint32_t pad[3];
+};
+static_assert(sizeof(FpsPacket) == 32, "packet must be two 16-byte pieces");
+
+// (value,key) arg-max across a warp: max value, then min key among the lanes holding it.
+__device__ __forceinline__ void warp_argmax(uint32_t u, uint32_t key_if_valid, uint32_t &mx, uint32_t &kmin)
+{
+    mx = __reduce_max_sync(0xffffffffu, u);
+    kmin = __reduce_min_sync(0xffffffffu, (u == mx) ? key_if_valid : KEY_INVALID);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Shared per-round machinery: given this thread's candidate (best value, slot, key), produce the
+// scene-wide winner.  MODE 0: packets carry xyz (c==3); MODE 1: (value,key) only.
+// ---------------------------------------------------------------------------------------------------
+template <int CL>
+struct FpsShared {
+    FpsPacket warp_pk[2][FPS_NW];
+    FpsPacket cl_pk[2][CL];
+    unsigned long long mbar[2];
+};
+
+template <int CL, bool WITH_XYZ>
+__device__ __forceinline__ void fps_exchange(FpsShared<CL> &sh, int j, uint32_t rank, float best, uint32_t my_key,
+                                             float cx, float cy, float cz, uint32_t &win_key, float &ox, float &oy,
+                                             float &oz)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int par = j & 1;
+    const uint32_t u = __float_as_uint(fmaxf(best, 0.0f));
+    uint32_t mx, kmin;
+    warp_argmax(u, best >= 0.0f ? my_key : KEY_INVALID, mx, kmin);
+    {
+        const uint32_t bal = __ballot_sync(0xffffffffu, (u == mx) && ((best >= 0.0f ? my_key : KEY_INVALID) == kmin));
+        if (lane == __ffs(bal) - 1) {
+            uint4 *dst = reinterpret_cast<uint4 *>(&sh.warp_pk[par][warp]);
+            dst[0] = make_uint4(mx, kmin, __float_as_uint(cx), __float_as_uint(cy));
+            if (WITH_XYZ) dst[1] = make_uint4(__float_as_uint(cz), 0u, 0u, 0u);
+        }
+    }
+    __syncthreads();
+    if (CL == 1 || warp == 0) {
+        const uint32_t v = lane < FPS_NW ? sh.warp_pk[par][lane].val : 0u;
+        const uint32_t kk = lane < FPS_NW ? sh.warp_pk[par][lane].key : KEY_INVALID;
+        uint32_t m2, k2;
+        warp_argmax(v, kk, m2, k2);
+        const uint32_t bal = __ballot_sync(0xffffffffu, lane < FPS_NW && v == m2 && kk == k2);
+        const int ww = __ffs(bal) - 1;
+        if (CL == 1) {
+            win_key = k2;
+            if (WITH_XYZ) {
+                const uint4 a = reinterpret_cast<const uint4 *>(&sh.warp_pk[par][ww])[0];
+                ox = __uint_as_float(a.z); oy = __uint_as_float(a.w);
+                oz = sh.warp_pk[par][ww].z;
+            }
+            return;
+        }
+        constexpr int PIECES = WITH_XYZ ? 2 : 1;
+        if (lane == 0) mbar_arrive_expect_tx(smem_u32(&sh.mbar[par]), CL * PIECES * 16);
+        if (lane < PIECES * CL) {
+            const int piece = WITH_XYZ ? (lane & 1) : 0;
+            const uint32_t peer = WITH_XYZ ? (lane >> 1) : lane;
+            const uint4 v4 = reinterpret_cast<const uint4 *>(&sh.warp_pk[par][ww])[piece];
+            st_async_v4(mapa(smem_u32(&sh.cl_pk[par][rank]) + piece * 16, peer), mapa(smem_u32(&sh.mbar[par]), peer), v4);
+        }
+    }
+    if (CL > 1) {
+        mbar_wait_cluster(smem_u32(&sh.mbar[par]), ((j - 1) >> 1) & 1);
+        const uint32_t v = lane < CL ? sh.cl_pk[par][lane].val : 0u;
+        const uint32_t kk = lane < CL ? sh.cl_pk[par][lane].key : KEY_INVALID;
+        uint32_t m3, k3;
+        warp_argmax(v, kk, m3, k3);
+        win_key = k3;
+        if (WITH_XYZ) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, lane < CL && v == m3 && kk == k3);
+            const int wr = __ffs(bal) - 1;
+            const uint4 a = reinterpret_cast<const uint4 *>(&sh.cl_pk[par][wr])[0];
+            ox = __uint_as_float(a.z); oy = __uint_as_float(a.w);
+            oz = sh.cl_pk[par][wr].z;
+        }
+    }
+}
+
+template <int CL>
+__device__ __forceinline__ void fps_shared_init(FpsShared<CL> &sh)
+{
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&sh.mbar[0]), 1);
+        mbar_init(smem_u32(&sh.mbar[1]), 1);
+        fence_mbar_init_cluster();
+    }
+    __syncthreads();
+    if (CL > 1) cluster_sync_all();  // every CTA's barriers exist before any peer st.async targets them
+}
+
+// ---------------------------------------------------------------------------------------------------
+// D-FPS on xyz (c == 3): points + running distances live in registers.
+// ---------------------------------------------------------------------------------------------------
+template <int CL, int P>
+__global__ void __launch_bounds__(FPS_T, 1)
+fps3_cluster_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out)
+{
+    using Map = FpsMap<CL * FPS_T, P>;
+    extern __shared__ float4 own_pts[];  // [P][FPS_T] xyz of this CTA's points (lookup by the round winner)
+    __shared__ FpsShared<CL> sh;
+
+    const int tid = threadIdx.x;
+    const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+    const int scene = blockIdx.x / CL;
+    const int g = (int)rank * FPS_T + tid;
+    const float *data = inp + (size_t)scene * n * 3;
+    int *idxs = out + (size_t)scene * m;
+
+    float px[P], py[P], pz[P], td[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        const int k = Map::k_of(g, i);
+        if (k < n) {
+            px[i] = data[3 * k]; py[i] = data[3 * k + 1]; pz[i] = data[3 * k + 2];
+            td[i] = 1e38f;  // tf_sampling_g.cu:136
+        } else {
+            px[i] = py[i] = pz[i] = 0.0f;
+            td[i] = -1.0f;  // padding slot: can never win (min(d,-1) stays -1, valid values are >= 0)
+        }
+        own_pts[i * FPS_T + tid] = make_float4(px[i], py[i], pz[i], 0.0f);
+    }
+    fps_shared_init<CL>(sh);
+
+    float ox = data[0], oy = data[1], oz = data[2];  // first sample is point 0 (:131-133)
+    if (g == 0) idxs[0] = 0;
+
+    for (int j = 1; j < m; j++) {
+        float best = -1.0f;
+        int bi = 0;
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+            const float dx = px[i] - ox, dy = py[i] - oy, dz = pz[i] - oz;
+            float d = __fmul_rn(dx, dx);
+            d = __fmaf_rn(dy, dy, d);
+            d = __fmaf_rn(dz, dz, d);
+            const float t = fminf(d, td[i]);
+            td[i] = t;
+            if (t > best) { best = t; bi = i; }
+        }
+        const float4 c = own_pts[bi * FPS_T + tid];
+        uint32_t wkey;
+        fps_exchange<CL, true>(sh, j, rank, best, fps_key(Map::k_of(g, bi)), c.x, c.y, c.z, wkey, ox, oy, oz);
+        if (g == 0) idxs[j] = fps_key_to_k(wkey);
+    }
+    if (CL > 1) cluster_sync_all();  // peers may still be storing into this CTA's shared memory
+}
+
+// ---------------------------------------------------------------------------------------------------
+// F-FPS given a precomputed distance matrix (tf_sampling_g.cu:181-230): one coalesced row read per round.
+// ---------------------------------------------------------------------------------------------------
+template <int CL, int P>
+__global__ void __launch_bounds__(FPS_T, 1)
+fpsdist_cluster_kernel(int n, int m, const float *__restrict__ dist, int *__restrict__ out)
+{
+    using Map = FpsMap<CL * FPS_T, P>;
+    __shared__ FpsShared<CL> sh;
+    const int tid = threadIdx.x;
+    const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+    const int scene = blockIdx.x / CL;
+    const int g = (int)rank * FPS_T + tid;
+    const float *mat = dist + (size_t)scene * n * n;
+    int *idxs = out + (size_t)scene * m;
+
+    float td[P];
+    int kk[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        kk[i] = Map::k_of(g, i);
+        td[i] = kk[i] < n ? 1e38f : -1.0f;
+    }
+    fps_shared_init<CL>(sh);
+    int old = 0;
+    if (g == 0) idxs[0] = 0;
+    for (int j = 1; j < m; j++) {
+        const float *row = mat + (size_t)old * n;
+        float dv[P];
+#pragma unroll
+        for (int i = 0; i < P; i++) dv[i] = kk[i] < n ? __ldg(row + kk[i]) : 0.0f;
+        float best = -1.0f;
+        int bi = 0;
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+            const float t = fminf(dv[i], td[i]);
+            td[i] = t;
+            if (t > best) { best = t; bi = i; }
+        }
+        uint32_t wkey;
+        float ux, uy, uz;
+        fps_exchange<CL, false>(sh, j, rank, best, fps_key(Map::k_of(g, bi)), 0.f, 0.f, 0.f, wkey, ux, uy, uz);
+        old = fps_key_to_k(wkey);
+        if (g == 0) idxs[j] = old;
+    }
+    if (CL > 1) cluster_sync_all();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FPS on generic c-dimensional points (the reference kernel's generic path, :146-150), used as the
+// matrix-free F-FPS on concat[xyz, features]: the scene's features stay in the cluster's shared memory
+// ([c][NL] per CTA), the winner's feature vector is fetched from its owner CTA through DSMEM.
+// ---------------------------------------------------------------------------------------------------
+template <int CL, int P>
+__global__ void __launch_bounds__(FPS_T, 1)
+fpsc_cluster_kernel(int n, int c, int m, const float *__restrict__ inp, int *__restrict__ out)
+{
+    using Map = FpsMap<CL * FPS_T, P>;
+    constexpr int NL = P * FPS_T;
+    constexpr int NLP = NL + 1;  // +1 pitch: conflict-free staging writes, reads stay conflict-free
+    extern __shared__ float4 dyn_smem[];
+    float *feat = reinterpret_cast<float *>(dyn_smem);  // [c][NLP]
+    float *old_f = feat + (size_t)c * NLP;               // [c]
+    __shared__ FpsShared<CL> sh;
+
+    const int tid = threadIdx.x;
+    const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+    const int scene = blockIdx.x / CL;
+    const int g = (int)rank * FPS_T + tid;
+    const float *data = inp + (size_t)scene * n * c;
+    int *idxs = out + (size_t)scene * m;
+
+    float td[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) td[i] = Map::k_of(g, i) < n ? 1e38f : -1.0f;
+    // stage features: one warp per point row for coalesced global reads
+    for (int s = tid >> 5; s < NL; s += FPS_NW) {
+        const int st = s % FPS_T, si = s / FPS_T;
+        const int k = Map::k_of((int)rank * FPS_T + st, si);
+        for (int l = tid & 31; l < c; l += 32) feat[(size_t)l * NLP + s] = k < n ? data[(size_t)k * c + l] : 0.0f;
+    }
+    for (int l = tid; l < c; l += FPS_T) old_f[l] = data[l];  // first sample is point 0
+    fps_shared_init<CL>(sh);  // contains __syncthreads
+    if (g == 0) idxs[0] = 0;
+
+    for (int j = 1; j < m; j++) {
+        float d[P];
+#pragma unroll
+        for (int i = 0; i < P; i++) d[i] = 0.0f;
+        for (int l = 0; l < c; l++) {
+            const float o = old_f[l];
+            const float *fl = feat + (size_t)l * NLP + tid;
+#pragma unroll
+            for (int i = 0; i < P; i++) {
+                const float diff = fl[i * FPS_T] - o;
+                d[i] = __fmaf_rn(diff, diff, d[i]);
+            }
+        }
+        float best = -1.0f;
+        int bi = 0;
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+            const float t = fminf(d[i], td[i]);
+            td[i] = t;
+            if (t > best) { best = t; bi = i; }
+        }
+        uint32_t wkey;
+        float ux, uy, uz;
+        fps_exchange<CL, false>(sh, j, rank, best, fps_key(Map::k_of(g, bi)), 0.f, 0.f, 0.f, wkey, ux, uy, uz);
+        const int old = fps_key_to_k(wkey);
+        if (g == 0) idxs[j] = old;
+        // fetch the winner's feature vector from its owner CTA (all threads passed the __syncthreads inside
+        // fps_exchange, so nobody still reads old_f of this round)
+        int og, oi;
+        Map::owner_of(old, og, oi);
+        const uint32_t orank = (uint32_t)(og / FPS_T);
+        const int oslot = oi * FPS_T + (og % FPS_T);
+        for (int l = tid; l < c; l += FPS_T) {
+            const uint32_t a = smem_u32(feat + (size_t)l * NLP + oslot);
+            old_f[l] = CL > 1 ? ld_dsmem_f32(mapa(a, orank)) : feat[(size_t)l * NLP + oslot];
+        }
+        __syncthreads();
+    }
+    if (CL > 1) cluster_sync_all();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fallback for shapes the on-chip kernels do not cover (very large n or c): one 1024-thread CTA per
+// scene, running distances in the caller's `temp` like the reference, warp-redux arg-max.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+fps_fallback_kernel(int n, int c, int m, const float *__restrict__ inp, const float *__restrict__ dist,
+                    float *__restrict__ temp, int *__restrict__ out)
+{
+    __shared__ uint32_t s_val[32], s_key[32];
+    __shared__ int s_old;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int scene = blockIdx.x;
+    const float *data = inp ? inp + (size_t)scene * n * c : nullptr;
+    const float *mat = dist ? dist + (size_t)scene * n * n : nullptr;
+    float *td = temp + (size_t)scene * n;
+    int *idxs = out + (size_t)scene * m;
+    for (int k = tid; k < n; k += 1024) td[k] = 1e38f;
+    if (tid == 0) idxs[0] = 0;
+    int old = 0;
+    __syncthreads();
+    for (int j = 1; j < m; j++) {
+        float best = -1.0f;
+        int bk = 0;
+        for (int k = tid; k < n; k += 1024) {
+            float d;
+            if (mat) d = mat[(size_t)old * n + k];
+            else {
+                d = 0.0f;
+                for (int l = 0; l < c; l++) {
+                    const float diff = data[(size_t)k * c + l] - data[(size_t)old * c + l];
+                    d = __fmaf_rn(diff, diff, d);
+                }
+            }
+            const float t = fminf(d, td[k]);
+            td[k] = t;
+            if (t > best) { best = t; bk = k; }
+        }
+        const uint32_t u = __float_as_uint(fmaxf(best, 0.0f));
+        const uint32_t key = best >= 0.0f ? fps_key(bk) : KEY_INVALID;
+        uint32_t mx, kmin;
+        warp_argmax(u, key, mx, kmin);
+        if (lane == 0) { s_val[warp] = mx; s_key[warp] = kmin; }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t m2, k2;
+            warp_argmax(s_val[lane], s_key[lane], m2, k2);
+            if (lane == 0) { s_old = fps_key_to_k(k2); idxs[j] = s_old; }
+        }
+        __syncthreads();
+        old = s_old;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Launch logic
+// ---------------------------------------------------------------------------------------------------
+template <typename K>
+static cudaError_t launch_cluster(K kernel, int cl, int b, size_t dyn_smem, cudaStream_t stream, void **args)
+{
+    cudaError_t e = cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    if (e != cudaSuccess) return e;
+    if (cl > 8) {
+        e = cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(b * cl));
+    cfg.blockDim = dim3(FPS_T);
+    cfg.dynamicSmemBytes = dyn_smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelExC(&cfg, (const void *)kernel, args);
+}
+
+// smallest power of two P >= need with P >= residue classes per thread
+static int pick_p(int n, int cl)
+{
+    const int tt = cl * FPS_T;
+    const int r = tt >= 1024 ? 1 : 1024 / tt;
+    int need = (n + tt - 1) / tt;
+    // a residue class holds ceil(n/1024) points; slots per class J = P/R must cover them
+    const int per_class = (n + 1023) / 1024;
+    const int s = tt >= 1024 ? tt / 1024 : 1;
+    const int j = (per_class + s - 1) / s;
+    need = r * j;
+    int p = r;
+    while (p < need) p *= 2;
+    return p;
+}
+
+static int g_fps_cluster_override = 0;  // test / tuning hook (ssd3d_tune_set)
+
+static int pick_cl_xyz(int n)
+{
+    if (g_fps_cluster_override > 0) return g_fps_cluster_override;
+    if (n <= 1024) return 1;
+    if (n <= 2048) return 2;
+    if (n <= 4096) return 4;
+    if (n <= 32768) return 8;
+    return 16;
+}
+
+}  // namespace ssd3d
+
+using namespace ssd3d;
+
+// The P values legal for a cluster size are the multiples of R = max(1, 1024/(CL*256)):
+//   CL=1 -> P in {4,8,16}; CL=2 -> {2,4,8,16}; CL>=4 -> {1,2,4,8,16}.
+#define SSD3D_FPS_SWITCH(KERNEL, SMEM_OF_P)                                                               \
+    do {                                                                                                  \
+        cudaError_t e = cudaErrorInvalidValue;                                                            \
+        const int p = pick_p(n, cl);                                                                      \
+        const size_t smem = (SMEM_OF_P);                                                                  \
+        if (cl == 1) {                                                                                    \
+            if (p == 4) e = launch_cluster(KERNEL<1, 4>, 1, b, smem, st, args);                           \
+            else if (p == 8) e = launch_cluster(KERNEL<1, 8>, 1, b, smem, st, args);                      \
+            else if (p == 16) e = launch_cluster(KERNEL<1, 16>, 1, b, smem, st, args);                    \
+            else return -100;                                                                             \
+        } else if (cl == 2) {                                                                             \
+            if (p == 2) e = launch_cluster(KERNEL<2, 2>, 2, b, smem, st, args);                           \
+            else if (p == 4) e = launch_cluster(KERNEL<2, 4>, 2, b, smem, st, args);                      \
+            else if (p == 8) e = launch_cluster(KERNEL<2, 8>, 2, b, smem, st, args);                      \
+            else if (p == 16) e = launch_cluster(KERNEL<2, 16>, 2, b, smem, st, args);                    \
+            else return -100;                                                                             \
+        } else if (cl == 4) {                                                                             \
+            if (p == 1) e = launch_cluster(KERNEL<4, 1>, 4, b, smem, st, args);                           \
+            else if (p == 2) e = launch_cluster(KERNEL<4, 2>, 4, b, smem, st, args);                      \
+            else if (p == 4) e = launch_cluster(KERNEL<4, 4>, 4, b, smem, st, args);                      \
+            else if (p == 8) e = launch_cluster(KERNEL<4, 8>, 4, b, smem, st, args);                      \
+            else if (p == 16) e = launch_cluster(KERNEL<4, 16>, 4, b, smem, st, args);                    \
+            else return -100;                                                                             \
+        } else if (cl == 8) {                                                                             \
+            if (p == 1) e = launch_cluster(KERNEL<8, 1>, 8, b, smem, st, args);                           \
+            else if (p == 2) e = launch_cluster(KERNEL<8, 2>, 8, b, smem, st, args);                      \
+            else if (p == 4) e = launch_cluster(KERNEL<8, 4>, 8, b, smem, st, args);                      \
+            else if (p == 8) e = launch_cluster(KERNEL<8, 8>, 8, b, smem, st, args);                      \
+            else if (p == 16) e = launch_cluster(KERNEL<8, 16>, 8, b, smem, st, args);                    \
+            else return -100;                                                                             \
+        } else if (cl == 16) {                                                                            \
+            if (p == 1) e = launch_cluster(KERNEL<16, 1>, 16, b, smem, st, args);                         \
+            else if (p == 2) e = launch_cluster(KERNEL<16, 2>, 16, b, smem, st, args);                    \
+            else if (p == 4) e = launch_cluster(KERNEL<16, 4>, 16, b, smem, st, args);                    \
+            else if (p == 8) e = launch_cluster(KERNEL<16, 8>, 16, b, smem, st, args);                    \
+            else if (p == 16) e = launch_cluster(KERNEL<16, 16>, 16, b, smem, st, args);                  \
+            else return -100;                                                                             \
+        } else return -100;                                                                               \
+        return (int)e;                                                                                    \
+    } while (0)
+
+static int launch_fps3(int b, int n, int m, int cl, const float *inp, int *out, cudaStream_t st)
+{
+    void *args[] = {&n, &m, (void *)&inp, (void *)&out};
+    SSD3D_FPS_SWITCH(fps3_cluster_kernel, (size_t)p * FPS_T * sizeof(float4));
+}
+static int launch_fpsdist(int b, int n, int m, int cl, const float *dist, int *out, cudaStream_t st)
+{
+    void *args[] = {&n, &m, (void *)&dist, (void *)&out};
+    SSD3D_FPS_SWITCH(fpsdist_cluster_kernel, (size_t)0);
+}
+static int launch_fpsc(int b, int n, int c, int m, int cl, const float *inp, int *out, cudaStream_t st)
+{
+    void *args[] = {&n, &c, &m, (void *)&inp, (void *)&out};
+    SSD3D_FPS_SWITCH(fpsc_cluster_kernel, ((size_t)c * (p * FPS_T + 1) + c) * sizeof(float) + 16);
+}
+
+// cluster size for the generic-c kernel: smallest CL whose per-CTA feature slab fits in shared memory
+static int pick_cl_generic(int n, int c)
+{
+    if (g_fps_cluster_override > 0) return g_fps_cluster_override;
+    const size_t budget = 200 * 1024;
+    for (int cl = 1; cl <= 16; cl *= 2) {
+        const int p = pick_p(n, cl);
+        if (p > 16) continue;
+        if (((size_t)c * (p * FPS_T + 1) + c) * sizeof(float) + 16 <= budget && (cl >= 8 || n <= cl * 1024)) return cl;
+    }
+    for (int cl = 1; cl <= 16; cl *= 2) {
+        const int p = pick_p(n, cl);
+        if (p <= 16 && ((size_t)c * (p * FPS_T + 1) + c) * sizeof(float) + 16 <= budget) return cl;
+    }
+    return 0;
+}
+
+extern "C" int ssd3d_fps_needs_temp(int n, int c)
+{
+    if (c == 3) return pick_p(n, 16) > 16;
+    return pick_cl_generic(n, c) == 0;
+}
+
+extern "C" void ssd3d_tune_set_fps_cluster(int cl) { g_fps_cluster_override = cl; }
+
+extern "C" int ssd3d_farthest_point_sample(int b, int n, int c, int m, const float *inp, float *temp, int *out,
+                                           ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(b >= 0 && n > 0 && c > 0 && m >= 0, "farthest_point_sample: bad shape b=%d n=%d c=%d m=%d", b, n, c, m);
+    SSD3D_REQUIRE(inp && out, "farthest_point_sample: null pointer");
+    if (b == 0 || m == 0) return 0;  // tf_sampling_g.cu:126-127
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = -100;
+    if (c == 3) {
+        int cl = pick_cl_xyz(n);
+        while (cl < 16 && pick_p(n, cl) > 16) cl *= 2;
+        if (pick_p(n, cl) <= 16) rc = launch_fps3(b, n, m, cl, inp, out, st);
+    } else {
+        const int cl = pick_cl_generic(n, c);
+        if (cl > 0) rc = launch_fpsc(b, n, c, m, cl, inp, out, st);
+    }
+    if (rc == -100) {
+        SSD3D_REQUIRE(temp != nullptr, "farthest_point_sample: n=%d c=%d needs the temp[b,n] workspace", n, c);
+        fps_fallback_kernel<<<b, 1024, 0, st>>>(n, c, m, inp, nullptr, temp, out);
+        SSD3D_LAUNCH_CHECK("fps_fallback_kernel");
+    }
+    return cuda_status((cudaError_t)rc, "farthest_point_sample launch");
+}
+
+extern "C" int ssd3d_farthest_point_sample_with_distance(int b, int n, int m, const float *dist, float *temp,
+                                                         int *out, ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0, "farthest_point_sample_with_distance: bad shape b=%d n=%d m=%d", b, n, m);
+    SSD3D_REQUIRE(dist && out, "farthest_point_sample_with_distance: null pointer");
+    if (b == 0 || m == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int cl = pick_cl_xyz(n);
+    while (cl < 16 && pick_p(n, cl) > 16) cl *= 2;
+    if (pick_p(n, cl) <= 16) return cuda_status((cudaError_t)launch_fpsdist(b, n, m, cl, dist, out, st), "fpsdist launch");
+    SSD3D_REQUIRE(temp != nullptr, "farthest_point_sample_with_distance: n=%d needs the temp[b,n] workspace", n);
+    fps_fallback_kernel<<<b, 1024, 0, st>>>(n, 0, m, nullptr, dist, temp, out);
+    SSD3D_LAUNCH_CHECK("fps_fallback_kernel");
+}

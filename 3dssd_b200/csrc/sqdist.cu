@@ -1,0 +1,98 @@
+// sqdist.cu -- pairwise squared feature distance, the F-FPS input of the reference:
+//   model_util.calc_square_dist(a, a, norm=False)  (/root/reference/lib/utils/model_util.py:144-160)
+//   out[b,i,j] = (|a_i|^2 + |a_j|^2) - 2 <a_i, a_j>
+// The reference gets <a_i,a_j> from a TF-1.4 cuBLAS SGEMM whose summation order is unspecified, so this
+// kernel PINS the order (sequential fp32 fma chain over the channel index, starting from 0) to make the
+// result reproducible bit-for-bit by the CPU oracle -- which is why it runs on the fp32 FMA pipe and not
+// on tensor cores.  64x64 output tile per block, both operand slabs ([c][64], channel-major) resident in
+// shared memory for the whole tile, 4x4 outputs per thread fed by two 16-byte broadcast loads per channel.
+#include "common.cuh"
+
+namespace ssd3d {
+
+constexpr int SQ_TILE = 64;
+constexpr int SQ_THREADS = 256;
+constexpr int SQ_PITCH = 68;  // 64 + 4: keeps 16-byte alignment of the float4 reads, 4-way (not 32-way) staging conflicts
+
+__global__ void __launch_bounds__(SQ_THREADS)
+sqdist_kernel(int n, int c, const float *__restrict__ a, float *__restrict__ out)
+{
+    extern __shared__ float4 dyn_smem[];
+    float *As = reinterpret_cast<float *>(dyn_smem);  // [c][64] rows of the i-tile
+    float *Bs = As + (size_t)c * SQ_PITCH;             // [c][64] rows of the j-tile
+    float *sqA = Bs + (size_t)c * SQ_PITCH;            // [64]
+    float *sqB = sqA + SQ_TILE;                        // [64]
+
+    const int scene = blockIdx.z;
+    const int i0 = blockIdx.y * SQ_TILE, j0 = blockIdx.x * SQ_TILE;
+    const float *A = a + (size_t)scene * n * c;
+    const int tid = threadIdx.x;
+
+    // stage both slabs transposed; consecutive threads read consecutive channels of one point (coalesced)
+    for (int e = tid; e < SQ_TILE * c; e += SQ_THREADS) {
+        const int r = e / c, l = e - r * c;
+        As[l * SQ_PITCH + r] = (i0 + r < n) ? A[(size_t)(i0 + r) * c + l] : 0.0f;
+        Bs[l * SQ_PITCH + r] = (j0 + r < n) ? A[(size_t)(j0 + r) * c + l] : 0.0f;
+    }
+    __syncthreads();
+    if (tid < 2 * SQ_TILE) {
+        const float *S = tid < SQ_TILE ? As : Bs;
+        const int r = tid & (SQ_TILE - 1);
+        float s = 0.0f;
+        for (int l = 0; l < c; l++) s = __fmaf_rn(S[l * SQ_PITCH + r], S[l * SQ_PITCH + r], s);
+        (tid < SQ_TILE ? sqA : sqB)[r] = s;
+    }
+    __syncthreads();
+
+    const int ty = tid / 16, tx = tid % 16;
+    float acc[4][4];
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+#pragma unroll
+        for (int x = 0; x < 4; x++) acc[y][x] = 0.0f;
+    for (int l = 0; l < c; l++) {
+        const float4 av = *reinterpret_cast<const float4 *>(As + l * SQ_PITCH + ty * 4);
+        const float4 bv = *reinterpret_cast<const float4 *>(Bs + l * SQ_PITCH + tx * 4);
+        const float ar[4] = {av.x, av.y, av.z, av.w};
+        const float br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) acc[y][x] = __fmaf_rn(ar[y], br[x], acc[y][x]);
+    }
+    float *O = out + (size_t)scene * n * n;
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        const int i = i0 + ty * 4 + y;
+        if (i >= n) continue;
+        const float si = sqA[ty * 4 + y];
+        float v[4];
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+            v[x] = __fsub_rn(__fadd_rn(si, sqB[tx * 4 + x]), __fmul_rn(2.0f, acc[y][x]));
+        const int j = j0 + tx * 4;
+        float *dst = O + (size_t)i * n + j;
+        if (j + 3 < n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        else
+            for (int x = 0; x < 4; x++)
+                if (j + x < n) dst[x] = v[x];
+    }
+}
+
+}  // namespace ssd3d
+
+using namespace ssd3d;
+
+extern "C" int ssd3d_calc_square_dist(int b, int n, int c, const float *a, float *out, ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(b >= 0 && n > 0 && c > 0, "calc_square_dist: bad shape b=%d n=%d c=%d", b, n, c);
+    SSD3D_REQUIRE(a && out, "calc_square_dist: null pointer");
+    if (b == 0) return 0;
+    const size_t smem = ((size_t)2 * c * SQ_PITCH + 2 * SQ_TILE) * sizeof(float);
+    SSD3D_REQUIRE(smem <= 220 * 1024, "calc_square_dist: c=%d too large for the shared-memory slabs", c);
+    cudaError_t e = cudaFuncSetAttribute((const void *)sqdist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "calc_square_dist attr");
+    dim3 grid((unsigned)ceil_div(n, SQ_TILE), (unsigned)ceil_div(n, SQ_TILE), (unsigned)b);
+    sqdist_kernel<<<grid, SQ_THREADS, smem, (cudaStream_t)stream>>>(n, c, a, out);
+    SSD3D_LAUNCH_CHECK("sqdist_kernel");
+}

@@ -1,0 +1,167 @@
+"""SA / FP / vote layers with the reference's signatures, on the B200 operators.
+
+Mirrors /root/reference/lib/utils/layers_util.py: vote_layer :12-24, pointnet_sa_module :27-55,
+pointnet_sa_module_msg :59-189, pointnet_fp_module :192-225 -- same positional arguments and return values,
+torch CUDA tensors instead of TF tensors.  What TF resolved through variable scopes is passed explicitly as
+`params` (a dict keyed by the reference's variable names, or a params.PreparedParams).  Inference only:
+is_training must be False (training-mode BN / backward ops are SURVEY.md section 8f-3, not built yet).
+"""
+import torch
+
+from . import config as _cfg
+from . import tf_ops
+from .params import prepare
+
+
+def _conv(pp, scope, x, bn=True, relu=True, pool=1, rowmask=None):
+    f = pp.conv(scope, bn)
+    return tf_ops.linear_bn_relu(x, f.w, f.scale, f.shift, relu=relu, pool=pool, rowmask=rowmask, cin=f.cin)
+
+
+_CONSTS = {}
+
+
+def _const(values, device):
+    """Small device constants, created once (so that layer calls stay CUDA-graph capturable)."""
+    key = (values, str(device))
+    if key not in _CONSTS:
+        _CONSTS[key] = torch.tensor(values, dtype=torch.float32, device=device)
+    return _CONSTS[key]
+
+
+def _arange_idx(bs, npoint, device):
+    return torch.arange(npoint, dtype=torch.int32, device=device).unsqueeze(0).repeat(bs, 1)
+
+
+def ffps_indices(npoint, xyz, points, mode):
+    """F-FPS on concat[xyz, points] (layers_util.py:94-96, :102-104).
+    mode 'matrix': calc_square_dist + farthest_point_sample_with_distance, the reference's route;
+    mode 'fused' : matrix-free -- the generic-c FPS kernel evaluates the feature distance on the fly (no
+                   [B,N,N] tensor); identical to the reference's own farthest_point_sample on the features."""
+    feats = torch.cat([xyz, points], dim=-1).contiguous()
+    if mode == "matrix":
+        return tf_ops.farthest_point_sample_with_distance(npoint, tf_ops.calc_square_dist(feats))
+    if mode == "fused":
+        return tf_ops.farthest_point_sample(npoint, feats)
+    raise ValueError("ffps_mode must be 'matrix' or 'fused'")
+
+
+def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_training, bn_decay, bn,
+                           fps_sample_range_list, fps_method_list, npoint_list, former_fps_idx, use_attention, scope,
+                           dilated_group, vote_ctr=None, aggregation_channel=None, debugging=False, epsilon=1e-5, *,
+                           params, ffps_mode="matrix", aggregation=None, return_debug=False):
+    """PointNet++ SA module with multi-scale grouping; returns (new_xyz, new_points, fps_idx)."""
+    if is_training:
+        raise NotImplementedError("training-mode BatchNorm / backward ops are out of scope (inference only)")
+    if use_attention:
+        raise NotImplementedError("query_ball_point_withidx (use_attention) is unused by the shipped 3DSSD configs")
+    pp = prepare(params, xyz.device)
+    aggregation = _cfg.AGGREGATION_SA_FEATURE if aggregation is None else aggregation
+    bs, n, _ = xyz.shape
+
+    cur, last = [], 0
+    for rng, method, npoint in zip(fps_sample_range_list, fps_method_list, npoint_list):
+        end = n if rng == -1 else last + rng                      # tf.slice size -1 (:86-87)
+        tmp_xyz = xyz[:, last:end].contiguous()
+        tmp_points = points[:, last:end]
+        if npoint == 0:                                           # :88-90
+            last += rng
+            continue
+        if vote_ctr is not None:                                  # :91-93
+            npoint = vote_ctr.shape[1]
+            fps_idx = _arange_idx(bs, npoint, xyz.device)
+        elif method == "FS":                                      # :94-99 fusion sampling
+            fps_idx = torch.cat([ffps_indices(npoint, tmp_xyz, tmp_points, ffps_mode),
+                                 tf_ops.farthest_point_sample(npoint, tmp_xyz)], dim=-1)
+        elif npoint == tmp_xyz.shape[1]:                          # :100-101
+            fps_idx = _arange_idx(bs, npoint, xyz.device)
+        elif method == "F-FPS":                                   # :102-105
+            fps_idx = ffps_indices(npoint, tmp_xyz, tmp_points, ffps_mode)
+        else:                                                     # D-FPS :106-107
+            fps_idx = tf_ops.farthest_point_sample(npoint, tmp_xyz)
+        cur.append(fps_idx + last if last else fps_idx)           # :109
+        last += rng
+    fps_idx = cur[0] if len(cur) == 1 else torch.cat(cur, dim=-1)
+    if former_fps_idx is not None:
+        fps_idx = torch.cat([fps_idx, former_fps_idx], dim=-1)    # :113-114
+    fps_idx = fps_idx.contiguous()
+    new_xyz = tf_ops.gather_point(vote_ctr if vote_ctr is not None else xyz, fps_idx)   # :116-119
+
+    debug = {"idx": [], "cnt": []}
+    outs = []
+    nscale = len(radius_list)
+    if nscale:
+        min_r = [0.0 if (i == 0 or not dilated_group) else radius_list[i - 1] for i in range(nscale)]   # :137-141
+        if nscale <= 4:   # one pass over the candidates for all shells
+            idx_list, cnt_list = tf_ops.query_ball_point_multi(min_r, radius_list, nsample_list, xyz, new_xyz,
+                                                               dilated_group)
+        else:
+            idx_list, cnt_list = [], []
+            for i in range(nscale):
+                if dilated_group:
+                    a, c = tf_ops.query_ball_point_dilated(min_r[i], radius_list[i], nsample_list[i], xyz, new_xyz)
+                else:
+                    a, c = tf_ops.query_ball_point(radius_list[i], nsample_list[i], xyz, new_xyz)
+                idx_list.append(a); cnt_list.append(c)
+        for i in range(nscale):
+            idx, cnt = idx_list[i], cnt_list[i]
+            # rows with cnt == 0 come back zero-filled, which is what idx * (cnt > 0) produces (:157-159)
+            debug["idx"].append(idx); debug["cnt"].append(cnt)
+            g = tf_ops.group_concat(xyz, points, new_xyz, idx)                    # :160-165 fused
+            nl = len(mlp_list[i])
+            for j in range(nl):
+                lastl = j == nl - 1
+                g = _conv(pp, "%s/conv%d_%d" % (scope, i, j), g, bn=bn,
+                          pool=nsample_list[i] if lastl else 1, rowmask=cnt if lastl else None)   # :167-180
+            outs.append(g)
+        new_points = outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
+        if aggregation and aggregation_channel is not None and aggregation_channel != -1:
+            new_points = _conv(pp, scope + "/ensemble", new_points, bn=bn)        # :183-185
+    else:
+        new_points = tf_ops.gather_point(points.contiguous(), fps_idx)           # :186-187
+    if return_debug:
+        return new_xyz, new_points, fps_idx, debug
+    return new_xyz, new_points, fps_idx
+
+
+def pointnet_sa_module(xyz, points, mlp, is_training, bn_decay, bn, scope, *, params):
+    """Global SA layer (layer type SA_Layer_SSG_Last): concat[xyz, points] -> MLP -> max over all points."""
+    if is_training:
+        raise NotImplementedError("inference only")
+    pp = prepare(params, xyz.device)
+    g = torch.cat([xyz, points], dim=-1).contiguous()              # xyz FIRST here (:42)
+    n = g.shape[1]
+    for j in range(len(mlp)):
+        g = _conv(pp, "%s/conv%d" % (scope, j), g, bn=bn)
+    return g.max(dim=1).values if n else g
+
+
+def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay, scope, bn=True, *, params):
+    """Feature propagation: inverse-distance interpolation from (xyz2, points2) onto xyz1, then an MLP."""
+    if is_training:
+        raise NotImplementedError("inference only")
+    pp = prepare(params, xyz1.device)
+    dist, idx = tf_ops.three_nn(xyz1, xyz2)
+    dist = torch.clamp_min(dist, 1e-10)                            # :207
+    inv = 1.0 / dist
+    weight = inv / inv.sum(dim=2, keepdim=True)                    # :208-210
+    x = tf_ops.three_interpolate(points2, idx, weight.contiguous())
+    if points1 is not None:
+        x = torch.cat([x, points1], dim=2).contiguous()            # :213-214
+    for i in range(len(mlp)):
+        x = _conv(pp, "%s/conv_%d" % (scope, i), x, bn=bn)
+    return x
+
+
+def vote_layer(xyz, points, mlp_list, is_training, bn_decay, bn, scope, *, params,
+               max_translate_range=_cfg.MAX_TRANSLATE_RANGE):
+    """Vote layer: per-point MLP -> 3 offsets, clamped to +-max_translate_range (layers_util.py:12-24)."""
+    if is_training:
+        raise NotImplementedError("inference only")
+    pp = prepare(params, xyz.device)
+    for i in range(len(mlp_list)):
+        points = _conv(pp, "%s/vote_layer_%d" % (scope, i), points, bn=bn)
+    off = _conv(pp, scope + "/vote_offsets", points, bn=False, relu=False)
+    lo = _const(tuple(max_translate_range), xyz.device).view(1, 1, 3)
+    lim = torch.minimum(torch.maximum(off, lo), -lo)
+    return xyz + lim, points, off

@@ -1,0 +1,120 @@
+"""Weights of the SA path: initialisation in the reference's variable layout and inference-time folding.
+
+Variable names follow the reference's TF scopes (lib/utils/layers_util.py:175,185 and
+lib/utils/tf_util.py:96,111,119):
+  <scope>/conv{i}_{j}/weights [cin,cout]   (TF kernel [1,1,cin,cout] squeezed)
+  <scope>/conv{i}_{j}/biases  [cout]
+  <scope>/conv{i}_{j}/bn/{gamma,beta,moving_mean,moving_variance} [cout]
+  <scope>/ensemble/...                      aggregation conv1d
+  <scope>/vote_layer_{i}/..., <scope>/vote_offsets/...  (vote layer, layers_util.py:18-19)
+"""
+import numpy as np
+import torch
+
+from . import config as _cfg
+
+BN_EPS = 1e-3  # tf.contrib.layers.batch_norm default epsilon (tf_util.py:439-444 does not override it)
+
+
+def _conv_init(rng, params, scope, cin, cout, bn):
+    limit = np.sqrt(6.0 / (cin + cout))  # tf.contrib.layers.xavier_initializer, uniform (tf_util.py:41)
+    params[scope + "/weights"] = rng.uniform(-limit, limit, size=(cin, cout)).astype(np.float32)
+    params[scope + "/biases"] = np.zeros((cout,), np.float32)  # tf_util.py:110
+    if bn:  # randomised statistics so that the folding is actually exercised
+        params[scope + "/bn/gamma"] = rng.uniform(0.5, 1.5, size=(cout,)).astype(np.float32)
+        params[scope + "/bn/beta"] = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+        params[scope + "/bn/moving_mean"] = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+        params[scope + "/bn/moving_variance"] = rng.uniform(0.5, 1.5, size=(cout,)).astype(np.float32)
+
+
+def init_params(arch, in_channels, seed=0, random_bias=False):
+    """Random weights for every conv of `arch` (numpy dict keyed by TF variable name)."""
+    rng = np.random.default_rng(seed)
+    params = {}
+    ch = _cfg.layer_channels(arch, in_channels)
+    for li, spec in enumerate(arch):
+        (_, feat_i, radius, _, mlps, bn, _, _, _, _, _, ltype, scope, _, _, agg) = spec
+        cin = ch[feat_i[0]]
+        if ltype == "SA_Layer":
+            if len(radius) == 0:
+                continue
+            for i, mlp in enumerate(mlps):
+                c = cin + 3
+                for j, cout in enumerate(mlp):
+                    _conv_init(rng, params, "%s/conv%d_%d" % (scope, i, j), c, cout, bn)
+                    c = cout
+            if agg is not None and agg != -1 and _cfg.AGGREGATION_SA_FEATURE:
+                _conv_init(rng, params, scope + "/ensemble", sum(m[-1] for m in mlps), agg, bn)
+        elif ltype == "Vote_Layer":
+            c = cin
+            for i, cout in enumerate(mlps):
+                _conv_init(rng, params, "%s/vote_layer_%d" % (scope, i), c, cout, bn)
+                c = cout
+            _conv_init(rng, params, scope + "/vote_offsets", c, 3, False)
+        elif ltype == "SA_Layer_SSG_Last":
+            c = cin + 3
+            for j, cout in enumerate(mlps):
+                _conv_init(rng, params, "%s/conv%d" % (scope, j), c, cout, bn)
+                c = cout
+        elif ltype == "FP_Layer":
+            c = cin + ch[feat_i[1]] if len(feat_i) > 1 else cin
+            for j, cout in enumerate(mlps):
+                _conv_init(rng, params, "%s/conv_%d" % (scope, j), c, cout, bn)
+                c = cout
+    if random_bias:
+        for k in list(params):
+            if k.endswith("/biases"):
+                params[k] = (0.1 * rng.standard_normal(params[k].shape)).astype(np.float32)
+    return params
+
+
+class FoldedConv:
+    """One conv+BN layer folded for inference: y = act((x @ w) * scale + shift)."""
+    __slots__ = ("w", "scale", "shift", "cin", "cout")
+
+    def __init__(self, w, scale, shift):
+        self.w, self.scale, self.shift = w, scale, shift
+        self.cin, self.cout = w.shape
+
+
+def fold(params, scope, bn, device):
+    """inv = gamma * rsqrt(var + eps);  y = (xW + b) * inv + (beta - mean * inv)   (tf_util.py:439-444)."""
+    w = np.asarray(params[scope + "/weights"], np.float64)
+    b = np.asarray(params.get(scope + "/biases", np.zeros(w.shape[1])), np.float64)
+    if bn:
+        g = np.asarray(params[scope + "/bn/gamma"], np.float64)
+        be = np.asarray(params[scope + "/bn/beta"], np.float64)
+        mu = np.asarray(params[scope + "/bn/moving_mean"], np.float64)
+        var = np.asarray(params[scope + "/bn/moving_variance"], np.float64)
+        inv = g / np.sqrt(var + BN_EPS)
+        scale, shift = inv, (b - mu) * inv + be
+    else:
+        scale, shift = np.ones_like(b), b
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
+    return FoldedConv(t(w), t(scale), t(shift))
+
+
+class PreparedParams:
+    """Device-resident folded weights, looked up by TF scope name (lazy, cached)."""
+
+    def __init__(self, params, device):
+        self.raw = params
+        self.device = torch.device(device)
+        self._cache = {}
+
+    def conv(self, scope, bn=True):
+        key = (scope, bool(bn))
+        if key not in self._cache:
+            self._cache[key] = fold(self.raw, scope, bn, self.device)
+        return self._cache[key]
+
+    def prepare_all(self):
+        for k in self.raw:
+            if k.endswith("/weights"):
+                scope = k[: -len("/weights")]
+                self.conv(scope, (scope + "/bn/gamma") in self.raw)
+        return self
+
+
+def prepare(params, device="cuda"):
+    return params if isinstance(params, PreparedParams) else PreparedParams(params, device)

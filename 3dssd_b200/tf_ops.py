@@ -1,0 +1,262 @@
+"""The reference's `tf_ops` operator surface on torch CUDA tensors.
+
+Same function names, argument orders and error behaviour as
+  /root/reference/lib/utils/tf_ops/sampling/tf_sampling.py      (:24 gather_point, :43 farthest_point_sample,
+                                                                  :54 farthest_point_sample_with_distance)
+  /root/reference/lib/utils/tf_ops/grouping/tf_grouping.py      (:53 query_ball_point, :68 query_ball_point_dilated,
+                                                                  :114 group_point)
+  /root/reference/lib/utils/tf_ops/interpolation/tf_interpolate.py (:8 three_nn, :21 three_interpolate)
+with the TF custom-op layer replaced by ctypes calls into libssd3d.so (include/ssd3d.h).  Shape / attribute
+checks mirror the reference's OP_REQUIRES (InvalidArgument -> ValueError); outputs are allocated here, like
+TF's allocate_output, and the kernels run on torch's current stream (CUDA-graph capturable).
+"""
+import ctypes
+
+import torch
+
+from ._lib import check, lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _req(t, name, dtype, rank, last=None):
+    if not isinstance(t, torch.Tensor):
+        raise ValueError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (there is no CPU path)" % name)
+    if t.dtype != dtype:
+        raise ValueError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if t.dim() != rank:
+        raise ValueError("%s must have rank %d, got shape %s" % (name, rank, tuple(t.shape)))
+    if last is not None and t.shape[-1] != last:
+        raise ValueError("%s must have last dimension %d, got shape %s" % (name, last, tuple(t.shape)))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def farthest_point_sample(npoint, inp):
+    """inp: (batch, ndataset, c) float32 -> (batch, npoint) int32.  tf_sampling.py:43-51; shape check
+    tf_sampling.cpp:142 (rank 3)."""
+    inp = _req(inp, "inp", torch.float32, 3)
+    npoint = int(npoint)
+    if npoint < 0:
+        raise ValueError("npoint must be non-negative")
+    b, n, c = inp.shape
+    out = torch.empty((b, npoint), dtype=torch.int32, device=inp.device)
+    temp = None
+    if lib().ssd3d_fps_needs_temp(n, c):
+        temp = torch.empty((b, n), dtype=torch.float32, device=inp.device)
+    check(lib().ssd3d_farthest_point_sample(b, n, c, npoint, _p(inp), _p(temp), _p(out), _stream()),
+          "farthest_point_sample")
+    return out
+
+
+furthest_point_sample = farthest_point_sample  # spelling used by BASELINE.json's north star
+
+
+def farthest_point_sample_with_distance(npoint, dist):
+    """dist: (batch, n, n) float32 distance matrix -> (batch, npoint) int32.  tf_sampling.py:54-62; the
+    square-matrix check is tf_sampling.cpp:175."""
+    dist = _req(dist, "dist", torch.float32, 3)
+    b, n, n2 = dist.shape
+    if n != n2:
+        raise ValueError("FarthestPointSampleWithDistance expects (batch_size,num_points,num_points) inp shape")
+    npoint = int(npoint)
+    out = torch.empty((b, npoint), dtype=torch.int32, device=dist.device)
+    temp = torch.empty((b, n), dtype=torch.float32, device=dist.device) if n > 65536 else None
+    check(lib().ssd3d_farthest_point_sample_with_distance(b, n, npoint, _p(dist), _p(temp), _p(out), _stream()),
+          "farthest_point_sample_with_distance")
+    return out
+
+
+def gather_point(inp, idx):
+    """inp (batch, ndataset, c) float32, idx (batch, npoints) int32 -> (batch, npoints, c).  tf_sampling.py:24-32."""
+    inp = _req(inp, "inp", torch.float32, 3)
+    idx = _req(idx, "idx", torch.int32, 2)
+    b, n, c = inp.shape
+    if idx.shape[0] != b:
+        raise ValueError("GatherPoint expects (batch_size,num_result) idx shape")
+    m = idx.shape[1]
+    out = torch.empty((b, m, c), dtype=torch.float32, device=inp.device)
+    check(lib().ssd3d_gather_point(b, n, m, c, _p(inp), _p(idx), _p(out), _stream()), "gather_point")
+    return out
+
+
+def _bq_shapes(xyz1, xyz2):
+    xyz1 = _req(xyz1, "xyz1", torch.float32, 3, 3)   # tf_grouping.cpp:283
+    xyz2 = _req(xyz2, "xyz2", torch.float32, 3, 3)   # tf_grouping.cpp:288
+    if xyz1.shape[0] != xyz2.shape[0]:
+        raise ValueError("xyz1 and xyz2 must share the batch dimension")
+    return xyz1, xyz2
+
+
+def query_ball_point(radius, nsample, xyz1, xyz2):
+    """xyz1 (batch, ndataset, 3), xyz2 (batch, npoint, 3) -> idx (batch, npoint, nsample) int32,
+    pts_cnt (batch, npoint) int32.  tf_grouping.py:53-65."""
+    xyz1, xyz2 = _bq_shapes(xyz1, xyz2)
+    if not radius > 0:
+        raise ValueError("QueryBallPoint expects positive radius")      # tf_grouping.cpp:275
+    if not int(nsample) > 0:
+        raise ValueError("QueryBallPoint expects positive nsample")     # tf_grouping.cpp:278
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    idx = torch.empty((b, m, int(nsample)), dtype=torch.int32, device=xyz1.device)
+    cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
+    check(lib().ssd3d_query_ball_point(b, n, m, float(radius), int(nsample), _p(xyz1), _p(xyz2), _p(idx), _p(cnt),
+                                       _stream()), "query_ball_point")
+    return idx, cnt
+
+
+def query_ball_point_dilated(min_radius, max_radius, nsample, xyz1, xyz2):
+    """Shell query  d == 0 or min_radius <= d < max_radius.  tf_grouping.py:68-81."""
+    xyz1, xyz2 = _bq_shapes(xyz1, xyz2)
+    if not max_radius > 0:
+        raise ValueError("QueryBallPointDilated expects positive radius")
+    if not int(nsample) > 0:
+        raise ValueError("QueryBallPointDilated expects positive nsample")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    idx = torch.empty((b, m, int(nsample)), dtype=torch.int32, device=xyz1.device)
+    cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
+    check(lib().ssd3d_query_ball_point_dilated(b, n, m, float(min_radius), float(max_radius), int(nsample), _p(xyz1),
+                                               _p(xyz2), _p(idx), _p(cnt), _stream()), "query_ball_point_dilated")
+    return idx, cnt
+
+
+def query_ball_point_multi(min_radius_list, max_radius_list, nsample_list, xyz1, xyz2, dilated):
+    """All radius shells of one SA layer in a single pass over the candidates (B200 fast path; same results
+    as calling query_ball_point[_dilated] once per shell).  Returns lists (idx_list, pts_cnt_list)."""
+    xyz1, xyz2 = _bq_shapes(xyz1, xyz2)
+    nq = len(max_radius_list)
+    if not (len(nsample_list) == nq and len(min_radius_list) == nq and 1 <= nq <= 4):
+        raise ValueError("query_ball_point_multi takes 1..4 shells with matching list lengths")
+    for r, k in zip(max_radius_list, nsample_list):
+        if not r > 0:
+            raise ValueError("QueryBallPoint expects positive radius")
+        if not int(k) > 0:
+            raise ValueError("QueryBallPoint expects positive nsample")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    idx = [torch.empty((b, m, int(k)), dtype=torch.int32, device=xyz1.device) for k in nsample_list]
+    cnt = [torch.empty((b, m), dtype=torch.int32, device=xyz1.device) for _ in nsample_list]
+    lo = (ctypes.c_float * nq)(*[float(v) for v in min_radius_list])
+    hi = (ctypes.c_float * nq)(*[float(v) for v in max_radius_list])
+    ks = (ctypes.c_int * nq)(*[int(v) for v in nsample_list])
+    pi = (ctypes.c_void_p * nq)(*[t.data_ptr() for t in idx])
+    pc = (ctypes.c_void_p * nq)(*[t.data_ptr() for t in cnt])
+    check(lib().ssd3d_query_ball_point_multi(b, n, m, nq, 1 if dilated else 0, ctypes.cast(lo, ctypes.c_void_p),
+                                             ctypes.cast(hi, ctypes.c_void_p), ctypes.cast(ks, ctypes.c_void_p),
+                                             _p(xyz1), _p(xyz2), ctypes.cast(pi, ctypes.c_void_p),
+                                             ctypes.cast(pc, ctypes.c_void_p), _stream()), "query_ball_point_multi")
+    return idx, cnt
+
+
+def group_point(points, idx):
+    """points (batch, ndataset, channel) float32, idx (batch, npoint, nsample) int32 ->
+    (batch, npoint, nsample, channel); idx == -1 gives zeros.  tf_grouping.py:114-122."""
+    points = _req(points, "points", torch.float32, 3)
+    idx = _req(idx, "idx", torch.int32, 3)
+    b, n, c = points.shape
+    if idx.shape[0] != b:
+        raise ValueError("GroupPoint expects (batch_size, npoints, nsample) idx shape")
+    _, m, ns = idx.shape
+    out = torch.empty((b, m, ns, c), dtype=torch.float32, device=points.device)
+    check(lib().ssd3d_group_point(b, n, c, m, ns, _p(points), _p(idx), _p(out), _stream()), "group_point")
+    return out
+
+
+def three_nn(xyz1, xyz2):
+    """xyz1 (b,n,3) unknown, xyz2 (b,m,3) known -> dist (b,n,3) float32 (squared), idx (b,n,3) int32.
+    tf_interpolate.py:8-19."""
+    xyz1 = _req(xyz1, "xyz1", torch.float32, 3, 3)   # tf_interpolate.cpp:222
+    xyz2 = _req(xyz2, "xyz2", torch.float32, 3, 3)   # tf_interpolate.cpp:227
+    if xyz1.shape[0] != xyz2.shape[0]:
+        raise ValueError("xyz1 and xyz2 must share the batch dimension")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dist = torch.empty((b, n, 3), dtype=torch.float32, device=xyz1.device)
+    idx = torch.empty((b, n, 3), dtype=torch.int32, device=xyz1.device)
+    check(lib().ssd3d_three_nn(b, n, m, _p(xyz1), _p(xyz2), _p(dist), _p(idx), _stream()), "three_nn")
+    return dist, idx
+
+
+def three_interpolate(points, idx, weight):
+    """points (b,m,c), idx (b,n,3) int32, weight (b,n,3) -> (b,n,c).  tf_interpolate.py:21-31."""
+    points = _req(points, "points", torch.float32, 3)
+    idx = _req(idx, "idx", torch.int32, 3, 3)
+    weight = _req(weight, "weight", torch.float32, 3, 3)
+    b, m, c = points.shape
+    n = idx.shape[1]
+    if idx.shape[0] != b or weight.shape != idx.shape:
+        raise ValueError("ThreeInterpolate expects (b,n,3) idx and weight shapes")
+    out = torch.empty((b, n, c), dtype=torch.float32, device=points.device)
+    check(lib().ssd3d_three_interpolate(b, m, c, n, _p(points), _p(idx), _p(weight), _p(out), _stream()),
+          "three_interpolate")
+    return out
+
+
+# ---- dense pieces that are stock TF ops in the reference -------------------------------------------------
+
+def calc_square_dist(a):
+    """model_util.calc_square_dist(a, a, norm=False) (/root/reference/lib/utils/model_util.py:144-160)."""
+    a = _req(a, "a", torch.float32, 3)
+    b, n, c = a.shape
+    out = torch.empty((b, n, n), dtype=torch.float32, device=a.device)
+    check(lib().ssd3d_calc_square_dist(b, n, c, _p(a), _p(out), _stream()), "calc_square_dist")
+    return out
+
+
+def group_concat(xyz, points, new_xyz, idx, ldx=None):
+    """concat[group_point(points, idx), group_point(xyz, idx) - new_xyz] (layers_util.py:160-165) in one kernel.
+    Returns x (b, m, nsample, ldx) with zero padding beyond c+3."""
+    xyz = _req(xyz, "xyz", torch.float32, 3, 3)
+    new_xyz = _req(new_xyz, "new_xyz", torch.float32, 3, 3)
+    idx = _req(idx, "idx", torch.int32, 3)
+    b, n, _ = xyz.shape
+    c = 0
+    if points is not None:
+        points = _req(points, "points", torch.float32, 3)
+        c = points.shape[2]
+    _, m, ns = idx.shape
+    ldx = c + 3 if ldx is None else int(ldx)
+    x = torch.empty((b, m, ns, ldx), dtype=torch.float32, device=xyz.device)
+    check(lib().ssd3d_group_concat(b, n, c, m, ns, _p(xyz), _p(points), _p(new_xyz), _p(idx), _p(x), ldx, _stream()),
+          "group_concat")
+    return x
+
+
+def linear_bn_relu(x, w, scale, shift, relu=True, pool=1, rowmask=None, cin=None):
+    """act((x[..., :cin] @ w) * scale + shift) over the last axis; pool > 1 max-pools runs of `pool` rows and
+    multiplies by rowmask != 0 (layers_util.py:178-180).  x (..., ldx), w (cin, cout)."""
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise ValueError("x must be a float32 CUDA tensor")
+    x = x if x.is_contiguous() else x.contiguous()
+    w = _req(w, "w", torch.float32, 2)
+    wcin, cout = w.shape
+    cin = wcin if cin is None else cin
+    ldx = x.shape[-1]
+    if cin != wcin or ldx < cin:
+        raise ValueError("linear_bn_relu: x last dim %d / cin %d do not match w %s" % (ldx, cin, tuple(w.shape)))
+    rows = x.numel() // ldx
+    pool = int(pool)
+    lead = tuple(x.shape[:-1])
+    if pool > 1:
+        if lead[-1] != pool:
+            raise ValueError("pool must equal the second-to-last dimension of x")
+        if 128 % pool != 0:
+            y = linear_bn_relu(x, w, scale, shift, relu, 1, None, cin)
+            out = torch.empty(lead[:-1] + (cout,), dtype=torch.float32, device=x.device)
+            check(lib().ssd3d_rowgroup_max(rows // pool, pool, cout, _p(y), cout, _p(rowmask), _p(out), _stream()),
+                  "rowgroup_max")
+            return out
+        y = torch.empty(lead[:-1] + (cout,), dtype=torch.float32, device=x.device)
+    else:
+        y = torch.empty(lead + (cout,), dtype=torch.float32, device=x.device)
+    check(lib().ssd3d_linear_bn_relu(rows, cin, cout, _p(x), ldx, _p(w), _p(scale), _p(shift), 1 if relu else 0, pool,
+                                     _p(rowmask), _p(y), cout, _stream()), "linear_bn_relu")
+    return y

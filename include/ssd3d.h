@@ -1,0 +1,134 @@
+/*
+ * ssd3d.h -- C ABI of libssd3d.so, the B200 (sm_100a) implementation of the set-abstraction
+ * operators of dvlab-research/3DSSD.
+ *
+ * Drop-in boundary (seam iii): the reference's TF custom ops call free C++
+ * "Launcher" functions that take plain ints and raw device pointers; each entry point below
+ * replaces one of them with the same argument list, plus a CUDA stream and an int status
+ * (0 = cudaSuccess, otherwise a cudaError_t or SSD3D_ERR_*).  Citations are file:line under
+ * /root/reference/lib/utils/tf_ops/ (declaration in the .cpp that the TF op binds, definition at
+ * the tail of the matching *_g.cu).
+ *
+ * Conventions, identical to the reference: dense row-major tensors, batch-major; fp32 values,
+ * int32 indices; every pointer is a DEVICE pointer owned by the caller; the library allocates
+ * nothing, keeps no state between calls, never synchronises the host, and is CUDA-graph
+ * capturable.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ */
+#ifndef SSD3D_H_
+#define SSD3D_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSD3D_ERR_INVALID_ARGUMENT (-1) /* mirrors the reference's OP_REQUIRES -> InvalidArgument */
+#define SSD3D_ERR_UNSUPPORTED      (-2)
+
+typedef void *ssd3d_stream_t;
+
+/* ABI version of this header (bumped on any signature change). */
+int ssd3d_version(void);
+/* Human-readable description of the last non-zero status returned on this thread. */
+const char *ssd3d_last_error(void);
+
+/* ---- sampling ------------------------------------------------------------------------------ */
+
+/* replaces farthestpointsamplingLauncher(b,n,c,m,inp,temp,out)
+ *   sampling/tf_sampling.cpp:131 (decl), sampling/tf_sampling_g.cu:392-394 (def), kernel :124-178.
+ * D-FPS over inp[b,n,c] (any c; c==3 takes the on-chip cluster kernel).  out[b,m] int32.
+ * temp[b,n] fp32 scratch is only touched by the large-n fallback; it may be NULL when
+ * ssd3d_fps_needs_temp(n,c)==0.  Bit-exact, including the reference's tie-break (value desc,
+ * k mod 1024 asc, k asc). */
+int ssd3d_farthest_point_sample(int b, int n, int c, int m, const float *inp, float *temp, int *out,
+                                ssd3d_stream_t stream);
+int ssd3d_fps_needs_temp(int n, int c);
+
+/* replaces farthestpointsamplingwithdistLauncher(b,n,m,inp,temp,out)
+ *   sampling/tf_sampling.cpp:164, sampling/tf_sampling_g.cu:396-398, kernel :181-230.
+ * F-FPS over a precomputed distance matrix dist[b,n,n]. */
+int ssd3d_farthest_point_sample_with_distance(int b, int n, int m, const float *dist, float *temp, int *out,
+                                              ssd3d_stream_t stream);
+
+/* replaces gatherpointLauncher(b,n,m,c,inp,idx,out)
+ *   sampling/tf_sampling.cpp:235, sampling/tf_sampling_g.cu:403-407, kernel :320-331.
+ * out[b,m,c] = inp[b, idx[b,m], c] */
+int ssd3d_gather_point(int b, int n, int m, int c, const float *inp, const int *idx, float *out,
+                       ssd3d_stream_t stream);
+
+/* ---- grouping ------------------------------------------------------------------------------ */
+
+/* replaces queryBallPointLauncher(b,n,m,radius,nsample,xyz1,xyz2,idx,pts_cnt)
+ *   grouping/tf_grouping.cpp:270, grouping/tf_grouping_g.cu:461-464, kernel :215-255.
+ * idx[b,m,nsample], pts_cnt[b,m].  Rows with pts_cnt==0 are written as zeros (the reference leaves
+ * them uninitialised and its caller masks them, lib/utils/layers_util.py:157-159). */
+int ssd3d_query_ball_point(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2,
+                           int *idx, int *pts_cnt, ssd3d_stream_t stream);
+
+/* replaces queryBallPointDilatedLauncher(b,n,m,min_radius,max_radius,nsample,xyz1,xyz2,idx,pts_cnt)
+ *   grouping/tf_grouping.cpp:363, grouping/tf_grouping_g.cu:465-468, kernel :308-357. */
+int ssd3d_query_ball_point_dilated(int b, int n, int m, float min_radius, float max_radius, int nsample,
+                                   const float *xyz1, const float *xyz2, int *idx, int *pts_cnt,
+                                   ssd3d_stream_t stream);
+
+/* B200 fast path used by pointnet_sa_module_msg: up to 4 (min_r,max_r,nsample) queries over the same
+ * (xyz1,xyz2) answered in ONE pass over the candidates (the reference scans once per radius,
+ * lib/utils/layers_util.py:134-147).  dilated!=0 selects the :308-357 predicate, else the :215-255 one
+ * (min_radius ignored).  idx[s] / pts_cnt[s] are per-query outputs as above. */
+int ssd3d_query_ball_point_multi(int b, int n, int m, int nqueries, int dilated, const float *min_radius,
+                                 const float *max_radius, const int *nsample, const float *xyz1, const float *xyz2,
+                                 int *const *idx, int *const *pts_cnt, ssd3d_stream_t stream);
+
+/* replaces groupPointLauncher(b,n,c,m,nsample,points,idx,out)
+ *   grouping/tf_grouping.cpp:446, grouping/tf_grouping_g.cu:476-479, kernel :362-379.
+ * out[b,m,nsample,c] = points[b, idx[b,m,nsample], c]; idx==-1 -> 0 */
+int ssd3d_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
+                      ssd3d_stream_t stream);
+
+/* ---- interpolation ------------------------------------------------------------------------- */
+
+/* replaces ThreeNNLauncher(b,n,m,xyz1,xyz2,dist,idx)
+ *   interpolation/tf_interpolate.cpp:215, interpolation/tf_interpolate_g.cu:191-195, kernel :24-84. */
+int ssd3d_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx,
+                   ssd3d_stream_t stream);
+
+/* replaces ThreeInterpolateLauncher(b,m,c,n,points,idx,weight,out)
+ *   interpolation/tf_interpolate.cpp:285, interpolation/tf_interpolate_g.cu:198-200, kernel :87-113. */
+int ssd3d_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx, const float *weight,
+                            float *out, ssd3d_stream_t stream);
+
+/* ---- dense parts of the SA layer (TF stock ops in the reference) ---------------------------- */
+
+/* model_util.calc_square_dist(a, a, norm=False)  (lib/utils/model_util.py:144-160) for a[b,n,c]:
+ * out[b,i,j] = (|a_i|^2 + |a_j|^2) - 2 a_i.a_j, fp32, channel sums as sequential fma chains
+ * (order pinned so the oracle can be bit-exact; the reference's cuBLAS order is unspecified). */
+int ssd3d_calc_square_dist(int b, int n, int c, const float *a, float *out, ssd3d_stream_t stream);
+
+/* Fused gather + concat of lib/utils/layers_util.py:160-165:
+ *   x[b,m,k,:] = concat( points[b, idx[b,m,k], 0:c],  xyz[b, idx[b,m,k], :] - new_xyz[b,m,:] )
+ * written with row stride ldx (>= c+3; columns c+3..ldx-1 are zero-filled). */
+int ssd3d_group_concat(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
+                       const float *new_xyz, const int *idx, float *x, int ldx, ssd3d_stream_t stream);
+
+/* One tf_util.conv2d/conv1d 1x1 layer at inference (lib/utils/tf_util.py:51-201, BN :424-444) with
+ * bias and BatchNorm pre-folded by the caller into per-channel (scale, shift):
+ *   y[r, o] = act( (sum_k x[r,k] * w[k,o]) * scale[o] + shift[o] ),  act = relu or identity.
+ * x[rows, ldx] (first cin columns used), w[cin, cout] (the TF kernel [1,1,cin,cout]), y[rows, ldy].
+ * pool > 1: instead of y, write ymax[rows/pool, cout] = max over each run of `pool` consecutive rows
+ * (tf.reduce_max(axis=2), layers_util.py:178) times rowmask[rows/pool] when rowmask != NULL (:180). */
+int ssd3d_linear_bn_relu(long rows, int cin, int cout, const float *x, int ldx, const float *w,
+                         const float *scale, const float *shift, int relu, int pool, const int *rowmask,
+                         float *y, int ldy, ssd3d_stream_t stream);
+
+/* ymax[g, 0:c] = max over rows g*pool .. g*pool+pool-1 of y[., 0:c] (times rowmask[g] != 0): the
+ * tf.reduce_max(axis=2) * mask of layers_util.py:178-180 for nsample values the fused epilogue of
+ * ssd3d_linear_bn_relu does not cover (pool must divide 128 there). */
+int ssd3d_rowgroup_max(long groups, int pool, int c, const float *y, int ldy, const int *rowmask, float *out,
+                       ssd3d_stream_t stream);
+
+/* Tuning hook (tests/benchmarks only): force the FPS cluster size (1,2,4,8,16); 0 restores the heuristic. */
+void ssd3d_tune_set_fps_cluster(int cluster_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSD3D_H_ */

@@ -1,0 +1,178 @@
+"""numpy front-end of the CPU oracle (oracle/ssd3d_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see the header of ssd3d_oracle.c.  Function names and argument
+orders follow the reference's Python operator surface
+(/root/reference/lib/utils/tf_ops/{sampling/tf_sampling.py:24-62, grouping/tf_grouping.py:53-122,
+interpolation/tf_interpolate.py:8-31}) with numpy arrays in place of TF tensors.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i32p = ctypes.POINTER(ctypes.c_int)
+
+
+def build(force=False):
+    """Compile liboracle.so with gcc (seconds)."""
+    src = os.path.join(_HERE, "ssd3d_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        _lib.oracle_get_threads.restype = ctypes.c_int
+    return _lib
+
+
+def set_threads(n):
+    lib().oracle_set_threads(ctypes.c_int(int(n)))
+
+
+def get_threads():
+    return int(lib().oracle_get_threads())
+
+
+def _f(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(_f32p)
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_i32p)
+
+
+def farthest_point_sample(npoint, inp):
+    inp, p = _f(inp)
+    b, n, c = inp.shape
+    out = np.zeros((b, npoint), np.int32)
+    temp = np.empty((b, n), np.float32)
+    lib().oracle_farthest_point_sample(b, n, c, int(npoint), p, temp.ctypes.data_as(_f32p), out.ctypes.data_as(_i32p))
+    return out
+
+
+def farthest_point_sample_with_distance(npoint, dist):
+    dist, p = _f(dist)
+    b, n, n2 = dist.shape
+    assert n == n2
+    out = np.zeros((b, npoint), np.int32)
+    temp = np.empty((b, n), np.float32)
+    lib().oracle_farthest_point_sample_with_distance(b, n, int(npoint), p, temp.ctypes.data_as(_f32p),
+                                                     out.ctypes.data_as(_i32p))
+    return out
+
+
+def gather_point(inp, idx):
+    inp, p = _f(inp)
+    idx, q = _i(idx)
+    b, n, c = inp.shape
+    m = idx.shape[1]
+    out = np.empty((b, m, c), np.float32)
+    lib().oracle_gather_point(b, n, m, c, p, q, out.ctypes.data_as(_f32p))
+    return out
+
+
+def query_ball_point(radius, nsample, xyz1, xyz2):
+    xyz1, p1 = _f(xyz1)
+    xyz2, p2 = _f(xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    idx = np.zeros((b, m, nsample), np.int32)
+    cnt = np.zeros((b, m), np.int32)
+    lib().oracle_query_ball_point(b, n, m, ctypes.c_float(radius), int(nsample), p1, p2,
+                                  idx.ctypes.data_as(_i32p), cnt.ctypes.data_as(_i32p))
+    return idx, cnt
+
+
+def query_ball_point_dilated(min_radius, max_radius, nsample, xyz1, xyz2):
+    xyz1, p1 = _f(xyz1)
+    xyz2, p2 = _f(xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    idx = np.zeros((b, m, nsample), np.int32)
+    cnt = np.zeros((b, m), np.int32)
+    lib().oracle_query_ball_point_dilated(b, n, m, ctypes.c_float(min_radius), ctypes.c_float(max_radius),
+                                          int(nsample), p1, p2, idx.ctypes.data_as(_i32p), cnt.ctypes.data_as(_i32p))
+    return idx, cnt
+
+
+def group_point(points, idx):
+    points, p = _f(points)
+    idx, q = _i(idx)
+    b, n, c = points.shape
+    _, m, ns = idx.shape
+    out = np.empty((b, m, ns, c), np.float32)
+    lib().oracle_group_point(b, n, c, m, ns, p, q, out.ctypes.data_as(_f32p))
+    return out
+
+
+def three_nn(xyz1, xyz2):
+    xyz1, p1 = _f(xyz1)
+    xyz2, p2 = _f(xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dist = np.empty((b, n, 3), np.float32)
+    idx = np.empty((b, n, 3), np.int32)
+    with np.errstate(over="ignore"):
+        lib().oracle_three_nn(b, n, m, p1, p2, dist.ctypes.data_as(_f32p), idx.ctypes.data_as(_i32p))
+    return dist, idx
+
+
+def three_interpolate(points, idx, weight):
+    points, p = _f(points)
+    idx, q = _i(idx)
+    weight, w = _f(weight)
+    b, m, c = points.shape
+    n = idx.shape[1]
+    out = np.empty((b, n, c), np.float32)
+    lib().oracle_three_interpolate(b, m, c, n, p, q, w, out.ctypes.data_as(_f32p))
+    return out
+
+
+def calc_square_dist(a):
+    """model_util.calc_square_dist(a, a, norm=False) with the pinned fp32 summation order."""
+    a, p = _f(a)
+    b, n, c = a.shape
+    out = np.empty((b, n, n), np.float32)
+    lib().oracle_calc_square_dist(b, n, c, p, out.ctypes.data_as(_f32p))
+    return out
+
+
+def linear_bn_relu(x, w, bias=None, bn=None, relu=True):
+    """conv(1x1)+BN+ReLU over the last axis; bn = (gamma, beta, moving_mean, moving_var) or None."""
+    x, px = _f(x)
+    w, pw = _f(w)
+    cin, cout = w.shape
+    assert x.shape[-1] == cin
+    rows = int(np.prod(x.shape[:-1]))
+    y = np.empty(x.shape[:-1] + (cout,), np.float32)
+    null = ctypes.cast(None, _f32p)
+    keep = []
+
+    def opt(v):
+        if v is None:
+            return null
+        v, pv = _f(v)
+        keep.append(v)
+        return pv
+
+    pb = opt(bias)
+    if bn is None:
+        g = be = mu = va = null
+    else:
+        g, be, mu, va = (opt(t) for t in bn)
+    lib().oracle_linear_bn_relu(ctypes.c_long(rows), cin, cout, px, pw, pb, g, be, mu, va, int(bool(relu)),
+                                y.ctypes.data_as(_f32p))
+    return y
