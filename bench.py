@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- KITTI-shape scenes/sec of the full 3DSSD SA backbone (BASELINE.json metric, configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (the reference arm, see below)
+
+A "step" is one pass of the whole backbone (layer1..layer4 of configs/kitti/3dssd/3dssd.yaml, incl. the vote
+layer) over one batch of 8 synthetic KITTI-shaped scenes [8,16384,4] per GPU (weak scaling: the batch is
+sharded by scene, no data-path collective; one NCCL all-gather of the per-scene detection blocks ends a step).
+
+value  : scenes/s, inputs resident in HBM, the step replayed from a CUDA graph, per-step CUDA-event time
+         (max over ranks), L2 flushed between steps.
+e2e    : same metric through the public API with HOST buffers: pinned H2D copy of the batch + backbone +
+         D2H read of the detection block inside the timed region.
+roofline: dominant kernel (D-FPS layer 1) timed live with CUDA events on its launch stream.
+cpu_baseline: the CPU restatement (oracle/, fp32 BLAS MLP) on a bounded sample of the same workload.
+
+--impl reference: the reference's implementation of this path is CUDA (lib/utils/tf_ops/*_g.cu) -- it has no
+CPU code for sampling/grouping (SURVEY.md finding 4).  The arm therefore runs the reference's OWN kernels,
+compiled unmodified into oracle/_ref/libref_ops.so, on the same GPU, with PyTorch fp32 ops standing in
+one-for-one for the TF stock ops (oracle/ref_layers.py); if that library is absent it falls back to the CPU
+port.  Its cpu_baseline object carries the CPU port timing in both cases.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "KITTI-shape scenes/sec (B×16384 pts) full SA backbone, 1/2/4/8×B200"
+UNIT = "scenes/s"
+SCENES_PER_GPU = 8
+NPOINTS = 16384
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi) during the timed region
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on a bounded sample
+# ----------------------------------------------------------------------------------------------------------
+def cpu_baseline(arch, params, pts_np, max_scenes=2):
+    """Times the CPU restatement of the whole backbone (oracle/, all host threads; MLP through numpy's fp32
+    BLAS instead of the double-precision checker loop) on the first `max_scenes` scenes of the workload."""
+    from oracle import layers as olayers
+    from oracle import ops as oops
+    oops.build()
+    cores = oops.get_threads()
+    saved = oops.linear_bn_relu
+
+    def fast_linear(x, w, bias=None, bn=None, relu=True):
+        y = x.reshape(-1, x.shape[-1]) @ w
+        if bias is not None:
+            y = y + bias
+        if bn is not None:
+            g, be, mu, var = bn
+            inv = g / np.sqrt(var + np.float32(1e-3))
+            y = y * inv + (be - mu * inv)
+        if relu:
+            np.maximum(y, 0, out=y)
+        return y.reshape(x.shape[:-1] + (w.shape[1],)).astype(np.float32, copy=False)
+
+    oops.linear_bn_relu = fast_linear
+    try:
+        sample = np.ascontiguousarray(pts_np[:max_scenes])
+        t0 = time.perf_counter()
+        olayers.backbone_forward(arch, sample, params, ffps_mode="matrix")
+        dt = time.perf_counter() - t0
+    finally:
+        oops.linear_bn_relu = saved
+    return {"value": sample.shape[0] / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of the %d scenes of one step, full backbone, oracle/ C restatement + numpy fp32 BLAS MLP, %.1f s"
+                      % (sample.shape[0], pts_np.shape[0], dt)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ffps-mode", default="matrix", choices=["matrix", "fused"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-scenes", type=int, default=2)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
+        return                                   # under torchrun rank 0 alone runs the reference arm
+
+    import torch
+    pkg = importlib.import_module("3dssd_b200")
+    synth = importlib.import_module("3dssd_b200.synth")
+    if args.impl == "reference":
+        rank, world, local = 0, int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    else:
+        rank, world, local = pkg.dist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    arch = pkg.config.ARCH_3DSSD
+    params = pkg.params.init_params(arch, 1, seed=0)
+    pts_np = synth.kitti_like(SCENES_PER_GPU, NPOINTS, seed=1000 + rank * SCENES_PER_GPU)
+
+    if args.impl == "reference":
+        return run_reference(args, torch, pkg, arch, params, pts_np, rank, world, dev)
+
+    import torch.distributed as dist
+    net = pkg.SABackbone(arch, params, in_channels=1, device=dev, ffps_mode=args.ffps_mode)
+    pts = torch.from_numpy(pts_np).to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    # launches per step, counted at the ctypes boundary (every C-ABI call below launches exactly one kernel)
+    counter = {"n": 0}
+    L = pkg.lib()
+    counted = [n for n in pkg.EXPORTS if n not in ("ssd3d_version", "ssd3d_last_error", "ssd3d_fps_needs_temp",
+                                                    "ssd3d_tune_set_fps_cluster")]
+    originals = {n: getattr(L, n) for n in counted}
+
+    class Counting:
+        def __init__(self, fn):
+            self.fn = fn
+
+        def __call__(self, *a):
+            counter["n"] += 1
+            return self.fn(*a)
+
+    for n in counted:
+        setattr(L, n, Counting(originals[n]))
+    out = net.forward(pts)
+    blk, cnt = net.detection_block(out[0], out[1])
+    torch.cuda.synchronize()
+    launches_per_step = counter["n"]
+    for n in counted:
+        setattr(L, n, originals[n])
+
+    replay = net.capture(pts)
+    gather_buf = None
+
+    def step_device():
+        outg, (b, c) = replay()
+        return pkg.dist.gather_detections(b, c) if world > 1 else (b, c)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    evs = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_device()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+
+    # ---- e2e: host buffers through the public API ---------------------------------------------------------
+    host_in = torch.from_numpy(pts_np).pin_memory()
+    host_out = torch.empty((SCENES_PER_GPU, 100, 9), dtype=torch.float32).pin_memory()
+    host_cnt = torch.empty((SCENES_PER_GPU,), dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        outg, (b, c) = replay(host_in)                       # pinned H2D into the graph's static input, then replay
+        if world > 1:
+            b, c = pkg.dist.gather_detections(b, c)
+            b, c = b[rank * SCENES_PER_GPU:(rank + 1) * SCENES_PER_GPU], c[rank * SCENES_PER_GPU:(rank + 1) * SCENES_PER_GPU]
+        host_out.copy_(b, non_blocking=True)
+        host_cnt.copy_(c, non_blocking=True)
+
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    evs2 = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_e2e()
+        e1.record()
+        evs2.append((e0, e1))
+    barrier()
+    e2e_ms = float(sum(a.elapsed_time(b) for a, b in evs2))
+
+    # ---- roofline of the dominant kernel: D-FPS layer 1, timed alone with events on its stream --------------
+    xyz = pts[..., :3].contiguous()
+    for _ in range(3):
+        pkg.farthest_point_sample(4096, xyz)
+    torch.cuda.synchronize()
+    kev = []
+    for _ in range(max(5, min(args.steps, 20))):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pkg.farthest_point_sample(4096, xyz)
+        e1.record()
+        kev.append((e0, e1))
+    torch.cuda.synchronize()
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms, k_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms, k_ms = (float(v) for v in t.tolist())
+
+    if rank == 0:
+        peaks = {}
+        ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(ppath):
+            peaks = json.load(open(ppath))
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        fps_bytes = SCENES_PER_GPU * (4096 - 1) * NPOINTS * 16          # B*(M-1)*N*(4c+4), SURVEY.md 8d
+        achieved = fps_bytes / (k_ms * 1e-3) / 1e9
+        scenes = SCENES_PER_GPU * world * args.steps
+        line = {
+            "metric": METRIC, "value": scenes / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: full 3DSSD SA backbone (3dssd.yaml layer1-4 + vote), synthetic KITTI "
+                                   "16384x4 clouds, batch 8 per GPU", "scenes_per_gpu": SCENES_PER_GPU,
+                       "global_batch": SCENES_PER_GPU * world, "points": NPOINTS, "parallelism": "scene-sharded dp%d" % world,
+                       "ffps": args.ffps_mode, "l2": "flushed (256 MiB write) between timed steps",
+                       "timing": "sum of per-step CUDA-event times on the launch stream, max over ranks; CUDA-graph replay",
+                       "wall_s_bracket": wall},
+            "e2e": {"value": scenes / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(host_in.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4 + host_cnt.numel() * 4)},
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "kernel": "fps3_cluster_kernel (D-FPS layer 1, 16384->4096, B=8)",
+                         "kernel_ms": k_ms,
+                         "note": "effective-stream bytes B*(M-1)*N*16 (what the reference streams per round, SURVEY 8d); "
+                                 "the kernel keeps them on-chip, so frac can exceed 1 and DRAM traffic is ~2 MB; peak = "
+                                 + ("MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)")},
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(arch, params, pts_np, args.cpu_scenes)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args, torch, pkg, arch, params, pts_np, rank, world, dev):
+    """Reference arm (see module docstring).  Under torchrun only rank 0 works."""
+    if rank != 0:
+        return
+    from oracle import ref_ops
+    cpu = cpu_baseline(arch, params, pts_np, args.cpu_scenes)
+    if not ref_ops.available():
+        line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": world,
+                "steps": 1, "warmup": 0, "ms_per_step": 1e3 * SCENES_PER_GPU / cpu["value"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[1] (CPU port: oracle/_ref not built)"},
+                "cpu_baseline": cpu,
+                "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+    from oracle import ref_layers
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    pts = torch.from_numpy(pts_np).to(dev)
+    cache = {}
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    for _ in range(max(1, min(args.warmup, 3))):
+        ref_layers.backbone_forward(arch, pts, params, cache)
+    torch.cuda.synchronize()
+    steps = args.steps
+    sampler = ClockSampler(dev.index or 0).start()
+    tot = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ref_layers.backbone_forward(arch, pts, params, cache)
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    val = SCENES_PER_GPU * steps / (tot * 1e-3)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 1, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": tot / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: full 3DSSD SA backbone, synthetic KITTI 16384x4 clouds, batch 8",
+                       "reference_device": "B200: the reference's own CUDA kernels (oracle/_ref/libref_ops.so, unmodified "
+                                           "sources, nvcc -O2 sm_100) + PyTorch fp32 ops one-for-one for the TF stock ops; "
+                                           "the reference has no CPU implementation of this path",
+                       "l2": "flushed between timed steps"},
+            "clocks": clocks,
+            "cpu_baseline": cpu,
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -85,7 +85,7 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
         outs.append(new_points)
     if outs:
         new_points = np.concatenate(outs, axis=-1)
-        if aggregation:                                            # cfg.MODEL.NETWORK.AGGREGATION_SA_FEATURE :183-185
+        if aggregation and aggregation_channel is not None and aggregation_channel != -1:   # cfg...AGGREGATION_SA_FEATURE :183-185
             new_points = _conv(params, scope + "/ensemble", new_points, bn=bn)
     else:
         new_points = ops.gather_point(points, fps_idx)             # :186-187

@@ -1,0 +1,165 @@
+"""GPU parity tests (-m gpu) of the layer / backbone orchestration: pointnet_sa_module_msg and the whole 3DSSD
+SA backbone against the CPU oracle (indices bit-exact, features <= 1e-3 relative fp32, BASELINE.json)."""
+import copy
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+synth = importlib.import_module("3dssd_b200.synth")
+TOL = 1e-3   # BASELINE.json north star: grouped-MLP features within 1e-3 relative fp32
+
+
+def rel_err(got, exp):
+    return float(np.abs(got.astype(np.float64) - exp.astype(np.float64)).max() / max(1e-12, np.abs(exp).max()))
+
+
+def scaled_arch(pkg, div):
+    """ARCH_3DSSD with every point count divided by `div` (same layer structure, radii, MLP widths)."""
+    arch = copy.deepcopy(pkg.config.ARCH_3DSSD)
+    for spec in arch:
+        spec[6] = [r if r == -1 else max(1, r // div) for r in spec[6]]
+        spec[8] = [p if p in (-1, 0) else max(1, p // div) for p in spec[8]]
+    return arch
+
+
+def compact_scene(batch, n, seed):
+    """KITTI-like cloud squeezed so that a 1/8-size scene keeps the point density the radii were tuned for."""
+    pts = synth.kitti_like(batch, n, seed=seed)
+    pts[..., 0] *= 0.35
+    pts[..., 2] *= 0.35
+    return pts
+
+
+def check_backbone(pkg, net_out, oracle_out, nlayers):
+    xyz_l, feat_l, fps_l, dbg = net_out
+    oxyz, ofeat, ofps, odbg = oracle_out
+    for li in range(1, nlayers + 1):
+        if ofps[li] is not None:
+            np.testing.assert_array_equal(fps_l[li].cpu().numpy(), ofps[li], err_msg="fps_idx of layer %d" % li)
+        d, od = dbg[li - 1], odbg[li - 1]
+        for s, (a, b) in enumerate(zip(d.get("idx", []), od.get("idx", []))):
+            np.testing.assert_array_equal(a.cpu().numpy(), b, err_msg="ball-query idx layer %d scale %d" % (li, s))
+        for s, (a, b) in enumerate(zip(d.get("cnt", []), od.get("cnt", []))):
+            np.testing.assert_array_equal(a.cpu().numpy(), b, err_msg="pts_cnt layer %d scale %d" % (li, s))
+        if oxyz[li] is not None:
+            e = rel_err(xyz_l[li].cpu().numpy(), oxyz[li])
+            assert e < TOL, "xyz of layer %d: rel err %g" % (li, e)
+        e = rel_err(feat_l[li].cpu().numpy(), ofeat[li])
+        assert e < TOL, "features of layer %d: rel err %g" % (li, e)
+
+
+@pytest.mark.parametrize("ffps_mode", ["matrix", "fused"])
+def test_backbone_small_vs_oracle(pkg, oracle_ops, cuda, ffps_mode):
+    from oracle import layers as olayers
+    arch = scaled_arch(pkg, 8)                                    # 2048 -> 512 -> 128 -> 64 -> 32 centres
+    params = pkg.params.init_params(arch, 1, seed=4, random_bias=True)
+    pts = compact_scene(2, 2048, seed=40)
+    net = pkg.SABackbone(arch, params, in_channels=1, device=cuda, ffps_mode=ffps_mode)
+    out = net.forward(torch.from_numpy(pts).to(cuda), return_debug=True)
+    exp = olayers.backbone_forward(arch, pts, params, ffps_mode=ffps_mode, return_debug=True)
+    check_backbone(pkg, out, exp, len(arch))
+    assert out[1][-1].shape == (2, 32, 512)
+
+
+def test_single_sa_layer_plain_query_vs_oracle(pkg, oracle_ops, cuda):
+    """BASELINE configs[0]: one SA layer N=4096 -> 1024, plain ball query r=0.4, K=32, C=64, MLP [64,64,128]."""
+    from oracle import layers as olayers
+    arch = pkg.config.ARCH_SINGLE_SA
+    rng = np.random.default_rng(0)
+    pts = np.concatenate([synth.uniform_cube(2, 4096, seed=1), rng.standard_normal((2, 4096, 64)).astype(np.float32)], -1)
+    params = pkg.params.init_params(arch, 64, seed=1, random_bias=True)
+    net = pkg.SABackbone(arch, params, in_channels=64, device=cuda)
+    out = net.forward(torch.from_numpy(pts).to(cuda), return_debug=True)
+    exp = olayers.backbone_forward(arch, pts, params, return_debug=True)
+    check_backbone(pkg, out, exp, 1)
+
+
+def test_sa_module_with_empty_balls_and_vote_ctr(pkg, oracle_ops, cuda):
+    """CG-layer shape: queries are free-floating centres (vote_ctr), plain query, some balls empty -> masked rows."""
+    from oracle import layers as olayers
+    rng = np.random.default_rng(5)
+    xyz = rng.uniform(0, 4, (2, 256, 3)).astype(np.float32)
+    feats = rng.standard_normal((2, 256, 32)).astype(np.float32)
+    ctr = rng.uniform(-1, 5, (2, 64, 3)).astype(np.float32)      # some far outside -> empty balls
+    arch = [[[0], [0], [0.6, 1.2], [16, 32], [[32, 32, 64], [32, 64, 64]], True, [-1], ['D-FPS'], [64],
+             -1, False, 'SA_Layer', 'cg', False, -1, 48]]
+    params = pkg.params.init_params(arch, 32, seed=2, random_bias=True)
+    args = (arch[0][2], arch[0][3], arch[0][4], False, None, True, [-1], ['D-FPS'], [64], None, False, 'cg', False)
+    got = pkg.pointnet_sa_module_msg(torch.from_numpy(xyz).to(cuda), torch.from_numpy(feats).to(cuda), *args,
+                                     vote_ctr=torch.from_numpy(ctr).to(cuda), aggregation_channel=48, params=params,
+                                     return_debug=True)
+    exp = olayers.pointnet_sa_module_msg(xyz, feats, *args, vote_ctr=ctr, aggregation_channel=48, params=params,
+                                         return_debug=True)
+    assert (exp[3]["cnt"][0] == 0).any(), "the case must contain empty balls"
+    np.testing.assert_array_equal(got[2].cpu().numpy(), exp[2])
+    for a, b in zip(got[3]["idx"], exp[3]["idx"]):
+        np.testing.assert_array_equal(a.cpu().numpy(), b)
+    np.testing.assert_array_equal(got[0].cpu().numpy(), exp[0])
+    assert rel_err(got[1].cpu().numpy(), exp[1]) < TOL
+
+
+def test_fp_and_global_sa_modules_vs_oracle(pkg, oracle_ops, cuda):
+    from oracle import layers as olayers
+    rng = np.random.default_rng(6)
+    xyz1 = rng.uniform(0, 1, (2, 300, 3)).astype(np.float32); xyz2 = rng.uniform(0, 1, (2, 70, 3)).astype(np.float32)
+    p1 = rng.standard_normal((2, 300, 8)).astype(np.float32); p2 = rng.standard_normal((2, 70, 24)).astype(np.float32)
+    arch = [[[0, 1], [0, 1], -1, -1, [32, 16], True, [-1], [-1], [-1], -1, -1, 'FP_Layer', 'fp', False, -1, -1]]
+    rngp = np.random.default_rng(1)
+    params = {}
+    P = pkg.params
+    P._conv_init(rngp, params, "fp/conv_0", 32, 32, True); P._conv_init(rngp, params, "fp/conv_1", 32, 16, True)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    got = pkg.pointnet_fp_module(t(xyz1), t(xyz2), t(p1), t(p2), [32, 16], False, None, "fp", True, params=params)
+    exp = olayers.pointnet_fp_module(xyz1, xyz2, p1, p2, [32, 16], False, None, "fp", True, params=params)
+    assert rel_err(got.cpu().numpy(), exp) < TOL
+    params = {}
+    P._conv_init(rngp, params, "g/conv0", 11, 32, True); P._conv_init(rngp, params, "g/conv1", 32, 64, True)
+    got = pkg.pointnet_sa_module(t(xyz1), t(p1), [32, 64], False, None, True, "g", params=params)
+    exp = olayers.pointnet_sa_module(xyz1, p1, [32, 64], False, None, True, "g", params=params)
+    assert got.shape == (2, 64) and rel_err(got.cpu().numpy(), exp) < TOL
+
+
+def test_backbone_full_size_one_scene_vs_oracle(pkg, oracle_ops, cuda):
+    """BASELINE configs[1] at full size (16384 points, real layer table), one scene so the CPU oracle finishes
+    in about a minute."""
+    from oracle import layers as olayers
+    arch = pkg.config.ARCH_3DSSD
+    params = pkg.params.init_params(arch, 1, seed=0)
+    pts = synth.kitti_like(1, 16384, seed=1000)
+    net = pkg.SABackbone(arch, params, in_channels=1, device=cuda)
+    out = net.forward(torch.from_numpy(pts).to(cuda), return_debug=True)
+    exp = olayers.backbone_forward(arch, pts, params, return_debug=True)
+    check_backbone(pkg, out, exp, len(arch))
+
+
+def test_backbone_full_size_properties_and_graph_replay(pkg, cuda):
+    """Full configs[1] batch: shapes, invariants the domain offers, and CUDA-graph replay == eager."""
+    net = pkg.SABackbone(device=cuda)
+    pts = torch.from_numpy(synth.kitti_like(8, 16384, seed=1000)).to(cuda)
+    xyz_l, feat_l, fps_l, dbg = net.forward(pts, return_debug=True)
+    assert [tuple(f.shape) for f in feat_l[1:]] == [(8, 4096, 64), (8, 1024, 128), (8, 512, 256), (8, 256, 256),
+                                                    (8, 256, 128), (8, 256, 512)]
+    f1 = fps_l[1]
+    assert (f1[:, 0] == 0).all()
+    # D-FPS samples of distinct locations are distinct while unsampled distinct points remain
+    assert all(len(set(row.tolist())) > 4000 for row in f1.cpu())
+    for d in dbg[:3]:                                             # dilated layers: self hit -> cnt >= 1
+        for c in d["cnt"]:
+            assert int(c.min()) >= 1
+    for f in feat_l[1:]:
+        assert torch.isfinite(f).all()
+    blk, cnt = net.detection_block(xyz_l, feat_l)
+    assert blk.shape == (8, 100, 9) and cnt.shape == (8,)
+    replay = net.capture(pts)
+    out2, (blk2, cnt2) = replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out2[1][-1], feat_l[-1]) and torch.equal(blk2, blk)
+    pts2 = torch.from_numpy(synth.kitti_like(8, 16384, seed=2000)).to(cuda)
+    out3, _ = replay(pts2)
+    torch.cuda.synchronize()
+    eager = net.forward(pts2)
+    assert torch.equal(out3[1][-1], eager[1][-1]) and torch.equal(out3[2][1], eager[2][1])

@@ -1,0 +1,300 @@
+"""GPU parity tests (-m gpu): every operator of libssd3d.so, called through the tf_ops surface (ctypes ->
+C ABI), against (a) the CPU oracle and (b) the reference's own kernels run live (oracle/_ref).
+Integer outputs must be bit-exact; fp32 copies / interpolation bit-exact; the MLP within 1e-3 relative."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+synth = importlib.import_module("3dssd_b200.synth")
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# farthest point sampling
+# ---------------------------------------------------------------------------------------------------------
+FPS_CASES = [
+    ("rand300", lambda: np.random.default_rng(0).uniform(-1, 1, (3, 300, 3)).astype(np.float32), 64),
+    ("rand1000", lambda: np.random.default_rng(1).uniform(-1, 1, (2, 1000, 3)).astype(np.float32), 100),
+    ("rand1500", lambda: np.random.default_rng(2).uniform(-1, 1, (2, 1500, 3)).astype(np.float32), 200),
+    ("rand5000", lambda: np.random.default_rng(3).uniform(-1, 1, (2, 5000, 3)).astype(np.float32), 300),
+    ("kitti4096", lambda: synth.kitti_like(2, 4096, seed=7)[..., :3].copy(), 512),
+    ("lattice3000", lambda: synth.lattice(2, 3000, seed=3), 256),
+    ("dups", lambda: np.repeat(np.random.default_rng(4).uniform(-1, 1, (1, 500, 3)).astype(np.float32), 3, axis=1), 600),
+    ("allsame", lambda: np.ones((2, 700, 3), np.float32), 50),
+    ("single", lambda: np.random.default_rng(5).uniform(-1, 1, (1, 1, 3)).astype(np.float32), 4),
+]
+
+
+@pytest.mark.parametrize("name,gen,m", FPS_CASES, ids=[c[0] for c in FPS_CASES])
+def test_fps_xyz_bit_exact_vs_oracle(pkg, oracle_ops, cuda, name, gen, m):
+    pts = gen()
+    exp = oracle_ops.farthest_point_sample(m, pts)
+    got = N(pkg.farthest_point_sample(m, T(pts, cuda)))
+    np.testing.assert_array_equal(got, exp)
+
+
+@pytest.mark.parametrize("cl", [1, 2, 4, 8, 16])
+def test_fps_every_cluster_size(pkg, oracle_ops, cuda, cl):
+    """The result must not depend on how a scene is split over the cluster."""
+    pts = synth.kitti_like(3, 4096, seed=21)[..., :3].copy()
+    pts[:, 2000:2100] = pts[:, 100:200]                              # extra duplicates
+    exp = oracle_ops.farthest_point_sample(300, pts)
+    pkg.lib().ssd3d_tune_set_fps_cluster(cl)
+    try:
+        got = N(pkg.farthest_point_sample(300, T(pts, cuda)))
+    finally:
+        pkg.lib().ssd3d_tune_set_fps_cluster(0)
+    np.testing.assert_array_equal(got, exp)
+
+
+def test_fps_full_size_vs_reference_kernel(pkg, ref_ops, cuda):
+    """BASELINE config-2 layer-1 shape: 16384 -> 4096 on KITTI-like clouds (with duplicate padding)."""
+    pts = T(synth.kitti_like(2, 16384, seed=1000)[..., :3].copy(), cuda)
+    exp = ref_ops.farthest_point_sample(4096, pts)
+    got = pkg.farthest_point_sample(4096, pts)
+    assert torch.equal(got, exp)
+    # size-independent properties: first index 0, every index in range
+    assert (got[:, 0] == 0).all() and int(got.min()) >= 0 and int(got.max()) < 16384
+
+
+@pytest.mark.parametrize("n,c,m", [(512, 67, 128), (512, 131, 256), (4096, 67, 512), (300, 5, 40), (1000, 19, 77)])
+def test_fps_generic_c_bit_exact(pkg, oracle_ops, cuda, n, c, m):
+    rng = np.random.default_rng(n + c)
+    f = rng.standard_normal((2, n, c)).astype(np.float32)
+    f[:, n // 2: n // 2 + 10] = f[:, :10]                            # duplicates
+    exp = oracle_ops.farthest_point_sample(m, f)
+    got = N(pkg.farthest_point_sample(m, T(f, cuda)))
+    np.testing.assert_array_equal(got, exp)
+
+
+def test_fps_generic_c_vs_reference_kernel(pkg, ref_ops, cuda):
+    f = T(np.random.default_rng(9).standard_normal((2, 2048, 67)).astype(np.float32), cuda)
+    assert torch.equal(pkg.farthest_point_sample(256, f), ref_ops.farthest_point_sample(256, f))
+
+
+@pytest.mark.parametrize("n,m,quant", [(384, 96, False), (384, 96, True), (1500, 128, False), (4096, 200, True)])
+def test_fps_with_distance_bit_exact(pkg, oracle_ops, ref_ops, cuda, n, m, quant):
+    rng = np.random.default_rng(n)
+    f = rng.standard_normal((2, n, 6)).astype(np.float32)
+    d = T(f, cuda)
+    dist = pkg.calc_square_dist(d)
+    if quant:
+        dist = torch.round(dist * 2) / 2                             # many exact ties
+    got = pkg.farthest_point_sample_with_distance(m, dist)
+    assert torch.equal(got, ref_ops.farthest_point_sample_with_distance(m, dist))
+    if n <= 1500:
+        np.testing.assert_array_equal(N(got), oracle_ops.farthest_point_sample_with_distance(m, N(dist)))
+
+
+def test_calc_square_dist_bit_exact_vs_oracle(pkg, oracle_ops, cuda):
+    rng = np.random.default_rng(12)
+    for n, c in ((200, 67), (333, 131), (64, 4)):
+        f = rng.standard_normal((2, n, c)).astype(np.float32)
+        np.testing.assert_array_equal(N(pkg.calc_square_dist(T(f, cuda))), oracle_ops.calc_square_dist(f))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ball query
+# ---------------------------------------------------------------------------------------------------------
+def _masked(idx, cnt):
+    return idx * (cnt > 0)[..., None].astype(idx.dtype)
+
+
+BQ_INPUTS = [
+    ("kitti4096", lambda: synth.kitti_like(2, 4096, seed=11)[..., :3].copy(), 384),
+    ("odd1001", lambda: np.random.default_rng(1).uniform(0, 1, (2, 1001, 3)).astype(np.float32), 77),   # n % 4 != 0: non-TMA path
+    ("lattice1500", lambda: synth.lattice(1, 1500, seed=5), 200),
+    ("tiny", lambda: np.random.default_rng(2).uniform(0, 1, (3, 5, 3)).astype(np.float32), 5),
+]
+
+
+@pytest.mark.parametrize("name,gen,m", BQ_INPUTS, ids=[c[0] for c in BQ_INPUTS])
+@pytest.mark.parametrize("radius,k", [(0.25, 16), (0.5, 32), (2.0, 64), (0.5, 5)])
+def test_query_ball_point_bit_exact(pkg, oracle_ops, ref_ops, cuda, name, gen, m, radius, k):
+    xyz1 = gen()
+    xyz2 = np.array(xyz1[:, :m], copy=True)
+    xyz2[:, -1] += 1000.0                                            # one query with an empty ball
+    eidx, ecnt = oracle_ops.query_ball_point(radius, k, xyz1, xyz2)
+    idx, cnt = pkg.query_ball_point(radius, k, T(xyz1, cuda), T(xyz2, cuda))
+    np.testing.assert_array_equal(N(cnt), ecnt)
+    np.testing.assert_array_equal(N(idx), eidx)
+    ridx, rcnt = ref_ops.query_ball_point(radius, k, T(xyz1, cuda), T(xyz2, cuda))
+    assert torch.equal(cnt, rcnt)
+    np.testing.assert_array_equal(N(idx), _masked(N(ridx), N(rcnt)))
+
+
+@pytest.mark.parametrize("name,gen,m", BQ_INPUTS, ids=[c[0] for c in BQ_INPUTS])
+@pytest.mark.parametrize("lo,hi,k", [(0.0, 0.25, 16), (0.25, 0.5, 32), (0.5, 2.0, 64)])
+def test_query_ball_point_dilated_bit_exact(pkg, oracle_ops, ref_ops, cuda, name, gen, m, lo, hi, k):
+    xyz1 = gen()
+    xyz2 = np.array(xyz1[:, :m], copy=True)
+    xyz2[:, -1] += 1000.0
+    eidx, ecnt = oracle_ops.query_ball_point_dilated(lo, hi, k, xyz1, xyz2)
+    idx, cnt = pkg.query_ball_point_dilated(lo, hi, k, T(xyz1, cuda), T(xyz2, cuda))
+    np.testing.assert_array_equal(N(cnt), ecnt)
+    np.testing.assert_array_equal(N(idx), eidx)
+    ridx, rcnt = ref_ops.query_ball_point_dilated(lo, hi, k, T(xyz1, cuda), T(xyz2, cuda))
+    assert torch.equal(cnt, rcnt)
+    np.testing.assert_array_equal(N(idx), _masked(N(ridx), N(rcnt)))
+
+
+@pytest.mark.parametrize("dilated", [True, False])
+def test_query_ball_point_multi_equals_single_calls(pkg, cuda, dilated):
+    xyz1 = T(synth.kitti_like(2, 4096, seed=31)[..., :3].copy(), cuda)
+    xyz2 = xyz1[:, :500].contiguous()
+    radii, ks = [0.4, 0.8, 1.6], [32, 32, 64]
+    lows = [0.0, 0.4, 0.8]
+    idxs, cnts = pkg.query_ball_point_multi(lows, radii, ks, xyz1, xyz2, dilated)
+    for i in range(3):
+        if dilated:
+            a, c = pkg.query_ball_point_dilated(lows[i], radii[i], ks[i], xyz1, xyz2)
+        else:
+            a, c = pkg.query_ball_point(radii[i], ks[i], xyz1, xyz2)
+        assert torch.equal(idxs[i], a) and torch.equal(cnts[i], c)
+
+
+def test_ball_query_full_size_vs_reference_kernel(pkg, ref_ops, cuda):
+    """Layer-1 shape of BASELINE config 2: 4096 D-FPS queries over 16384 points, the three dilated shells."""
+    pts = T(synth.kitti_like(1, 16384, seed=1003)[..., :3].copy(), cuda)
+    fidx = pkg.farthest_point_sample(4096, pts)
+    q = pkg.gather_point(pts, fidx)
+    idxs, cnts = pkg.query_ball_point_multi([0.0, 0.2, 0.4], [0.2, 0.4, 0.8], [32, 32, 64], pts, q, True)
+    for i, (lo, hi, k) in enumerate(((0.0, 0.2, 32), (0.2, 0.4, 32), (0.4, 0.8, 64))):
+        ridx, rcnt = ref_ops.query_ball_point_dilated(lo, hi, k, pts, q)
+        assert torch.equal(cnts[i], rcnt)
+        assert torch.equal(idxs[i], ridx * (rcnt > 0).unsqueeze(-1).to(ridx.dtype))
+        assert int(cnts[i].min()) >= 1                               # queries are input points: d == 0 self hit
+        valid = torch.arange(1, k, device=cuda)[None, None, :] < cnts[i][..., None]   # slots 1..cnt-1
+        ascending = idxs[i][..., 1:] > idxs[i][..., :-1]             # neighbour lists are strictly ascending up to cnt
+        assert bool((ascending | ~valid).all())
+        backfill = idxs[i] == idxs[i][..., :1]                       # slots >= cnt repeat the first hit
+        assert bool((backfill[..., 1:] | valid).all())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# gather / group / interpolation
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c", [3, 13, 64])
+def test_gather_and_group_point(pkg, oracle_ops, cuda, c):
+    rng = np.random.default_rng(c)
+    feats = rng.standard_normal((2, 700, c)).astype(np.float32)
+    gi = rng.integers(0, 700, (2, 90)).astype(np.int32)
+    np.testing.assert_array_equal(N(pkg.gather_point(T(feats, cuda), T(gi, cuda))), oracle_ops.gather_point(feats, gi))
+    gidx = rng.integers(-1, 700, (2, 40, 6)).astype(np.int32)
+    np.testing.assert_array_equal(N(pkg.group_point(T(feats, cuda), T(gidx, cuda))), oracle_ops.group_point(feats, gidx))
+
+
+def test_group_concat_equals_reference_op_sequence(pkg, oracle_ops, cuda):
+    rng = np.random.default_rng(3)
+    xyz = rng.uniform(0, 1, (2, 300, 3)).astype(np.float32)
+    feats = rng.standard_normal((2, 300, 7)).astype(np.float32)
+    new_xyz = np.ascontiguousarray(xyz[:, :20])
+    idx = rng.integers(0, 300, (2, 20, 8)).astype(np.int32)
+    exp = np.concatenate([oracle_ops.group_point(feats, idx), oracle_ops.group_point(xyz, idx) - new_xyz[:, :, None]], -1)
+    got = N(pkg.group_concat(T(xyz, cuda), T(feats, cuda), T(new_xyz, cuda), T(idx, cuda), ldx=12))
+    np.testing.assert_array_equal(got[..., :10], exp)
+    assert (got[..., 10:] == 0).all()
+
+
+@pytest.mark.parametrize("n,m", [(600, 150), (1030, 2100), (17, 2), (5, 1)])
+def test_three_nn_bit_exact(pkg, oracle_ops, ref_ops, cuda, n, m):
+    rng = np.random.default_rng(n + m)
+    u = rng.uniform(0, 1, (2, n, 3)).astype(np.float32)
+    kn = rng.uniform(0, 1, (2, m, 3)).astype(np.float32)
+    ed, ei = oracle_ops.three_nn(u, kn)
+    d, i = pkg.three_nn(T(u, cuda), T(kn, cuda))
+    np.testing.assert_array_equal(N(i), ei)
+    np.testing.assert_array_equal(N(d), ed)
+    rd, ri = ref_ops.three_nn(T(u, cuda), T(kn, cuda))
+    assert torch.equal(i, ri) and torch.equal(d, rd)
+
+
+def test_three_nn_ties_lattice(pkg, oracle_ops, cuda):
+    u, kn = synth.lattice(1, 400, seed=8), synth.lattice(1, 120, seed=9)
+    ed, ei = oracle_ops.three_nn(u, kn)
+    d, i = pkg.three_nn(T(u, cuda), T(kn, cuda))
+    np.testing.assert_array_equal(N(i), ei)
+    np.testing.assert_array_equal(N(d), ed)
+
+
+def test_three_interpolate_bit_exact(pkg, oracle_ops, ref_ops, cuda):
+    rng = np.random.default_rng(6)
+    pf = rng.standard_normal((2, 150, 20)).astype(np.float32)
+    idx = rng.integers(0, 150, (2, 600, 3)).astype(np.int32)
+    w = rng.uniform(0, 1, (2, 600, 3)).astype(np.float32)
+    got = pkg.three_interpolate(T(pf, cuda), T(idx, cuda), T(w, cuda))
+    np.testing.assert_array_equal(N(got), oracle_ops.three_interpolate(pf, idx, w))
+    assert torch.equal(got, ref_ops.three_interpolate(T(pf, cuda), T(idx, cuda), T(w, cuda)))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# conv + BN + ReLU (+ max-pool): 1e-3 relative fp32 (BASELINE.json north star)
+# ---------------------------------------------------------------------------------------------------------
+def rel_err(got, exp):
+    return float(np.abs(got.astype(np.float64) - exp.astype(np.float64)).max() / max(1e-12, np.abs(exp).max()))
+
+
+@pytest.mark.parametrize("rows,cin,cout", [(1000, 4, 16), (4096, 67, 64), (777, 131, 128), (512, 259, 256), (130, 512, 1024)])
+def test_linear_bn_relu_vs_oracle(pkg, oracle_ops, cuda, rows, cin, cout):
+    rng = np.random.default_rng(rows)
+    x = rng.standard_normal((rows, cin)).astype(np.float32)
+    w = (rng.standard_normal((cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    bn = (rng.uniform(0.5, 1.5, cout).astype(np.float32), rng.standard_normal(cout).astype(np.float32),
+          rng.standard_normal(cout).astype(np.float32), rng.uniform(0.5, 1.5, cout).astype(np.float32))
+    exp = oracle_ops.linear_bn_relu(x, w, b, bn, relu=True)
+    P = importlib.import_module("3dssd_b200.params")
+    params = {"s/weights": w, "s/biases": b, "s/bn/gamma": bn[0], "s/bn/beta": bn[1], "s/bn/moving_mean": bn[2],
+              "s/bn/moving_variance": bn[3]}
+    f = P.fold(params, "s", True, cuda)
+    got = N(pkg.linear_bn_relu(T(x, cuda), f.w, f.scale, f.shift, relu=True))
+    assert rel_err(got, exp) < 1e-4                                  # fp32 FMA path: far inside the 1e-3 budget
+
+
+@pytest.mark.parametrize("pool", [16, 32, 64, 24])
+def test_linear_pool_mask(pkg, oracle_ops, cuda, pool):
+    rng = np.random.default_rng(pool)
+    b, m, cin, cout = 2, 37, 35, 48
+    x = rng.standard_normal((b, m, pool, cin)).astype(np.float32)
+    w = rng.standard_normal((cin, cout)).astype(np.float32)
+    cnt = rng.integers(0, 3, (b, m)).astype(np.int32)
+    y = oracle_ops.linear_bn_relu(x, w, None, None, relu=True)
+    exp = y.max(axis=2) * (cnt > 0)[..., None]
+    one = torch.ones(cout, device=cuda); zero = torch.zeros(cout, device=cuda)
+    got = N(pkg.linear_bn_relu(T(x, cuda), T(w, cuda), one, zero, relu=True, pool=pool, rowmask=T(cnt, cuda)))
+    assert got.shape == (b, m, cout)
+    assert rel_err(got, exp) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------
+# error behaviour (reference: OP_REQUIRES -> InvalidArgument)
+# ---------------------------------------------------------------------------------------------------------
+def test_argument_validation(pkg, cuda):
+    xyz = torch.zeros((1, 10, 3), device=cuda)
+    with pytest.raises(ValueError):
+        pkg.query_ball_point(-1.0, 4, xyz, xyz)                      # tf_grouping.cpp:275
+    with pytest.raises(ValueError):
+        pkg.query_ball_point(1.0, 0, xyz, xyz)                       # tf_grouping.cpp:278
+    with pytest.raises(ValueError):
+        pkg.query_ball_point(1.0, 4, torch.zeros((1, 10, 4), device=cuda), xyz)   # last dim must be 3
+    with pytest.raises(ValueError):
+        pkg.farthest_point_sample(4, torch.zeros((10, 3), device=cuda))           # rank 3 (tf_sampling.cpp:142)
+    with pytest.raises(ValueError):
+        pkg.farthest_point_sample_with_distance(4, torch.zeros((1, 10, 9), device=cuda))  # square (cpp:175)
+    with pytest.raises(ValueError):
+        pkg.gather_point(xyz, torch.zeros((1, 4), dtype=torch.int64, device=cuda))  # int32 indices
+    with pytest.raises(ValueError):
+        pkg.farthest_point_sample(4, torch.zeros((1, 10, 3)))                     # CPU tensor: no CPU path
+    # empty batch / zero samples are no-ops like the reference's early return
+    assert pkg.farthest_point_sample(0, xyz).shape == (1, 0)
