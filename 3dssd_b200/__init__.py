@@ -7,7 +7,8 @@ from .backbone import SABackbone  # noqa: F401
 from .layers_util import (pointnet_fp_module, pointnet_sa_module, pointnet_sa_module_msg,  # noqa: F401
                           vote_layer)
 from .tf_ops import (calc_square_dist, farthest_point_sample, farthest_point_sample_with_distance,  # noqa: F401
-                     furthest_point_sample, gather_point, group_concat, group_point, linear_bn_relu,
+                     furthest_point_sample, gather_point, group_concat, group_concat_split, group_point, linear_bn_relu,
+                     linear_tc, split_rows,
                      query_ball_point, query_ball_point_dilated, query_ball_point_multi, three_interpolate,
                      three_nn)
 

@@ -534,8 +534,8 @@ extern "C" int ssd3d_farthest_point_sample(int b, int n, int c, int m, const flo
                                            ssd3d_stream_t stream)
 {
     SSD3D_REQUIRE(b >= 0 && n > 0 && c > 0 && m >= 0, "farthest_point_sample: bad shape b=%d n=%d c=%d m=%d", b, n, c, m);
-    SSD3D_REQUIRE(inp && out, "farthest_point_sample: null pointer");
     if (b == 0 || m == 0) return 0;  // tf_sampling_g.cu:126-127
+    SSD3D_REQUIRE(inp && out, "farthest_point_sample: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = -100;
     if (c == 3) {
@@ -558,8 +558,8 @@ extern "C" int ssd3d_farthest_point_sample_with_distance(int b, int n, int m, co
                                                          int *out, ssd3d_stream_t stream)
 {
     SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0, "farthest_point_sample_with_distance: bad shape b=%d n=%d m=%d", b, n, m);
-    SSD3D_REQUIRE(dist && out, "farthest_point_sample_with_distance: null pointer");
     if (b == 0 || m == 0) return 0;
+    SSD3D_REQUIRE(dist && out, "farthest_point_sample_with_distance: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     int cl = pick_cl_xyz(n);
     while (cl < 16 && pick_p(n, cl) > 16) cl *= 2;

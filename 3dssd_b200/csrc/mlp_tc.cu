@@ -1,0 +1,433 @@
+// mlp_tc.cu -- the grouped-MLP layers on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// One layer of the SA point MLP, y = act((x . W) * scale + shift) [+ max-pool over the neighbour axis], i.e. the
+// conv2d/bias/BN/ReLU/reduce_max chain of /root/reference/lib/utils/tf_util.py:127-201, :424-444 and
+// /root/reference/lib/utils/layers_util.py:167-180, as ONE persistent warp-specialised GEMM kernel.
+//
+// Precision (DESIGN.md "Grouped MLP"): the reference computes in fp32 and the parity budget is 1e-3 relative.
+// A single TF32/BF16 pass does not hold that through three chained layers, so every fp32 operand is split into
+// two bf16 terms, x = x_hi + x_lo (16 mantissa bits), and the product is evaluated as three bf16 MMAs
+//     x.W ~= x_hi.W_hi + x_lo.W_hi + x_hi.W_lo          (error ~2^-16, fp32 accumulation in TMEM)
+// at 3x the bf16 tensor rate instead of the 2x-slower TF32 pipe.  Activations travel between layers already
+// split (two bf16 matrices, row-major == K-major), so every operand tile is a plain TMA box in the 128B-swizzled
+// canonical UMMA layout and no conversion happens on the load path.
+//
+// Kernel shape: 256 threads; warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (TMEM -> registers -> scale/shift/ReLU -> fp32 / split-bf16 / pooled store).
+// Tile 128 rows x BN<=256 columns, K streamed in 64-element blocks through a multi-stage mbarrier ring;
+// two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ssd3d {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int TC_THREADS = 256;
+constexpr int TC_EPI_WARP0 = 4;           // warps 4..7 are the epilogue (warp%4 selects the TMEM lane quarter)
+constexpr int TC_MAX_STAGES = 4;
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;   // one A tile (hi or lo): 16 KiB
+
+struct TcParams {
+    long rows;
+    int kp;          // K padded to a multiple of 16
+    int n;           // output channels
+    int bn;          // tile width (multiple of 16, <= 256)
+    int n_tiles, m_tiles, stages;
+    const float *scale, *shift;
+    int relu, pool;
+    const int *rowmask;
+    float *out_f32; int ld_f32;
+    __nv_bfloat16 *out_hi, *out_lo; int ld_split;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major, 128B-swizzled operand tile: rows are 128 bytes, 8-row groups are 1024 bytes apart (SBO), version 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+                 const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+                 const TcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages] x { A_hi | A_lo | B_hi | B_lo }, then the pooling staging tile
+    const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
+    const uint32_t stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float *pool_stage = reinterpret_cast<float *>(smem + (size_t)p.stages * stage_bytes);   // [128][33]
+
+    __shared__ unsigned long long full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int nkb = (p.kp + TC_BK - 1) / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ahi) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_alo) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bhi) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait_cta(smem_u32(&empty_bar[s]), ph ^ 1u);
+                    const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    mbar_arrive_expect_tx(fb, stage_bytes);
+                    tma_load_2d(base, &map_ahi, kb * TC_BK, mt * TC_BM, fb);
+                    tma_load_2d(base + TC_A_BYTES, &map_alo, kb * TC_BK, mt * TC_BM, fb);
+                    tma_load_2d(base + 2 * TC_A_BYTES, &map_bhi, kb * TC_BK, nt * p.bn, fb);
+                    tma_load_2d(base + 2 * TC_A_BYTES + b_bytes, &map_blo, kb * TC_BK, nt * p.bn, fb);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N = bn, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            int it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+                const int acc = tcount & 1;
+                mbar_wait_cta(smem_u32(&tempty_bar[acc]), (((uint32_t)(tcount >> 1)) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % p.stages;
+                    mbar_wait_cta(smem_u32(&full_bar[s]), (uint32_t)(it / p.stages) & 1u);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+                    const int ksteps = min(TC_BK, p.kp - kb * TC_BK) / 16;
+                    for (int ks = 0; ks < ksteps; ks++) {
+                        const uint64_t a_hi = umma_desc(base + ks * 32);
+                        const uint64_t a_lo = umma_desc(base + TC_A_BYTES + ks * 32);
+                        const uint64_t b_hi = umma_desc(base + 2 * TC_A_BYTES + ks * 32);
+                        const uint64_t b_lo = umma_desc(base + 2 * TC_A_BYTES + b_bytes + ks * 32);
+                        umma_bf16(d_tmem, a_hi, b_hi, idesc, (kb | ks) ? 1u : 0u);
+                        umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
+                        umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+                    }
+                    umma_commit(smem_u32(&empty_bar[s]));       // smem stage free once these MMAs retire
+                }
+                umma_commit(smem_u32(&tfull_bar[acc]));         // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp >= TC_EPI_WARP0) {
+        // ===== epilogue =====
+        const int q = warp & 3;                                  // TMEM lane quarter
+        const int et = threadIdx.x - TC_EPI_WARP0 * 32;          // 0..127
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+            const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+            const int acc = tcount & 1;
+            mbar_wait_cta(smem_u32(&tfull_bar[acc]), ((uint32_t)(tcount >> 1)) & 1u);
+            tc_fence_after();
+            const long row = (long)mt * TC_BM + q * 32 + lane;
+            const bool row_ok = row < p.rows;
+            for (int c0 = 0; c0 < p.bn; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.bn + c0), r);
+                const int col0 = nt * p.bn + c0;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int col = col0 + j;
+                    const bool ok = col < p.n;
+                    const float sc = ok ? __ldg(p.scale + col) : 0.0f;
+                    const float sh = ok ? __ldg(p.shift + col) : 0.0f;
+                    float x = fmaf(__uint_as_float(r[j]), sc, sh);
+                    if (p.relu) x = fmaxf(x, 0.0f);
+                    v[j] = x;
+                }
+                if (p.pool <= 1) {
+                    if (row_ok) {
+                        if (p.out_f32) {
+                            float *dst = p.out_f32 + (size_t)row * p.ld_f32 + col0;
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                if (col0 + j < p.n) dst[j] = v[j];
+                        }
+                        if (p.out_hi) {
+                            // split x = hi + lo (bf16 each); columns n..ld_split-1 are written as zeros (K padding of the next layer)
+                            __nv_bfloat16 *dh = p.out_hi + (size_t)row * p.ld_split + col0;
+                            __nv_bfloat16 *dl = p.out_lo + (size_t)row * p.ld_split + col0;
+#pragma unroll
+                            for (int j8 = 0; j8 < 32; j8 += 8) {
+                                if (col0 + j8 >= p.ld_split) break;
+                                uint32_t hw[4], lw[4];
+#pragma unroll
+                                for (int t = 0; t < 4; t++) {
+                                    const float x0 = v[j8 + 2 * t], x1 = v[j8 + 2 * t + 1];
+                                    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                                    const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                                    const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                                    hw[t] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                                    lw[t] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                                }
+                                *reinterpret_cast<uint4 *>(dh + j8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                                *reinterpret_cast<uint4 *>(dl + j8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                            }
+                        }
+                    }
+                } else {
+                    // max-pool over runs of `pool` rows (tf.reduce_max(axis=2)) through a shared staging tile
+                    epi_bar_sync();                               // previous chunk fully consumed
+#pragma unroll
+                    for (int j = 0; j < 32; j++) pool_stage[(q * 32 + lane) * 33 + j] = v[j];
+                    epi_bar_sync();
+                    const int groups = TC_BM / p.pool;
+                    for (int e = et; e < groups * 32; e += 128) {
+                        const int g = e >> 5, j = e & 31;
+                        const long gg = (long)mt * groups + g;
+                        const int col = col0 + j;
+                        if (gg * p.pool >= p.rows || col >= p.n) continue;
+                        float mx = -INFINITY;
+                        for (int rr = 0; rr < p.pool; rr++) mx = fmaxf(mx, pool_stage[(g * p.pool + rr) * 33 + j]);
+                        if (p.rowmask && p.rowmask[gg] == 0) mx = 0.0f;
+                        if (p.out_f32) p.out_f32[(size_t)gg * p.ld_f32 + col] = mx;
+                        if (p.out_hi) {
+                            const __nv_bfloat16 h = __float2bfloat16_rn(mx);
+                            p.out_hi[(size_t)gg * p.ld_split + col] = h;
+                            p.out_lo[(size_t)gg * p.ld_split + col] = __float2bfloat16_rn(mx - __bfloat162float(h));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));   // 4 arrivals (one per epilogue warp) free the buffer
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- fp32 -> split bf16 producers -------------------------------------------------------------------------
+__device__ __forceinline__ void split_store(float x, __nv_bfloat16 *hi, __nv_bfloat16 *lo)
+{
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    *hi = h;
+    *lo = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+
+// hi/lo[row, 0:kp] = split(x[row, 0:c]) zero-padded
+__global__ void split_rows_kernel(long rows, int c, const float *__restrict__ x, int ldx, __nv_bfloat16 *__restrict__ hi,
+                                  __nv_bfloat16 *__restrict__ lo, int kp)
+{
+    const long total = rows * kp;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long row = e / kp;
+        const int col = (int)(e - row * kp);
+        split_store(col < c ? __ldg(x + (size_t)row * ldx + col) : 0.0f, hi + e, lo + e);
+    }
+}
+
+// fused gather + concat[features, rel-xyz] + split (layers_util.py:160-165), zero-padded to kp columns
+__global__ void group_concat_split_kernel(long rows, int n, int c, int m, int ns, const float *__restrict__ xyz,
+                                          const float *__restrict__ points, const float *__restrict__ new_xyz,
+                                          const int *__restrict__ idx, __nv_bfloat16 *__restrict__ hi,
+                                          __nv_bfloat16 *__restrict__ lo, int kp)
+{
+    const long total = rows * kp;
+    const long rows_per_scene = (long)m * ns;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long row = e / kp;
+        const int col = (int)(e - row * kp);
+        const long scene = row / rows_per_scene;
+        const int a = __ldg(idx + row);
+        float val = 0.0f;
+        if (col < c) val = __ldg(points + ((size_t)scene * n + a) * c + col);
+        else if (col < c + 3) {
+            const long q = row / ns;
+            val = __ldg(xyz + ((size_t)scene * n + a) * 3 + (col - c)) - __ldg(new_xyz + q * 3 + (col - c));
+        }
+        split_store(val, hi + e, lo + e);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// bf16 matrix [nrows x kp] row-major -> 2D tensor map, box = 64 columns x box_rows, 128B swizzle, zero OOB fill
+static int make_map(CUtensorMap *map, const void *ptr, long nrows, int kp, int box_rows)
+{
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return SSD3D_ERR_UNSUPPORTED; }
+    cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)nrows};
+    cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d) for [%ld x %d]", (int)r, nrows, kp); return SSD3D_ERR_INVALID_ARGUMENT; }
+    return 0;
+}
+
+}  // namespace ssd3d
+
+using namespace ssd3d;
+
+extern "C" int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const void *a_lo, const void *b_hi,
+                               const void *b_lo, const float *scale, const float *shift, int relu, int pool,
+                               const int *rowmask, float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split,
+                               ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(rows >= 0 && kp > 0 && n > 0, "linear_tc: bad shape rows=%ld kp=%d n=%d", rows, kp, n);
+    SSD3D_REQUIRE(kp % 16 == 0, "linear_tc: kp=%d must be a multiple of 16", kp);
+    SSD3D_REQUIRE(a_hi && a_lo && b_hi && b_lo && scale && shift, "linear_tc: null operand pointer");
+    SSD3D_REQUIRE(out_f32 || (out_hi && out_lo), "linear_tc: no output requested");
+    SSD3D_REQUIRE(!out_f32 || ld_f32 >= n, "linear_tc: ld_f32=%d < n=%d", ld_f32, n);
+    SSD3D_REQUIRE(!out_hi || (out_lo && ld_split >= n && ld_split % 8 == 0), "linear_tc: bad split output (ld_split=%d)", ld_split);
+    SSD3D_REQUIRE(pool >= 1 && rows % pool == 0 && TC_BM % pool == 0, "linear_tc: pool=%d must divide 128 and rows=%ld", pool, rows);
+    for (const void *ptr : {a_hi, a_lo, b_hi, b_lo, (const void *)out_hi, (const void *)out_lo})
+        SSD3D_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "linear_tc: operand pointers must be 16-byte aligned");
+    if (rows == 0) return 0;
+
+    TcParams p = {};
+    p.rows = rows; p.kp = kp; p.n = n;
+    const int n16 = (n + 15) / 16 * 16;
+    // when split outputs are requested the tile must also cover (and zero) the padding columns n..ld_split-1
+    const int ncover = out_hi && pool <= 1 ? (ld_split > n16 ? ld_split : n16) : n16;
+    p.bn = ncover < 256 ? ncover : 256;
+    p.n_tiles = (ncover + p.bn - 1) / p.bn;
+    p.m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
+    const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)p.bn * TC_BK * 2;
+    const size_t budget = 200 * 1024;
+    const size_t pool_bytes = TC_BM * 33 * sizeof(float);
+    int stages = (int)((budget - pool_bytes) / stage_bytes);
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    SSD3D_REQUIRE(stages >= 2, "linear_tc: tile does not fit shared memory");
+    p.stages = stages;
+    p.scale = scale; p.shift = shift; p.relu = relu; p.pool = pool; p.rowmask = rowmask;
+    p.out_f32 = out_f32; p.ld_f32 = ld_f32;
+    p.out_hi = (__nv_bfloat16 *)out_hi; p.out_lo = (__nv_bfloat16 *)out_lo; p.ld_split = ld_split;
+
+    CUtensorMap mah, mal, mbh, mbl;
+    int rc;
+    if ((rc = make_map(&mah, a_hi, rows, kp, TC_BM)) != 0) return rc;
+    if ((rc = make_map(&mal, a_lo, rows, kp, TC_BM)) != 0) return rc;
+    if ((rc = make_map(&mbh, b_hi, n, kp, p.bn)) != 0) return rc;
+    if ((rc = make_map(&mbl, b_lo, n, kp, p.bn)) != 0) return rc;
+
+    const size_t smem = stages * stage_bytes + pool_bytes + 1024;
+    cudaError_t e = cudaFuncSetAttribute((const void *)linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "linear_tc attr");
+    const int total = p.m_tiles * p.n_tiles;
+    const int grid = total < kNumSMs ? total : kNumSMs;
+    linear_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mah, mal, mbh, mbl, p);
+    SSD3D_LAUNCH_CHECK("linear_tc_kernel");
+}
+
+extern "C" int ssd3d_split_rows(long rows, int c, const float *x, int ldx, void *hi, void *lo, int kp, ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(rows >= 0 && c > 0 && ldx >= c && kp >= c && kp % 8 == 0, "split_rows: bad shape rows=%ld c=%d ldx=%d kp=%d", rows, c, ldx, kp);
+    SSD3D_REQUIRE(x && hi && lo, "split_rows: null pointer");
+    const long total = rows * kp;
+    if (total == 0) return 0;
+    const long want = (total + 255) / 256;
+    const int blocks = (int)(want < (long)kNumSMs * 16 ? want : (long)kNumSMs * 16);
+    split_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rows, c, x, ldx, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, kp);
+    SSD3D_LAUNCH_CHECK("split_rows_kernel");
+}
+
+extern "C" int ssd3d_group_concat_split(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
+                                        const float *new_xyz, const int *idx, void *hi, void *lo, int kp,
+                                        ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0 && c >= 0 && nsample > 0, "group_concat_split: bad shape");
+    SSD3D_REQUIRE(kp >= c + 3 && kp % 8 == 0, "group_concat_split: kp=%d must be >= c+3=%d and a multiple of 8", kp, c + 3);
+    SSD3D_REQUIRE(xyz && new_xyz && idx && hi && lo && (points || c == 0), "group_concat_split: null pointer");
+    const long rows = (long)b * m * nsample;
+    const long total = rows * kp;
+    if (total == 0) return 0;
+    const long want = (total + 255) / 256;
+    const int blocks = (int)(want < (long)kNumSMs * 16 ? want : (long)kNumSMs * 16);
+    group_concat_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rows, n, c, m, nsample, xyz, points, new_xyz, idx,
+                                                                        (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, kp);
+    SSD3D_LAUNCH_CHECK("group_concat_split_kernel");
+}

@@ -49,7 +49,7 @@ def ffps_indices(npoint, xyz, points, mode):
 def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_training, bn_decay, bn,
                            fps_sample_range_list, fps_method_list, npoint_list, former_fps_idx, use_attention, scope,
                            dilated_group, vote_ctr=None, aggregation_channel=None, debugging=False, epsilon=1e-5, *,
-                           params, ffps_mode="matrix", aggregation=None, return_debug=False):
+                           params, ffps_mode="matrix", aggregation=None, return_debug=False, mlp_mode="tc"):
     """PointNet++ SA module with multi-scale grouping; returns (new_xyz, new_points, fps_idx)."""
     if is_training:
         raise NotImplementedError("training-mode BatchNorm / backward ops are out of scope (inference only)")
@@ -103,20 +103,54 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                 else:
                     a, c = tf_ops.query_ball_point(radius_list[i], nsample_list[i], xyz, new_xyz)
                 idx_list.append(a); cnt_list.append(c)
-        for i in range(nscale):
-            idx, cnt = idx_list[i], cnt_list[i]
-            # rows with cnt == 0 come back zero-filled, which is what idx * (cnt > 0) produces (:157-159)
-            debug["idx"].append(idx); debug["cnt"].append(cnt)
-            g = tf_ops.group_concat(xyz, points, new_xyz, idx)                    # :160-165 fused
-            nl = len(mlp_list[i])
-            for j in range(nl):
-                lastl = j == nl - 1
-                g = _conv(pp, "%s/conv%d_%d" % (scope, i, j), g, bn=bn,
-                          pool=nsample_list[i] if lastl else 1, rowmask=cnt if lastl else None)   # :167-180
-            outs.append(g)
-        new_points = outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
-        if aggregation and aggregation_channel is not None and aggregation_channel != -1:
-            new_points = _conv(pp, scope + "/ensemble", new_points, bn=bn)        # :183-185
+        use_agg = bool(aggregation and aggregation_channel is not None and aggregation_channel != -1)
+        tc = mlp_mode == "tc" and all(128 % k == 0 for k in nsample_list)
+        if mlp_mode not in ("tc", "fp32"):
+            raise ValueError("mlp_mode must be 'tc' or 'fp32'")
+        if tc:
+            # tensor-core path: every scale pools straight into its slice of the concat buffer (fp32 for the
+            # caller, split bf16 for the aggregation conv), activations stay split between layers
+            m_q = new_xyz.shape[1]
+            ctot = sum(m[-1] for m in mlp_list)
+            concat = torch.empty((bs, m_q, ctot), dtype=torch.float32, device=xyz.device)
+            cat_hi = cat_lo = None
+            if use_agg:
+                ldc = tf_ops.round16(ctot)
+                mk = torch.zeros if ldc != ctot else torch.empty
+                cat_hi = mk((bs, m_q, ldc), dtype=torch.bfloat16, device=xyz.device)
+                cat_lo = mk((bs, m_q, ldc), dtype=torch.bfloat16, device=xyz.device)
+            off = 0
+            for i in range(nscale):
+                idx, cnt = idx_list[i], cnt_list[i]
+                debug["idx"].append(idx); debug["cnt"].append(cnt)
+                hi, lo = tf_ops.group_concat_split(xyz, points, new_xyz, idx)      # :160-165 fused with the split
+                nl = len(mlp_list[i])
+                for j in range(nl):
+                    f = pp.conv("%s/conv%d_%d" % (scope, i, j), bn)
+                    if j < nl - 1:
+                        _, (hi, lo) = tf_ops.linear_tc(hi, lo, f, want_f32=False, want_split=True)
+                    else:                                                          # :167-180 conv+BN+ReLU+max+mask
+                        tf_ops.linear_tc(hi, lo, f, pool=nsample_list[i], rowmask=cnt, out_f32=(concat, off),
+                                         out_split=(cat_hi, cat_lo, off) if use_agg else None)
+                off += mlp_list[i][-1]
+            new_points = concat
+            if use_agg:                                                            # :183-185
+                new_points, _ = tf_ops.linear_tc(cat_hi, cat_lo, pp.conv(scope + "/ensemble", bn))
+        else:
+            for i in range(nscale):
+                idx, cnt = idx_list[i], cnt_list[i]
+                # rows with cnt == 0 come back zero-filled, which is what idx * (cnt > 0) produces (:157-159)
+                debug["idx"].append(idx); debug["cnt"].append(cnt)
+                g = tf_ops.group_concat(xyz, points, new_xyz, idx)                    # :160-165 fused
+                nl = len(mlp_list[i])
+                for j in range(nl):
+                    lastl = j == nl - 1
+                    g = _conv(pp, "%s/conv%d_%d" % (scope, i, j), g, bn=bn,
+                              pool=nsample_list[i] if lastl else 1, rowmask=cnt if lastl else None)   # :167-180
+                outs.append(g)
+            new_points = outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
+            if use_agg:
+                new_points = _conv(pp, scope + "/ensemble", new_points, bn=bn)        # :183-185
     else:
         new_points = tf_ops.gather_point(points.contiguous(), fps_idx)           # :186-187
     if return_debug:
@@ -154,14 +188,20 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay,
 
 
 def vote_layer(xyz, points, mlp_list, is_training, bn_decay, bn, scope, *, params,
-               max_translate_range=_cfg.MAX_TRANSLATE_RANGE):
+               max_translate_range=_cfg.MAX_TRANSLATE_RANGE, mlp_mode="tc"):
     """Vote layer: per-point MLP -> 3 offsets, clamped to +-max_translate_range (layers_util.py:12-24)."""
     if is_training:
         raise NotImplementedError("inference only")
     pp = prepare(params, xyz.device)
-    for i in range(len(mlp_list)):
-        points = _conv(pp, "%s/vote_layer_%d" % (scope, i), points, bn=bn)
-    off = _conv(pp, scope + "/vote_offsets", points, bn=False, relu=False)
+    if mlp_mode == "tc":
+        hi, lo = tf_ops.split_rows(points)
+        for i in range(len(mlp_list)):
+            points, (hi, lo) = tf_ops.linear_tc(hi, lo, pp.conv("%s/vote_layer_%d" % (scope, i), bn), want_split=True)
+        off, _ = tf_ops.linear_tc(hi, lo, pp.conv(scope + "/vote_offsets", False), relu=False)
+    else:
+        for i in range(len(mlp_list)):
+            points = _conv(pp, "%s/vote_layer_%d" % (scope, i), points, bn=bn)
+        off = _conv(pp, scope + "/vote_offsets", points, bn=False, relu=False)
     lo = _const(tuple(max_translate_range), xyz.device).view(1, 1, 3)
     lim = torch.minimum(torch.maximum(off, lo), -lo)
     return xyz + lim, points, off

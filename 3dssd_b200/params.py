@@ -68,13 +68,24 @@ def init_params(arch, in_channels, seed=0, random_bias=False):
     return params
 
 
+def round16(x):
+    return (int(x) + 15) // 16 * 16
+
+
 class FoldedConv:
-    """One conv+BN layer folded for inference: y = act((x @ w) * scale + shift)."""
-    __slots__ = ("w", "scale", "shift", "cin", "cout")
+    """One conv+BN layer folded for inference: y = act((x @ w) * scale + shift).
+    For the tensor-core path the weight also exists split in two bf16 terms, transposed to K-major:
+    b_hi + b_lo ~= w^T, shape [cout, kp] with kp = round16(cin) (zero padded)."""
+    __slots__ = ("w", "scale", "shift", "cin", "cout", "kp", "b_hi", "b_lo")
 
     def __init__(self, w, scale, shift):
         self.w, self.scale, self.shift = w, scale, shift
         self.cin, self.cout = w.shape
+        self.kp = round16(self.cin)
+        wt = torch.zeros((self.cout, self.kp), dtype=torch.float32, device=w.device)
+        wt[:, : self.cin] = w.t()
+        self.b_hi = wt.to(torch.bfloat16)                       # round-to-nearest-even, like the device split
+        self.b_lo = (wt - self.b_hi.to(torch.float32)).to(torch.bfloat16)
 
 
 def fold(params, scope, bn, device):

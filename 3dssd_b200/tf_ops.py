@@ -260,3 +260,93 @@ def linear_bn_relu(x, w, scale, shift, relu=True, pool=1, rowmask=None, cin=None
     check(lib().ssd3d_linear_bn_relu(rows, cin, cout, _p(x), ldx, _p(w), _p(scale), _p(shift), 1 if relu else 0, pool,
                                      _p(rowmask), _p(y), cout, _stream()), "linear_bn_relu")
     return y
+
+
+# ---- tensor-core (tcgen05) path of the MLP: operands split in two bf16 terms ---------------------------------
+
+def round16(x):
+    return (int(x) + 15) // 16 * 16
+
+
+def split_rows(x, kp=None):
+    """fp32 (..., c) -> (hi, lo) bf16 (..., kp) with hi + lo ~= x (16 mantissa bits), zero padded to kp."""
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise ValueError("x must be a float32 CUDA tensor")
+    x = x if x.is_contiguous() else x.contiguous()
+    c = x.shape[-1]
+    kp = round16(c) if kp is None else int(kp)
+    rows = x.numel() // c
+    hi = torch.empty(tuple(x.shape[:-1]) + (kp,), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi)
+    check(lib().ssd3d_split_rows(rows, c, _p(x), c, _p(hi), _p(lo), kp, _stream()), "split_rows")
+    return hi, lo
+
+
+def group_concat_split(xyz, points, new_xyz, idx, kp=None):
+    """group_concat + split in one kernel: (hi, lo) bf16 (b, m, nsample, kp)."""
+    xyz = _req(xyz, "xyz", torch.float32, 3, 3)
+    new_xyz = _req(new_xyz, "new_xyz", torch.float32, 3, 3)
+    idx = _req(idx, "idx", torch.int32, 3)
+    b, n, _ = xyz.shape
+    c = 0
+    if points is not None:
+        points = _req(points, "points", torch.float32, 3)
+        c = points.shape[2]
+    _, m, ns = idx.shape
+    kp = round16(c + 3) if kp is None else int(kp)
+    hi = torch.empty((b, m, ns, kp), dtype=torch.bfloat16, device=xyz.device)
+    lo = torch.empty_like(hi)
+    check(lib().ssd3d_group_concat_split(b, n, c, m, ns, _p(xyz), _p(points), _p(new_xyz), _p(idx), _p(hi), _p(lo), kp,
+                                         _stream()), "group_concat_split")
+    return hi, lo
+
+
+def linear_tc(a_hi, a_lo, f, relu=True, pool=1, rowmask=None, want_f32=True, want_split=False, out_f32=None,
+              out_split=None):
+    """One folded conv layer on the tensor cores.  a_hi/a_lo (..., kp) bf16; f: params.FoldedConv.
+    Returns (y_f32 or None, (hi, lo) or None).  out_f32=(buffer, col_offset) / out_split=(hi_buf, lo_buf, col_offset)
+    write into slices of preallocated (..., ld) buffers (the concat of the SA scales) instead of allocating."""
+    if a_hi.dtype != torch.bfloat16 or a_lo.dtype != torch.bfloat16 or a_hi.shape != a_lo.shape:
+        raise ValueError("a_hi / a_lo must be bfloat16 tensors of the same shape")
+    kp = a_hi.shape[-1]
+    if kp != f.kp:
+        raise ValueError("operand K (%d) does not match the layer's padded K (%d)" % (kp, f.kp))
+    rows = a_hi.numel() // kp
+    pool = int(pool)
+    lead = tuple(a_hi.shape[:-1])
+    if pool > 1:
+        if lead[-1] != pool or 128 % pool != 0:
+            raise ValueError("pool must equal the second-to-last dimension and divide 128")
+        lead = lead[:-1]
+    n = f.cout
+    dev = a_hi.device
+    y = None
+    pf, ldf = 0, 0
+    if out_f32 is not None:
+        buf, off = out_f32
+        ldf = buf.shape[-1]
+        pf = buf.data_ptr() + 4 * off
+        y = buf
+    elif want_f32:
+        y = torch.empty(lead + (n,), dtype=torch.float32, device=dev)
+        pf, ldf = y.data_ptr(), n
+    sp = None
+    ph = pl = 0
+    lds = 0
+    if out_split is not None:
+        hb, lb, off = out_split
+        lds = hb.shape[-1]
+        ph, pl = hb.data_ptr() + 2 * off, lb.data_ptr() + 2 * off
+        sp = (hb, lb)
+    elif want_split:
+        lds = round16(n)
+        alloc = torch.zeros if (pool > 1 and lds != n) else torch.empty
+        hb = alloc(lead + (lds,), dtype=torch.bfloat16, device=dev)
+        lb = alloc(lead + (lds,), dtype=torch.bfloat16, device=dev)
+        ph, pl = hb.data_ptr(), lb.data_ptr()
+        sp = (hb, lb)
+    vp = ctypes.c_void_p
+    check(lib().ssd3d_linear_tc(rows, kp, n, _p(a_hi), _p(a_lo), _p(f.b_hi), _p(f.b_lo), _p(f.scale), _p(f.shift),
+                                1 if relu else 0, pool, _p(rowmask), vp(pf), ldf, vp(ph), vp(pl), lds, _stream()),
+          "linear_tc")
+    return y, sp

@@ -138,6 +138,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ffps-mode", default="matrix", choices=["matrix", "fused"])
+    ap.add_argument("--mlp-mode", default="tc", choices=["tc", "fp32"])
+    ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu captures)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-scenes", type=int, default=2)
     args = ap.parse_args()
@@ -165,7 +167,7 @@ def main():
         return run_reference(args, torch, pkg, arch, params, pts_np, rank, world, dev)
 
     import torch.distributed as dist
-    net = pkg.SABackbone(arch, params, in_channels=1, device=dev, ffps_mode=args.ffps_mode)
+    net = pkg.SABackbone(arch, params, in_channels=1, device=dev, ffps_mode=args.ffps_mode, mlp_mode=args.mlp_mode)
     pts = torch.from_numpy(pts_np).to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
@@ -193,8 +195,16 @@ def main():
     for n in counted:
         setattr(L, n, originals[n])
 
-    replay = net.capture(pts)
-    gather_buf = None
+    if args.no_graph:
+        static_in = pts.clone()
+
+        def replay(points=None):
+            if points is not None:
+                static_in.copy_(points, non_blocking=True)
+            o = net.forward(static_in)
+            return o, net.detection_block(o[0], o[1])
+    else:
+        replay = net.capture(pts)
 
     def step_device():
         outg, (b, c) = replay()
@@ -289,7 +299,7 @@ def main():
             "config": {"workload": "configs[1]: full 3DSSD SA backbone (3dssd.yaml layer1-4 + vote), synthetic KITTI "
                                    "16384x4 clouds, batch 8 per GPU", "scenes_per_gpu": SCENES_PER_GPU,
                        "global_batch": SCENES_PER_GPU * world, "points": NPOINTS, "parallelism": "scene-sharded dp%d" % world,
-                       "ffps": args.ffps_mode, "l2": "flushed (256 MiB write) between timed steps",
+                       "ffps": args.ffps_mode, "mlp": args.mlp_mode, "cuda_graph": not args.no_graph, "l2": "flushed (256 MiB write) between timed steps",
                        "timing": "sum of per-step CUDA-event times on the launch stream, max over ranks; CUDA-graph replay",
                        "wall_s_bracket": wall},
             "e2e": {"value": scenes / (e2e_ms * 1e-3), "unit": UNIT,

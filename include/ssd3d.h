@@ -119,6 +119,21 @@ int ssd3d_linear_bn_relu(long rows, int cin, int cout, const float *x, int ldx, 
                          const float *scale, const float *shift, int relu, int pool, const int *rowmask,
                          float *y, int ldy, ssd3d_stream_t stream);
 
+/* ---- tensor-core (tcgen05) path of the same layer -------------------------------------------------
+ * fp32 operands travel as TWO bf16 matrices (x = hi + lo, 16 mantissa bits); the product is evaluated as
+ * hi.hi + lo.hi + hi.lo with fp32 accumulation in TMEM (error ~2^-16, inside the 1e-3 parity budget).
+ *   a_hi/a_lo [rows, kp] bf16 row-major (kp % 16 == 0, zero padded); b_hi/b_lo [n, kp] bf16 = W^T split;
+ *   outputs (any subset): out_f32 [rows or rows/pool, ld_f32] and/or out_hi/out_lo [.., ld_split] bf16 for the
+ *   next layer (columns n..ld_split-1 are written as zeros when pool == 1).  pool / rowmask as above. */
+int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const void *a_lo, const void *b_hi, const void *b_lo,
+                    const float *scale, const float *shift, int relu, int pool, const int *rowmask, float *out_f32,
+                    int ld_f32, void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream);
+/* hi/lo[row, 0:kp] = split(x[row, 0:c]), zero padded (kp % 8 == 0). */
+int ssd3d_split_rows(long rows, int c, const float *x, int ldx, void *hi, void *lo, int kp, ssd3d_stream_t stream);
+/* ssd3d_group_concat fused with the split: hi/lo [b*m*nsample, kp] bf16. */
+int ssd3d_group_concat_split(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
+                             const float *new_xyz, const int *idx, void *hi, void *lo, int kp, ssd3d_stream_t stream);
+
 /* ymax[g, 0:c] = max over rows g*pool .. g*pool+pool-1 of y[., 0:c] (times rowmask[g] != 0): the
  * tf.reduce_max(axis=2) * mask of layers_util.py:178-180 for nsample values the fused epilogue of
  * ssd3d_linear_bn_relu does not cover (pool must divide 128 there). */

@@ -298,3 +298,89 @@ def test_argument_validation(pkg, cuda):
         pkg.farthest_point_sample(4, torch.zeros((1, 10, 3)))                     # CPU tensor: no CPU path
     # empty batch / zero samples are no-ops like the reference's early return
     assert pkg.farthest_point_sample(0, xyz).shape == (1, 0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tensor-core path (tcgen05, bf16 hi/lo split, 3 MMAs): same 1e-3 budget, expected error ~1e-5
+# ---------------------------------------------------------------------------------------------------------
+def _fold(pkg, cuda, rng, cin, cout, bn=True):
+    P = importlib.import_module("3dssd_b200.params")
+    prm = {}
+    P._conv_init(rng, prm, "s", cin, cout, bn)
+    prm["s/biases"] = rng.standard_normal(cout).astype(np.float32)
+    return prm, P.fold(prm, "s", bn, cuda)
+
+
+def _oracle_conv(oracle_ops, prm, x, bn=True, relu=True):
+    bnp = tuple(prm["s/bn/" + k] for k in ("gamma", "beta", "moving_mean", "moving_variance")) if bn else None
+    return oracle_ops.linear_bn_relu(x, prm["s/weights"], prm["s/biases"], bnp, relu)
+
+
+@pytest.mark.parametrize("rows,cin,cout", [(1000, 4, 16), (4096, 67, 64), (777, 131, 128), (512, 259, 256),
+                                           (130, 512, 1024), (300, 64, 96), (2048, 128, 192), (256, 128, 3)])
+def test_linear_tc_vs_oracle(pkg, oracle_ops, cuda, rows, cin, cout):
+    rng = np.random.default_rng(rows + cin)
+    prm, f = _fold(pkg, cuda, rng, cin, cout)
+    x = rng.standard_normal((rows, cin)).astype(np.float32)
+    exp = _oracle_conv(oracle_ops, prm, x)
+    hi, lo = pkg.split_rows(T(x, cuda))
+    assert hi.shape == (rows, f.kp) and rel_err(N(hi.float() + lo.float())[:, :cin], x) < 2e-5
+    y, sp = pkg.linear_tc(hi, lo, f, want_f32=True, want_split=True)
+    assert rel_err(N(y), exp) < 1e-4
+    yh, yl = sp
+    rec = N(yh.float() + yl.float())
+    assert rel_err(rec[:, :cout], exp) < 1e-4 and (rec[:, cout:] == 0).all()     # padding columns are zero
+
+
+@pytest.mark.parametrize("pool", [16, 32, 64])
+def test_linear_tc_pool_mask_and_concat_slices(pkg, oracle_ops, cuda, pool):
+    rng = np.random.default_rng(pool)
+    b, m, cin, cout = 2, 37, 67, 64
+    prm, f = _fold(pkg, cuda, rng, cin, cout)
+    x = rng.standard_normal((b, m, pool, cin)).astype(np.float32)
+    cnt = rng.integers(0, 3, (b, m)).astype(np.int32)
+    exp = _oracle_conv(oracle_ops, prm, x).max(axis=2) * (cnt > 0)[..., None]
+    hi, lo = pkg.split_rows(T(x, cuda))
+    concat = torch.full((b, m, 160), -7.0, device=cuda)
+    ch = torch.zeros((b, m, 160), dtype=torch.bfloat16, device=cuda); cl = torch.zeros_like(ch)
+    pkg.linear_tc(hi, lo, f, pool=pool, rowmask=T(cnt, cuda), out_f32=(concat, 32), out_split=(ch, cl, 32))
+    got = N(concat)
+    assert rel_err(got[..., 32:96], exp) < 1e-4
+    assert (got[..., :32] == -7.0).all() and (got[..., 96:] == -7.0).all()      # neighbours of the slice untouched
+    assert rel_err(N(ch.float() + cl.float())[..., 32:96], exp) < 1e-4
+
+
+def test_linear_tc_three_layer_chain(pkg, oracle_ops, cuda):
+    """A whole SA scale as the backbone runs it: gather+concat+split -> 2 split layers -> pooled layer."""
+    rng = np.random.default_rng(77)
+    b, n, c, m, k = 2, 600, 64, 50, 32
+    xyz = rng.uniform(0, 1, (b, n, 3)).astype(np.float32)
+    feats = rng.standard_normal((b, n, c)).astype(np.float32)
+    new_xyz = np.array(xyz[:, :m], copy=True)
+    idx = rng.integers(0, n, (b, m, k)).astype(np.int32)
+    cnt = rng.integers(0, 2, (b, m)).astype(np.int32)
+    dims = [c + 3, 64, 96, 128]
+    g = np.concatenate([oracle_ops.group_point(feats, idx), oracle_ops.group_point(xyz, idx) - new_xyz[:, :, None]], -1)
+    hi, lo = pkg.group_concat_split(T(xyz, cuda), T(feats, cuda), T(new_xyz, cuda), T(idx, cuda))
+    assert rel_err(N(hi.float() + lo.float())[..., :c + 3], g) < 2e-5
+    for li in range(3):
+        prm, f = _fold(pkg, cuda, rng, dims[li], dims[li + 1])
+        g = _oracle_conv(oracle_ops, prm, g)
+        if li < 2:
+            _, (hi, lo) = pkg.linear_tc(hi, lo, f, want_f32=False, want_split=True)
+        else:
+            y, _ = pkg.linear_tc(hi, lo, f, pool=k, rowmask=T(cnt, cuda))
+    exp = g.max(axis=2) * (cnt > 0)[..., None]
+    assert rel_err(N(y), exp) < 1e-4
+
+
+def test_linear_tc_large_gemm_matches_fp32_path(pkg, cuda):
+    """Layer-4-sized GEMM (65536 x 512 x 1024): tensor-core path vs the exact-fp32 FFMA kernel."""
+    torch.manual_seed(0)
+    x = torch.randn((8, 256, 32, 512), device=cuda)
+    rng = np.random.default_rng(1)
+    prm, f = _fold(pkg, cuda, rng, 512, 1024)
+    ref = pkg.linear_bn_relu(x, f.w, f.scale, f.shift, relu=True, pool=32)
+    hi, lo = pkg.split_rows(x)
+    y, _ = pkg.linear_tc(hi, lo, f, pool=32)
+    assert rel_err(N(y), N(ref)) < 1e-4
