@@ -78,6 +78,20 @@ struct FpsShared {
     unsigned long long mbar[2];
 };
 
+// index of the packet that wins among `count` packets held one per lane (v = value bits, kk = key):
+// max value, ties -> min key.  One redux + ballot in the common case of a unique maximum.
+__device__ __forceinline__ int packet_argmax(uint32_t v, uint32_t kk, bool has)
+{
+    const uint32_t mx = __reduce_max_sync(0xffffffffu, has ? v : 0u);
+    const bool elig = has && v == mx;
+    uint32_t bal = __ballot_sync(0xffffffffu, elig);
+    if (bal & (bal - 1u)) {  // several packets share the maximum: smallest key decides (keys are unique)
+        const uint32_t kmin = __reduce_min_sync(0xffffffffu, elig ? kk : 0xffffffffu);
+        bal = __ballot_sync(0xffffffffu, elig && kk == kmin);
+    }
+    return __ffs(bal) - 1;
+}
+
 template <int CL, bool WITH_XYZ>
 __device__ __forceinline__ void fps_exchange(FpsShared<CL> &sh, int j, uint32_t rank, float best, uint32_t my_key,
                                              float cx, float cy, float cz, uint32_t &win_key, float &ox, float &oy,
@@ -85,34 +99,42 @@ __device__ __forceinline__ void fps_exchange(FpsShared<CL> &sh, int j, uint32_t 
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int par = j & 1;
-    const uint32_t u = __float_as_uint(fmaxf(best, 0.0f));
-    uint32_t mx, kmin;
-    warp_argmax(u, best >= 0.0f ? my_key : KEY_INVALID, mx, kmin);
+    // ---- stage 1: warp arg-max of (value, key); the winning lane publishes the warp's packet
     {
-        const uint32_t bal = __ballot_sync(0xffffffffu, (u == mx) && ((best >= 0.0f ? my_key : KEY_INVALID) == kmin));
-        if (lane == __ffs(bal) - 1) {
+        const uint32_t u = __float_as_uint(fmaxf(best, 0.0f));
+        const uint32_t mx = __reduce_max_sync(0xffffffffu, u);
+        const bool elig = (best >= 0.0f) && (u == mx);
+        const uint32_t bal = __ballot_sync(0xffffffffu, elig);
+        bool iwin;
+        uint32_t key = my_key;
+        if (bal == 0u) { iwin = lane == 0; key = KEY_INVALID; }          // warp owns padding slots only
+        else if ((bal & (bal - 1u)) == 0u) iwin = elig;                    // unique maximum (the common case)
+        else {
+            const uint32_t kmin = __reduce_min_sync(0xffffffffu, elig ? my_key : KEY_INVALID);
+            iwin = elig && my_key == kmin;
+        }
+        if (iwin) {
             uint4 *dst = reinterpret_cast<uint4 *>(&sh.warp_pk[par][warp]);
-            dst[0] = make_uint4(mx, kmin, __float_as_uint(cx), __float_as_uint(cy));
+            dst[0] = make_uint4(mx, key, __float_as_uint(cx), __float_as_uint(cy));
             if (WITH_XYZ) dst[1] = make_uint4(__float_as_uint(cz), 0u, 0u, 0u);
         }
     }
-    __syncthreads();
-    if (CL == 1 || warp == 0) {
-        const uint32_t v = lane < FPS_NW ? sh.warp_pk[par][lane].val : 0u;
-        const uint32_t kk = lane < FPS_NW ? sh.warp_pk[par][lane].key : KEY_INVALID;
-        uint32_t m2, k2;
-        warp_argmax(v, kk, m2, k2);
-        const uint32_t bal = __ballot_sync(0xffffffffu, lane < FPS_NW && v == m2 && kk == k2);
-        const int ww = __ffs(bal) - 1;
-        if (CL == 1) {
-            win_key = k2;
-            if (WITH_XYZ) {
-                const uint4 a = reinterpret_cast<const uint4 *>(&sh.warp_pk[par][ww])[0];
-                ox = __uint_as_float(a.z); oy = __uint_as_float(a.w);
-                oz = sh.warp_pk[par][ww].z;
-            }
-            return;
-        }
+    if (CL == 1) {
+        __syncthreads();
+        const bool has = lane < FPS_NW;
+        const int ww = packet_argmax(has ? sh.warp_pk[par][lane].val : 0u, has ? sh.warp_pk[par][lane].key : 0u, has);
+        const uint4 a = reinterpret_cast<const uint4 *>(&sh.warp_pk[par][ww])[0];
+        win_key = a.y;
+        if (WITH_XYZ) { ox = __uint_as_float(a.z); oy = __uint_as_float(a.w); oz = sh.warp_pk[par][ww].z; }
+        return;
+    }
+    // ---- stage 2: warp 0 reduces the FPS_NW warp packets and pushes the CTA's packet to every peer.
+    // Only warp 0 has to wait for the packets (bar.sync); the other warps just signal (bar.arrive) and go on
+    // to wait for the cluster-wide result.
+    if (warp == 0) {
+        asm volatile("bar.sync 1, %0;" ::"n"(FPS_T) : "memory");
+        const bool has = lane < FPS_NW;
+        const int ww = packet_argmax(has ? sh.warp_pk[par][lane].val : 0u, has ? sh.warp_pk[par][lane].key : 0u, has);
         constexpr int PIECES = WITH_XYZ ? 2 : 1;
         if (lane == 0) mbar_arrive_expect_tx(smem_u32(&sh.mbar[par]), CL * PIECES * 16);
         if (lane < PIECES * CL) {
@@ -121,21 +143,17 @@ __device__ __forceinline__ void fps_exchange(FpsShared<CL> &sh, int j, uint32_t 
             const uint4 v4 = reinterpret_cast<const uint4 *>(&sh.warp_pk[par][ww])[piece];
             st_async_v4(mapa(smem_u32(&sh.cl_pk[par][rank]) + piece * 16, peer), mapa(smem_u32(&sh.mbar[par]), peer), v4);
         }
+    } else {
+        asm volatile("bar.arrive 1, %0;" ::"n"(FPS_T) : "memory");
     }
-    if (CL > 1) {
-        mbar_wait_cluster(smem_u32(&sh.mbar[par]), ((j - 1) >> 1) & 1);
-        const uint32_t v = lane < CL ? sh.cl_pk[par][lane].val : 0u;
-        const uint32_t kk = lane < CL ? sh.cl_pk[par][lane].key : KEY_INVALID;
-        uint32_t m3, k3;
-        warp_argmax(v, kk, m3, k3);
-        win_key = k3;
-        if (WITH_XYZ) {
-            const uint32_t bal = __ballot_sync(0xffffffffu, lane < CL && v == m3 && kk == k3);
-            const int wr = __ffs(bal) - 1;
-            const uint4 a = reinterpret_cast<const uint4 *>(&sh.cl_pk[par][wr])[0];
-            ox = __uint_as_float(a.z); oy = __uint_as_float(a.w);
-            oz = sh.cl_pk[par][wr].z;
-        }
+    // ---- stage 3: every warp reduces the CL packets redundantly
+    mbar_wait_cluster(smem_u32(&sh.mbar[par]), ((j - 1) >> 1) & 1);
+    {
+        const bool has = lane < CL;
+        const int wr = packet_argmax(has ? sh.cl_pk[par][lane].val : 0u, has ? sh.cl_pk[par][lane].key : 0u, has);
+        const uint4 a = reinterpret_cast<const uint4 *>(&sh.cl_pk[par][wr])[0];
+        win_key = a.y;
+        if (WITH_XYZ) { ox = __uint_as_float(a.z); oy = __uint_as_float(a.w); oz = sh.cl_pk[par][wr].z; }
     }
 }
 

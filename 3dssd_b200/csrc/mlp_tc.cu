@@ -377,7 +377,7 @@ extern "C" int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const
     p.n_tiles = (ncover + p.bn - 1) / p.bn;
     p.m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
     const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)p.bn * TC_BK * 2;
-    const size_t budget = 200 * 1024;
+    const size_t budget = 224 * 1024 - 1024;   // 227 KiB per CTA minus static barriers and the 1 KiB alignment slack
     const size_t pool_bytes = TC_BM * 33 * sizeof(float);
     int stages = (int)((budget - pool_bytes) / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;

@@ -23,6 +23,10 @@ sqdist_kernel(int n, int c, const float *__restrict__ a, float *__restrict__ out
     float *sqA = Bs + (size_t)c * SQ_PITCH;            // [64]
     float *sqB = sqA + SQ_TILE;                        // [64]
 
+    // The pinned arithmetic is exactly symmetric (fma(a,b,.) == fma(b,a,.), fp add commutes), so only tile pairs on
+    // or above the diagonal are computed and each result is stored twice: out[i,j] and out[j,i].
+    if (blockIdx.x < blockIdx.y) return;
+    const bool mirror = blockIdx.x != blockIdx.y;
     const int scene = blockIdx.z;
     const int i0 = blockIdx.y * SQ_TILE, j0 = blockIdx.x * SQ_TILE;
     const float *A = a + (size_t)scene * n * c;
@@ -63,19 +67,36 @@ sqdist_kernel(int n, int c, const float *__restrict__ a, float *__restrict__ out
     float *O = out + (size_t)scene * n * n;
 #pragma unroll
     for (int y = 0; y < 4; y++) {
-        const int i = i0 + ty * 4 + y;
-        if (i >= n) continue;
         const float si = sqA[ty * 4 + y];
-        float v[4];
 #pragma unroll
         for (int x = 0; x < 4; x++)
-            v[x] = __fsub_rn(__fadd_rn(si, sqB[tx * 4 + x]), __fmul_rn(2.0f, acc[y][x]));
+            acc[y][x] = __fsub_rn(__fadd_rn(si, sqB[tx * 4 + x]), __fmul_rn(2.0f, acc[y][x]));
+    }
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        const int i = i0 + ty * 4 + y;
+        if (i >= n) continue;
         const int j = j0 + tx * 4;
         float *dst = O + (size_t)i * n + j;
-        if (j + 3 < n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        if (j + 3 < n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0))
+            *reinterpret_cast<float4 *>(dst) = make_float4(acc[y][0], acc[y][1], acc[y][2], acc[y][3]);
         else
             for (int x = 0; x < 4; x++)
-                if (j + x < n) dst[x] = v[x];
+                if (j + x < n) dst[x] = acc[y][x];
+    }
+    if (mirror) {
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            const int j = j0 + tx * 4 + x;
+            if (j >= n) continue;
+            const int i = i0 + ty * 4;
+            float *dst = O + (size_t)j * n + i;
+            if (i + 3 < n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0))
+                *reinterpret_cast<float4 *>(dst) = make_float4(acc[0][x], acc[1][x], acc[2][x], acc[3][x]);
+            else
+                for (int y = 0; y < 4; y++)
+                    if (i + y < n) dst[y] = acc[y][x];
+        }
     }
 }
 
