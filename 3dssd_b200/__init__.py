@@ -8,7 +8,7 @@ from .layers_util import (pointnet_fp_module, pointnet_sa_module, pointnet_sa_mo
                           vote_layer)
 from .tf_ops import (calc_square_dist, farthest_point_sample, farthest_point_sample_with_distance,  # noqa: F401
                      furthest_point_sample, gather_point, group_concat, group_concat_split, group_point, linear_bn_relu,
-                     linear_tc, split_rows,
+                     linear_tc, sa_mlp_fused, split_rows,
                      query_ball_point, query_ball_point_dilated, query_ball_point_multi, three_interpolate,
                      three_nn)
 

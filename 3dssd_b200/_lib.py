@@ -35,6 +35,9 @@ _SIGNATURES = {
     "ssd3d_split_rows": [c_long, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "ssd3d_group_concat_split": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_int, c_void_p],
+    "ssd3d_sa_fused_smem": [c_int, c_int, c_void_p],
+    "ssd3d_sa_mlp_fused": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "ssd3d_tune_set_fps_cluster": [c_int],
 }
 
@@ -52,7 +55,8 @@ def lib():
         for name, argtypes in _SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = argtypes
-            fn.restype = None if name == "ssd3d_tune_set_fps_cluster" else c_int
+            fn.restype = (None if name == "ssd3d_tune_set_fps_cluster" else
+                          ctypes.c_size_t if name == "ssd3d_sa_fused_smem" else c_int)
         l.ssd3d_last_error.restype = ctypes.c_char_p
         l.ssd3d_last_error.argtypes = []
         _lib = l

@@ -12,8 +12,9 @@
 // split (two bf16 matrices, row-major == K-major), so every operand tile is a plain TMA box in the 128B-swizzled
 // canonical UMMA layout and no conversion happens on the load path.
 //
-// Kernel shape: 256 threads; warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warp 2 = TMEM
-// allocator, warps 4-7 = epilogue (TMEM -> registers -> scale/shift/ReLU -> fp32 / split-bf16 / pooled store).
+// Kernel shape: 384 threads; warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warp 2 = TMEM
+// allocator, warps 4-11 = epilogue (TMEM -> registers -> scale/shift/ReLU -> fp32 / split-bf16 / pooled store;
+// two warps per TMEM lane quarter share the 32-column chunks; max-pool = redux.sync across the lanes of a group).
 // Tile 128 rows x BN<=256 columns, K streamed in 64-element blocks through a multi-stage mbarrier ring;
 // two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
@@ -25,8 +26,9 @@ namespace ssd3d {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int TC_THREADS = 256;
-constexpr int TC_EPI_WARP0 = 4;           // warps 4..7 are the epilogue (warp%4 selects the TMEM lane quarter)
+constexpr int TC_EPI_WARP0 = 4;           // warps 4..11 are the epilogue (warp%4 selects the TMEM lane quarter)
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = (TC_EPI_WARP0 + TC_EPI_WARPS) * 32;
 constexpr int TC_MAX_STAGES = 4;
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;   // one A tile (hi or lo): 16 KiB
 
@@ -85,7 +87,70 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// ---- epilogue helpers ---------------------------------------------------------------------------------------
+// order-preserving float <-> uint map (so that an unsigned redux.max is a float max, also for negative values)
+__device__ __forceinline__ uint32_t f2ord(float x)
+{
+    const uint32_t b = __float_as_uint(x);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t &hw, uint32_t &lw)
+{
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+    hw = *reinterpret_cast<const uint32_t *>(&h);
+    lw = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+// Max-pool of one 32-column chunk over runs of POOL rows (tf.reduce_max(axis=2), layers_util.py:178) + mask (:180).
+// A thread holds one row; the rows of a group are lanes of a warp (POOL <= 32) or of 2-4 warps (64, 128).
+template <int POOL>
+__device__ __forceinline__ void pooled_chunk(const TcParams &p, const float (&v)[32], int lane, int q, int h, int mt,
+                                             int col0, uint32_t *xs /* [2 halves][4 quarters][32] */)
+{
+    constexpr int GP = POOL >= 32 ? 32 : POOL;       // lanes per group inside a warp
+    constexpr int KEEP = 32 / GP;                    // columns a lane ends up owning
+    const uint32_t gmask = POOL >= 32 ? 0xffffffffu : (((1u << GP) - 1u) << ((lane / GP) * GP));
+    const int lg = lane % GP;
+    uint32_t keep[KEEP];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const uint32_t m = __reduce_max_sync(gmask, f2ord(v[j]));
+        if ((j % GP) == lg) keep[j / GP] = m;
+    }
+    if (POOL > 32) {                                 // combine the 2 (4) warps that share a group
+        constexpr int WPG = POOL > 32 ? POOL / 32 : 1;
+        xs[(h * 4 + q) * 32 + lane] = keep[0];
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory");      // the 4 quarter-warps of this column half
+        if ((q % WPG) == 0) {
+#pragma unroll
+            for (int w = 1; w < WPG; w++) keep[0] = max(keep[0], xs[(h * 4 + q + w) * 32 + lane]);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory");      // xs reusable by the next chunk
+        if ((q % WPG) != 0) return;
+    }
+    const long gg = (long)mt * (TC_BM / POOL) + (q * 32 + lane) / POOL;
+    if (gg * POOL >= p.rows) return;
+    const bool masked = p.rowmask && p.rowmask[gg] == 0;
+#pragma unroll
+    for (int k = 0; k < KEEP; k++) {
+        const int col = col0 + k * GP + lg;
+        if (col >= p.n) continue;
+        const float mx = masked ? 0.0f : ord2f(keep[k]);
+        if (p.out_f32) p.out_f32[(size_t)gg * p.ld_f32 + col] = mx;
+        if (p.out_hi) {
+            const __nv_bfloat16 hb = __float2bfloat16_rn(mx);
+            p.out_hi[(size_t)gg * p.ld_split + col] = hb;
+            p.out_lo[(size_t)gg * p.ld_split + col] = __float2bfloat16_rn(mx - __bfloat162float(hb));
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -94,14 +159,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                  const TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stages] x { A_hi | A_lo | B_hi | B_lo }, then the pooling staging tile
+    // carve: [stages] x { A_hi | A_lo | B_hi | B_lo }, then per-channel scale/shift of the covered columns
     const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
     const uint32_t stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float *pool_stage = reinterpret_cast<float *>(smem + (size_t)p.stages * stage_bytes);   // [128][33]
+    const int ncov = p.n_tiles * p.bn + 32;
+    float *s_scale = reinterpret_cast<float *>(smem + (size_t)p.stages * stage_bytes);
+    float *s_shift = s_scale + ncov;
 
     __shared__ unsigned long long full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ uint32_t pool_xs[2 * 4 * 32];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles;
@@ -109,12 +177,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < ncov; i += TC_THREADS) {      // columns >= n: scale = shift = 0 -> exact zeros
+        s_scale[i] = i < p.n ? __ldg(p.scale + i) : 0.0f;
+        s_shift[i] = i < p.n ? __ldg(p.shift + i) : 0.0f;
     }
     tc_fence_before();
     __syncthreads();
@@ -177,9 +249,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
             }
         }
     } else if (warp >= TC_EPI_WARP0) {
-        // ===== epilogue =====
-        const int q = warp & 3;                                  // TMEM lane quarter
-        const int et = threadIdx.x - TC_EPI_WARP0 * 32;          // 0..127
+        // ===== epilogue: 8 warps; warp%4 = TMEM lane quarter (rows), (warp-4)/4 = which half of the 32-column chunks
+        const int q = warp & 3;
+        const int h = (warp - TC_EPI_WARP0) >> 2;
+        const int nchunks = (p.bn + 31) / 32;
         int tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
             const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
@@ -188,31 +261,41 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
             tc_fence_after();
             const long row = (long)mt * TC_BM + q * 32 + lane;
             const bool row_ok = row < p.rows;
-            for (int c0 = 0; c0 < p.bn; c0 += 32) {
+            for (int ci = h; ci < nchunks; ci += 2) {
+                const int c0 = ci * 32;
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.bn + c0), r);
                 const int col0 = nt * p.bn + c0;
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int col = col0 + j;
-                    const bool ok = col < p.n;
-                    const float sc = ok ? __ldg(p.scale + col) : 0.0f;
-                    const float sh = ok ? __ldg(p.shift + col) : 0.0f;
-                    float x = fmaf(__uint_as_float(r[j]), sc, sh);
-                    if (p.relu) x = fmaxf(x, 0.0f);
-                    v[j] = x;
+                for (int j4 = 0; j4 < 32; j4 += 4) {
+                    const float4 sc = *reinterpret_cast<const float4 *>(s_scale + col0 + j4);
+                    const float4 sh = *reinterpret_cast<const float4 *>(s_shift + col0 + j4);
+                    v[j4 + 0] = fmaf(__uint_as_float(r[j4 + 0]), sc.x, sh.x);
+                    v[j4 + 1] = fmaf(__uint_as_float(r[j4 + 1]), sc.y, sh.y);
+                    v[j4 + 2] = fmaf(__uint_as_float(r[j4 + 2]), sc.z, sh.z);
+                    v[j4 + 3] = fmaf(__uint_as_float(r[j4 + 3]), sc.w, sh.w);
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.0f);
                 }
                 if (p.pool <= 1) {
                     if (row_ok) {
                         if (p.out_f32) {
                             float *dst = p.out_f32 + (size_t)row * p.ld_f32 + col0;
+                            if (col0 + 32 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
-                            for (int j = 0; j < 32; j++)
-                                if (col0 + j < p.n) dst[j] = v[j];
+                                for (int j4 = 0; j4 < 32; j4 += 4)
+                                    *reinterpret_cast<float4 *>(dst + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; j++)
+                                    if (col0 + j < p.n) dst[j] = v[j];
+                            }
                         }
                         if (p.out_hi) {
-                            // split x = hi + lo (bf16 each); columns n..ld_split-1 are written as zeros (K padding of the next layer)
+                            // x = hi + lo (bf16 each); columns n..ld_split-1 come out as exact zeros (next layer's K padding)
                             __nv_bfloat16 *dh = p.out_hi + (size_t)row * p.ld_split + col0;
                             __nv_bfloat16 *dl = p.out_lo + (size_t)row * p.ld_split + col0;
 #pragma unroll
@@ -220,46 +303,25 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                                 if (col0 + j8 >= p.ld_split) break;
                                 uint32_t hw[4], lw[4];
 #pragma unroll
-                                for (int t = 0; t < 4; t++) {
-                                    const float x0 = v[j8 + 2 * t], x1 = v[j8 + 2 * t + 1];
-                                    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                                    const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-                                    const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-                                    hw[t] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                                    lw[t] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                                }
+                                for (int t = 0; t < 4; t++) split_pair(v[j8 + 2 * t], v[j8 + 2 * t + 1], hw[t], lw[t]);
                                 *reinterpret_cast<uint4 *>(dh + j8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                                 *reinterpret_cast<uint4 *>(dl + j8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                             }
                         }
                     }
                 } else {
-                    // max-pool over runs of `pool` rows (tf.reduce_max(axis=2)) through a shared staging tile
-                    epi_bar_sync();                               // previous chunk fully consumed
-#pragma unroll
-                    for (int j = 0; j < 32; j++) pool_stage[(q * 32 + lane) * 33 + j] = v[j];
-                    epi_bar_sync();
-                    const int groups = TC_BM / p.pool;
-                    for (int e = et; e < groups * 32; e += 128) {
-                        const int g = e >> 5, j = e & 31;
-                        const long gg = (long)mt * groups + g;
-                        const int col = col0 + j;
-                        if (gg * p.pool >= p.rows || col >= p.n) continue;
-                        float mx = -INFINITY;
-                        for (int rr = 0; rr < p.pool; rr++) mx = fmaxf(mx, pool_stage[(g * p.pool + rr) * 33 + j]);
-                        if (p.rowmask && p.rowmask[gg] == 0) mx = 0.0f;
-                        if (p.out_f32) p.out_f32[(size_t)gg * p.ld_f32 + col] = mx;
-                        if (p.out_hi) {
-                            const __nv_bfloat16 h = __float2bfloat16_rn(mx);
-                            p.out_hi[(size_t)gg * p.ld_split + col] = h;
-                            p.out_lo[(size_t)gg * p.ld_split + col] = __float2bfloat16_rn(mx - __bfloat162float(h));
-                        }
+                    switch (p.pool) {
+                        case 8: pooled_chunk<8>(p, v, lane, q, h, mt, col0, pool_xs); break;
+                        case 16: pooled_chunk<16>(p, v, lane, q, h, mt, col0, pool_xs); break;
+                        case 32: pooled_chunk<32>(p, v, lane, q, h, mt, col0, pool_xs); break;
+                        case 64: pooled_chunk<64>(p, v, lane, q, h, mt, col0, pool_xs); break;
+                        default: pooled_chunk<128>(p, v, lane, q, h, mt, col0, pool_xs); break;
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));   // 4 arrivals (one per epilogue warp) free the buffer
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));   // 8 arrivals (one per epilogue warp) free the buffer
         }
     }
 
@@ -363,7 +425,9 @@ extern "C" int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const
     SSD3D_REQUIRE(out_f32 || (out_hi && out_lo), "linear_tc: no output requested");
     SSD3D_REQUIRE(!out_f32 || ld_f32 >= n, "linear_tc: ld_f32=%d < n=%d", ld_f32, n);
     SSD3D_REQUIRE(!out_hi || (out_lo && ld_split >= n && ld_split % 8 == 0), "linear_tc: bad split output (ld_split=%d)", ld_split);
-    SSD3D_REQUIRE(pool >= 1 && rows % pool == 0 && TC_BM % pool == 0, "linear_tc: pool=%d must divide 128 and rows=%ld", pool, rows);
+    SSD3D_REQUIRE(pool == 1 || pool == 8 || pool == 16 || pool == 32 || pool == 64 || pool == 128,
+                  "linear_tc: pool=%d must be one of 1, 8, 16, 32, 64, 128", pool);
+    SSD3D_REQUIRE(rows % pool == 0, "linear_tc: rows=%ld not a multiple of pool=%d", rows, pool);
     for (const void *ptr : {a_hi, a_lo, b_hi, b_lo, (const void *)out_hi, (const void *)out_lo})
         SSD3D_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "linear_tc: operand pointers must be 16-byte aligned");
     if (rows == 0) return 0;
@@ -378,7 +442,8 @@ extern "C" int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const
     p.m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
     const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)p.bn * TC_BK * 2;
     const size_t budget = 224 * 1024 - 1024;   // 227 KiB per CTA minus static barriers and the 1 KiB alignment slack
-    const size_t pool_bytes = TC_BM * 33 * sizeof(float);
+    const size_t pool_bytes = 2 * ((size_t)p.n_tiles * p.bn + 32) * sizeof(float);   // staged scale / shift
+    SSD3D_REQUIRE(pool_bytes <= 32 * 1024, "linear_tc: n=%d too wide for the staged scale/shift", n);
     int stages = (int)((budget - pool_bytes) / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     SSD3D_REQUIRE(stages >= 2, "linear_tc: tile does not fit shared memory");

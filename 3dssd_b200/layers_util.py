@@ -49,7 +49,8 @@ def ffps_indices(npoint, xyz, points, mode):
 def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_training, bn_decay, bn,
                            fps_sample_range_list, fps_method_list, npoint_list, former_fps_idx, use_attention, scope,
                            dilated_group, vote_ctr=None, aggregation_channel=None, debugging=False, epsilon=1e-5, *,
-                           params, ffps_mode="matrix", aggregation=None, return_debug=False, mlp_mode="tc"):
+                           params, ffps_mode="matrix", aggregation=None, return_debug=False, mlp_mode="tc",
+                           fuse_scale=True):
     """PointNet++ SA module with multi-scale grouping; returns (new_xyz, new_points, fps_idx)."""
     if is_training:
         raise NotImplementedError("training-mode BatchNorm / backward ops are out of scope (inference only)")
@@ -104,7 +105,7 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                     a, c = tf_ops.query_ball_point(radius_list[i], nsample_list[i], xyz, new_xyz)
                 idx_list.append(a); cnt_list.append(c)
         use_agg = bool(aggregation and aggregation_channel is not None and aggregation_channel != -1)
-        tc = mlp_mode == "tc" and all(128 % k == 0 for k in nsample_list)
+        tc = mlp_mode == "tc" and all(k in (8, 16, 32, 64, 128) for k in nsample_list)
         if mlp_mode not in ("tc", "fp32"):
             raise ValueError("mlp_mode must be 'tc' or 'fp32'")
         if tc:
@@ -123,8 +124,15 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
             for i in range(nscale):
                 idx, cnt = idx_list[i], cnt_list[i]
                 debug["idx"].append(idx); debug["cnt"].append(cnt)
-                hi, lo = tf_ops.group_concat_split(xyz, points, new_xyz, idx)      # :160-165 fused with the split
                 nl = len(mlp_list[i])
+                stack = pp.fused_stack(["%s/conv%d_%d" % (scope, i, j) for j in range(nl)], bn, points.shape[-1] + 3) \
+                    if fuse_scale else None
+                if stack is not None:                                              # whole scale in one kernel
+                    tf_ops.sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=(concat, off),
+                                        out_split=(cat_hi, cat_lo, off) if use_agg else None)
+                    off += mlp_list[i][-1]
+                    continue
+                hi, lo = tf_ops.group_concat_split(xyz, points, new_xyz, idx)      # :160-165 fused with the split
                 for j in range(nl):
                     f = pp.conv("%s/conv%d_%d" % (scope, i, j), bn)
                     if j < nl - 1:

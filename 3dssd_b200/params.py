@@ -105,6 +105,48 @@ def fold(params, scope, bn, device):
     return FoldedConv(t(w), t(scale), t(shift))
 
 
+def _swizzled_image(wt_bf16):
+    """[npad, kp] bf16 (W^T, K-major) -> bytes of the canonical UMMA K-major SWIZZLE_128B operand image:
+    k-blocks of [npad x 64] elements, rows of 128 bytes, 16-byte chunk j of row r stored at chunk j ^ (r % 8)."""
+    npad, kp = wt_bf16.shape
+    nkb = (kp + 63) // 64
+    full = torch.zeros((npad, nkb * 64), dtype=torch.bfloat16, device=wt_bf16.device)
+    full[:, :kp] = wt_bf16
+    t = full.view(npad, nkb, 8, 8).permute(1, 0, 2, 3).contiguous()          # [kb, r, chunk, elem]
+    r = torch.arange(npad, device=t.device).view(1, npad, 1, 1)
+    j = torch.arange(8, device=t.device).view(1, 1, 8, 1)
+    src = (j ^ (r % 8)).expand(nkb, npad, 8, 8)
+    return torch.gather(t, 2, src).contiguous().view(-1)
+
+
+class FusedStack:
+    """Operands of ssd3d_sa_mlp_fused for one SA scale: the split, pre-swizzled weight images of its conv layers
+    packed as { hi | lo } per layer, and the folded { scale | shift } per layer (zero beyond the true width)."""
+
+    def __init__(self, convs, cin):
+        dev = convs[0].w.device
+        self.nout = [f.cout for f in convs]
+        self.cin = cin
+        wparts, sparts = [], []
+        kp = round16(cin)
+        for f in convs:
+            npad = round16(f.cout)
+            assert f.kp == kp, (f.kp, kp)
+            hi = torch.zeros((npad, kp), dtype=torch.bfloat16, device=dev)
+            lo = torch.zeros_like(hi)
+            hi[: f.cout] = f.b_hi
+            lo[: f.cout] = f.b_lo
+            wparts += [_swizzled_image(hi), _swizzled_image(lo)]
+            sc = torch.zeros(npad, dtype=torch.float32, device=dev)
+            sh = torch.zeros(npad, dtype=torch.float32, device=dev)
+            sc[: f.cout] = f.scale
+            sh[: f.cout] = f.shift
+            sparts += [sc, sh]
+            kp = npad
+        self.w_blob = torch.cat(wparts).contiguous()
+        self.ss_blob = torch.cat(sparts).contiguous()
+
+
 class PreparedParams:
     """Device-resident folded weights, looked up by TF scope name (lazy, cached)."""
 
@@ -117,6 +159,18 @@ class PreparedParams:
         key = (scope, bool(bn))
         if key not in self._cache:
             self._cache[key] = fold(self.raw, scope, bn, self.device)
+        return self._cache[key]
+
+    def fused_stack(self, scopes, bn, cin):
+        """FusedStack for a list of conv scopes (one SA scale), or None when the stack does not fit the fused kernel."""
+        key = ("fused",) + tuple(scopes) + (bool(bn), cin)
+        if key not in self._cache:
+            import ctypes
+            from ._lib import lib
+            convs = [self.conv(sc, bn) for sc in scopes]
+            nout = (ctypes.c_int * len(convs))(*[f.cout for f in convs])
+            fits = len(convs) <= 3 and lib().ssd3d_sa_fused_smem(cin - 3, len(convs), ctypes.cast(nout, ctypes.c_void_p)) > 0
+            self._cache[key] = FusedStack(convs, cin) if fits else None
         return self._cache[key]
 
     def prepare_all(self):

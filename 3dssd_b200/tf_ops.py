@@ -315,8 +315,8 @@ def linear_tc(a_hi, a_lo, f, relu=True, pool=1, rowmask=None, want_f32=True, wan
     pool = int(pool)
     lead = tuple(a_hi.shape[:-1])
     if pool > 1:
-        if lead[-1] != pool or 128 % pool != 0:
-            raise ValueError("pool must equal the second-to-last dimension and divide 128")
+        if lead[-1] != pool or pool not in (8, 16, 32, 64, 128):
+            raise ValueError("pool must equal the second-to-last dimension and be one of 8, 16, 32, 64, 128")
         lead = lead[:-1]
     n = f.cout
     dev = a_hi.device
@@ -350,3 +350,39 @@ def linear_tc(a_hi, a_lo, f, relu=True, pool=1, rowmask=None, want_f32=True, wan
                                 1 if relu else 0, pool, _p(rowmask), vp(pf), ldf, vp(ph), vp(pl), lds, _stream()),
           "linear_tc")
     return y, sp
+
+
+def sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=None, out_split=None):
+    """One SA scale in one kernel: gather + concat + conv stack + max-pool + mask (layers_util.py:157-180).
+    stack: params.FusedStack.  out_f32=(buffer, col_offset) / out_split=(hi, lo, col_offset) as linear_tc;
+    without them a fresh (b, m, C3) fp32 tensor is returned."""
+    xyz = _req(xyz, "xyz", torch.float32, 3, 3)
+    new_xyz = _req(new_xyz, "new_xyz", torch.float32, 3, 3)
+    idx = _req(idx, "idx", torch.int32, 3)
+    b, n, _ = xyz.shape
+    c = 0
+    if points is not None:
+        points = _req(points, "points", torch.float32, 3)
+        c = points.shape[2]
+    if c + 3 != stack.cin:
+        raise ValueError("feature channels (%d) do not match the stack's input width (%d)" % (c, stack.cin - 3))
+    _, m, ns = idx.shape
+    n3 = stack.nout[-1]
+    y = None
+    pf, ldf = 0, 0
+    if out_f32 is not None:
+        buf, off = out_f32
+        ldf, pf, y = buf.shape[-1], buf.data_ptr() + 4 * off, buf
+    elif out_split is None:
+        y = torch.empty((b, m, n3), dtype=torch.float32, device=xyz.device)
+        pf, ldf = y.data_ptr(), n3
+    ph = pl = lds = 0
+    if out_split is not None:
+        hb, lb, off = out_split
+        lds, ph, pl = hb.shape[-1], hb.data_ptr() + 2 * off, lb.data_ptr() + 2 * off
+    nout = (ctypes.c_int * len(stack.nout))(*stack.nout)
+    vp = ctypes.c_void_p
+    check(lib().ssd3d_sa_mlp_fused(b, n, c, m, ns, _p(xyz), _p(points), _p(new_xyz), _p(idx), _p(cnt), len(stack.nout),
+                                   ctypes.cast(nout, vp), _p(stack.w_blob), _p(stack.ss_blob), vp(pf), ldf, vp(ph),
+                                   vp(pl), lds, _stream()), "sa_mlp_fused")
+    return y

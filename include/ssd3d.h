@@ -17,6 +17,8 @@
 #ifndef SSD3D_H_
 #define SSD3D_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -133,6 +135,17 @@ int ssd3d_split_rows(long rows, int c, const float *x, int ldx, void *hi, void *
 /* ssd3d_group_concat fused with the split: hi/lo [b*m*nsample, kp] bf16. */
 int ssd3d_group_concat_split(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
                              const float *new_xyz, const int *idx, void *hi, void *lo, int kp, ssd3d_stream_t stream);
+
+/* A whole SA scale in one kernel (gather + concat + up to 3 conv/BN/ReLU layers + max-pool + mask,
+ * lib/utils/layers_util.py:157-180) for layer stacks whose weights fit in shared memory.
+ * ssd3d_sa_fused_smem returns the shared-memory bytes needed, or 0 if the stack does not fit (use the per-layer
+ * path then).  w_blob / ss_blob are the pre-swizzled split weights and folded scale/shift built by the host
+ * (3dssd_b200/params.py: FusedStack).  Outputs as ssd3d_linear_tc with pool = nsample. */
+size_t ssd3d_sa_fused_smem(int c, int nl, const int *nout);
+int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
+                       const float *new_xyz, const int *idx, const int *pts_cnt, int nl, const int *nout,
+                       const void *w_blob, const float *ss_blob, float *out_f32, int ld_f32, void *out_hi, void *out_lo,
+                       int ld_split, ssd3d_stream_t stream);
 
 /* ymax[g, 0:c] = max over rows g*pool .. g*pool+pool-1 of y[., 0:c] (times rowmask[g] != 0): the
  * tf.reduce_max(axis=2) * mask of layers_util.py:178-180 for nsample values the fused epilogue of

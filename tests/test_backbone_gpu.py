@@ -52,13 +52,15 @@ def check_backbone(pkg, net_out, oracle_out, nlayers):
         assert e < TOL, "features of layer %d: rel err %g" % (li, e)
 
 
-@pytest.mark.parametrize("ffps_mode,mlp_mode", [("matrix", "tc"), ("fused", "tc"), ("matrix", "fp32")])
-def test_backbone_small_vs_oracle(pkg, oracle_ops, cuda, ffps_mode, mlp_mode):
+@pytest.mark.parametrize("ffps_mode,mlp_mode,fuse", [("matrix", "tc", True), ("fused", "tc", True), ("matrix", "tc", False),
+                                                     ("matrix", "fp32", False)])
+def test_backbone_small_vs_oracle(pkg, oracle_ops, cuda, ffps_mode, mlp_mode, fuse):
     from oracle import layers as olayers
     arch = scaled_arch(pkg, 8)                                    # 2048 -> 512 -> 128 -> 64 -> 32 centres
     params = pkg.params.init_params(arch, 1, seed=4, random_bias=True)
     pts = compact_scene(2, 2048, seed=40)
-    net = pkg.SABackbone(arch, params, in_channels=1, device=cuda, ffps_mode=ffps_mode, mlp_mode=mlp_mode)
+    net = pkg.SABackbone(arch, params, in_channels=1, device=cuda, ffps_mode=ffps_mode, mlp_mode=mlp_mode,
+                         fuse_scale=fuse)
     out = net.forward(torch.from_numpy(pts).to(cuda), return_debug=True)
     exp = olayers.backbone_forward(arch, pts, params, ffps_mode=ffps_mode, return_debug=True)
     check_backbone(pkg, out, exp, len(arch))

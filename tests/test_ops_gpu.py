@@ -332,7 +332,7 @@ def test_linear_tc_vs_oracle(pkg, oracle_ops, cuda, rows, cin, cout):
     assert rel_err(rec[:, :cout], exp) < 1e-4 and (rec[:, cout:] == 0).all()     # padding columns are zero
 
 
-@pytest.mark.parametrize("pool", [16, 32, 64])
+@pytest.mark.parametrize("pool", [8, 16, 32, 64, 128])
 def test_linear_tc_pool_mask_and_concat_slices(pkg, oracle_ops, cuda, pool):
     rng = np.random.default_rng(pool)
     b, m, cin, cout = 2, 37, 67, 64
@@ -384,3 +384,61 @@ def test_linear_tc_large_gemm_matches_fp32_path(pkg, cuda):
     hi, lo = pkg.split_rows(x)
     y, _ = pkg.linear_tc(hi, lo, f, pool=32)
     assert rel_err(N(y), N(ref)) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------
+# whole SA scale in one kernel (gather + concat + conv stack + max-pool + mask)
+# ---------------------------------------------------------------------------------------------------------
+FUSED_CASES = [  # b, n, c, m, nsample, mlp
+    (2, 700, 1, 96, 32, [16, 16, 32]),       # layer-1 scale 1 shape
+    (2, 700, 1, 70, 64, [32, 32, 64]),       # layer-1 scale 3, rows not a multiple of 128 per scene
+    (2, 500, 64, 64, 32, [64, 64, 128]),     # layer-2 scale 1
+    (1, 500, 64, 50, 64, [64, 96, 128]),     # layer-2 scale 3 (K = 96: partial k-block)
+    (3, 300, 29, 33, 16, [48, 32]),          # two layers, nsample 16, odd channel counts
+    (2, 300, 5, 17, 8, [16]),                # one layer, nsample 8
+    (1, 400, 8, 9, 128, [32, 32, 64]),       # nsample 128: group = whole tile
+]
+
+
+@pytest.mark.parametrize("b,n,c,m,k,mlp", FUSED_CASES)
+def test_sa_mlp_fused_vs_oracle(pkg, oracle_ops, cuda, b, n, c, m, k, mlp):
+    rng = np.random.default_rng(n + c + k)
+    xyz = rng.uniform(0, 1, (b, n, 3)).astype(np.float32)
+    feats = rng.standard_normal((b, n, c)).astype(np.float32)
+    new_xyz = np.array(xyz[:, :m], copy=True)
+    idx = rng.integers(0, n, (b, m, k)).astype(np.int32)
+    cnt = rng.integers(0, 3, (b, m)).astype(np.int32)
+    P = importlib.import_module("3dssd_b200.params")
+    prm, scopes, cin = {}, [], c + 3
+    for j, cout in enumerate(mlp):
+        P._conv_init(rng, prm, "s/conv0_%d" % j, cin, cout, True)
+        prm["s/conv0_%d/biases" % j] = rng.standard_normal(cout).astype(np.float32)
+        scopes.append("s/conv0_%d" % j)
+        cin = cout
+    pp = P.prepare(prm, cuda)
+    stack = pp.fused_stack(scopes, True, c + 3)
+    assert stack is not None
+    g = np.concatenate([oracle_ops.group_point(feats, idx), oracle_ops.group_point(xyz, idx) - new_xyz[:, :, None]], -1)
+    for sc in scopes:
+        bnp = tuple(prm[sc + "/bn/" + kk] for kk in ("gamma", "beta", "moving_mean", "moving_variance"))
+        g = oracle_ops.linear_bn_relu(g, prm[sc + "/weights"], prm[sc + "/biases"], bnp, True)
+    exp = g.max(axis=2) * (cnt > 0)[..., None]
+    y = pkg.sa_mlp_fused(T(xyz, cuda), T(feats, cuda), T(new_xyz, cuda), T(idx, cuda), T(cnt, cuda), stack)
+    assert y.shape == (b, m, mlp[-1]) and rel_err(N(y), exp) < 1e-4
+    # writing into slices of the concat buffers (fp32 + split bf16)
+    ld = mlp[-1] + 48
+    concat = torch.full((b, m, ld), -3.0, device=cuda)
+    ch = torch.zeros((b, m, ld), dtype=torch.bfloat16, device=cuda); cl = torch.zeros_like(ch)
+    pkg.sa_mlp_fused(T(xyz, cuda), T(feats, cuda), T(new_xyz, cuda), T(idx, cuda), T(cnt, cuda), stack,
+                     out_f32=(concat, 16), out_split=(ch, cl, 16))
+    got = N(concat)
+    assert rel_err(got[..., 16:16 + mlp[-1]], exp) < 1e-4 and (got[..., :16] == -3.0).all() and (got[..., 16 + mlp[-1]:] == -3.0).all()
+    assert rel_err(N(ch.float() + cl.float())[..., 16:16 + mlp[-1]], exp) < 1e-4
+
+
+def test_sa_mlp_fused_rejects_oversized_stack(pkg, cuda):
+    import ctypes
+    nout = (ctypes.c_int * 3)(256, 512, 1024)
+    assert pkg.lib().ssd3d_sa_fused_smem(256, 3, ctypes.cast(nout, ctypes.c_void_p)) == 0   # layer-4 does not fit
+    nout = (ctypes.c_int * 3)(64, 64, 128)
+    assert pkg.lib().ssd3d_sa_fused_smem(64, 3, ctypes.cast(nout, ctypes.c_void_p)) > 0
