@@ -39,6 +39,7 @@ _SIGNATURES = {
     "ssd3d_sa_mlp_fused": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "ssd3d_tune_set_fps_cluster": [c_int],
+    "ssd3d_tune_set_fps_variant": [c_int],
 }
 
 EXPORTS = sorted(list(_SIGNATURES) + ["ssd3d_last_error"])
@@ -55,7 +56,7 @@ def lib():
         for name, argtypes in _SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = argtypes
-            fn.restype = (None if name == "ssd3d_tune_set_fps_cluster" else
+            fn.restype = (None if name.startswith("ssd3d_tune_set") else
                           ctypes.c_size_t if name == "ssd3d_sa_fused_smem" else c_int)
         l.ssd3d_last_error.restype = ctypes.c_char_p
         l.ssd3d_last_error.argtypes = []

@@ -75,6 +75,8 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         "DONE_%=:\n\t}"
         ::"r"(bar), "r"(parity) : "memory");
 }
+// CTA-scope acquire: enough for data that lands in THIS CTA's shared memory (TMA, st.async from peers); a
+// cluster-scope acquire makes ptxas emit CCTL.IVALL (an L1 invalidate) on every wait -- 32% of the FPS round.
 __device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity)
 {
     asm volatile(

@@ -78,20 +78,6 @@ struct FpsShared {
     unsigned long long mbar[2];
 };
 
-// index of the packet that wins among `count` packets held one per lane (v = value bits, kk = key):
-// max value, ties -> min key.  One redux + ballot in the common case of a unique maximum.
-__device__ __forceinline__ int packet_argmax(uint32_t v, uint32_t kk, bool has)
-{
-    const uint32_t mx = __reduce_max_sync(0xffffffffu, has ? v : 0u);
-    const bool elig = has && v == mx;
-    uint32_t bal = __ballot_sync(0xffffffffu, elig);
-    if (bal & (bal - 1u)) {  // several packets share the maximum: smallest key decides (keys are unique)
-        const uint32_t kmin = __reduce_min_sync(0xffffffffu, elig ? kk : 0xffffffffu);
-        bal = __ballot_sync(0xffffffffu, elig && kk == kmin);
-    }
-    return __ffs(bal) - 1;
-}
-
 template <int CL, bool WITH_XYZ>
 __device__ __forceinline__ void fps_exchange(FpsShared<CL> &sh, int j, uint32_t rank, float best, uint32_t my_key,
                                              float cx, float cy, float cz, uint32_t &win_key, float &ox, float &oy,
@@ -99,42 +85,34 @@ __device__ __forceinline__ void fps_exchange(FpsShared<CL> &sh, int j, uint32_t 
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int par = j & 1;
-    // ---- stage 1: warp arg-max of (value, key); the winning lane publishes the warp's packet
+    const uint32_t u = __float_as_uint(fmaxf(best, 0.0f));
+    uint32_t mx, kmin;
+    warp_argmax(u, best >= 0.0f ? my_key : KEY_INVALID, mx, kmin);
     {
-        const uint32_t u = __float_as_uint(fmaxf(best, 0.0f));
-        const uint32_t mx = __reduce_max_sync(0xffffffffu, u);
-        const bool elig = (best >= 0.0f) && (u == mx);
-        const uint32_t bal = __ballot_sync(0xffffffffu, elig);
-        bool iwin;
-        uint32_t key = my_key;
-        if (bal == 0u) { iwin = lane == 0; key = KEY_INVALID; }          // warp owns padding slots only
-        else if ((bal & (bal - 1u)) == 0u) iwin = elig;                    // unique maximum (the common case)
-        else {
-            const uint32_t kmin = __reduce_min_sync(0xffffffffu, elig ? my_key : KEY_INVALID);
-            iwin = elig && my_key == kmin;
-        }
-        if (iwin) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, (u == mx) && ((best >= 0.0f ? my_key : KEY_INVALID) == kmin));
+        if (lane == __ffs(bal) - 1) {
             uint4 *dst = reinterpret_cast<uint4 *>(&sh.warp_pk[par][warp]);
-            dst[0] = make_uint4(mx, key, __float_as_uint(cx), __float_as_uint(cy));
+            dst[0] = make_uint4(mx, kmin, __float_as_uint(cx), __float_as_uint(cy));
             if (WITH_XYZ) dst[1] = make_uint4(__float_as_uint(cz), 0u, 0u, 0u);
         }
     }
-    if (CL == 1) {
-        __syncthreads();
-        const bool has = lane < FPS_NW;
-        const int ww = packet_argmax(has ? sh.warp_pk[par][lane].val : 0u, has ? sh.warp_pk[par][lane].key : 0u, has);
-        const uint4 a = reinterpret_cast<const uint4 *>(&sh.warp_pk[par][ww])[0];
-        win_key = a.y;
-        if (WITH_XYZ) { ox = __uint_as_float(a.z); oy = __uint_as_float(a.w); oz = sh.warp_pk[par][ww].z; }
-        return;
-    }
-    // ---- stage 2: warp 0 reduces the FPS_NW warp packets and pushes the CTA's packet to every peer.
-    // Only warp 0 has to wait for the packets (bar.sync); the other warps just signal (bar.arrive) and go on
-    // to wait for the cluster-wide result.
-    if (warp == 0) {
-        asm volatile("bar.sync 1, %0;" ::"n"(FPS_T) : "memory");
-        const bool has = lane < FPS_NW;
-        const int ww = packet_argmax(has ? sh.warp_pk[par][lane].val : 0u, has ? sh.warp_pk[par][lane].key : 0u, has);
+    __syncthreads();
+    if (CL == 1 || warp == 0) {
+        const uint32_t v = lane < FPS_NW ? sh.warp_pk[par][lane].val : 0u;
+        const uint32_t kk = lane < FPS_NW ? sh.warp_pk[par][lane].key : KEY_INVALID;
+        uint32_t m2, k2;
+        warp_argmax(v, kk, m2, k2);
+        const uint32_t bal = __ballot_sync(0xffffffffu, lane < FPS_NW && v == m2 && kk == k2);
+        const int ww = __ffs(bal) - 1;
+        if (CL == 1) {
+            win_key = k2;
+            if (WITH_XYZ) {
+                const uint4 a = reinterpret_cast<const uint4 *>(&sh.warp_pk[par][ww])[0];
+                ox = __uint_as_float(a.z); oy = __uint_as_float(a.w);
+                oz = sh.warp_pk[par][ww].z;
+            }
+            return;
+        }
         constexpr int PIECES = WITH_XYZ ? 2 : 1;
         if (lane == 0) mbar_arrive_expect_tx(smem_u32(&sh.mbar[par]), CL * PIECES * 16);
         if (lane < PIECES * CL) {
@@ -143,17 +121,21 @@ __device__ __forceinline__ void fps_exchange(FpsShared<CL> &sh, int j, uint32_t 
             const uint4 v4 = reinterpret_cast<const uint4 *>(&sh.warp_pk[par][ww])[piece];
             st_async_v4(mapa(smem_u32(&sh.cl_pk[par][rank]) + piece * 16, peer), mapa(smem_u32(&sh.mbar[par]), peer), v4);
         }
-    } else {
-        asm volatile("bar.arrive 1, %0;" ::"n"(FPS_T) : "memory");
     }
-    // ---- stage 3: every warp reduces the CL packets redundantly
-    mbar_wait_cluster(smem_u32(&sh.mbar[par]), ((j - 1) >> 1) & 1);
-    {
-        const bool has = lane < CL;
-        const int wr = packet_argmax(has ? sh.cl_pk[par][lane].val : 0u, has ? sh.cl_pk[par][lane].key : 0u, has);
-        const uint4 a = reinterpret_cast<const uint4 *>(&sh.cl_pk[par][wr])[0];
-        win_key = a.y;
-        if (WITH_XYZ) { ox = __uint_as_float(a.z); oy = __uint_as_float(a.w); oz = sh.cl_pk[par][wr].z; }
+    if (CL > 1) {
+        mbar_wait_cta(smem_u32(&sh.mbar[par]), ((j - 1) >> 1) & 1);
+        const uint32_t v = lane < CL ? sh.cl_pk[par][lane].val : 0u;
+        const uint32_t kk = lane < CL ? sh.cl_pk[par][lane].key : KEY_INVALID;
+        uint32_t m3, k3;
+        warp_argmax(v, kk, m3, k3);
+        win_key = k3;
+        if (WITH_XYZ) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, lane < CL && v == m3 && kk == k3);
+            const int wr = __ffs(bal) - 1;
+            const uint4 a = reinterpret_cast<const uint4 *>(&sh.cl_pk[par][wr])[0];
+            ox = __uint_as_float(a.z); oy = __uint_as_float(a.w);
+            oz = sh.cl_pk[par][wr].z;
+        }
     }
 }
 
@@ -224,6 +206,94 @@ fps3_cluster_kernel(int n, int m, const float *__restrict__ inp, int *__restrict
         if (g == 0) idxs[j] = fps_key_to_k(wkey);
     }
     if (CL > 1) cluster_sync_all();  // peers may still be storing into this CTA's shared memory
+}
+
+// ---------------------------------------------------------------------------------------------------
+// D-FPS, "direct" variant for scenes whose xyz fit in one CTA's shared memory (n <= ~18k, the 3DSSD sizes):
+// every CTA keeps a full copy of the scene's coordinates (one bulk TMA copy), so a packet is just (value, key)
+// = 8 bytes and EVERY WARP pushes its candidate straight to all peers -- the intra-CTA reduction stage and its
+// barrier disappear; a round is: register update -> 2 redux -> st.async -> mbarrier wait -> 2 redux -> 3 LDS.
+// ---------------------------------------------------------------------------------------------------
+template <int CL, int P>
+__global__ void __launch_bounds__(FPS_T, 1)
+fps3_direct_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out)
+{
+    using Map = FpsMap<CL * FPS_T, P>;
+    constexpr int NSLOT = CL * FPS_NW;                   // packets received per round
+    extern __shared__ float4 dyn_smem[];
+    float *sxyz = reinterpret_cast<float *>(dyn_smem);   // [n][3] raw copy of the scene
+    __shared__ __align__(16) unsigned long long slots[2][NSLOT];
+    __shared__ __align__(8) unsigned long long mbar[2], load_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+    const int scene = blockIdx.x / CL;
+    const int g = (int)rank * FPS_T + tid;
+    const float *data = inp + (size_t)scene * n * 3;
+    int *idxs = out + (size_t)scene * m;
+
+    if (tid == 0) {
+        mbar_init(smem_u32(&mbar[0]), 1);
+        mbar_init(smem_u32(&mbar[1]), 1);
+        mbar_init(smem_u32(&load_bar), 1);
+        fence_mbar_init_cluster();
+        mbar_arrive_expect_tx(smem_u32(&load_bar), (uint32_t)n * 12u);
+        bulk_g2s(smem_u32(sxyz), data, (uint32_t)n * 12u, smem_u32(&load_bar));
+    }
+    __syncthreads();
+    mbar_wait_cta(smem_u32(&load_bar), 0);
+
+    float px[P], py[P], pz[P], td[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        const int k = Map::k_of(g, i);
+        if (k < n) { px[i] = sxyz[3 * k]; py[i] = sxyz[3 * k + 1]; pz[i] = sxyz[3 * k + 2]; td[i] = 1e38f; }
+        else { px[i] = py[i] = pz[i] = 0.0f; td[i] = -1.0f; }
+    }
+    if (CL > 1) cluster_sync_all();                      // all peers' barriers are initialised
+
+    float ox = sxyz[0], oy = sxyz[1], oz = sxyz[2];
+    if (g == 0) idxs[0] = 0;
+
+    for (int j = 1; j < m; j++) {
+        const int par = j & 1;
+        if (tid == 0) mbar_arrive_expect_tx(smem_u32(&mbar[par]), NSLOT * 8);
+        float best = -1.0f;
+        int bi = 0;
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+            const float dx = px[i] - ox, dy = py[i] - oy, dz = pz[i] - oz;
+            float d = __fmul_rn(dx, dx);
+            d = __fmaf_rn(dy, dy, d);
+            d = __fmaf_rn(dz, dz, d);
+            const float t = fminf(d, td[i]);
+            td[i] = t;
+            if (t > best) { best = t; bi = i; }
+        }
+        const uint32_t u = __float_as_uint(fmaxf(best, 0.0f));
+        uint32_t mx, kmin;
+        warp_argmax(u, best >= 0.0f ? fps_key(Map::k_of(g, bi)) : KEY_INVALID, mx, kmin);
+        if (lane < CL) {
+            const unsigned long long pk = ((unsigned long long)mx << 32) | (unsigned long long)kmin;
+            st_async_b64(mapa(smem_u32(&slots[par][rank * FPS_NW + warp]), (uint32_t)lane),
+                         mapa(smem_u32(&mbar[par]), (uint32_t)lane), pk);
+        }
+        mbar_wait_cta(smem_u32(&mbar[par]), ((j - 1) >> 1) & 1);
+        // reduce the NSLOT packets: value desc, key asc
+        unsigned long long a = lane < NSLOT ? slots[par][lane] : 0x00000000ffffffffull;
+#pragma unroll
+        for (int sidx = 32; sidx < NSLOT; sidx += 32) {
+            const unsigned long long b2 = slots[par][lane + sidx];
+            const uint32_t av = (uint32_t)(a >> 32), bv = (uint32_t)(b2 >> 32);
+            if (bv > av || (bv == av && (uint32_t)b2 < (uint32_t)a)) a = b2;
+        }
+        uint32_t m3, k3;
+        warp_argmax((uint32_t)(a >> 32), (uint32_t)a, m3, k3);
+        const int old = fps_key_to_k(k3);
+        ox = sxyz[3 * old]; oy = sxyz[3 * old + 1]; oz = sxyz[3 * old + 2];
+        if (g == 0) idxs[j] = old;
+    }
+    if (CL > 1) cluster_sync_all();
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -449,6 +519,7 @@ static int pick_p(int n, int cl)
 }
 
 static int g_fps_cluster_override = 0;  // test / tuning hook (ssd3d_tune_set)
+static int g_fps_variant = 0;           // 0 = auto (direct when it fits), 1 = force the packet-with-xyz kernel
 
 static int pick_cl_xyz(int n)
 {
@@ -512,6 +583,11 @@ static int launch_fps3(int b, int n, int m, int cl, const float *inp, int *out, 
     void *args[] = {&n, &m, (void *)&inp, (void *)&out};
     SSD3D_FPS_SWITCH(fps3_cluster_kernel, (size_t)p * FPS_T * sizeof(float4));
 }
+static int launch_fps3_direct(int b, int n, int m, int cl, const float *inp, int *out, cudaStream_t st)
+{
+    void *args[] = {&n, &m, (void *)&inp, (void *)&out};
+    SSD3D_FPS_SWITCH(fps3_direct_kernel, (size_t)n * 12 + 16);
+}
 static int launch_fpsdist(int b, int n, int m, int cl, const float *dist, int *out, cudaStream_t st)
 {
     void *args[] = {&n, &m, (void *)&dist, (void *)&out};
@@ -547,6 +623,7 @@ extern "C" int ssd3d_fps_needs_temp(int n, int c)
 }
 
 extern "C" void ssd3d_tune_set_fps_cluster(int cl) { g_fps_cluster_override = cl; }
+extern "C" void ssd3d_tune_set_fps_variant(int v) { g_fps_variant = v; }
 
 extern "C" int ssd3d_farthest_point_sample(int b, int n, int c, int m, const float *inp, float *temp, int *out,
                                            ssd3d_stream_t stream)
@@ -559,7 +636,11 @@ extern "C" int ssd3d_farthest_point_sample(int b, int n, int c, int m, const flo
     if (c == 3) {
         int cl = pick_cl_xyz(n);
         while (cl < 16 && pick_p(n, cl) > 16) cl *= 2;
-        if (pick_p(n, cl) <= 16) rc = launch_fps3(b, n, m, cl, inp, out, st);
+        // direct variant: whole scene resident in every CTA (bulk copy needs 16-byte aligned source and size)
+        const bool direct_ok = g_fps_variant != 1 && cl >= 2 && (size_t)n * 12 + 16 <= 200 * 1024 && (n % 4) == 0 &&
+                               (reinterpret_cast<uintptr_t>(inp) & 15u) == 0 && pick_p(n, cl) <= 16;
+        if (direct_ok) rc = launch_fps3_direct(b, n, m, cl, inp, out, st);
+        else if (pick_p(n, cl) <= 16) rc = launch_fps3(b, n, m, cl, inp, out, st);
     } else {
         const int cl = pick_cl_generic(n, c);
         if (cl > 0) rc = launch_fpsc(b, n, c, m, cl, inp, out, st);
@@ -579,7 +660,8 @@ extern "C" int ssd3d_farthest_point_sample_with_distance(int b, int n, int m, co
     if (b == 0 || m == 0) return 0;
     SSD3D_REQUIRE(dist && out, "farthest_point_sample_with_distance: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    int cl = pick_cl_xyz(n);
+    // the per-round row read is a DRAM-latency-bound gather: more CTAs per scene = more loads in flight
+    int cl = g_fps_cluster_override > 0 ? g_fps_cluster_override : (n <= 1024 ? 1 : (n <= 2048 ? 4 : 8));
     while (cl < 16 && pick_p(n, cl) > 16) cl *= 2;
     if (pick_p(n, cl) <= 16) return cuda_status((cudaError_t)launch_fpsdist(b, n, m, cl, dist, out, st), "fpsdist launch");
     SSD3D_REQUIRE(temp != nullptr, "farthest_point_sample_with_distance: n=%d needs the temp[b,n] workspace", n);

@@ -43,6 +43,7 @@ struct TcParams {
     const int *rowmask;
     float *out_f32; int ld_f32;
     __nv_bfloat16 *out_hi, *out_lo; int ld_split;
+    int tma_store;   // non-pooled outputs leave through per-warp shared-memory blocks + TMA tensor stores
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -81,6 +82,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int x, int y)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // K-major, 128B-swizzled operand tile: rows are 128 bytes, 8-row groups are 1024 bytes apart (SBO), version 1
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
 {
@@ -156,15 +166,17 @@ __device__ __forceinline__ void pooled_chunk(const TcParams &p, const float (&v)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                  const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
-                 const TcParams p)
+                 const __grid_constant__ CUtensorMap map_ohi, const __grid_constant__ CUtensorMap map_olo,
+                 const __grid_constant__ CUtensorMap map_of32, const TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stages] x { A_hi | A_lo | B_hi | B_lo }, then per-channel scale/shift of the covered columns
+    // carve: [stages] x { A_hi | A_lo | B_hi | B_lo }, per-warp output blocks (4 KiB each), then scale/shift
     const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
     const uint32_t stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int ncov = p.n_tiles * p.bn + 32;
-    float *s_scale = reinterpret_cast<float *>(smem + (size_t)p.stages * stage_bytes);
+    uint8_t *out_stage = smem + (size_t)p.stages * stage_bytes;          // [8 warps][4 KiB], 4 KiB aligned
+    float *s_scale = reinterpret_cast<float *>(out_stage + (p.tma_store ? TC_EPI_WARPS * 4096 : 0));
     float *s_shift = s_scale + ncov;
 
     __shared__ unsigned long long full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tfull_bar[2], tempty_bar[2];
@@ -280,7 +292,41 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.0f);
                 }
-                if (p.pool <= 1) {
+                if (p.pool <= 1 && p.tma_store) {
+                    // Each warp owns a [32 rows x 32 columns] block: stage it in shared memory in the TMA swizzle and
+                    // let one bulk tensor store write whole 64/128-byte row segments (rows / columns beyond the tensor
+                    // are clipped by the hardware); the block is reused once the previous store has read it.
+                    uint8_t *blk = out_stage + (warp - TC_EPI_WARP0) * 4096;
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+                    const int row0 = mt * TC_BM + q * 32;
+                    if (p.out_f32) {                                   // 128-byte rows, SWIZZLE_128B
+#pragma unroll
+                        for (int c = 0; c < 8; c++)
+                            *reinterpret_cast<float4 *>(blk + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                                make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) { tma_store_2d(&map_of32, smem_u32(blk), col0, row0); tma_store_commit(); }
+                    } else {                                           // two 64-byte-row blocks (hi, lo), SWIZZLE_64B
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            uint32_t hw[4], lw[4];
+#pragma unroll
+                            for (int t = 0; t < 4; t++) split_pair(v[8 * c + 2 * t], v[8 * c + 2 * t + 1], hw[t], lw[t]);
+                            const uint32_t off = (uint32_t)lane * 64u + (uint32_t)((c ^ ((lane >> 1) & 3)) << 4);
+                            *reinterpret_cast<uint4 *>(blk + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            *reinterpret_cast<uint4 *>(blk + 2048 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        }
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&map_ohi, smem_u32(blk), col0, row0);
+                            tma_store_2d(&map_olo, smem_u32(blk + 2048), col0, row0);
+                            tma_store_commit();
+                        }
+                    }
+                } else if (p.pool <= 1) {
                     if (row_ok) {
                         if (p.out_f32) {
                             float *dst = p.out_f32 + (size_t)row * p.ld_f32 + col0;
@@ -323,6 +369,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));   // 8 arrivals (one per epilogue warp) free the buffer
         }
+        if (p.tma_store && lane == 0) tma_store_wait_all();           // global writes complete before the CTA retires
     }
 
     tc_fence_before();
@@ -410,6 +457,24 @@ static int make_map(CUtensorMap *map, const void *ptr, long nrows, int kp, int b
     return 0;
 }
 
+// output matrix [nrows x ncols] (row pitch ld elements) -> 2D map with a [32 x 32] box for the per-warp stores
+static int make_out_map(CUtensorMap *map, const void *ptr, long nrows, int ncols, int ld, bool f32)
+{
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return SSD3D_ERR_UNSUPPORTED; }
+    const int esz = f32 ? 4 : 2;
+    cuuint64_t dims[2] = {(cuuint64_t)ncols, (cuuint64_t)nrows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr),
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output) failed (CUresult %d)", (int)r); return SSD3D_ERR_INVALID_ARGUMENT; }
+    return 0;
+}
+
 }  // namespace ssd3d
 
 using namespace ssd3d;
@@ -437,12 +502,19 @@ extern "C" int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const
     const int n16 = (n + 15) / 16 * 16;
     // when split outputs are requested the tile must also cover (and zero) the padding columns n..ld_split-1
     const int ncover = out_hi && pool <= 1 ? (ld_split > n16 ? ld_split : n16) : n16;
-    p.bn = ncover < 256 ? ncover : 256;
+    // Non-pooled outputs go through TMA tensor stores when exactly one kind is requested and it is 16-byte
+    // addressable; their tiles are capped at 128 columns to leave shared memory for the per-warp store blocks.
+    const bool want_f32 = out_f32 != nullptr, want_split = out_hi != nullptr;
+    bool tma_store = pool <= 1 && (want_f32 != want_split);
+    if (tma_store && want_f32) tma_store = (ld_f32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out_f32) & 15u) == 0);
+    p.tma_store = tma_store ? 1 : 0;
+    const int bn_cap = tma_store ? 128 : 256;
+    p.bn = ncover < bn_cap ? ncover : bn_cap;
     p.n_tiles = (ncover + p.bn - 1) / p.bn;
     p.m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
     const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)p.bn * TC_BK * 2;
     const size_t budget = 224 * 1024 - 1024;   // 227 KiB per CTA minus static barriers and the 1 KiB alignment slack
-    const size_t pool_bytes = 2 * ((size_t)p.n_tiles * p.bn + 32) * sizeof(float);   // staged scale / shift
+    const size_t pool_bytes = 2 * ((size_t)p.n_tiles * p.bn + 32) * sizeof(float) + (tma_store ? TC_EPI_WARPS * 4096 : 0);
     SSD3D_REQUIRE(pool_bytes <= 32 * 1024, "linear_tc: n=%d too wide for the staged scale/shift", n);
     int stages = (int)((budget - pool_bytes) / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -458,13 +530,19 @@ extern "C" int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const
     if ((rc = make_map(&mal, a_lo, rows, kp, TC_BM)) != 0) return rc;
     if ((rc = make_map(&mbh, b_hi, n, kp, p.bn)) != 0) return rc;
     if ((rc = make_map(&mbl, b_lo, n, kp, p.bn)) != 0) return rc;
+    CUtensorMap moh = mah, mol = mah, mof = mah;   // placeholders when unused (never dereferenced by the kernel)
+    if (tma_store && want_split) {
+        if ((rc = make_out_map(&moh, out_hi, rows, ld_split, ld_split, false)) != 0) return rc;
+        if ((rc = make_out_map(&mol, out_lo, rows, ld_split, ld_split, false)) != 0) return rc;
+    }
+    if (tma_store && want_f32 && (rc = make_out_map(&mof, out_f32, rows, n, ld_f32, true)) != 0) return rc;
 
     const size_t smem = stages * stage_bytes + pool_bytes + 1024;
     cudaError_t e = cudaFuncSetAttribute((const void *)linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e, "linear_tc attr");
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < kNumSMs ? total : kNumSMs;
-    linear_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mah, mal, mbh, mbl, p);
+    linear_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mah, mal, mbh, mbl, moh, mol, mof, p);
     SSD3D_LAUNCH_CHECK("linear_tc_kernel");
 }
 

@@ -29,6 +29,16 @@ def _const(values, device):
     return _CONSTS[key]
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def _arange_idx(bs, npoint, device):
     return torch.arange(npoint, dtype=torch.int32, device=device).unsqueeze(0).repeat(bs, 1)
 
@@ -61,6 +71,7 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
     bs, n, _ = xyz.shape
 
     cur, last = [], 0
+    join_side = False
     for rng, method, npoint in zip(fps_sample_range_list, fps_method_list, npoint_list):
         end = n if rng == -1 else last + rng                      # tf.slice size -1 (:86-87)
         tmp_xyz = xyz[:, last:end].contiguous()
@@ -72,16 +83,41 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
             npoint = vote_ctr.shape[1]
             fps_idx = _arange_idx(bs, npoint, xyz.device)
         elif method == "FS":                                      # :94-99 fusion sampling
-            fps_idx = torch.cat([ffps_indices(npoint, tmp_xyz, tmp_points, ffps_mode),
-                                 tf_ops.farthest_point_sample(npoint, tmp_xyz)], dim=-1)
+            # F-FPS and D-FPS are independent latency-bound chains on a handful of SMs each: run them concurrently
+            side = _side_stream(xyz.device)
+            cur_s = torch.cuda.current_stream()
+            side.wait_stream(cur_s)
+            tmp_xyz.record_stream(side)
+            with torch.cuda.stream(side):
+                d_idx = tf_ops.farthest_point_sample(npoint, tmp_xyz)
+            f_idx = ffps_indices(npoint, tmp_xyz, tmp_points, ffps_mode)
+            cur_s.wait_stream(side)
+            d_idx.record_stream(cur_s)
+            fps_idx = torch.cat([f_idx, d_idx], dim=-1)
         elif npoint == tmp_xyz.shape[1]:                          # :100-101
             fps_idx = _arange_idx(bs, npoint, xyz.device)
         elif method == "F-FPS":                                   # :102-105
             fps_idx = ffps_indices(npoint, tmp_xyz, tmp_points, ffps_mode)
+        elif len(npoint_list) > 1:                                # D-FPS segment next to other segments: side stream
+            side = _side_stream(xyz.device)
+            cur_s = torch.cuda.current_stream()
+            side.wait_stream(cur_s)
+            tmp_xyz.record_stream(side)
+            with torch.cuda.stream(side):
+                fps_idx = tf_ops.farthest_point_sample(npoint, tmp_xyz)
+                if last:
+                    fps_idx = fps_idx + last
+            fps_idx.record_stream(cur_s)
+            cur.append(fps_idx)
+            last += rng
+            join_side = True
+            continue
         else:                                                     # D-FPS :106-107
             fps_idx = tf_ops.farthest_point_sample(npoint, tmp_xyz)
         cur.append(fps_idx + last if last else fps_idx)           # :109
         last += rng
+    if join_side:
+        torch.cuda.current_stream().wait_stream(_side_stream(xyz.device))
     fps_idx = cur[0] if len(cur) == 1 else torch.cat(cur, dim=-1)
     if former_fps_idx is not None:
         fps_idx = torch.cat([fps_idx, former_fps_idx], dim=-1)    # :113-114

@@ -155,6 +155,8 @@ int ssd3d_rowgroup_max(long groups, int pool, int c, const float *y, int ldy, co
 
 /* Tuning hook (tests/benchmarks only): force the FPS cluster size (1,2,4,8,16); 0 restores the heuristic. */
 void ssd3d_tune_set_fps_cluster(int cluster_size);
+/* 0 = automatic D-FPS kernel choice, 1 = force the general (coordinates-in-packet) cluster kernel. */
+void ssd3d_tune_set_fps_variant(int variant);
 
 #ifdef __cplusplus
 }

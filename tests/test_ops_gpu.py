@@ -44,17 +44,21 @@ def test_fps_xyz_bit_exact_vs_oracle(pkg, oracle_ops, cuda, name, gen, m):
     np.testing.assert_array_equal(got, exp)
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("cl", [1, 2, 4, 8, 16])
-def test_fps_every_cluster_size(pkg, oracle_ops, cuda, cl):
-    """The result must not depend on how a scene is split over the cluster."""
+def test_fps_every_cluster_size(pkg, oracle_ops, cuda, cl, variant):
+    """The result must not depend on how a scene is split over the cluster, nor on the kernel variant
+    (0 = automatic: scene-resident 'direct' kernel when it fits; 1 = coordinates-in-packet kernel)."""
     pts = synth.kitti_like(3, 4096, seed=21)[..., :3].copy()
     pts[:, 2000:2100] = pts[:, 100:200]                              # extra duplicates
     exp = oracle_ops.farthest_point_sample(300, pts)
     pkg.lib().ssd3d_tune_set_fps_cluster(cl)
+    pkg.lib().ssd3d_tune_set_fps_variant(variant)
     try:
         got = N(pkg.farthest_point_sample(300, T(pts, cuda)))
     finally:
         pkg.lib().ssd3d_tune_set_fps_cluster(0)
+        pkg.lib().ssd3d_tune_set_fps_variant(0)
     np.testing.assert_array_equal(got, exp)
 
 
@@ -330,6 +334,11 @@ def test_linear_tc_vs_oracle(pkg, oracle_ops, cuda, rows, cin, cout):
     yh, yl = sp
     rec = N(yh.float() + yl.float())
     assert rel_err(rec[:, :cout], exp) < 1e-4 and (rec[:, cout:] == 0).all()     # padding columns are zero
+    # single-output calls leave through the TMA-store epilogue: must equal the direct-store results bit for bit
+    y2, none = pkg.linear_tc(hi, lo, f, want_f32=True, want_split=False)
+    assert none is None and torch.equal(y2, y)
+    none, (yh2, yl2) = pkg.linear_tc(hi, lo, f, want_f32=False, want_split=True)
+    assert none is None and torch.equal(yh2, yh) and torch.equal(yl2, yl)
 
 
 @pytest.mark.parametrize("pool", [8, 16, 32, 64, 128])

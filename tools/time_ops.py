@@ -38,14 +38,17 @@ def main(out_path):
     xyz = pts4[..., :3].contiguous()
     have_ref = ref_ops.available()
 
-    # ---- D-FPS layer 1: 16384 -> 4096
-    for cl in (0, 4, 8, 16):
-        pkg.lib().ssd3d_tune_set_fps_cluster(cl)
-        try:
-            res["fps_L1_16384_4096_cl%d_ms" % cl] = timeit(lambda: pkg.farthest_point_sample(4096, xyz))
-        except Exception as e:  # noqa: BLE001
-            res["fps_L1_16384_4096_cl%d_ms" % cl] = "ERR " + str(e)
+    # ---- D-FPS layer 1: 16384 -> 4096   (variant 0 = direct/scene-resident when it fits, 1 = xyz-in-packet)
+    for variant in (0, 1):
+        pkg.lib().ssd3d_tune_set_fps_variant(variant)
+        for cl in (0, 4, 8, 16):
+            pkg.lib().ssd3d_tune_set_fps_cluster(cl)
+            try:
+                res["fps_L1_16384_4096_v%d_cl%d_ms" % (variant, cl)] = timeit(lambda: pkg.farthest_point_sample(4096, xyz))
+            except Exception as e:  # noqa: BLE001
+                res["fps_L1_16384_4096_v%d_cl%d_ms" % (variant, cl)] = "ERR " + str(e)
     pkg.lib().ssd3d_tune_set_fps_cluster(0)
+    pkg.lib().ssd3d_tune_set_fps_variant(0)
     if have_ref:
         res["ref_fps_L1_ms"] = timeit(lambda: ref_ops.farthest_point_sample(4096, xyz, sync=False), 1, 3)
     fidx = pkg.farthest_point_sample(4096, xyz)
