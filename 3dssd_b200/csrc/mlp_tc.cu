@@ -400,26 +400,46 @@ __global__ void split_rows_kernel(long rows, int c, const float *__restrict__ x,
     }
 }
 
-// fused gather + concat[features, rel-xyz] + split (layers_util.py:160-165), zero-padded to kp columns
-__global__ void group_concat_split_kernel(long rows, int n, int c, int m, int ns, const float *__restrict__ xyz,
-                                          const float *__restrict__ points, const float *__restrict__ new_xyz,
-                                          const int *__restrict__ idx, __nv_bfloat16 *__restrict__ hi,
-                                          __nv_bfloat16 *__restrict__ lo, int kp)
+// fused gather + concat[features, rel-xyz] + split (layers_util.py:160-165), zero-padded to kp columns.
+// One warp per output row: the source feature row is one contiguous run (coalesced 16-byte loads when c % 4 == 0),
+// the two bf16 rows are written as contiguous 8-byte pieces.
+__global__ void __launch_bounds__(256)
+group_concat_split_kernel(long rows, int n, int c, int m, int ns, const float *__restrict__ xyz,
+                          const float *__restrict__ points, const float *__restrict__ new_xyz,
+                          const int *__restrict__ idx, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
+                          int kp, int vec4)
 {
-    const long total = rows * kp;
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
     const long rows_per_scene = (long)m * ns;
-    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const long row = e / kp;
-        const int col = (int)(e - row * kp);
+    for (long row = warp0; row < rows; row += nwarps) {
         const long scene = row / rows_per_scene;
         const int a = __ldg(idx + row);
-        float val = 0.0f;
-        if (col < c) val = __ldg(points + ((size_t)scene * n + a) * c + col);
-        else if (col < c + 3) {
-            const long q = row / ns;
-            val = __ldg(xyz + ((size_t)scene * n + a) * 3 + (col - c)) - __ldg(new_xyz + q * 3 + (col - c));
+        const float *src = points + ((size_t)scene * n + a) * c;
+        __nv_bfloat16 *dh = hi + (size_t)row * kp, *dl = lo + (size_t)row * kp;
+        int k4 = 0;
+        if (vec4) {                                   // c % 4 == 0, 16-byte aligned feature rows
+            for (k4 = lane * 4; k4 + 3 < c; k4 += 128) {
+                const float4 f = __ldg(reinterpret_cast<const float4 *>(src + k4));
+                uint32_t h0, l0, h1, l1;
+                split_pair(f.x, f.y, h0, l0);
+                split_pair(f.z, f.w, h1, l1);
+                *reinterpret_cast<uint2 *>(dh + k4) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2 *>(dl + k4) = make_uint2(l0, l1);
+            }
+            k4 = c & ~3;
         }
-        split_store(val, hi + e, lo + e);
+        // tail: remaining feature columns, the 3 relative coordinates, zero padding up to kp
+        for (int k = k4 + lane; k < kp; k += 32) {
+            float val = 0.0f;
+            if (k < c) val = __ldg(src + k);
+            else if (k < c + 3) {
+                const long q = row / ns;
+                val = __ldg(xyz + ((size_t)scene * n + a) * 3 + (k - c)) - __ldg(new_xyz + q * 3 + (k - c));
+            }
+            split_store(val, dh + k, dl + k);
+        }
     }
 }
 
@@ -515,7 +535,7 @@ extern "C" int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const
     const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)p.bn * TC_BK * 2;
     const size_t budget = 224 * 1024 - 1024;   // 227 KiB per CTA minus static barriers and the 1 KiB alignment slack
     const size_t pool_bytes = 2 * ((size_t)p.n_tiles * p.bn + 32) * sizeof(float) + (tma_store ? TC_EPI_WARPS * 4096 : 0);
-    SSD3D_REQUIRE(pool_bytes <= 32 * 1024, "linear_tc: n=%d too wide for the staged scale/shift", n);
+    SSD3D_REQUIRE((size_t)p.n_tiles * p.bn <= 4096, "linear_tc: n=%d too wide for the staged scale/shift", n);
     int stages = (int)((budget - pool_bytes) / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     SSD3D_REQUIRE(stages >= 2, "linear_tc: tile does not fit shared memory");
@@ -566,11 +586,11 @@ extern "C" int ssd3d_group_concat_split(int b, int n, int c, int m, int nsample,
     SSD3D_REQUIRE(kp >= c + 3 && kp % 8 == 0, "group_concat_split: kp=%d must be >= c+3=%d and a multiple of 8", kp, c + 3);
     SSD3D_REQUIRE(xyz && new_xyz && idx && hi && lo && (points || c == 0), "group_concat_split: null pointer");
     const long rows = (long)b * m * nsample;
-    const long total = rows * kp;
-    if (total == 0) return 0;
-    const long want = (total + 255) / 256;
-    const int blocks = (int)(want < (long)kNumSMs * 16 ? want : (long)kNumSMs * 16);
+    if (rows == 0) return 0;
+    const long want = (rows + 7) / 8;                               // 8 warps (rows) per block
+    const int blocks = (int)(want < (long)kNumSMs * 32 ? want : (long)kNumSMs * 32);
+    const int vec4 = (c >= 4 && c % 4 == 0 && (reinterpret_cast<uintptr_t>(points) & 15u) == 0) ? 1 : 0;
     group_concat_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rows, n, c, m, nsample, xyz, points, new_xyz, idx,
-                                                                        (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, kp);
+                                                                        (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, kp, vec4);
     SSD3D_LAUNCH_CHECK("group_concat_split_kernel");
 }

@@ -100,6 +100,97 @@ sqdist_kernel(int n, int c, const float *__restrict__ a, float *__restrict__ out
     }
 }
 
+// 128x128 tile, 8x8 outputs per thread: 64 FFMA per 4 shared-memory loads, so the fp32 FMA pipe (not the LSU) is
+// the limiter.  Same pinned arithmetic, same symmetric double store.
+constexpr int SQ2_TILE = 128;
+constexpr int SQ2_PITCH = 132;
+
+__global__ void __launch_bounds__(SQ_THREADS)
+sqdist128_kernel(int n, int c, const float *__restrict__ a, float *__restrict__ out)
+{
+    if (blockIdx.x < blockIdx.y) return;
+    const bool mirror = blockIdx.x != blockIdx.y;
+    extern __shared__ float4 dyn_smem[];
+    float *As = reinterpret_cast<float *>(dyn_smem);
+    float *Bs = As + (size_t)c * SQ2_PITCH;
+    float *sqA = Bs + (size_t)c * SQ2_PITCH;
+    float *sqB = sqA + SQ2_TILE;
+    const int scene = blockIdx.z;
+    const int i0 = blockIdx.y * SQ2_TILE, j0 = blockIdx.x * SQ2_TILE;
+    const float *A = a + (size_t)scene * n * c;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < SQ2_TILE * c; e += SQ_THREADS) {
+        const int r = e / c, l = e - r * c;
+        As[l * SQ2_PITCH + r] = (i0 + r < n) ? A[(size_t)(i0 + r) * c + l] : 0.0f;
+        Bs[l * SQ2_PITCH + r] = (j0 + r < n) ? A[(size_t)(j0 + r) * c + l] : 0.0f;
+    }
+    __syncthreads();
+    {
+        const float *S = tid < SQ2_TILE ? As : Bs;
+        const int r = tid & (SQ2_TILE - 1);
+        float sacc = 0.0f;
+        for (int l = 0; l < c; l++) sacc = __fmaf_rn(S[l * SQ2_PITCH + r], S[l * SQ2_PITCH + r], sacc);
+        (tid < SQ2_TILE ? sqA : sqB)[r] = sacc;
+    }
+    __syncthreads();
+    const int ty = tid / 16, tx = tid % 16;
+    float acc[8][8];
+#pragma unroll
+    for (int y = 0; y < 8; y++)
+#pragma unroll
+        for (int x = 0; x < 8; x++) acc[y][x] = 0.0f;
+    for (int l = 0; l < c; l++) {
+        const float4 a0 = *reinterpret_cast<const float4 *>(As + l * SQ2_PITCH + ty * 8);
+        const float4 a1 = *reinterpret_cast<const float4 *>(As + l * SQ2_PITCH + ty * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4 *>(Bs + l * SQ2_PITCH + tx * 8);
+        const float4 b1 = *reinterpret_cast<const float4 *>(Bs + l * SQ2_PITCH + tx * 8 + 4);
+        const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float br[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int y = 0; y < 8; y++)
+#pragma unroll
+            for (int x = 0; x < 8; x++) acc[y][x] = __fmaf_rn(ar[y], br[x], acc[y][x]);
+    }
+    float *O = out + (size_t)scene * n * n;
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+        const float si = sqA[ty * 8 + y];
+#pragma unroll
+        for (int x = 0; x < 8; x++) acc[y][x] = __fsub_rn(__fadd_rn(si, sqB[tx * 8 + x]), __fmul_rn(2.0f, acc[y][x]));
+    }
+    const bool vec = (n % 4) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+        const int i = i0 + ty * 8 + y;
+        if (i >= n) continue;
+#pragma unroll
+        for (int xh = 0; xh < 8; xh += 4) {
+            const int j = j0 + tx * 8 + xh;
+            float *dst = O + (size_t)i * n + j;
+            if (vec && j + 3 < n) *reinterpret_cast<float4 *>(dst) = make_float4(acc[y][xh], acc[y][xh + 1], acc[y][xh + 2], acc[y][xh + 3]);
+            else
+                for (int x = 0; x < 4; x++)
+                    if (j + x < n) dst[x] = acc[y][xh + x];
+        }
+    }
+    if (mirror) {
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+            const int j = j0 + tx * 8 + x;
+            if (j >= n) continue;
+#pragma unroll
+            for (int yh = 0; yh < 8; yh += 4) {
+                const int i = i0 + ty * 8 + yh;
+                float *dst = O + (size_t)j * n + i;
+                if (vec && i + 3 < n) *reinterpret_cast<float4 *>(dst) = make_float4(acc[yh][x], acc[yh + 1][x], acc[yh + 2][x], acc[yh + 3][x]);
+                else
+                    for (int y = 0; y < 4; y++)
+                        if (i + y < n) dst[y] = acc[yh + y][x];
+            }
+        }
+    }
+}
+
 }  // namespace ssd3d
 
 using namespace ssd3d;
@@ -109,6 +200,14 @@ extern "C" int ssd3d_calc_square_dist(int b, int n, int c, const float *a, float
     SSD3D_REQUIRE(b >= 0 && n > 0 && c > 0, "calc_square_dist: bad shape b=%d n=%d c=%d", b, n, c);
     SSD3D_REQUIRE(a && out, "calc_square_dist: null pointer");
     if (b == 0) return 0;
+    const size_t smem128 = ((size_t)2 * c * SQ2_PITCH + 2 * SQ2_TILE) * sizeof(float);
+    if (n >= 256 && smem128 <= 200 * 1024) {
+        cudaError_t e2 = cudaFuncSetAttribute((const void *)sqdist128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128);
+        if (e2 != cudaSuccess) return cuda_status(e2, "calc_square_dist attr");
+        dim3 grid2((unsigned)ceil_div(n, SQ2_TILE), (unsigned)ceil_div(n, SQ2_TILE), (unsigned)b);
+        sqdist128_kernel<<<grid2, SQ_THREADS, smem128, (cudaStream_t)stream>>>(n, c, a, out);
+        SSD3D_LAUNCH_CHECK("sqdist128_kernel");
+    }
     const size_t smem = ((size_t)2 * c * SQ_PITCH + 2 * SQ_TILE) * sizeof(float);
     SSD3D_REQUIRE(smem <= 220 * 1024, "calc_square_dist: c=%d too large for the shared-memory slabs", c);
     cudaError_t e = cudaFuncSetAttribute((const void *)sqdist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -13,6 +13,7 @@ import torch
 
 from . import config as _cfg
 
+FUSED_SMEM_LIMIT = 110 * 1024
 BN_EPS = 1e-3  # tf.contrib.layers.batch_norm default epsilon (tf_util.py:439-444 does not override it)
 
 
@@ -169,7 +170,10 @@ class PreparedParams:
             from ._lib import lib
             convs = [self.conv(sc, bn) for sc in scopes]
             nout = (ctypes.c_int * len(convs))(*[f.cout for f in convs])
-            fits = len(convs) <= 3 and lib().ssd3d_sa_fused_smem(cin - 3, len(convs), ctypes.cast(nout, ctypes.c_void_p)) > 0
+            need = lib().ssd3d_sa_fused_smem(cin - 3, len(convs), ctypes.cast(nout, ctypes.c_void_p)) if len(convs) <= 3 else 0
+            # the fused kernel runs its phases (gather, MMA, epilogue) back to back per tile and relies on several
+            # co-resident CTAs per SM to overlap them: only worth it while >= 2 CTAs fit (layer-1 sized stacks)
+            fits = 0 < need <= FUSED_SMEM_LIMIT
             self._cache[key] = FusedStack(convs, cin) if fits else None
         return self._cache[key]
 

@@ -8,8 +8,10 @@ A "step" is one pass of the whole backbone (layer1..layer4 of configs/kitti/3dss
 layer) over one batch of 8 synthetic KITTI-shaped scenes [8,16384,4] per GPU (weak scaling: the batch is
 sharded by scene, no data-path collective; one NCCL all-gather of the per-scene detection blocks ends a step).
 
-value  : scenes/s, inputs resident in HBM, the step replayed from a CUDA graph, per-step CUDA-event time
-         (max over ranks), L2 flushed between steps.
+value  : scenes/s, inputs resident in HBM; every step is one CUDA-graph replay, `--pipeline` (default 2) steps are
+         in flight on separate streams (a step chains latency-bound FPS stages and throughput-bound MLP stages, so
+         the FPS of step i+1 overlaps the MLP of step i); timed with ONE CUDA-event pair around all K steps, L2
+         flushed before every step, max over ranks.  config.latency_ms_single_step is the un-overlapped step time.
 e2e    : same metric through the public API with HOST buffers: pinned H2D copy of the batch + backbone +
          D2H read of the detection block inside the timed region.
 roofline: dominant kernel (D-FPS layer 1) timed live with CUDA events on its launch stream.
@@ -140,6 +142,7 @@ def main():
     ap.add_argument("--ffps-mode", default="matrix", choices=["matrix", "fused"])
     ap.add_argument("--mlp-mode", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu captures)")
+    ap.add_argument("--pipeline", type=int, default=2, help="steps in flight (independent CUDA graphs on separate streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-scenes", type=int, default=2)
     args = ap.parse_args()
@@ -195,71 +198,82 @@ def main():
     for n in counted:
         setattr(L, n, originals[n])
 
-    if args.no_graph:
-        static_in = pts.clone()
+    # ---- steps in flight: P independent step pipelines (own CUDA graph + static buffers + stream each).  A step is a
+    # chain of latency-bound stages (FPS) and throughput-bound stages (MLP); with two steps in flight the FPS of step
+    # i+1 runs on SMs the MLP of step i leaves idle.  P=1 gives plain back-to-back steps.
+    P = 1 if args.no_graph else max(1, args.pipeline)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(P)]
+    runners = []
+    for _ in range(P):
+        if args.no_graph:
+            static_in = pts.clone()
 
-        def replay(points=None):
-            if points is not None:
-                static_in.copy_(points, non_blocking=True)
-            o = net.forward(static_in)
-            return o, net.detection_block(o[0], o[1])
-    else:
-        replay = net.capture(pts)
-
-    def step_device():
-        outg, (b, c) = replay()
-        return pkg.dist.gather_detections(b, c) if world > 1 else (b, c)
+            def replay(points=None, static_in=static_in):
+                if points is not None:
+                    static_in.copy_(points, non_blocking=True)
+                o = net.forward(static_in)
+                return o, net.detection_block(o[0], o[1])
+            runners.append(replay)
+        else:
+            runners.append(net.capture(pts))
+    main = torch.cuda.current_stream()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local).start() if rank == 0 else None
-    evs = []
-    t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step_device()
-        e1.record()
-        evs.append((e0, e1))
-    barrier()
-    wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if sampler else None
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = float(sum(step_ms))
-
-    # ---- e2e: host buffers through the public API ---------------------------------------------------------
     host_in = torch.from_numpy(pts_np).pin_memory()
-    host_out = torch.empty((SCENES_PER_GPU, 100, 9), dtype=torch.float32).pin_memory()
-    host_cnt = torch.empty((SCENES_PER_GPU,), dtype=torch.int32).pin_memory()
+    host_out = [torch.empty((SCENES_PER_GPU, 100, 9), dtype=torch.float32).pin_memory() for _ in range(P)]
+    host_cnt = [torch.empty((SCENES_PER_GPU,), dtype=torch.int32).pin_memory() for _ in range(P)]
 
-    def step_e2e():
-        outg, (b, c) = replay(host_in)                       # pinned H2D into the graph's static input, then replay
+    def one_step(i, e2e):
+        k = i % P
+        outg, (b, c) = runners[k](host_in if e2e else None)      # e2e: pinned H2D into the graph's static input first
         if world > 1:
             b, c = pkg.dist.gather_detections(b, c)
             b, c = b[rank * SCENES_PER_GPU:(rank + 1) * SCENES_PER_GPU], c[rank * SCENES_PER_GPU:(rank + 1) * SCENES_PER_GPU]
-        host_out.copy_(b, non_blocking=True)
-        host_cnt.copy_(c, non_blocking=True)
+        if e2e:
+            host_out[k].copy_(b, non_blocking=True)
+            host_cnt[k].copy_(c, non_blocking=True)
 
-    for _ in range(args.warmup):
-        step_e2e()
+    def timed_run(nsteps, e2e, pipelined):
+        """K steps; returns (total device ms from one event pair around the whole region, list of per-step ms)."""
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        per = []
+        start.record(main)
+        for s_ in streams:
+            s_.wait_event(start)
+        for i in range(nsteps):
+            s_ = streams[i % P] if pipelined else streams[0]
+            with torch.cuda.stream(s_):
+                flush.zero_()                                      # L2 flush between steps (inside the bracket)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(s_)
+                one_step(i if pipelined else 0, e2e)
+                e1.record(s_)
+                per.append((e0, e1))
+        for s_ in streams:
+            main.wait_stream(s_)
+        end.record(main)
+        barrier()
+        return start.elapsed_time(end), [a.elapsed_time(b) for a, b in per]
+
+    timed_run(args.warmup, False, True)
     barrier()
-    evs2 = []
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step_e2e()
-        e1.record()
-        evs2.append((e0, e1))
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    t_wall0 = time.perf_counter()
+    total_ms, _ = timed_run(args.steps, False, True)
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    # single-step latency (no overlap between steps), for the record
+    _, lat = timed_run(max(3, min(args.steps, 10)), False, False)
+    latency_ms = float(np.median(lat))
+
+    # ---- e2e: host buffers through the public API ---------------------------------------------------------
+    timed_run(args.warmup, True, True)
     barrier()
-    e2e_ms = float(sum(a.elapsed_time(b) for a, b in evs2))
+    e2e_ms, _ = timed_run(args.steps, True, True)
 
     # ---- roofline of the dominant kernel: D-FPS layer 1, timed alone with events on its stream --------------
     xyz = pts[..., :3].contiguous()
@@ -299,11 +313,13 @@ def main():
             "config": {"workload": "configs[1]: full 3DSSD SA backbone (3dssd.yaml layer1-4 + vote), synthetic KITTI "
                                    "16384x4 clouds, batch 8 per GPU", "scenes_per_gpu": SCENES_PER_GPU,
                        "global_batch": SCENES_PER_GPU * world, "points": NPOINTS, "parallelism": "scene-sharded dp%d" % world,
-                       "ffps": args.ffps_mode, "mlp": args.mlp_mode, "cuda_graph": not args.no_graph, "l2": "flushed (256 MiB write) between timed steps",
-                       "timing": "sum of per-step CUDA-event times on the launch stream, max over ranks; CUDA-graph replay",
+                       "ffps": args.ffps_mode, "mlp": args.mlp_mode, "cuda_graph": not args.no_graph, "l2": "flushed (256 MiB write) before every timed step",
+                       "steps_in_flight": P, "latency_ms_single_step": latency_ms,
+                       "timing": "one CUDA-event pair around all K steps (L2 flushes included), max over ranks; each step is a "
+                                 "CUDA-graph replay, %d step pipelines on separate streams" % P,
                        "wall_s_bracket": wall},
             "e2e": {"value": scenes / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(host_in.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4 + host_cnt.numel() * 4)},
+                    "h2d_bytes_per_step": int(host_in.numel() * 4), "d2h_bytes_per_step": int(host_out[0].numel() * 4 + host_cnt[0].numel() * 4)},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,
