@@ -115,39 +115,45 @@ ball_query_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2
             for (int s = 0; s < NS; s++) warp_done = warp_done && (cnt[q][s] >= p.nsample[s]);
 
         if (!warp_done) {
-            for (int step = 0; step * 32 < npts; step++) {
+            const int nsteps = (npts + 31) >> 5;
+            for (int step = 0; step < nsteps; step++) {
                 const int local = step * 32 + lane;
-                const bool in = local < npts;
+                const bool in = local < npts;                       // false only in the last, partial step of a scene
                 const int li = in ? local : 0;
                 const float cx = pts[li * 3], cy = pts[li * 3 + 1], cz = pts[li * 3 + 2];
-                const int k = base + local;
-                bool all_full = true;
+                float tt[BQ_QW];
+                bool near_any = false;
 #pragma unroll
                 for (int q = 0; q < BQ_QW; q++) {
                     // reference recipe: t = dy*dy ; t = fma(dx,dx,t) ; t = fma(dz,dz,t)   (PTX of :243 / :336)
                     const float dx = qx[q] - cx, dy = qy[q] - cy, dz = qz[q] - cz;
-                    float tt = __fmul_rn(dy, dy);
-                    tt = __fmaf_rn(dx, dx, tt);
-                    tt = __fmaf_rn(dz, dz, tt);
-                    const bool near = in && (DILATED ? (tt < p.t_max) : !(tt >= p.t_max));
-                    if (__ballot_sync(0xffffffffu, near)) {
+                    float t = __fmul_rn(dy, dy);
+                    t = __fmaf_rn(dx, dx, t);
+                    t = __fmaf_rn(dz, dz, t);
+                    tt[q] = t;
+                    near_any = near_any || (DILATED ? (t < p.t_max) : !(t >= p.t_max));
+                }
+                // one vote per step in the common case (no candidate of this step is inside any query's largest ball)
+                if (!__any_sync(0xffffffffu, near_any && in)) continue;
+                const int k = base + local;
+                bool all_full = true;
 #pragma unroll
-                        for (int s = 0; s < NS; s++) {
-                            const bool hit = in && (DILATED ? (tt == 0.0f || (tt >= p.t_lo[s] && tt < p.t_hi[s]))
-                                                            : !(tt >= p.t_hi[s]));
-                            const uint32_t hs = __ballot_sync(0xffffffffu, hit);
-                            const int c0 = cnt[q][s];
-                            const int ns = p.nsample[s];
-                            if (hs != 0u && c0 < ns) {
-                                int *row = my_stage + q * p.ktot + p.koff[s];
-                                const int pos = c0 + __popc(hs & ((1u << lane) - 1u));
-                                if (hit && pos < ns) row[pos] = k;
-                                cnt[q][s] = min(ns, c0 + __popc(hs));
-                            }
+                for (int q = 0; q < BQ_QW; q++) {
+#pragma unroll
+                    for (int s = 0; s < NS; s++) {
+                        const bool hit = in && (DILATED ? (tt[q] == 0.0f || (tt[q] >= p.t_lo[s] && tt[q] < p.t_hi[s]))
+                                                        : !(tt[q] >= p.t_hi[s]));
+                        const uint32_t hs = __ballot_sync(0xffffffffu, hit);
+                        const int c0 = cnt[q][s];
+                        const int ns = p.nsample[s];
+                        if (hs != 0u && c0 < ns) {
+                            int *row = my_stage + q * p.ktot + p.koff[s];
+                            const int pos = c0 + __popc(hs & ((1u << lane) - 1u));
+                            if (hit && pos < ns) row[pos] = k;
+                            cnt[q][s] = min(ns, c0 + __popc(hs));
                         }
+                        all_full = all_full && (cnt[q][s] >= ns);
                     }
-#pragma unroll
-                    for (int s = 0; s < NS; s++) all_full = all_full && (cnt[q][s] >= p.nsample[s]);
                 }
                 if (all_full) { warp_done = true; break; }
             }

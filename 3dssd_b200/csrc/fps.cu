@@ -78,10 +78,13 @@ struct FpsShared {
     unsigned long long mbar[2];
 };
 
+// pf_rows != nullptr (with-distance kernel): while the CTA's candidate travels to the peers, warp 0 prefetches that
+// candidate's matrix row into L2 -- the winner of the round is one of the CL candidates, so the row every CTA reads
+// next round is (almost always) an L2 hit instead of a DRAM-latency miss on the critical path.
 template <int CL, bool WITH_XYZ>
 __device__ __forceinline__ void fps_exchange(FpsShared<CL> &sh, int j, uint32_t rank, float best, uint32_t my_key,
                                              float cx, float cy, float cz, uint32_t &win_key, float &ox, float &oy,
-                                             float &oz)
+                                             float &oz, const float *pf_rows = nullptr, int pf_n = 0)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int par = j & 1;
@@ -120,6 +123,11 @@ __device__ __forceinline__ void fps_exchange(FpsShared<CL> &sh, int j, uint32_t 
             const uint32_t peer = WITH_XYZ ? (lane >> 1) : lane;
             const uint4 v4 = reinterpret_cast<const uint4 *>(&sh.warp_pk[par][ww])[piece];
             st_async_v4(mapa(smem_u32(&sh.cl_pk[par][rank]) + piece * 16, peer), mapa(smem_u32(&sh.mbar[par]), peer), v4);
+        }
+        if (pf_rows != nullptr && k2 != KEY_INVALID) {
+            const float *row = pf_rows + (size_t)fps_key_to_k(k2) * pf_n;
+            for (int e = lane * 32; e < pf_n; e += 32 * 32)          // one 128-byte line per prefetch
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + e) : "memory");
         }
     }
     if (CL > 1) {
@@ -337,7 +345,7 @@ fpsdist_cluster_kernel(int n, int m, const float *__restrict__ dist, int *__rest
         }
         uint32_t wkey;
         float ux, uy, uz;
-        fps_exchange<CL, false>(sh, j, rank, best, fps_key(Map::k_of(g, bi)), 0.f, 0.f, 0.f, wkey, ux, uy, uz);
+        fps_exchange<CL, false>(sh, j, rank, best, fps_key(Map::k_of(g, bi)), 0.f, 0.f, 0.f, wkey, ux, uy, uz, mat, n);
         old = fps_key_to_k(wkey);
         if (g == 0) idxs[j] = old;
     }

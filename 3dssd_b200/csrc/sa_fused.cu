@@ -22,7 +22,6 @@ namespace ssd3d {
 
 constexpr int SF_THREADS = 128;
 constexpr int SF_MAX_LAYERS = 3;
-constexpr uint32_t SF_TILE_BYTES = 128 * 128;   // one [128 rows x 64 bf16] operand tile (hi or lo)
 
 struct SfParams {
     int n, c, m, ns;                 // points per scene, feature channels, queries per scene, neighbours per query
@@ -40,6 +39,7 @@ struct SfParams {
     uint32_t w_total, ss_total;      // bytes / floats
     const uint8_t *w_blob;
     const float *ss_blob;
+    int rb[SF_MAX_LAYERS];           // bytes per operand row of layer l's A buffer: 32 / 64 (one block) or 128 (64-wide k-blocks)
     uint32_t bufx_bytes, bufy_bytes;
     uint32_t tmem_cols;
     float *out_f32; int ld_f32;
@@ -49,10 +49,13 @@ struct SfParams {
 __device__ __forceinline__ void sf_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void sf_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void sf_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ uint64_t sf_desc(uint32_t smem_addr)
+// K-major operand descriptor; rb = bytes per row = swizzle span (128 -> SWIZZLE_128B, 64 -> _64B, 32 -> _32B),
+// 8-row groups are 8*rb bytes apart (SBO), descriptor version 1
+__device__ __forceinline__ uint64_t sf_desc(uint32_t smem_addr, int rb)
 {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-           (2ull << 61);
+    const uint64_t layout = rb == 128 ? 2ull : (rb == 64 ? 4ull : 6ull);
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((8 * rb) >> 4) << 32) | (1ull << 46) |
+           (layout << 61);
 }
 __device__ __forceinline__ void sf_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc)
 {
@@ -87,12 +90,15 @@ __device__ __forceinline__ void sf_split_pair(float x0, float x1, uint32_t &hw, 
     lw = *reinterpret_cast<const uint32_t *>(&l);
 }
 // byte offset of the 16-byte chunk holding columns [8*c16g, 8*c16g+8) of row r inside an A buffer laid out as
-// k-blocks of { hi tile (16 KiB) | lo tile (16 KiB) }, each tile in the canonical K-major SWIZZLE_128B layout
-__device__ __forceinline__ uint32_t sf_a_chunk(int r, int c16g)
+// k-blocks of { hi tile | lo tile } (128 rows x rb bytes each), each tile in the canonical K-major swizzled layout
+// of span rb: chunk j of row r sits at chunk j ^ ((r >> log2(128/rb)) & (rb/16 - 1)).
+__device__ __forceinline__ uint32_t sf_a_chunk(int r, int c16g, int rb)
 {
-    const int kb = c16g >> 3, c16 = c16g & 7;
-    return (uint32_t)kb * (2 * SF_TILE_BYTES) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
-           (uint32_t)((c16 ^ (r & 7)) << 4);
+    const int nc = rb >> 4;                                  // chunks per row: 8 / 4 / 2
+    const int sh = rb == 128 ? 0 : (rb == 64 ? 1 : 2);
+    const int kb = c16g / nc, c16 = c16g % nc;
+    return (uint32_t)kb * (uint32_t)(2 * 128 * rb) + (uint32_t)(r >> 3) * (uint32_t)(8 * rb) + (uint32_t)(r & 7) * (uint32_t)rb +
+           (uint32_t)((c16 ^ ((r >> sh) & (nc - 1))) << 4);
 }
 __device__ __forceinline__ uint32_t sf_f2ord(float x)
 {
@@ -208,9 +214,9 @@ sa_fused_kernel(const SfParams p)
                 uint32_t hw[4], lw[4];
 #pragma unroll
                 for (int t = 0; t < 4; t++) sf_split_pair(f[2 * t], f[2 * t + 1], hw[t], lw[t]);
-                const uint32_t off = sf_a_chunk(r, cg);
+                const uint32_t off = sf_a_chunk(r, cg, p.rb[0]);
                 *reinterpret_cast<uint4 *>(bufx + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4 *>(bufx + off + SF_TILE_BYTES) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                *reinterpret_cast<uint4 *>(bufx + off + 128 * p.rb[0]) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
         }
         for (int l = 0; l < p.nl; l++) {
@@ -227,12 +233,14 @@ sa_fused_kernel(const SfParams p)
                 const uint32_t wbase = smem_u32(wsm + p.w_off[l]);
                 const uint32_t wtile = (uint32_t)p.npad[l] * 128u;
                 const int nks = p.kp[l] >> 4;
+                const int rb = p.rb[l];
+                const uint32_t atile = 128u * (uint32_t)rb;
                 for (int ks = 0; ks < nks; ks++) {
-                    const int kb = ks >> 2, kin = ks & 3;
-                    const uint64_t a_hi = sf_desc(abase + kb * (2 * SF_TILE_BYTES) + kin * 32);
-                    const uint64_t a_lo = sf_desc(abase + kb * (2 * SF_TILE_BYTES) + SF_TILE_BYTES + kin * 32);
-                    const uint64_t b_hi = sf_desc(wbase + kb * wtile + kin * 32);
-                    const uint64_t b_lo = sf_desc(wbase + p.w_half[l] + kb * wtile + kin * 32);
+                    const int kb = ks >> 2, kin = ks & 3;            // A uses 64-wide k-blocks only when rb == 128 (else kb == 0)
+                    const uint64_t a_hi = sf_desc(abase + kb * (2 * atile) + kin * 32, rb);
+                    const uint64_t a_lo = sf_desc(abase + kb * (2 * atile) + atile + kin * 32, rb);
+                    const uint64_t b_hi = sf_desc(wbase + kb * wtile + kin * 32, 128);
+                    const uint64_t b_lo = sf_desc(wbase + p.w_half[l] + kb * wtile + kin * 32, 128);
                     sf_mma(tmem, a_hi, b_hi, idesc, ks ? 1u : 0u);
                     sf_mma(tmem, a_lo, b_hi, idesc, 1u);
                     sf_mma(tmem, a_hi, b_lo, idesc, 1u);
@@ -265,9 +273,9 @@ sa_fused_kernel(const SfParams p)
                         uint32_t hw[4], lw[4];
 #pragma unroll
                         for (int t = 0; t < 4; t++) sf_split_pair(v[j8 + 2 * t], v[j8 + 2 * t + 1], hw[t], lw[t]);
-                        const uint32_t off = sf_a_chunk(r, (c0 + j8) >> 3);
+                        const uint32_t off = sf_a_chunk(r, (c0 + j8) >> 3, p.rb[l + 1]);
                         *reinterpret_cast<uint4 *>(aout + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                        *reinterpret_cast<uint4 *>(aout + off + SF_TILE_BYTES) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        *reinterpret_cast<uint4 *>(aout + off + 128 * p.rb[l + 1]) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     }
                 } else {
                     switch (p.ns) {
@@ -296,6 +304,16 @@ sa_fused_kernel(const SfParams p)
 
 using namespace ssd3d;
 
+// A-operand buffer of a layer with padded K = kp: { hi | lo } tiles of 128 rows; rows are 32 / 64 bytes when the
+// whole K fits (kp 16 / 32), else 128-byte rows in 64-wide k-blocks.  Rounded up to 1 KiB (descriptor alignment).
+static int sf_row_bytes(int kp) { return kp <= 16 ? 32 : (kp <= 32 ? 64 : 128); }
+static size_t sf_abuf_bytes(int kp)
+{
+    const int rb = sf_row_bytes(kp);
+    const int nkb = rb == 128 ? (kp + 63) / 64 : 1;
+    return ((size_t)nkb * 2 * 128 * rb + 1023) / 1024 * 1024;
+}
+
 // Shared-memory bytes of the fused kernel for a layer stack, or 0 when it cannot hold it.
 extern "C" size_t ssd3d_sa_fused_smem(int c, int nl, const int *nout)
 {
@@ -312,9 +330,9 @@ extern "C" size_t ssd3d_sa_fused_smem(int c, int nl, const int *nout)
         ssf += (size_t)2 * npad[l];
         kprev = npad[l];
     }
-    const int nkb0 = (kp[0] + 63) / 64, nkb2 = nl > 2 ? (kp[2] + 63) / 64 : 0, nkb1 = nl > 1 ? (kp[1] + 63) / 64 : 0;
-    const size_t bufx = (size_t)(nkb0 > nkb2 ? nkb0 : nkb2) * 2 * SF_TILE_BYTES;
-    const size_t bufy = (size_t)nkb1 * 2 * SF_TILE_BYTES;
+    const size_t a0 = sf_abuf_bytes(kp[0]), a1 = nl > 1 ? sf_abuf_bytes(kp[1]) : 0, a2 = nl > 2 ? sf_abuf_bytes(kp[2]) : 0;
+    const size_t bufx = a0 > a2 ? a0 : a2;
+    const size_t bufy = a1;
     const size_t total = bufx + bufy + w + ssf * sizeof(float) + 1024;
     return total <= 226 * 1024 ? total : 0;
 }
@@ -359,9 +377,10 @@ extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const
     }
     p.w_total = woff; p.ss_total = ssoff;
     p.w_blob = (const uint8_t *)w_blob; p.ss_blob = ss_blob;
-    const int nkb0 = (p.kp[0] + 63) / 64, nkb2 = nl > 2 ? (p.kp[2] + 63) / 64 : 0, nkb1 = nl > 1 ? (p.kp[1] + 63) / 64 : 0;
-    p.bufx_bytes = (uint32_t)(nkb0 > nkb2 ? nkb0 : nkb2) * 2 * SF_TILE_BYTES;
-    p.bufy_bytes = (uint32_t)nkb1 * 2 * SF_TILE_BYTES;
+    for (int l = 0; l < nl; l++) p.rb[l] = sf_row_bytes(p.kp[l]);
+    const size_t a0 = sf_abuf_bytes(p.kp[0]), a1 = nl > 1 ? sf_abuf_bytes(p.kp[1]) : 0, a2 = nl > 2 ? sf_abuf_bytes(p.kp[2]) : 0;
+    p.bufx_bytes = (uint32_t)(a0 > a2 ? a0 : a2);
+    p.bufy_bytes = (uint32_t)a1;
     uint32_t cols = 32;
     while ((int)cols < maxn) cols *= 2;
     p.tmem_cols = cols;
@@ -374,7 +393,7 @@ extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm > (int)(512 / cols)) per_sm = 512 / cols;
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > 4) per_sm = 4;                                       // register file: 4 x 128 threads x ~123 registers
     int grid = kNumSMs * per_sm;
     if (grid > p.tiles) grid = p.tiles;
     sa_fused_kernel<<<grid, SF_THREADS, smem, (cudaStream_t)stream>>>(p);

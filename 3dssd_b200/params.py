@@ -162,9 +162,11 @@ class PreparedParams:
             self._cache[key] = fold(self.raw, scope, bn, self.device)
         return self._cache[key]
 
-    def fused_stack(self, scopes, bn, cin):
-        """FusedStack for a list of conv scopes (one SA scale), or None when the stack does not fit the fused kernel."""
-        key = ("fused",) + tuple(scopes) + (bool(bn), cin)
+    def fused_stack(self, scopes, bn, cin, limit=None):
+        """FusedStack for a list of conv scopes (one SA scale), or None when the stack does not fit the fused kernel
+        (limit = shared-memory bytes the policy allows; default FUSED_SMEM_LIMIT, pass 0 for 'whatever fits')."""
+        limit = FUSED_SMEM_LIMIT if limit is None else (limit or 1 << 30)
+        key = ("fused",) + tuple(scopes) + (bool(bn), cin, limit)
         if key not in self._cache:
             import ctypes
             from ._lib import lib
@@ -173,7 +175,7 @@ class PreparedParams:
             need = lib().ssd3d_sa_fused_smem(cin - 3, len(convs), ctypes.cast(nout, ctypes.c_void_p)) if len(convs) <= 3 else 0
             # the fused kernel runs its phases (gather, MMA, epilogue) back to back per tile and relies on several
             # co-resident CTAs per SM to overlap them: only worth it while >= 2 CTAs fit (layer-1 sized stacks)
-            fits = 0 < need <= FUSED_SMEM_LIMIT
+            fits = 0 < need <= limit
             self._cache[key] = FusedStack(convs, cin) if fits else None
         return self._cache[key]
 

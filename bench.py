@@ -143,6 +143,8 @@ def main():
     ap.add_argument("--mlp-mode", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu captures)")
     ap.add_argument("--pipeline", type=int, default=2, help="steps in flight (independent CUDA graphs on separate streams)")
+    ap.add_argument("--fps-cluster", type=int, default=0, help="tuning: force the FPS cluster size (0 = heuristic)")
+    ap.add_argument("--fps-variant", type=int, default=0, help="tuning: 0 = auto, 1 = force the xyz-in-packet D-FPS kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-scenes", type=int, default=2)
     args = ap.parse_args()
@@ -170,6 +172,8 @@ def main():
         return run_reference(args, torch, pkg, arch, params, pts_np, rank, world, dev)
 
     import torch.distributed as dist
+    pkg.lib().ssd3d_tune_set_fps_cluster(args.fps_cluster)
+    pkg.lib().ssd3d_tune_set_fps_variant(args.fps_variant)
     net = pkg.SABackbone(arch, params, in_channels=1, device=dev, ffps_mode=args.ffps_mode, mlp_mode=args.mlp_mode)
     pts = torch.from_numpy(pts_np).to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
