@@ -40,6 +40,7 @@ _SIGNATURES = {
                            c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "ssd3d_tune_set_fps_cluster": [c_int],
     "ssd3d_tune_set_fps_variant": [c_int],
+    "ssd3d_tune_set_fps_cluster_cap": [c_int],
 }
 
 EXPORTS = sorted(list(_SIGNATURES) + ["ssd3d_last_error"])

@@ -528,15 +528,27 @@ static int pick_p(int n, int cl)
 
 static int g_fps_cluster_override = 0;  // test / tuning hook (ssd3d_tune_set)
 static int g_fps_variant = 0;           // 0 = auto (direct when it fits), 1 = force the packet-with-xyz kernel
+static int g_fps_cluster_cap = 0;       // > 0: upper bound on the heuristic cluster size (throughput mode: FPS is
+                                        // latency-bound, so fewer SMs per scene cost little time and free SMs for
+                                        // other work running concurrently)
+
+static int cap_cl(int cl, int n)
+{
+    if (g_fps_cluster_cap > 0)
+        while (cl > g_fps_cluster_cap && cl > 1 && (n + (cl / 2) * FPS_T - 1) / ((cl / 2) * FPS_T) <= 16) cl /= 2;
+    return cl;
+}
 
 static int pick_cl_xyz(int n)
 {
     if (g_fps_cluster_override > 0) return g_fps_cluster_override;
-    if (n <= 1024) return 1;
-    if (n <= 2048) return 2;
-    if (n <= 4096) return 4;
-    if (n <= 32768) return 8;
-    return 16;
+    int cl;
+    if (n <= 1024) cl = 1;
+    else if (n <= 2048) cl = 2;
+    else if (n <= 4096) cl = 4;
+    else if (n <= 32768) cl = 8;
+    else cl = 16;
+    return cap_cl(cl, n);
 }
 
 }  // namespace ssd3d
@@ -632,6 +644,7 @@ extern "C" int ssd3d_fps_needs_temp(int n, int c)
 
 extern "C" void ssd3d_tune_set_fps_cluster(int cl) { g_fps_cluster_override = cl; }
 extern "C" void ssd3d_tune_set_fps_variant(int v) { g_fps_variant = v; }
+extern "C" void ssd3d_tune_set_fps_cluster_cap(int cl) { g_fps_cluster_cap = cl; }
 
 extern "C" int ssd3d_farthest_point_sample(int b, int n, int c, int m, const float *inp, float *temp, int *out,
                                            ssd3d_stream_t stream)
@@ -669,7 +682,7 @@ extern "C" int ssd3d_farthest_point_sample_with_distance(int b, int n, int m, co
     SSD3D_REQUIRE(dist && out, "farthest_point_sample_with_distance: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     // the per-round row read is a DRAM-latency-bound gather: more CTAs per scene = more loads in flight
-    int cl = g_fps_cluster_override > 0 ? g_fps_cluster_override : (n <= 1024 ? 1 : (n <= 2048 ? 4 : 8));
+    int cl = g_fps_cluster_override > 0 ? g_fps_cluster_override : cap_cl(n <= 1024 ? 1 : (n <= 2048 ? 4 : 8), n);
     while (cl < 16 && pick_p(n, cl) > 16) cl *= 2;
     if (pick_p(n, cl) <= 16) return cuda_status((cudaError_t)launch_fpsdist(b, n, m, cl, dist, out, st), "fpsdist launch");
     SSD3D_REQUIRE(temp != nullptr, "farthest_point_sample_with_distance: n=%d needs the temp[b,n] workspace", n);

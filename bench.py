@@ -8,7 +8,7 @@ A "step" is one pass of the whole backbone (layer1..layer4 of configs/kitti/3dss
 layer) over one batch of 8 synthetic KITTI-shaped scenes [8,16384,4] per GPU (weak scaling: the batch is
 sharded by scene, no data-path collective; one NCCL all-gather of the per-scene detection blocks ends a step).
 
-value  : scenes/s, inputs resident in HBM; every step is one CUDA-graph replay, `--pipeline` (default 2) steps are
+value  : scenes/s, inputs resident in HBM; every step is one CUDA-graph replay, `--pipeline` (default 4) steps are
          in flight on separate streams (a step chains latency-bound FPS stages and throughput-bound MLP stages, so
          the FPS of step i+1 overlaps the MLP of step i); timed with ONE CUDA-event pair around all K steps, L2
          flushed before every step, max over ranks.  config.latency_ms_single_step is the un-overlapped step time.
@@ -142,8 +142,10 @@ def main():
     ap.add_argument("--ffps-mode", default="matrix", choices=["matrix", "fused"])
     ap.add_argument("--mlp-mode", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu captures)")
-    ap.add_argument("--pipeline", type=int, default=2, help="steps in flight (independent CUDA graphs on separate streams)")
+    ap.add_argument("--pipeline", type=int, default=4, help="steps in flight (independent CUDA graphs on separate streams)")
     ap.add_argument("--fps-cluster", type=int, default=0, help="tuning: force the FPS cluster size (0 = heuristic)")
+    ap.add_argument("--fps-cluster-cap", type=int, default=-1,
+                    help="cap on the heuristic FPS cluster size; default 4 when steps are pipelined (frees SMs), else none")
     ap.add_argument("--fps-variant", type=int, default=0, help="tuning: 0 = auto, 1 = force the xyz-in-packet D-FPS kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-scenes", type=int, default=2)
@@ -172,6 +174,9 @@ def main():
         return run_reference(args, torch, pkg, arch, params, pts_np, rank, world, dev)
 
     import torch.distributed as dist
+    if args.fps_cluster_cap < 0:
+        args.fps_cluster_cap = 4 if (args.pipeline > 1 and not args.no_graph) else 0
+    pkg.lib().ssd3d_tune_set_fps_cluster_cap(args.fps_cluster_cap)
     pkg.lib().ssd3d_tune_set_fps_cluster(args.fps_cluster)
     pkg.lib().ssd3d_tune_set_fps_variant(args.fps_variant)
     net = pkg.SABackbone(arch, params, in_channels=1, device=dev, ffps_mode=args.ffps_mode, mlp_mode=args.mlp_mode)
@@ -318,7 +323,7 @@ def main():
                                    "16384x4 clouds, batch 8 per GPU", "scenes_per_gpu": SCENES_PER_GPU,
                        "global_batch": SCENES_PER_GPU * world, "points": NPOINTS, "parallelism": "scene-sharded dp%d" % world,
                        "ffps": args.ffps_mode, "mlp": args.mlp_mode, "cuda_graph": not args.no_graph, "l2": "flushed (256 MiB write) before every timed step",
-                       "steps_in_flight": P, "latency_ms_single_step": latency_ms,
+                       "steps_in_flight": P, "latency_ms_single_step": latency_ms, "fps_cluster_cap": args.fps_cluster_cap,
                        "timing": "one CUDA-event pair around all K steps (L2 flushes included), max over ranks; each step is a "
                                  "CUDA-graph replay, %d step pipelines on separate streams" % P,
                        "wall_s_bracket": wall},

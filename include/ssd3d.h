@@ -157,6 +157,9 @@ int ssd3d_rowgroup_max(long groups, int pool, int c, const float *y, int ldy, co
 void ssd3d_tune_set_fps_cluster(int cluster_size);
 /* 0 = automatic D-FPS kernel choice, 1 = force the general (coordinates-in-packet) cluster kernel. */
 void ssd3d_tune_set_fps_variant(int variant);
+/* Throughput mode: cap the heuristic FPS cluster size (0 = no cap).  FPS is latency-bound, so a smaller cluster
+ * costs little time per scene and leaves SMs to concurrently running work. */
+void ssd3d_tune_set_fps_cluster_cap(int cluster_size);
 
 #ifdef __cplusplus
 }
