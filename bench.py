@@ -333,7 +333,7 @@ def main():
             "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "kernel": "fps3_cluster_kernel (D-FPS layer 1, 16384->4096, B=8)",
+                         "traffic": None, "kernel": "fps3_direct_kernel (D-FPS layer 1, 16384->4096, B=8, cluster of %d CTAs per scene)" % (min(8, args.fps_cluster_cap) if args.fps_cluster_cap else 8),
                          "kernel_ms": k_ms,
                          "note": "effective-stream bytes B*(M-1)*N*16 (what the reference streams per round, SURVEY 8d); "
                                  "the kernel keeps them on-chip, so frac can exceed 1 and DRAM traffic is ~2 MB; peak = "
