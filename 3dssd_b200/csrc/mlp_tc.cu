@@ -21,6 +21,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "pool.cuh"
 
 namespace ssd3d {
 
@@ -121,26 +122,19 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t &hw, uin
 // Max-pool of one 32-column chunk over runs of POOL rows (tf.reduce_max(axis=2), layers_util.py:178) + mask (:180).
 // A thread holds one row; the rows of a group are lanes of a warp (POOL <= 32) or of 2-4 warps (64, 128).
 template <int POOL>
-__device__ __forceinline__ void pooled_chunk(const TcParams &p, const float (&v)[32], int lane, int q, int h, int mt,
-                                             int col0, uint32_t *xs /* [2 halves][4 quarters][32] */)
+__device__ __forceinline__ void pooled_chunk(const TcParams &p, float (&v)[32], int lane, int q, int h, int mt,
+                                             int col0, float *xs /* [2 halves][4 quarters][32] */)
 {
     constexpr int GP = POOL >= 32 ? 32 : POOL;       // lanes per group inside a warp
     constexpr int KEEP = 32 / GP;                    // columns a lane ends up owning
-    const uint32_t gmask = POOL >= 32 ? 0xffffffffu : (((1u << GP) - 1u) << ((lane / GP) * GP));
-    const int lg = lane % GP;
-    uint32_t keep[KEEP];
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-        const uint32_t m = __reduce_max_sync(gmask, f2ord(v[j]));
-        if ((j % GP) == lg) keep[j / GP] = m;
-    }
+    warp_colmax_transpose<GP>(v, lane);              // lane owns columns (lane % GP) * KEEP + k in v[k]
     if (POOL > 32) {                                 // combine the 2 (4) warps that share a group
         constexpr int WPG = POOL > 32 ? POOL / 32 : 1;
-        xs[(h * 4 + q) * 32 + lane] = keep[0];
+        xs[(h * 4 + q) * 32 + lane] = v[0];
         asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory");      // the 4 quarter-warps of this column half
         if ((q % WPG) == 0) {
 #pragma unroll
-            for (int w = 1; w < WPG; w++) keep[0] = max(keep[0], xs[(h * 4 + q + w) * 32 + lane]);
+            for (int w = 1; w < WPG; w++) v[0] = fmaxf(v[0], xs[(h * 4 + q + w) * 32 + lane]);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory");      // xs reusable by the next chunk
         if ((q % WPG) != 0) return;
@@ -150,9 +144,9 @@ __device__ __forceinline__ void pooled_chunk(const TcParams &p, const float (&v)
     const bool masked = p.rowmask && p.rowmask[gg] == 0;
 #pragma unroll
     for (int k = 0; k < KEEP; k++) {
-        const int col = col0 + k * GP + lg;
+        const int col = col0 + (lane % GP) * KEEP + k;
         if (col >= p.n) continue;
-        const float mx = masked ? 0.0f : ord2f(keep[k]);
+        const float mx = masked ? 0.0f : v[k];
         if (p.out_f32) p.out_f32[(size_t)gg * p.ld_f32 + col] = mx;
         if (p.out_hi) {
             const __nv_bfloat16 hb = __float2bfloat16_rn(mx);
@@ -181,7 +175,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
 
     __shared__ unsigned long long full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ uint32_t pool_xs[2 * 4 * 32];
+    __shared__ float pool_xs[2 * 4 * 32];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles;

@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "pool.cuh"
 
 namespace ssd3d {
 
@@ -39,6 +40,7 @@ struct SfParams {
     uint32_t w_total, ss_total;      // bytes / floats
     const uint8_t *w_blob;
     const float *ss_blob;
+    int sspad[SF_MAX_LAYERS];        // npad rounded up to 32 (scale/shift arrays are zero padded to this)
     int rb[SF_MAX_LAYERS];           // bytes per operand row of layer l's A buffer: 32 / 64 (one block) or 128 (64-wide k-blocks)
     uint32_t bufx_bytes, bufy_bytes;
     uint32_t tmem_cols;
@@ -108,38 +110,31 @@ __device__ __forceinline__ uint32_t sf_f2ord(float x)
 __device__ __forceinline__ float sf_ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 
 template <int POOL>
-__device__ __forceinline__ void sf_pool_store(const SfParams &p, const float (&v)[32], int lane, int q, long tile,
-                                              int col0, int nout, uint32_t *xs)
+__device__ __forceinline__ void sf_pool_store(const SfParams &p, float (&v)[32], int lane, int q, int tile,
+                                              int col0, int nout, float *xs)
 {
     constexpr int GP = POOL >= 32 ? 32 : POOL;
     constexpr int KEEP = 32 / GP;
     constexpr int WPG = POOL > 32 ? POOL / 32 : 1;
-    const uint32_t gmask = POOL >= 32 ? 0xffffffffu : (((1u << GP) - 1u) << ((lane / GP) * GP));
-    const int lg = lane % GP;
-    uint32_t keep[KEEP];
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-        const uint32_t mx = __reduce_max_sync(gmask, sf_f2ord(v[j]));
-        if ((j % GP) == lg) keep[j / GP] = mx;
-    }
-    if (POOL > 32) {
-        xs[q * 32 + lane] = keep[0];
+    warp_colmax_transpose<GP>(v, lane);                   // lane owns columns (lane % GP) * KEEP + k in v[k]
+    if (POOL > 32) {                                      // groups spanning 2 or 4 warps: combine through shared memory
+        xs[q * 32 + lane] = v[0];
         __syncthreads();
         if ((q % WPG) == 0) {
 #pragma unroll
-            for (int w = 1; w < WPG; w++) keep[0] = max(keep[0], xs[(q + w) * 32 + lane]);
+            for (int w = 1; w < WPG; w++) v[0] = fmaxf(v[0], xs[(q + w) * 32 + lane]);
         }
         __syncthreads();
         if ((q % WPG) != 0) return;
     }
-    const long gg = tile * (128 / POOL) + (q * 32 + lane) / POOL;
-    if (gg * POOL >= p.rows) return;
+    const int gg = tile * (128 / POOL) + (q * 32 + lane) / POOL;
+    if ((long)gg * POOL >= p.rows) return;
     const bool masked = p.cnt && p.cnt[gg] == 0;
 #pragma unroll
     for (int k = 0; k < KEEP; k++) {
-        const int col = col0 + k * GP + lg;
+        const int col = col0 + (lane % GP) * KEEP + k;
         if (col >= nout) continue;
-        const float mx = masked ? 0.0f : sf_ord2f(keep[k]);
+        const float mx = masked ? 0.0f : v[k];
         if (p.out_f32) p.out_f32[(size_t)gg * p.ld_f32 + col] = mx;
         if (p.out_hi) {
             const __nv_bfloat16 hb = __float2bfloat16_rn(mx);
@@ -149,7 +144,7 @@ __device__ __forceinline__ void sf_pool_store(const SfParams &p, const float (&v
     }
 }
 
-__global__ void __launch_bounds__(SF_THREADS)
+__global__ void __launch_bounds__(SF_THREADS, 4)
 sa_fused_kernel(const SfParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -161,7 +156,7 @@ sa_fused_kernel(const SfParams p)
 
     __shared__ unsigned long long w_bar, mma_bar;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ uint32_t xs[4 * 32];
+    __shared__ float xs[4 * 32];
 
     const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
 
@@ -187,17 +182,17 @@ sa_fused_kernel(const SfParams p)
     const int r = tid;                                   // row of the tile this thread owns
     const int k0 = p.c + 3;
 
-    for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
         // ---- gather + centre-subtract + concat + split -> bufx (layers_util.py:157-165)
         {
-            const long row = tile * 128 + r;
-            const bool ok = row < p.rows;
-            const long qi = ok ? row / p.ns : 0;                       // == scene*m + query
-            const long scene = qi / p.m;
+            const uint32_t row = (uint32_t)tile * 128u + (uint32_t)r;  // rows < 2^31 (checked by the launcher)
+            const bool ok = (long)row < p.rows;
+            const uint32_t qi = ok ? row / (uint32_t)p.ns : 0u;        // == scene*m + query
+            const uint32_t scene = qi / (uint32_t)p.m;
             const int a = ok ? __ldg(p.idx + row) : 0;
             const float *src_f = p.points + ((size_t)scene * p.n + a) * p.c;
             const float *src_x = p.xyz + ((size_t)scene * p.n + a) * 3;
-            const float *ctr = p.new_xyz + qi * 3;
+            const float *ctr = p.new_xyz + (size_t)qi * 3;
             const int nchunk = p.kp[0] >> 3;
             for (int cg = 0; cg < nchunk; cg++) {
                 float f[8];
@@ -252,7 +247,7 @@ sa_fused_kernel(const SfParams p)
             sf_fence_after();
             // ---- epilogue of layer l
             const float *sc = ss + p.ss_off[l];
-            const float *sh = sc + p.npad[l];
+            const float *sh = sc + p.sspad[l];
             const bool last = l == p.nl - 1;
             const int nchunks = (p.npad[l] + 31) / 32;
             for (int ci = 0; ci < nchunks; ci++) {
@@ -261,10 +256,13 @@ sa_fused_kernel(const SfParams p)
                 sf_tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const bool in = c0 + j < p.npad[l];
-                    const float x = in ? fmaf(__uint_as_float(rr[j]), sc[c0 + j], sh[c0 + j]) : 0.0f;
-                    v[j] = fmaxf(x, 0.0f);                             // every conv of the SA stack has a ReLU
+                for (int j4 = 0; j4 < 32; j4 += 4) {                  // scale/shift are zero-padded to 32-column chunks
+                    const float4 s4 = *reinterpret_cast<const float4 *>(sc + c0 + j4);
+                    const float4 h4 = *reinterpret_cast<const float4 *>(sh + c0 + j4);
+                    v[j4 + 0] = fmaxf(fmaf(__uint_as_float(rr[j4 + 0]), s4.x, h4.x), 0.0f);   // every conv has a ReLU
+                    v[j4 + 1] = fmaxf(fmaf(__uint_as_float(rr[j4 + 1]), s4.y, h4.y), 0.0f);
+                    v[j4 + 2] = fmaxf(fmaf(__uint_as_float(rr[j4 + 2]), s4.z, h4.z), 0.0f);
+                    v[j4 + 3] = fmaxf(fmaf(__uint_as_float(rr[j4 + 3]), s4.w, h4.w), 0.0f);
                 }
                 if (!last) {
 #pragma unroll
@@ -327,7 +325,7 @@ extern "C" size_t ssd3d_sa_fused_smem(int c, int nl, const int *nout)
         if (npad[l] > 256) return 0;
         const int nkb = (kp[l] + 63) / 64;
         w += (size_t)2 * nkb * npad[l] * 128;
-        ssf += (size_t)2 * npad[l];
+        ssf += (size_t)2 * ((npad[l] + 31) / 32 * 32);
         kprev = npad[l];
     }
     const size_t a0 = sf_abuf_bytes(kp[0]), a1 = nl > 1 ? sf_abuf_bytes(kp[1]) : 0, a2 = nl > 2 ? sf_abuf_bytes(kp[2]) : 0;
@@ -356,6 +354,7 @@ extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const
     p.n = n; p.c = c; p.m = m; p.ns = nsample;
     p.rows = (long)b * m * nsample;
     if (p.rows == 0) return 0;
+    SSD3D_REQUIRE(p.rows < (1L << 31) - 128, "sa_mlp_fused: too many grouped rows (%ld)", p.rows);
     p.tiles = (int)((p.rows + 127) / 128);
     p.xyz = xyz; p.points = points; p.new_xyz = new_xyz; p.idx = idx; p.cnt = pts_cnt;
     p.nl = nl;
@@ -371,7 +370,8 @@ extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const
         p.w_half[l] = (uint32_t)nkb * p.npad[l] * 128;
         woff += 2 * p.w_half[l];
         p.ss_off[l] = ssoff;
-        ssoff += 2 * p.npad[l];
+        p.sspad[l] = (p.npad[l] + 31) / 32 * 32;
+        ssoff += 2 * p.sspad[l];
         kprev = p.npad[l];
         if (p.npad[l] > maxn) maxn = p.npad[l];
     }

@@ -138,8 +138,9 @@ class FusedStack:
             hi[: f.cout] = f.b_hi
             lo[: f.cout] = f.b_lo
             wparts += [_swizzled_image(hi), _swizzled_image(lo)]
-            sc = torch.zeros(npad, dtype=torch.float32, device=dev)
-            sh = torch.zeros(npad, dtype=torch.float32, device=dev)
+            sspad = (npad + 31) // 32 * 32                 # the kernel reads scale/shift in 32-column chunks
+            sc = torch.zeros(sspad, dtype=torch.float32, device=dev)
+            sh = torch.zeros(sspad, dtype=torch.float32, device=dev)
             sc[: f.cout] = f.scale
             sh[: f.cout] = f.shift
             sparts += [sc, sh]
