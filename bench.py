@@ -8,7 +8,7 @@ A "step" is one pass of the whole backbone (layer1..layer4 of configs/kitti/3dss
 layer) over one batch of 8 synthetic KITTI-shaped scenes [8,16384,4] per GPU (weak scaling: the batch is
 sharded by scene, no data-path collective; one NCCL all-gather of the per-scene detection blocks ends a step).
 
-value  : scenes/s, inputs resident in HBM; every step is one CUDA-graph replay, `--pipeline` (default 4) steps are
+value  : scenes/s, inputs resident in HBM; every step is one CUDA-graph replay, `--pipeline` (default 8) steps are
          in flight on separate streams (a step chains latency-bound FPS stages and throughput-bound MLP stages, so
          the FPS of step i+1 overlaps the MLP of step i); timed with ONE CUDA-event pair around all K steps, L2
          flushed before every step, max over ranks.  config.latency_ms_single_step is the un-overlapped step time.
@@ -142,7 +142,7 @@ def main():
     ap.add_argument("--ffps-mode", default="matrix", choices=["matrix", "fused"])
     ap.add_argument("--mlp-mode", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu captures)")
-    ap.add_argument("--pipeline", type=int, default=4, help="steps in flight (independent CUDA graphs on separate streams)")
+    ap.add_argument("--pipeline", type=int, default=8, help="steps in flight (independent CUDA graphs on separate streams)")
     ap.add_argument("--fps-cluster", type=int, default=0, help="tuning: force the FPS cluster size (0 = heuristic)")
     ap.add_argument("--fps-cluster-cap", type=int, default=-1,
                     help="cap on the heuristic FPS cluster size; default 4 when steps are pipelined (frees SMs), else none")
