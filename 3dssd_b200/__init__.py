@@ -1,12 +1,13 @@
 """3dssd_b200 -- B200 (sm_100a) set-abstraction operators behind the tf_ops / layers_util surface of
 dvlab-research/3DSSD.  Import with importlib.import_module("3dssd_b200") or through the `ssd3d_b200` alias.
 """
-from . import config, dist, layers_util, params, tf_ops  # noqa: F401
+from . import config, dist, head, layers_util, params, tf_ops  # noqa: F401
 from ._lib import EXPORTS, LIB_PATH, lib  # noqa: F401
 from .backbone import SABackbone  # noqa: F401
+from .head import DetectionHead  # noqa: F401
 from .layers_util import (pointnet_fp_module, pointnet_sa_module, pointnet_sa_module_msg,  # noqa: F401
                           vote_layer)
-from .tf_ops import (calc_square_dist, farthest_point_sample, farthest_point_sample_with_distance,  # noqa: F401
+from .tf_ops import (bev_nms, calc_square_dist, farthest_point_sample, farthest_point_sample_with_distance,  # noqa: F401
                      furthest_point_sample, gather_point, group_concat, group_concat_split, group_point, linear_bn_relu,
                      linear_tc, sa_mlp_fused, split_rows,
                      query_ball_point, query_ball_point_dilated, query_ball_point_multi, three_interpolate,

@@ -21,7 +21,7 @@ class SABackbone:
     """
 
     def __init__(self, arch=None, params=None, in_channels=_cfg.INPUT_CHANNELS - 3, device="cuda", ffps_mode="matrix",
-                 seed=0, mlp_mode="tc", fuse_scale=True):
+                 seed=0, mlp_mode="tc", fuse_scale=True, head=None):
         self.arch = _cfg.ARCH_3DSSD if arch is None else arch
         self.in_channels = in_channels
         self.device = torch.device(device)
@@ -31,6 +31,7 @@ class SABackbone:
         self.ffps_mode = ffps_mode
         self.mlp_mode = mlp_mode
         self.fuse_scale = fuse_scale
+        self.head = head                      # optional head.DetectionHead: real detections instead of the stand-in block
         self._graph = None
 
     def forward(self, points, return_debug=False):
@@ -75,6 +76,13 @@ class SABackbone:
     __call__ = forward
 
     # ---- per-scene detection block (stand-in until the head/NMS rows of SURVEY.md section 8f exist) -------
+    def detections(self, xyz_list, feat_list):
+        """Per-scene detection block [B,100,9] + count [B]: the detection head + decode + BEV NMS when a head is
+        attached, otherwise the stand-in derived from the CG layer."""
+        if self.head is not None:
+            return self.head(xyz_list, feat_list)
+        return self.detection_block(xyz_list, feat_list)
+
     @staticmethod
     def detection_block(xyz_list, feat_list, max_output=100):
         """[B, 100, 9] fp32 + [B] int32, the shape of the reference's per-scene output (MAX_OUTPUT_NUM: 100,
@@ -103,13 +111,13 @@ class SABackbone:
         with torch.cuda.stream(s):
             for _ in range(warmup):
                 out = self.forward(static_in)
-                blk = self.detection_block(out[0], out[1])
+                blk = self.detections(out[0], out[1])
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             out = self.forward(static_in)
-            blk = self.detection_block(out[0], out[1])
+            blk = self.detections(out[0], out[1])
         self._graph = (g, static_in, out, blk)
 
         def replay(points=None):

@@ -73,6 +73,26 @@ def round16(x):
     return (int(x) + 15) // 16 * 16
 
 
+def init_head_params(cin, mlp=(128,), cls_channels=1, reg_channels=6 + 2 * 12, seed=1, scope=''):
+    """Random weights of the detection head (head_builder.py:93-95, head_util.py:26-41) keyed by the reference's
+    variable names: conv1d_{i}, pred_cls_base, pred_cls, pred_reg_base, pred_reg (scope '' in 3dssd.yaml:68)."""
+    rng = np.random.default_rng(seed)
+    pre = "" if scope == "" else scope + "/"
+    params = {}
+    c = cin
+    for i, ch in enumerate(mlp):
+        _conv_init(rng, params, "%sconv1d_%d" % (pre, i), c, ch, True)
+        c = ch
+    _conv_init(rng, params, pre + "pred_cls_base", c, 128, True)
+    _conv_init(rng, params, pre + "pred_cls", 128, cls_channels, False)
+    _conv_init(rng, params, pre + "pred_reg_base", c, 128, True)
+    _conv_init(rng, params, pre + "pred_reg", 128, reg_channels, False)
+    for k in list(params):
+        if k.endswith("/biases"):
+            params[k] = (0.1 * rng.standard_normal(params[k].shape)).astype(np.float32)
+    return params
+
+
 class FoldedConv:
     """One conv+BN layer folded for inference: y = act((x @ w) * scale + shift).
     For the tensor-core path the weight also exists split in two bf16 terms, transposed to K-major:

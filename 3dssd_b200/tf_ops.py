@@ -386,3 +386,18 @@ def sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=None, out_split=
                                    ctypes.cast(nout, vp), _p(stack.w_blob), _p(stack.ss_blob), vp(pf), ldf, vp(ph),
                                    vp(pl), lds, _stream()), "sa_mlp_fused")
     return y
+
+
+def bev_nms(boxes, scores, iou_threshold, max_output, cls_id=0):
+    """Greedy BEV NMS per scene (postprocessor.py:76-88): boxes (b,n,7) = (x,y,z,l,h,w,ry), scores (b,n) ->
+    block (b,max_output,9) = (box7, score, class) zero padded, count (b,) int32."""
+    boxes = _req(boxes, "boxes", torch.float32, 3, 7)
+    scores = _req(scores, "scores", torch.float32, 2)
+    b, n, _ = boxes.shape
+    if scores.shape != (b, n):
+        raise ValueError("scores must be (b, n)")
+    block = torch.empty((b, int(max_output), 9), dtype=torch.float32, device=boxes.device)
+    cnt = torch.empty((b,), dtype=torch.int32, device=boxes.device)
+    check(lib().ssd3d_bev_nms(b, n, _p(boxes), _p(scores), float(iou_threshold), int(max_output), int(cls_id),
+                              _p(block), _p(cnt), _stream()), "bev_nms")
+    return block, cnt

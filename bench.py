@@ -168,6 +168,7 @@ def main():
     dev = torch.device("cuda", local)
     arch = pkg.config.ARCH_3DSSD
     params = pkg.params.init_params(arch, 1, seed=0)
+    head_params = pkg.params.init_head_params(pkg.config.layer_channels(arch, 1)[-1], seed=1)
     pts_np = synth.kitti_like(SCENES_PER_GPU, NPOINTS, seed=1000 + rank * SCENES_PER_GPU)
 
     if args.impl == "reference":
@@ -179,7 +180,9 @@ def main():
     pkg.lib().ssd3d_tune_set_fps_cluster_cap(args.fps_cluster_cap)
     pkg.lib().ssd3d_tune_set_fps_cluster(args.fps_cluster)
     pkg.lib().ssd3d_tune_set_fps_variant(args.fps_variant)
-    net = pkg.SABackbone(arch, params, in_channels=1, device=dev, ffps_mode=args.ffps_mode, mlp_mode=args.mlp_mode)
+    # detection head + decode + GPU BEV-NMS produce the per-scene detection block that is gathered / copied to the host
+    head = pkg.DetectionHead(params=head_params, device=dev)
+    net = pkg.SABackbone(arch, params, in_channels=1, device=dev, ffps_mode=args.ffps_mode, mlp_mode=args.mlp_mode, head=head)
     pts = torch.from_numpy(pts_np).to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
@@ -201,7 +204,7 @@ def main():
     for n in counted:
         setattr(L, n, Counting(originals[n]))
     out = net.forward(pts)
-    blk, cnt = net.detection_block(out[0], out[1])
+    blk, cnt = net.detections(out[0], out[1])
     torch.cuda.synchronize()
     launches_per_step = counter["n"]
     for n in counted:
@@ -221,7 +224,7 @@ def main():
                 if points is not None:
                     static_in.copy_(points, non_blocking=True)
                 o = net.forward(static_in)
-                return o, net.detection_block(o[0], o[1])
+                return o, net.detections(o[0], o[1])
             runners.append(replay)
         else:
             runners.append(net.capture(pts))
@@ -319,8 +322,8 @@ def main():
             "metric": METRIC, "value": scenes / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: full 3DSSD SA backbone (3dssd.yaml layer1-4 + vote), synthetic KITTI "
-                                   "16384x4 clouds, batch 8 per GPU", "scenes_per_gpu": SCENES_PER_GPU,
+            "config": {"workload": "configs[1]: full 3DSSD SA backbone (3dssd.yaml layer1-4 + vote) + detection head, decode and "
+                                   "BEV NMS, synthetic KITTI 16384x4 clouds, batch 8 per GPU", "scenes_per_gpu": SCENES_PER_GPU,
                        "global_batch": SCENES_PER_GPU * world, "points": NPOINTS, "parallelism": "scene-sharded dp%d" % world,
                        "ffps": args.ffps_mode, "mlp": args.mlp_mode, "cuda_graph": not args.no_graph, "l2": "flushed (256 MiB write) before every timed step",
                        "steps_in_flight": P, "latency_ms_single_step": latency_ms, "fps_cluster_cap": args.fps_cluster_cap,

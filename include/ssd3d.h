@@ -147,6 +147,14 @@ int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const float *xyz
                        const void *w_blob, const float *ss_blob, float *out_f32, int ld_f32, void *out_hi, void *out_lo,
                        int ld_split, ssd3d_stream_t stream);
 
+/* Per-scene greedy BEV NMS on the GPU: replaces box_3d_to_anchor + project_to_bev + tf.image.non_max_suppression
+ * of lib/builder/postprocessor.py:76-88 (one class per call).  boxes [b,n,7] = (x,y,z,l,h,w,ry), scores [b,n];
+ * candidates in descending score order (ties: lower index), dropped when axis-aligned BEV IoU with a kept box is
+ * > iou_threshold, at most max_output kept.  out_block [b,max_output,9] = (box7, score, class) zero padded,
+ * out_cnt [b] = number kept.  n <= 512. */
+int ssd3d_bev_nms(int b, int n, const float *boxes, const float *scores, float iou_threshold, int max_output,
+                  int cls_id, float *out_block, int *out_cnt, ssd3d_stream_t stream);
+
 /* ymax[g, 0:c] = max over rows g*pool .. g*pool+pool-1 of y[., 0:c] (times rowmask[g] != 0): the
  * tf.reduce_max(axis=2) * mask of layers_util.py:178-180 for nsample values the fused epilogue of
  * ssd3d_linear_bn_relu does not cover (pool must divide 128 there). */

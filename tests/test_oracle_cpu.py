@@ -223,3 +223,15 @@ def test_oracle_against_reference_golden_vectors(oracle_ops, path):
         np.testing.assert_array_equal(oracle_ops.three_interpolate(z["points"], z["idx"], z["weight"]), z["out"])
     else:
         raise AssertionError("unknown golden op " + op)
+
+
+def test_oracle_bev_nms_hand_case():
+    """Greedy NMS restatement: ties go to the lower index, identical boxes suppress each other, far boxes survive."""
+    from oracle import head
+    b = np.array([[[0, 0, 0, 2, 1, 2, 0], [0.1, 0, 0.1, 2, 1, 2, 0], [10, 0, 10, 2, 1, 2, 0.3], [0, 0, 0, 2, 1, 2, 0]]], np.float32)
+    s = np.array([[0.9, 0.8, 0.7, 0.9]], np.float32)
+    blk, cnt = head.bev_nms(b, s, 0.1, 100)
+    assert cnt.tolist() == [2]
+    np.testing.assert_array_equal(blk[0, 0, :7], b[0, 0])
+    np.testing.assert_array_equal(blk[0, 1, :7], b[0, 2])
+    assert (blk[0, 2:] == 0).all()
