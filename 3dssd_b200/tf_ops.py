@@ -74,17 +74,47 @@ def farthest_point_sample_with_distance(npoint, dist):
     return out
 
 
-def gather_point(inp, idx):
-    """inp (batch, ndataset, c) float32, idx (batch, npoints) int32 -> (batch, npoints, c).  tf_sampling.py:24-32."""
-    inp = _req(inp, "inp", torch.float32, 3)
-    idx = _req(idx, "idx", torch.int32, 2)
+def _gather_point_fwd(inp, idx):
     b, n, c = inp.shape
-    if idx.shape[0] != b:
-        raise ValueError("GatherPoint expects (batch_size,num_result) idx shape")
     m = idx.shape[1]
     out = torch.empty((b, m, c), dtype=torch.float32, device=inp.device)
     check(lib().ssd3d_gather_point(b, n, m, c, _p(inp), _p(idx), _p(out), _stream()), "gather_point")
     return out
+
+
+def gather_point_grad(inp, idx, out_g):
+    """Gradient of gather_point w.r.t. inp (tf_sampling.py:38-42 _gather_point_grad): scatter-add of out_g."""
+    idx = _req(idx, "idx", torch.int32, 2)
+    out_g = _req(out_g, "out_g", torch.float32, 3)
+    b, n, c = inp.shape
+    inp_g = torch.empty((b, n, c), dtype=torch.float32, device=out_g.device)
+    check(lib().ssd3d_gather_point_grad(b, n, idx.shape[1], c, _p(out_g), _p(idx), _p(inp_g), _stream()), "gather_point_grad")
+    return inp_g
+
+
+class _GatherPoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp, idx):
+        ctx.save_for_backward(idx)
+        ctx.shape = inp.shape
+        return _gather_point_fwd(inp, idx)
+
+    @staticmethod
+    def backward(ctx, out_g):
+        (idx,) = ctx.saved_tensors
+        return gather_point_grad(torch.empty(ctx.shape, device="meta"), idx, out_g.contiguous()), None
+
+
+def gather_point(inp, idx):
+    """inp (batch, ndataset, c) float32, idx (batch, npoints) int32 -> (batch, npoints, c).  tf_sampling.py:24-32.
+    Differentiable w.r.t. inp (the reference registers GatherPoint's gradient, tf_sampling.py:37-42)."""
+    inp = _req(inp, "inp", torch.float32, 3)
+    idx = _req(idx, "idx", torch.int32, 2)
+    if idx.shape[0] != inp.shape[0]:
+        raise ValueError("GatherPoint expects (batch_size,num_result) idx shape")
+    if inp.requires_grad and torch.is_grad_enabled():
+        return _GatherPoint.apply(inp, idx)
+    return _gather_point_fwd(inp, idx)
 
 
 def _bq_shapes(xyz1, xyz2):
@@ -156,18 +186,48 @@ def query_ball_point_multi(min_radius_list, max_radius_list, nsample_list, xyz1,
     return idx, cnt
 
 
-def group_point(points, idx):
-    """points (batch, ndataset, channel) float32, idx (batch, npoint, nsample) int32 ->
-    (batch, npoint, nsample, channel); idx == -1 gives zeros.  tf_grouping.py:114-122."""
-    points = _req(points, "points", torch.float32, 3)
-    idx = _req(idx, "idx", torch.int32, 3)
+def _group_point_fwd(points, idx):
     b, n, c = points.shape
-    if idx.shape[0] != b:
-        raise ValueError("GroupPoint expects (batch_size, npoints, nsample) idx shape")
     _, m, ns = idx.shape
     out = torch.empty((b, m, ns, c), dtype=torch.float32, device=points.device)
     check(lib().ssd3d_group_point(b, n, c, m, ns, _p(points), _p(idx), _p(out), _stream()), "group_point")
     return out
+
+
+def group_point_grad(points, idx, grad_out):
+    """Gradient of group_point w.r.t. points (tf_grouping.py:123-128 _group_point_grad)."""
+    idx = _req(idx, "idx", torch.int32, 3)
+    grad_out = _req(grad_out, "grad_out", torch.float32, 4)
+    b, n, c = points.shape
+    _, m, ns = idx.shape
+    g = torch.empty((b, n, c), dtype=torch.float32, device=grad_out.device)
+    check(lib().ssd3d_group_point_grad(b, n, c, m, ns, _p(grad_out), _p(idx), _p(g), _stream()), "group_point_grad")
+    return g
+
+
+class _GroupPoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx):
+        ctx.save_for_backward(idx)
+        ctx.shape = points.shape
+        return _group_point_fwd(points, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        return group_point_grad(torch.empty(ctx.shape, device="meta"), idx, grad_out.contiguous()), None
+
+
+def group_point(points, idx):
+    """points (batch, ndataset, channel) float32, idx (batch, npoint, nsample) int32 ->
+    (batch, npoint, nsample, channel); idx == -1 gives zeros.  tf_grouping.py:114-122; differentiable w.r.t. points."""
+    points = _req(points, "points", torch.float32, 3)
+    idx = _req(idx, "idx", torch.int32, 3)
+    if idx.shape[0] != points.shape[0]:
+        raise ValueError("GroupPoint expects (batch_size, npoints, nsample) idx shape")
+    if points.requires_grad and torch.is_grad_enabled():
+        return _GroupPoint.apply(points, idx)
+    return _group_point_fwd(points, idx)
 
 
 def three_nn(xyz1, xyz2):
@@ -194,10 +254,42 @@ def three_interpolate(points, idx, weight):
     n = idx.shape[1]
     if idx.shape[0] != b or weight.shape != idx.shape:
         raise ValueError("ThreeInterpolate expects (b,n,3) idx and weight shapes")
+    if points.requires_grad and torch.is_grad_enabled():
+        return _ThreeInterpolate.apply(points, idx, weight)
+    return _three_interpolate_fwd(points, idx, weight)
+
+
+def _three_interpolate_fwd(points, idx, weight):
+    b, m, c = points.shape
+    n = idx.shape[1]
     out = torch.empty((b, n, c), dtype=torch.float32, device=points.device)
     check(lib().ssd3d_three_interpolate(b, m, c, n, _p(points), _p(idx), _p(weight), _p(out), _stream()),
           "three_interpolate")
     return out
+
+
+def three_interpolate_grad(points, idx, weight, grad_out):
+    """Gradient of three_interpolate w.r.t. points (tf_interpolate.py:32-37 _three_interpolate_grad)."""
+    grad_out = _req(grad_out, "grad_out", torch.float32, 3)
+    b, m, c = points.shape
+    n = idx.shape[1]
+    g = torch.empty((b, m, c), dtype=torch.float32, device=grad_out.device)
+    check(lib().ssd3d_three_interpolate_grad(b, n, c, m, _p(grad_out), _p(idx), _p(weight), _p(g), _stream()),
+          "three_interpolate_grad")
+    return g
+
+
+class _ThreeInterpolate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx, weight):
+        ctx.save_for_backward(idx, weight)
+        ctx.shape = points.shape
+        return _three_interpolate_fwd(points, idx, weight)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, weight = ctx.saved_tensors
+        return three_interpolate_grad(torch.empty(ctx.shape, device="meta"), idx, weight, grad_out.contiguous()), None, None
 
 
 # ---- dense pieces that are stock TF ops in the reference -------------------------------------------------

@@ -147,6 +147,25 @@ int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const float *xyz
                        const void *w_blob, const float *ss_blob, float *out_f32, int ld_f32, void *out_hi, void *out_lo,
                        int ld_split, ssd3d_stream_t stream);
 
+/* ---- backward operators (training graphs) ---------------------------------------------------
+ * Each zero-fills its output first, as the reference's TF ops do with cudaMemset before the launcher. */
+
+/* replaces scatteraddpointLauncher(b,n,m,c,out_g,idx,inp_g)
+ *   sampling/tf_sampling.cpp:261 (decl, memset :286), sampling/tf_sampling_g.cu:408-410, kernel :335-346.
+ * inp_g[b, idx[b,j], :] += out_g[b,j,:] */
+int ssd3d_gather_point_grad(int b, int n, int m, int c, const float *out_g, const int *idx, float *inp_g,
+                            ssd3d_stream_t stream);
+
+/* replaces groupPointGradLauncher(b,n,c,m,nsample,grad_out,idx,grad_points)
+ *   grouping/tf_grouping.cpp:479 (memset :510), grouping/tf_grouping_g.cu:480-484, kernel :383-398 (idx == -1 skipped). */
+int ssd3d_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
+                           float *grad_points, ssd3d_stream_t stream);
+
+/* replaces ThreeInterpolateGradLauncher(b,n,c,m,grad_out,idx,weight,grad_points)
+ *   interpolation/tf_interpolate.cpp:363 (memset :398), interpolation/tf_interpolate_g.cu:202-206, kernel :115-140. */
+int ssd3d_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx,
+                                 const float *weight, float *grad_points, ssd3d_stream_t stream);
+
 /* Per-scene greedy BEV NMS on the GPU: replaces box_3d_to_anchor + project_to_bev + tf.image.non_max_suppression
  * of lib/builder/postprocessor.py:76-88 (one class per call).  boxes [b,n,7] = (x,y,z,l,h,w,ry), scores [b,n];
  * candidates in descending score order (ties: lower index), dropped when axis-aligned BEV IoU with a kept box is

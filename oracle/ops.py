@@ -176,3 +176,36 @@ def linear_bn_relu(x, w, bias=None, bn=None, relu=True):
     lib().oracle_linear_bn_relu(ctypes.c_long(rows), cin, cout, px, pw, pb, g, be, mu, va, int(bool(relu)),
                                 y.ctypes.data_as(_f32p))
     return y
+
+
+def gather_point_grad(inp_shape, idx, out_g):
+    idx, q = _i(idx)
+    out_g, p = _f(out_g)
+    b, n, c = inp_shape
+    m = idx.shape[1]
+    g = np.empty((b, n, c), np.float32)
+    lib().oracle_scatter_add_rows(ctypes.c_long(b * m), ctypes.c_long(m), n, c, p, q, g.ctypes.data_as(_f32p),
+                                  ctypes.c_long(g.size), 0)
+    return g
+
+
+def group_point_grad(points_shape, idx, grad_out):
+    idx, q = _i(idx)
+    grad_out, p = _f(grad_out)
+    b, n, c = points_shape
+    _, m, ns = idx.shape
+    g = np.empty((b, n, c), np.float32)
+    lib().oracle_scatter_add_rows(ctypes.c_long(b * m * ns), ctypes.c_long(m * ns), n, c, p, q, g.ctypes.data_as(_f32p),
+                                  ctypes.c_long(g.size), 1)
+    return g
+
+
+def three_interpolate_grad(points_shape, idx, weight, grad_out):
+    idx, q = _i(idx)
+    weight, w = _f(weight)
+    grad_out, p = _f(grad_out)
+    b, m, c = points_shape
+    n = idx.shape[1]
+    g = np.empty((b, m, c), np.float32)
+    lib().oracle_three_interpolate_grad(b, n, c, m, p, q, w, g.ctypes.data_as(_f32p))
+    return g

@@ -393,3 +393,36 @@ void oracle_linear_bn_relu(long rows, int cin, int cout, const float *x, const f
 }
 
 int oracle_version(void) { return 1; }
+
+/* ---- backward ops (row f3): sampling/tf_sampling_g.cu:335-346, grouping/tf_grouping_g.cu:383-398,
+ *      interpolation/tf_interpolate_g.cu:115-140.  Sequential double-precision accumulation (the GPU kernels use
+ *      fp32 atomics whose order is not fixed): tolerance oracle. */
+void oracle_scatter_add_rows(long rows, long rows_per_scene, int n, int c, const float *src, const int *idx, float *dst,
+                             long dst_elems, int skip_neg)
+{
+    double *acc = (double *)calloc((size_t)dst_elems, sizeof(double));
+    for (long r = 0; r < rows; r++) {
+        int a = idx[r];
+        if (skip_neg && a == -1) continue;
+        long scene = r / rows_per_scene;
+        for (int ch = 0; ch < c; ch++) acc[((size_t)scene * n + a) * c + ch] += (double)src[(size_t)r * c + ch];
+    }
+    for (long i = 0; i < dst_elems; i++) dst[i] = (float)acc[i];
+    free(acc);
+}
+
+void oracle_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx, const float *weight,
+                                   float *grad_points)
+{
+    size_t total = (size_t)b * m * c;
+    double *acc = (double *)calloc(total, sizeof(double));
+    for (long q = 0; q < (long)b * n; q++) {
+        long bi = q / n;
+        for (int k = 0; k < 3; k++) {
+            size_t base = ((size_t)bi * m + idx[q * 3 + k]) * c;
+            for (int ch = 0; ch < c; ch++) acc[base + ch] += (double)(grad_out[(size_t)q * c + ch] * weight[q * 3 + k]);
+        }
+    }
+    for (size_t i = 0; i < total; i++) grad_points[i] = (float)acc[i];
+    free(acc);
+}

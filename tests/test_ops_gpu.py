@@ -451,3 +451,64 @@ def test_sa_mlp_fused_rejects_oversized_stack(pkg, cuda):
     assert pkg.lib().ssd3d_sa_fused_smem(256, 3, ctypes.cast(nout, ctypes.c_void_p)) == 0   # layer-4 does not fit
     nout = (ctypes.c_int * 3)(64, 64, 128)
     assert pkg.lib().ssd3d_sa_fused_smem(64, 3, ctypes.cast(nout, ctypes.c_void_p)) > 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# backward ops (row f3): vs the oracle, and the reference's own style of test (gradient error on random data,
+# lib/utils/tf_ops/grouping/tf_grouping_op_test.py:9-25, interpolation/tf_interpolate_op_test.py:9-21)
+# ---------------------------------------------------------------------------------------------------------
+def test_backward_ops_vs_oracle(pkg, oracle_ops, cuda):
+    rng = np.random.default_rng(11)
+    feats = rng.standard_normal((2, 300, 13)).astype(np.float32)
+    gi = rng.integers(0, 300, (2, 90)).astype(np.int32)
+    og = rng.standard_normal((2, 90, 13)).astype(np.float32)
+    got = pkg.gather_point_grad(torch.empty((2, 300, 13), device="meta"), T(gi, cuda), T(og, cuda))
+    assert rel_err(N(got), oracle_ops.gather_point_grad((2, 300, 13), gi, og)) < 1e-5
+    gidx = rng.integers(-1, 300, (2, 40, 6)).astype(np.int32)
+    gg = rng.standard_normal((2, 40, 6, 13)).astype(np.float32)
+    got = pkg.group_point_grad(torch.empty((2, 300, 13), device="meta"), T(gidx, cuda), T(gg, cuda))
+    assert rel_err(N(got), oracle_ops.group_point_grad((2, 300, 13), gidx, gg)) < 1e-5
+    idx3 = rng.integers(0, 50, (2, 200, 3)).astype(np.int32)
+    w3 = rng.uniform(0, 1, (2, 200, 3)).astype(np.float32)
+    go = rng.standard_normal((2, 200, 13)).astype(np.float32)
+    got = pkg.three_interpolate_grad(torch.empty((2, 50, 13), device="meta"), T(idx3, cuda), T(w3, cuda), T(go, cuda))
+    assert rel_err(N(got), oracle_ops.three_interpolate_grad((2, 50, 13), idx3, w3, go)) < 1e-5
+
+
+def test_group_point_gradient_error_like_reference_test(pkg, cuda):
+    """The reference's only test of this path: gradient error of group_point on random (1,128,16) points with
+    query_ball_point(0.3, 32), asserted < 1e-4 (tf_grouping_op_test.py:9-25); same for three_interpolate."""
+    torch.manual_seed(0)
+    points = torch.rand((1, 128, 16), device=cuda, requires_grad=True)
+    xyz1 = torch.rand((1, 128, 3), device=cuda)
+    xyz2 = torch.rand((1, 8, 3), device=cuda)
+    idx, _ = pkg.query_ball_point(0.3, 32, xyz1, xyz2)
+    out = pkg.group_point(points, idx)
+    wgt = torch.rand_like(out)
+    (out * wgt).sum().backward()
+    analytic = points.grad.clone()
+    # the op is linear in `points`: the exact gradient is the scatter-add of the weights
+    expected = torch.zeros_like(analytic)
+    expected.index_put_((torch.zeros_like(idx, dtype=torch.long).flatten(), idx.flatten().long()),
+                        wgt.reshape(-1, 16), accumulate=True)
+    assert float((analytic - expected).abs().max()) < 1e-4
+    # three_interpolate
+    pts = torch.rand((1, 8, 16), device=cuda, requires_grad=True)
+    dist, nidx = pkg.three_nn(xyz1, xyz2)
+    w = torch.ones_like(dist) / 3.0
+    y = pkg.three_interpolate(pts, nidx, w)
+    wy = torch.rand_like(y)
+    (y * wy).sum().backward()
+    exp = torch.zeros_like(pts)
+    for k in range(3):
+        exp.index_put_((torch.zeros((128,), dtype=torch.long, device=cuda), nidx[0, :, k].long()), wy[0] * w[0, :, k:k + 1],
+                       accumulate=True)
+    assert float((pts.grad - exp).abs().max()) < 1e-4
+    # gather_point
+    src = torch.rand((2, 64, 5), device=cuda, requires_grad=True)
+    gi = torch.randint(0, 64, (2, 20), device=cuda, dtype=torch.int32)
+    g = pkg.gather_point(src, gi)
+    g.sum().backward()
+    cnt = torch.zeros((2, 64), device=cuda)
+    cnt.scatter_add_(1, gi.long(), torch.ones((2, 20), device=cuda))
+    assert torch.allclose(src.grad, cnt.unsqueeze(-1).expand(-1, -1, 5))
