@@ -45,6 +45,11 @@ struct TcParams {
     float *out_f32; int ld_f32;
     __nv_bfloat16 *out_hi, *out_lo; int ld_split;
     int tma_store;   // non-pooled outputs leave through per-warp shared-memory blocks + TMA tensor stores
+    // gather mode (first layer of an SA scale): the A operand is not read from memory but BUILT by two producer warps:
+    // x[row] = concat(points[scene, idx[row], :], xyz[scene, idx[row], :] - new_xyz[scene, row/ns, :])  (layers_util.py:160-165)
+    int gather, g_n, g_c, g_m, g_ns;
+    const float *g_xyz, *g_points, *g_new_xyz;
+    const int *g_idx;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -182,7 +187,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     const int nkb = (p.kp + TC_BK - 1) / TC_BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        // full barrier: the TMA thread's expect_tx arrival (+ one arrival per producer warp in gather mode)
+        for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&full_bar[s]), p.gather ? 3 : 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
         for (int a = 0; a < 2; a++) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -215,9 +221,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                     mbar_wait_cta(smem_u32(&empty_bar[s]), ph ^ 1u);
                     const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t fb = smem_u32(&full_bar[s]);
-                    mbar_arrive_expect_tx(fb, stage_bytes);
-                    tma_load_2d(base, &map_ahi, kb * TC_BK, mt * TC_BM, fb);
-                    tma_load_2d(base + TC_A_BYTES, &map_alo, kb * TC_BK, mt * TC_BM, fb);
+                    mbar_arrive_expect_tx(fb, p.gather ? 2 * b_bytes : stage_bytes);
+                    if (!p.gather) {
+                        tma_load_2d(base, &map_ahi, kb * TC_BK, mt * TC_BM, fb);
+                        tma_load_2d(base + TC_A_BYTES, &map_alo, kb * TC_BK, mt * TC_BM, fb);
+                    }
                     tma_load_2d(base + 2 * TC_A_BYTES, &map_bhi, kb * TC_BK, nt * p.bn, fb);
                     tma_load_2d(base + 2 * TC_A_BYTES + b_bytes, &map_blo, kb * TC_BK, nt * p.bn, fb);
                 }
@@ -252,6 +260,70 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                     umma_commit(smem_u32(&empty_bar[s]));       // smem stage free once these MMAs retire
                 }
                 umma_commit(smem_u32(&tfull_bar[acc]));         // accumulator ready for the epilogue
+            }
+        }
+    } else if ((warp == 2 || warp == 3) && p.gather) {
+        // ===== A-operand producers (gather mode): 64 threads, two rows of the tile each.  A row's source features
+        // are one contiguous run (16-byte loads when c % 4 == 0); values are split into bf16 hi/lo and stored as
+        // 16-byte chunks in the K-major SWIZZLE_128B layout the UMMA descriptor expects.
+        const int pt = threadIdx.x - 64;
+        const uint32_t rps = (uint32_t)p.g_m * (uint32_t)p.g_ns;
+        const bool vec4 = (p.g_c % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.g_points) & 15u) == 0);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mt = tile / p.n_tiles;
+            const float *src_f[2], *src_x[2], *ctr[2];
+            bool ok[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t row = (uint32_t)mt * TC_BM + (uint32_t)(pt + 64 * h);
+                ok[h] = (long)row < p.rows;
+                const uint32_t rr = ok[h] ? row : 0u;
+                const uint32_t scene = rr / rps, q = rr / (uint32_t)p.g_ns;
+                const int a = __ldg(p.g_idx + rr);
+                src_f[h] = p.g_points + ((size_t)scene * p.g_n + a) * p.g_c;
+                src_x[h] = p.g_xyz + ((size_t)scene * p.g_n + a) * 3;
+                ctr[h] = p.g_new_xyz + (size_t)q * 3;
+            }
+            for (int kb = 0; kb < nkb; kb++, it++) {
+                const int s = it % p.stages;
+                mbar_wait_cta(smem_u32(&empty_bar[s]), ((uint32_t)(it / p.stages) & 1u) ^ 1u);
+                uint8_t *abase = smem + (size_t)s * stage_bytes;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int r = pt + 64 * h;
+                    uint8_t *rowp = abase + (r >> 3) * 1024 + (r & 7) * 128;
+                    for (int c16 = 0; c16 < 8; c16++) {
+                        const int k0 = kb * TC_BK + c16 * 8;
+                        if (k0 >= p.kp) break;
+                        float f[8];
+                        if (vec4 && ok[h] && k0 + 8 <= p.g_c) {
+                            const float4 u0 = __ldg(reinterpret_cast<const float4 *>(src_f[h] + k0));
+                            const float4 u1 = __ldg(reinterpret_cast<const float4 *>(src_f[h] + k0 + 4));
+                            f[0] = u0.x; f[1] = u0.y; f[2] = u0.z; f[3] = u0.w; f[4] = u1.x; f[5] = u1.y; f[6] = u1.z; f[7] = u1.w;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; e++) {
+                                const int k = k0 + e;
+                                float val = 0.0f;
+                                if (ok[h]) {
+                                    if (k < p.g_c) val = __ldg(src_f[h] + k);
+                                    else if (k < p.g_c + 3) val = __ldg(src_x[h] + (k - p.g_c)) - __ldg(ctr[h] + (k - p.g_c));
+                                }
+                                f[e] = val;
+                            }
+                        }
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int t = 0; t < 4; t++) split_pair(f[2 * t], f[2 * t + 1], hw[t], lw[t]);
+                        const uint32_t off = (uint32_t)((c16 ^ (r & 7)) << 4);
+                        *reinterpret_cast<uint4 *>(rowp + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        *reinterpret_cast<uint4 *>(rowp + TC_A_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    }
+                }
+                fence_async_smem();                                   // generic-proxy stores -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
             }
         }
     } else if (warp >= TC_EPI_WARP0) {
@@ -403,37 +475,73 @@ group_concat_split_kernel(long rows, int n, int c, int m, int ns, const float *_
                           const int *__restrict__ idx, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
                           int kp, int vec4)
 {
-    const int lane = threadIdx.x & 31;
+    constexpr int U = 4;                              // rows in flight per warp (independent load chains)
+    extern __shared__ __align__(16) __nv_bfloat16 gcs_stage[];   // [8 warps][U rows][hi kp | lo kp]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    __nv_bfloat16 *st = gcs_stage + (size_t)wib * U * 2 * kp;
     const long warp0 = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
     const long rows_per_scene = (long)m * ns;
-    for (long row = warp0; row < rows; row += nwarps) {
-        const long scene = row / rows_per_scene;
-        const int a = __ldg(idx + row);
-        const float *src = points + ((size_t)scene * n + a) * c;
-        __nv_bfloat16 *dh = hi + (size_t)row * kp, *dl = lo + (size_t)row * kp;
+    const int nchunk = kp >> 3;                       // 16-byte chunks per (hi or lo) row
+    for (long rbase = warp0 * U; rbase < rows; rbase += nwarps * U) {
+        int a[U];
+        long scene[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long row = rbase + u;
+            a[u] = row < rows ? __ldg(idx + row) : 0;
+            scene[u] = row < rows ? row / rows_per_scene : 0;
+        }
         int k4 = 0;
         if (vec4) {                                   // c % 4 == 0, 16-byte aligned feature rows
             for (k4 = lane * 4; k4 + 3 < c; k4 += 128) {
-                const float4 f = __ldg(reinterpret_cast<const float4 *>(src + k4));
-                uint32_t h0, l0, h1, l1;
-                split_pair(f.x, f.y, h0, l0);
-                split_pair(f.z, f.w, h1, l1);
-                *reinterpret_cast<uint2 *>(dh + k4) = make_uint2(h0, h1);
-                *reinterpret_cast<uint2 *>(dl + k4) = make_uint2(l0, l1);
+                float4 f[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    f[u] = __ldg(reinterpret_cast<const float4 *>(points + ((size_t)scene[u] * n + a[u]) * c + k4));
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    uint32_t h0, l0, h1, l1;
+                    split_pair(f[u].x, f[u].y, h0, l0);
+                    split_pair(f[u].z, f[u].w, h1, l1);
+                    *reinterpret_cast<uint2 *>(st + (size_t)u * 2 * kp + k4) = make_uint2(h0, h1);
+                    *reinterpret_cast<uint2 *>(st + (size_t)u * 2 * kp + kp + k4) = make_uint2(l0, l1);
+                }
             }
             k4 = c & ~3;
         }
         // tail: remaining feature columns, the 3 relative coordinates, zero padding up to kp
-        for (int k = k4 + lane; k < kp; k += 32) {
-            float val = 0.0f;
-            if (k < c) val = __ldg(src + k);
-            else if (k < c + 3) {
-                const long q = row / ns;
-                val = __ldg(xyz + ((size_t)scene * n + a) * 3 + (k - c)) - __ldg(new_xyz + q * 3 + (k - c));
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long row = rbase + u;
+            const float *src = points + ((size_t)scene[u] * n + a[u]) * c;
+            for (int k = k4 + lane; k < kp; k += 32) {
+                float val = 0.0f;
+                if (row < rows) {
+                    if (k < c) val = __ldg(src + k);
+                    else if (k < c + 3) {
+                        const long q = row / ns;
+                        val = __ldg(xyz + ((size_t)scene[u] * n + a[u]) * 3 + (k - c)) - __ldg(new_xyz + q * 3 + (k - c));
+                    }
+                }
+                split_store(val, st + (size_t)u * 2 * kp + k, st + (size_t)u * 2 * kp + kp + k);
             }
-            split_store(val, dh + k, dl + k);
         }
+        __syncwarp();
+        // whole 16-byte chunks to global: the U rows are consecutive, so hi (and lo) of the warp is one contiguous run
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long row = rbase + u;
+            if (row >= rows) break;
+            const uint4 *sv = reinterpret_cast<const uint4 *>(st + (size_t)u * 2 * kp);
+            uint4 *dh = reinterpret_cast<uint4 *>(hi + (size_t)row * kp);
+            uint4 *dl = reinterpret_cast<uint4 *>(lo + (size_t)row * kp);
+            for (int ch = lane; ch < 2 * nchunk; ch += 32) {
+                if (ch < nchunk) dh[ch] = sv[ch];
+                else dl[ch - nchunk] = sv[ch];
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -493,26 +601,33 @@ static int make_out_map(CUtensorMap *map, const void *ptr, long nrows, int ncols
 
 using namespace ssd3d;
 
-extern "C" int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const void *a_lo, const void *b_hi,
-                               const void *b_lo, const float *scale, const float *shift, int relu, int pool,
-                               const int *rowmask, float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split,
-                               ssd3d_stream_t stream)
+struct TcGather { int b, n, c, m, ns; const float *xyz, *points, *new_xyz; const int *idx; };
+
+static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const void *a_lo, const TcGather *g,
+                            const void *b_hi, const void *b_lo, const float *scale, const float *shift, int relu, int pool,
+                            const int *rowmask, float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split,
+                            cudaStream_t stream)
 {
     SSD3D_REQUIRE(rows >= 0 && kp > 0 && n > 0, "linear_tc: bad shape rows=%ld kp=%d n=%d", rows, kp, n);
     SSD3D_REQUIRE(kp % 16 == 0, "linear_tc: kp=%d must be a multiple of 16", kp);
-    SSD3D_REQUIRE(a_hi && a_lo && b_hi && b_lo && scale && shift, "linear_tc: null operand pointer");
+    SSD3D_REQUIRE((g || (a_hi && a_lo)) && b_hi && b_lo && scale && shift, "linear_tc: null operand pointer");
     SSD3D_REQUIRE(out_f32 || (out_hi && out_lo), "linear_tc: no output requested");
     SSD3D_REQUIRE(!out_f32 || ld_f32 >= n, "linear_tc: ld_f32=%d < n=%d", ld_f32, n);
     SSD3D_REQUIRE(!out_hi || (out_lo && ld_split >= n && ld_split % 8 == 0), "linear_tc: bad split output (ld_split=%d)", ld_split);
     SSD3D_REQUIRE(pool == 1 || pool == 8 || pool == 16 || pool == 32 || pool == 64 || pool == 128,
                   "linear_tc: pool=%d must be one of 1, 8, 16, 32, 64, 128", pool);
     SSD3D_REQUIRE(rows % pool == 0, "linear_tc: rows=%ld not a multiple of pool=%d", rows, pool);
+    SSD3D_REQUIRE(rows < (1L << 31) - 256, "linear_tc: too many rows (%ld)", rows);
     for (const void *ptr : {a_hi, a_lo, b_hi, b_lo, (const void *)out_hi, (const void *)out_lo})
         SSD3D_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "linear_tc: operand pointers must be 16-byte aligned");
     if (rows == 0) return 0;
 
     TcParams p = {};
     p.rows = rows; p.kp = kp; p.n = n;
+    if (g) {
+        p.gather = 1; p.g_n = g->n; p.g_c = g->c; p.g_m = g->m; p.g_ns = g->ns;
+        p.g_xyz = g->xyz; p.g_points = g->points; p.g_new_xyz = g->new_xyz; p.g_idx = g->idx;
+    }
     const int n16 = (n + 15) / 16 * 16;
     // when split outputs are requested the tile must also cover (and zero) the padding columns n..ld_split-1
     const int ncover = out_hi && pool <= 1 ? (ld_split > n16 ? ld_split : n16) : n16;
@@ -540,11 +655,14 @@ extern "C" int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const
 
     CUtensorMap mah, mal, mbh, mbl;
     int rc;
-    if ((rc = make_map(&mah, a_hi, rows, kp, TC_BM)) != 0) return rc;
-    if ((rc = make_map(&mal, a_lo, rows, kp, TC_BM)) != 0) return rc;
     if ((rc = make_map(&mbh, b_hi, n, kp, p.bn)) != 0) return rc;
     if ((rc = make_map(&mbl, b_lo, n, kp, p.bn)) != 0) return rc;
-    CUtensorMap moh = mah, mol = mah, mof = mah;   // placeholders when unused (never dereferenced by the kernel)
+    mah = mbh; mal = mbh;                          // placeholders in gather mode (never dereferenced)
+    if (!g) {
+        if ((rc = make_map(&mah, a_hi, rows, kp, TC_BM)) != 0) return rc;
+        if ((rc = make_map(&mal, a_lo, rows, kp, TC_BM)) != 0) return rc;
+    }
+    CUtensorMap moh = mbh, mol = mbh, mof = mbh;   // placeholders when unused
     if (tma_store && want_split) {
         if ((rc = make_out_map(&moh, out_hi, rows, ld_split, ld_split, false)) != 0) return rc;
         if ((rc = make_out_map(&mol, out_lo, rows, ld_split, ld_split, false)) != 0) return rc;
@@ -556,8 +674,32 @@ extern "C" int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const
     if (e != cudaSuccess) return cuda_status(e, "linear_tc attr");
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < kNumSMs ? total : kNumSMs;
-    linear_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mah, mal, mbh, mbl, moh, mol, mof, p);
+    linear_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mah, mal, mbh, mbl, moh, mol, mof, p);
     SSD3D_LAUNCH_CHECK("linear_tc_kernel");
+}
+
+extern "C" int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const void *a_lo, const void *b_hi,
+                               const void *b_lo, const float *scale, const float *shift, int relu, int pool,
+                               const int *rowmask, float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split,
+                               ssd3d_stream_t stream)
+{
+    return linear_tc_launch(rows, kp, n, a_hi, a_lo, nullptr, b_hi, b_lo, scale, shift, relu, pool, rowmask, out_f32, ld_f32,
+                            out_hi, out_lo, ld_split, (cudaStream_t)stream);
+}
+
+// First layer of an SA scale with the gather fused into the operand load: rows = b*m*nsample, K = c+3 (kp = round16).
+extern "C" int ssd3d_linear_tc_gather(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
+                                      const float *new_xyz, const int *idx, int nout, const void *b_hi, const void *b_lo,
+                                      const float *scale, const float *shift, int relu, int pool, const int *rowmask,
+                                      float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split,
+                                      ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0 && c >= 0 && nsample > 0, "linear_tc_gather: bad shape");
+    SSD3D_REQUIRE(xyz && new_xyz && idx && (points || c == 0), "linear_tc_gather: null pointer");
+    TcGather g = {b, n, c, m, nsample, xyz, points, new_xyz, idx};
+    const int kp = (c + 3 + 15) / 16 * 16;
+    return linear_tc_launch((long)b * m * nsample, kp, nout, nullptr, nullptr, &g, b_hi, b_lo, scale, shift, relu, pool,
+                            rowmask, out_f32, ld_f32, out_hi, out_lo, ld_split, (cudaStream_t)stream);
 }
 
 extern "C" int ssd3d_split_rows(long rows, int c, const float *x, int ldx, void *hi, void *lo, int kp, ssd3d_stream_t stream)
@@ -581,10 +723,13 @@ extern "C" int ssd3d_group_concat_split(int b, int n, int c, int m, int nsample,
     SSD3D_REQUIRE(xyz && new_xyz && idx && hi && lo && (points || c == 0), "group_concat_split: null pointer");
     const long rows = (long)b * m * nsample;
     if (rows == 0) return 0;
-    const long want = (rows + 7) / 8;                               // 8 warps (rows) per block
+    const long want = (rows + 31) / 32;                             // 8 warps x 4 rows per block
     const int blocks = (int)(want < (long)kNumSMs * 32 ? want : (long)kNumSMs * 32);
     const int vec4 = (c >= 4 && c % 4 == 0 && (reinterpret_cast<uintptr_t>(points) & 15u) == 0) ? 1 : 0;
-    group_concat_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rows, n, c, m, nsample, xyz, points, new_xyz, idx,
-                                                                        (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, kp, vec4);
+    const size_t gsm = (size_t)8 * 4 * 2 * kp * sizeof(__nv_bfloat16);
+    SSD3D_REQUIRE(gsm <= 96 * 1024, "group_concat_split: kp=%d too wide", kp);
+    cudaFuncSetAttribute((const void *)group_concat_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
+    group_concat_split_kernel<<<blocks, 256, gsm, (cudaStream_t)stream>>>(rows, n, c, m, nsample, xyz, points, new_xyz, idx,
+                                                                          (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, kp, vec4);
     SSD3D_LAUNCH_CHECK("group_concat_split_kernel");
 }

@@ -60,7 +60,7 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                            fps_sample_range_list, fps_method_list, npoint_list, former_fps_idx, use_attention, scope,
                            dilated_group, vote_ctr=None, aggregation_channel=None, debugging=False, epsilon=1e-5, *,
                            params, ffps_mode="matrix", aggregation=None, return_debug=False, mlp_mode="tc",
-                           fuse_scale=True):
+                           fuse_scale=True, gather_in_kernel=False):
     """PointNet++ SA module with multi-scale grouping; returns (new_xyz, new_points, fps_idx)."""
     if is_training:
         raise NotImplementedError("training-mode BatchNorm / backward ops are out of scope (inference only)")
@@ -168,14 +168,23 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                                         out_split=(cat_hi, cat_lo, off) if use_agg else None)
                     off += mlp_list[i][-1]
                     continue
-                hi, lo = tf_ops.group_concat_split(xyz, points, new_xyz, idx)      # :160-165 fused with the split
+                hi = lo = None
                 for j in range(nl):
                     f = pp.conv("%s/conv%d_%d" % (scope, i, j), bn)
+                    last_kw = dict(pool=nsample_list[i], rowmask=cnt, out_f32=(concat, off),
+                                   out_split=(cat_hi, cat_lo, off) if use_agg else None)   # :167-180 conv+BN+ReLU+max+mask
+                    if j == 0 and gather_in_kernel:   # :160-165 inside the kernel's operand load (no [B,M,K,C] tensor)
+                        if nl == 1:
+                            tf_ops.linear_tc_gather(xyz, points, new_xyz, idx, f, want_split=False, **last_kw)
+                        else:
+                            _, (hi, lo) = tf_ops.linear_tc_gather(xyz, points, new_xyz, idx, f)
+                        continue
+                    if j == 0:                        # :160-165 fused with the split, materialised once in bf16 hi/lo
+                        hi, lo = tf_ops.group_concat_split(xyz, points, new_xyz, idx)
                     if j < nl - 1:
                         _, (hi, lo) = tf_ops.linear_tc(hi, lo, f, want_f32=False, want_split=True)
-                    else:                                                          # :167-180 conv+BN+ReLU+max+mask
-                        tf_ops.linear_tc(hi, lo, f, pool=nsample_list[i], rowmask=cnt, out_f32=(concat, off),
-                                         out_split=(cat_hi, cat_lo, off) if use_agg else None)
+                    else:
+                        tf_ops.linear_tc(hi, lo, f, **last_kw)
                 off += mlp_list[i][-1]
             new_points = concat
             if use_agg:                                                            # :183-185

@@ -393,25 +393,8 @@ def group_concat_split(xyz, points, new_xyz, idx, kp=None):
     return hi, lo
 
 
-def linear_tc(a_hi, a_lo, f, relu=True, pool=1, rowmask=None, want_f32=True, want_split=False, out_f32=None,
-              out_split=None):
-    """One folded conv layer on the tensor cores.  a_hi/a_lo (..., kp) bf16; f: params.FoldedConv.
-    Returns (y_f32 or None, (hi, lo) or None).  out_f32=(buffer, col_offset) / out_split=(hi_buf, lo_buf, col_offset)
-    write into slices of preallocated (..., ld) buffers (the concat of the SA scales) instead of allocating."""
-    if a_hi.dtype != torch.bfloat16 or a_lo.dtype != torch.bfloat16 or a_hi.shape != a_lo.shape:
-        raise ValueError("a_hi / a_lo must be bfloat16 tensors of the same shape")
-    kp = a_hi.shape[-1]
-    if kp != f.kp:
-        raise ValueError("operand K (%d) does not match the layer's padded K (%d)" % (kp, f.kp))
-    rows = a_hi.numel() // kp
-    pool = int(pool)
-    lead = tuple(a_hi.shape[:-1])
-    if pool > 1:
-        if lead[-1] != pool or pool not in (8, 16, 32, 64, 128):
-            raise ValueError("pool must equal the second-to-last dimension and be one of 8, 16, 32, 64, 128")
-        lead = lead[:-1]
-    n = f.cout
-    dev = a_hi.device
+def _tc_outputs(lead, n, pool, dev, want_f32, want_split, out_f32, out_split):
+    """Resolve the output arguments shared by linear_tc / linear_tc_gather -> (y, pf, ldf, sp, ph, pl, lds)."""
     y = None
     pf, ldf = 0, 0
     if out_f32 is not None:
@@ -437,10 +420,60 @@ def linear_tc(a_hi, a_lo, f, relu=True, pool=1, rowmask=None, want_f32=True, wan
         lb = alloc(lead + (lds,), dtype=torch.bfloat16, device=dev)
         ph, pl = hb.data_ptr(), lb.data_ptr()
         sp = (hb, lb)
+    return y, pf, ldf, sp, ph, pl, lds
+
+
+def linear_tc(a_hi, a_lo, f, relu=True, pool=1, rowmask=None, want_f32=True, want_split=False, out_f32=None,
+              out_split=None):
+    """One folded conv layer on the tensor cores.  a_hi/a_lo (..., kp) bf16; f: params.FoldedConv.
+    Returns (y_f32 or None, (hi, lo) or None).  out_f32=(buffer, col_offset) / out_split=(hi_buf, lo_buf, col_offset)
+    write into slices of preallocated (..., ld) buffers (the concat of the SA scales) instead of allocating."""
+    if a_hi.dtype != torch.bfloat16 or a_lo.dtype != torch.bfloat16 or a_hi.shape != a_lo.shape:
+        raise ValueError("a_hi / a_lo must be bfloat16 tensors of the same shape")
+    kp = a_hi.shape[-1]
+    if kp != f.kp:
+        raise ValueError("operand K (%d) does not match the layer's padded K (%d)" % (kp, f.kp))
+    rows = a_hi.numel() // kp
+    pool = int(pool)
+    lead = tuple(a_hi.shape[:-1])
+    if pool > 1:
+        if lead[-1] != pool or pool not in (8, 16, 32, 64, 128):
+            raise ValueError("pool must equal the second-to-last dimension and be one of 8, 16, 32, 64, 128")
+        lead = lead[:-1]
+    n = f.cout
+    y, pf, ldf, sp, ph, pl, lds = _tc_outputs(lead, n, pool, a_hi.device, want_f32, want_split, out_f32, out_split)
     vp = ctypes.c_void_p
     check(lib().ssd3d_linear_tc(rows, kp, n, _p(a_hi), _p(a_lo), _p(f.b_hi), _p(f.b_lo), _p(f.scale), _p(f.shift),
                                 1 if relu else 0, pool, _p(rowmask), vp(pf), ldf, vp(ph), vp(pl), lds, _stream()),
           "linear_tc")
+    return y, sp
+
+
+def linear_tc_gather(xyz, points, new_xyz, idx, f, relu=True, pool=1, rowmask=None, want_f32=False, want_split=True,
+                     out_f32=None, out_split=None):
+    """First conv layer of an SA scale with the gather / centre-subtract / concat of layers_util.py:160-165 fused
+    into the tensor-core kernel's operand load (no [B,M,K,C] tensor in HBM).  Outputs as linear_tc, leading shape
+    (b, m, nsample) or (b, m) when pooled."""
+    xyz = _req(xyz, "xyz", torch.float32, 3, 3)
+    new_xyz = _req(new_xyz, "new_xyz", torch.float32, 3, 3)
+    idx = _req(idx, "idx", torch.int32, 3)
+    b, n, _ = xyz.shape
+    c = 0
+    if points is not None:
+        points = _req(points, "points", torch.float32, 3)
+        c = points.shape[2]
+    if round16(c + 3) != f.kp or c + 3 != f.cin:
+        raise ValueError("layer input width %d does not match c+3 = %d" % (f.cin, c + 3))
+    _, m, ns = idx.shape
+    pool = int(pool)
+    if pool > 1 and (pool != ns or pool not in (8, 16, 32, 64, 128)):
+        raise ValueError("pool must equal nsample and be one of 8, 16, 32, 64, 128")
+    lead = (b, m) if pool > 1 else (b, m, ns)
+    y, pf, ldf, sp, ph, pl, lds = _tc_outputs(lead, f.cout, pool, xyz.device, want_f32, want_split, out_f32, out_split)
+    vp = ctypes.c_void_p
+    check(lib().ssd3d_linear_tc_gather(b, n, c, m, ns, _p(xyz), _p(points), _p(new_xyz), _p(idx), f.cout, _p(f.b_hi),
+                                       _p(f.b_lo), _p(f.scale), _p(f.shift), 1 if relu else 0, pool, _p(rowmask), vp(pf),
+                                       ldf, vp(ph), vp(pl), lds, _stream()), "linear_tc_gather")
     return y, sp
 
 

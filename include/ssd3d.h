@@ -130,6 +130,13 @@ int ssd3d_linear_bn_relu(long rows, int cin, int cout, const float *x, int ldx, 
 int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const void *a_lo, const void *b_hi, const void *b_lo,
                     const float *scale, const float *shift, int relu, int pool, const int *rowmask, float *out_f32,
                     int ld_f32, void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream);
+/* ssd3d_linear_tc for the FIRST layer of an SA scale with the gather fused into the operand load: the A operand
+ * x[b,m,k,:] = concat(points[b, idx[b,m,k], :], xyz[b, idx[b,m,k], :] - new_xyz[b,m,:]) (layers_util.py:160-165) is
+ * built in shared memory by producer warps instead of being materialised in HBM.  b_hi/b_lo [nout, round16(c+3)]. */
+int ssd3d_linear_tc_gather(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
+                           const float *new_xyz, const int *idx, int nout, const void *b_hi, const void *b_lo,
+                           const float *scale, const float *shift, int relu, int pool, const int *rowmask,
+                           float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream);
 /* hi/lo[row, 0:kp] = split(x[row, 0:c]), zero padded (kp % 8 == 0). */
 int ssd3d_split_rows(long rows, int c, const float *x, int ldx, void *hi, void *lo, int kp, ssd3d_stream_t stream);
 /* ssd3d_group_concat fused with the split: hi/lo [b*m*nsample, kp] bf16. */

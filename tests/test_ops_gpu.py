@@ -512,3 +512,32 @@ def test_group_point_gradient_error_like_reference_test(pkg, cuda):
     cnt = torch.zeros((2, 64), device=cuda)
     cnt.scatter_add_(1, gi.long(), torch.ones((2, 20), device=cuda))
     assert torch.allclose(src.grad, cnt.unsqueeze(-1).expand(-1, -1, 5))
+
+
+@pytest.mark.parametrize("b,n,c,m,k,cout,pooled", [(2, 600, 64, 50, 32, 64, False), (2, 500, 128, 33, 32, 128, False),
+                                                   (1, 700, 256, 20, 16, 256, False), (2, 300, 29, 17, 16, 48, False),
+                                                   (2, 300, 5, 40, 32, 16, True), (1, 256, 1, 9, 64, 32, False)])
+def test_linear_tc_gather_equals_materialised_path(pkg, oracle_ops, cuda, b, n, c, m, k, cout, pooled):
+    """Gather fused into the operand load == group_concat_split + linear_tc (bit for bit), and both match the oracle."""
+    rng = np.random.default_rng(n + c)
+    xyz = rng.uniform(0, 1, (b, n, 3)).astype(np.float32)
+    feats = rng.standard_normal((b, n, c)).astype(np.float32)
+    new_xyz = np.array(xyz[:, :m], copy=True)
+    idx = rng.integers(0, n, (b, m, k)).astype(np.int32)
+    cnt = rng.integers(0, 3, (b, m)).astype(np.int32)
+    prm, f = _fold(pkg, cuda, rng, c + 3, cout)
+    t = lambda a: T(a, cuda)
+    hi, lo = pkg.group_concat_split(t(xyz), t(feats), t(new_xyz), t(idx))
+    g = np.concatenate([oracle_ops.group_point(feats, idx), oracle_ops.group_point(xyz, idx) - new_xyz[:, :, None]], -1)
+    exp = _oracle_conv(oracle_ops, prm, g)
+    if pooled:
+        y0, _ = pkg.linear_tc(hi, lo, f, pool=k, rowmask=t(cnt))
+        y1, _ = pkg.linear_tc_gather(t(xyz), t(feats), t(new_xyz), t(idx), f, pool=k, rowmask=t(cnt), want_f32=True,
+                                     want_split=False)
+        assert torch.equal(y0, y1)
+        assert rel_err(N(y1), exp.max(axis=2) * (cnt > 0)[..., None]) < 1e-4
+    else:
+        _, (h0, l0) = pkg.linear_tc(hi, lo, f, want_f32=False, want_split=True)
+        _, (h1, l1) = pkg.linear_tc_gather(t(xyz), t(feats), t(new_xyz), t(idx), f)
+        assert torch.equal(h0, h1) and torch.equal(l0, l1)
+        assert rel_err(N(h1.float() + l1.float())[..., :cout], exp) < 1e-4
