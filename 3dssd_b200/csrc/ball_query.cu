@@ -123,15 +123,20 @@ ball_query_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2
                 const float cx = pts[li * 3], cy = pts[li * 3 + 1], cz = pts[li * 3 + 2];
                 float tt[BQ_QW];
                 bool near_any = false;
+                // packed fp32 (FADD2 / FMUL2 / FFMA2, sm_100): two queries per instruction, each lane-half an independent
+                // IEEE operation -> same bits as the reference recipe t = dy*dy ; t = fma(dx,dx,t) ; t = fma(dz,dz,t)
+                const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
 #pragma unroll
-                for (int q = 0; q < BQ_QW; q++) {
-                    // reference recipe: t = dy*dy ; t = fma(dx,dx,t) ; t = fma(dz,dz,t)   (PTX of :243 / :336)
-                    const float dx = qx[q] - cx, dy = qy[q] - cy, dz = qz[q] - cz;
-                    float t = __fmul_rn(dy, dy);
-                    t = __fmaf_rn(dx, dx, t);
-                    t = __fmaf_rn(dz, dz, t);
-                    tt[q] = t;
-                    near_any = near_any || (DILATED ? (t < p.t_max) : !(t >= p.t_max));
+                for (int q = 0; q < BQ_QW; q += 2) {
+                    const float2 dx = __fadd2_rn(make_float2(qx[q], qx[q + 1]), ncx);
+                    const float2 dy = __fadd2_rn(make_float2(qy[q], qy[q + 1]), ncy);
+                    const float2 dz = __fadd2_rn(make_float2(qz[q], qz[q + 1]), ncz);
+                    float2 t = __fmul2_rn(dy, dy);
+                    t = __ffma2_rn(dx, dx, t);
+                    t = __ffma2_rn(dz, dz, t);
+                    tt[q] = t.x; tt[q + 1] = t.y;
+                    near_any = near_any || (DILATED ? (t.x < p.t_max) : !(t.x >= p.t_max)) ||
+                               (DILATED ? (t.y < p.t_max) : !(t.y >= p.t_max));
                 }
                 // one vote per step in the common case (no candidate of this step is inside any query's largest ball)
                 if (!__any_sync(0xffffffffu, near_any && in)) continue;

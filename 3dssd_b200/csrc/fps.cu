@@ -268,15 +268,32 @@ fps3_direct_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
         if (tid == 0) mbar_arrive_expect_tx(smem_u32(&mbar[par]), NSLOT * 8);
         float best = -1.0f;
         int bi = 0;
+        {
+            // packed fp32 pairs (FADD2 / FMUL2 / FFMA2): same IEEE operations as d = fma(dz,dz, fma(dy,dy, dx*dx))
+            const float2 nox = make_float2(-ox, -ox), noy = make_float2(-oy, -oy), noz = make_float2(-oz, -oz);
 #pragma unroll
-        for (int i = 0; i < P; i++) {
-            const float dx = px[i] - ox, dy = py[i] - oy, dz = pz[i] - oz;
-            float d = __fmul_rn(dx, dx);
-            d = __fmaf_rn(dy, dy, d);
-            d = __fmaf_rn(dz, dz, d);
-            const float t = fminf(d, td[i]);
-            td[i] = t;
-            if (t > best) { best = t; bi = i; }
+            for (int i = 0; i + 1 < P; i += 2) {
+                const float2 dx = __fadd2_rn(make_float2(px[i], px[i + 1]), nox);
+                const float2 dy = __fadd2_rn(make_float2(py[i], py[i + 1]), noy);
+                const float2 dz = __fadd2_rn(make_float2(pz[i], pz[i + 1]), noz);
+                float2 d = __fmul2_rn(dx, dx);
+                d = __ffma2_rn(dy, dy, d);
+                d = __ffma2_rn(dz, dz, d);
+                const float t0 = fminf(d.x, td[i]), t1 = fminf(d.y, td[i + 1]);
+                td[i] = t0; td[i + 1] = t1;
+                if (t0 > best) { best = t0; bi = i; }
+                if (t1 > best) { best = t1; bi = i + 1; }
+            }
+            if (P & 1) {
+                constexpr int i = P - 1;
+                const float dx = px[i] - ox, dy = py[i] - oy, dz = pz[i] - oz;
+                float d = __fmul_rn(dx, dx);
+                d = __fmaf_rn(dy, dy, d);
+                d = __fmaf_rn(dz, dz, d);
+                const float t = fminf(d, td[i]);
+                td[i] = t;
+                if (t > best) { best = t; bi = i; }
+            }
         }
         const uint32_t u = __float_as_uint(fmaxf(best, 0.0f));
         uint32_t mx, kmin;

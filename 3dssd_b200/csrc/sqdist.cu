@@ -134,23 +134,32 @@ sqdist128_kernel(int n, int c, const float *__restrict__ a, float *__restrict__ 
     }
     __syncthreads();
     const int ty = tid / 16, tx = tid % 16;
-    float acc[8][8];
+    // Packed fp32 FMAs (FFMA2, sm_100): two independent IEEE fmas per instruction -- bit-identical to the scalar
+    // chain, twice the throughput of the fp32 pipe.
+    float2 acc2[8][4];
 #pragma unroll
     for (int y = 0; y < 8; y++)
 #pragma unroll
-        for (int x = 0; x < 8; x++) acc[y][x] = 0.0f;
+        for (int x = 0; x < 4; x++) acc2[y][x] = make_float2(0.0f, 0.0f);
     for (int l = 0; l < c; l++) {
         const float4 a0 = *reinterpret_cast<const float4 *>(As + l * SQ2_PITCH + ty * 8);
         const float4 a1 = *reinterpret_cast<const float4 *>(As + l * SQ2_PITCH + ty * 8 + 4);
         const float4 b0 = *reinterpret_cast<const float4 *>(Bs + l * SQ2_PITCH + tx * 8);
         const float4 b1 = *reinterpret_cast<const float4 *>(Bs + l * SQ2_PITCH + tx * 8 + 4);
         const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float br[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float2 bp[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
-        for (int y = 0; y < 8; y++)
+        for (int y = 0; y < 8; y++) {
+            const float2 ap = make_float2(ar[y], ar[y]);
 #pragma unroll
-            for (int x = 0; x < 8; x++) acc[y][x] = __fmaf_rn(ar[y], br[x], acc[y][x]);
+            for (int x = 0; x < 4; x++) acc2[y][x] = __ffma2_rn(ap, bp[x], acc2[y][x]);
+        }
     }
+    float acc[8][8];
+#pragma unroll
+    for (int y = 0; y < 8; y++)
+#pragma unroll
+        for (int x = 0; x < 4; x++) { acc[y][2 * x] = acc2[y][x].x; acc[y][2 * x + 1] = acc2[y][x].y; }
     float *O = out + (size_t)scene * n * n;
 #pragma unroll
     for (int y = 0; y < 8; y++) {
