@@ -144,7 +144,7 @@ __device__ __forceinline__ void sf_pool_store(const SfParams &p, float (&v)[32],
     }
 }
 
-__global__ void __launch_bounds__(SF_THREADS, 4)
+__global__ void __launch_bounds__(SF_THREADS, 6)
 sa_fused_kernel(const SfParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -226,7 +226,7 @@ sa_fused_kernel(const SfParams p)
                 const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.npad[l] >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
                 const uint32_t abase = smem_u32(ain);
                 const uint32_t wbase = smem_u32(wsm + p.w_off[l]);
-                const uint32_t wtile = (uint32_t)p.npad[l] * 128u;
+                const uint32_t wtile = (uint32_t)p.npad[l] * (uint32_t)p.rb[l];
                 const int nks = p.kp[l] >> 4;
                 const int rb = p.rb[l];
                 const uint32_t atile = 128u * (uint32_t)rb;
@@ -234,8 +234,8 @@ sa_fused_kernel(const SfParams p)
                     const int kb = ks >> 2, kin = ks & 3;            // A uses 64-wide k-blocks only when rb == 128 (else kb == 0)
                     const uint64_t a_hi = sf_desc(abase + kb * (2 * atile) + kin * 32, rb);
                     const uint64_t a_lo = sf_desc(abase + kb * (2 * atile) + atile + kin * 32, rb);
-                    const uint64_t b_hi = sf_desc(wbase + kb * wtile + kin * 32, 128);
-                    const uint64_t b_lo = sf_desc(wbase + p.w_half[l] + kb * wtile + kin * 32, 128);
+                    const uint64_t b_hi = sf_desc(wbase + kb * wtile + kin * 32, rb);     // weights use the same row span
+                    const uint64_t b_lo = sf_desc(wbase + p.w_half[l] + kb * wtile + kin * 32, rb);
                     sf_mma(tmem, a_hi, b_hi, idesc, ks ? 1u : 0u);
                     sf_mma(tmem, a_lo, b_hi, idesc, 1u);
                     sf_mma(tmem, a_hi, b_lo, idesc, 1u);
@@ -323,8 +323,9 @@ extern "C" size_t ssd3d_sa_fused_smem(int c, int nl, const int *nout)
         kp[l] = kprev;
         npad[l] = (nout[l] + 15) / 16 * 16;
         if (npad[l] > 256) return 0;
-        const int nkb = (kp[l] + 63) / 64;
-        w += (size_t)2 * nkb * npad[l] * 128;
+        const int rbw = sf_row_bytes(kp[l]);
+        const int nkb = rbw == 128 ? (kp[l] + 63) / 64 : 1;
+        w += (size_t)2 * nkb * npad[l] * rbw;
         ssf += (size_t)2 * ((npad[l] + 31) / 32 * 32);
         kprev = npad[l];
     }
@@ -365,9 +366,10 @@ extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const
         p.kp[l] = kprev;
         p.nout[l] = nout[l];
         p.npad[l] = (nout[l] + 15) / 16 * 16;
-        const int nkb = (p.kp[l] + 63) / 64;
+        const int rbw = sf_row_bytes(p.kp[l]);
+        const int nkb = rbw == 128 ? (p.kp[l] + 63) / 64 : 1;
         p.w_off[l] = woff;
-        p.w_half[l] = (uint32_t)nkb * p.npad[l] * 128;
+        p.w_half[l] = (uint32_t)nkb * p.npad[l] * rbw;
         woff += 2 * p.w_half[l];
         p.ss_off[l] = ssoff;
         p.sspad[l] = (p.npad[l] + 31) / 32 * 32;
@@ -393,7 +395,7 @@ extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm > (int)(512 / cols)) per_sm = 512 / cols;
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;                                       // register file: 4 x 128 threads x ~123 registers
+    if (per_sm > 6) per_sm = 6;                                       // register file: 6 x 128 threads x 80 registers
     int grid = kNumSMs * per_sm;
     if (grid > p.tiles) grid = p.tiles;
     sa_fused_kernel<<<grid, SF_THREADS, smem, (cudaStream_t)stream>>>(p);

@@ -167,34 +167,45 @@ sqdist128_kernel(int n, int c, const float *__restrict__ a, float *__restrict__ 
 #pragma unroll
         for (int x = 0; x < 8; x++) acc[y][x] = __fsub_rn(__fadd_rn(si, sqB[tx * 8 + x]), __fmul_rn(2.0f, acc[y][x]));
     }
+    // Stage the finished tile in shared memory (the operand slabs are dead by now) so that both the tile and its
+    // mirror image leave as whole 512-byte rows instead of 16-byte fragments scattered over 32 rows.
+    constexpr int SP = SQ2_TILE + 1;
+    float *stage = reinterpret_cast<float *>(dyn_smem);
+    __syncthreads();
+#pragma unroll
+    for (int y = 0; y < 8; y++)
+#pragma unroll
+        for (int x = 0; x < 8; x++) stage[(ty * 8 + y) * SP + tx * 8 + x] = acc[y][x];
+    __syncthreads();
     const bool vec = (n % 4) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
-#pragma unroll
-    for (int y = 0; y < 8; y++) {
-        const int i = i0 + ty * 8 + y;
-        if (i >= n) continue;
-#pragma unroll
-        for (int xh = 0; xh < 8; xh += 4) {
-            const int j = j0 + tx * 8 + xh;
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int r = wid; r < SQ2_TILE; r += SQ_THREADS / 32) {
+        const int i = i0 + r, j = j0 + lane * 4;
+        if (i < n) {
+            const float v0 = stage[r * SP + lane * 4], v1 = stage[r * SP + lane * 4 + 1];
+            const float v2 = stage[r * SP + lane * 4 + 2], v3 = stage[r * SP + lane * 4 + 3];
             float *dst = O + (size_t)i * n + j;
-            if (vec && j + 3 < n) *reinterpret_cast<float4 *>(dst) = make_float4(acc[y][xh], acc[y][xh + 1], acc[y][xh + 2], acc[y][xh + 3]);
-            else
-                for (int x = 0; x < 4; x++)
-                    if (j + x < n) dst[x] = acc[y][xh + x];
+            if (vec && j + 3 < n) *reinterpret_cast<float4 *>(dst) = make_float4(v0, v1, v2, v3);
+            else {
+                if (j < n) dst[0] = v0;
+                if (j + 1 < n) dst[1] = v1;
+                if (j + 2 < n) dst[2] = v2;
+                if (j + 3 < n) dst[3] = v3;
+            }
         }
-    }
-    if (mirror) {
-#pragma unroll
-        for (int x = 0; x < 8; x++) {
-            const int j = j0 + tx * 8 + x;
-            if (j >= n) continue;
-#pragma unroll
-            for (int yh = 0; yh < 8; yh += 4) {
-                const int i = i0 + ty * 8 + yh;
-                float *dst = O + (size_t)j * n + i;
-                if (vec && i + 3 < n) *reinterpret_cast<float4 *>(dst) = make_float4(acc[yh][x], acc[yh + 1][x], acc[yh + 2][x], acc[yh + 3][x]);
-                else
-                    for (int y = 0; y < 4; y++)
-                        if (i + y < n) dst[y] = acc[yh + y][x];
+        if (mirror) {                                     // out[j0 + r'][i0 + ...] = tile[...][r']  with r' = r
+            const int jj = j0 + r, ii = i0 + lane * 4;
+            if (jj < n) {
+                const float v0 = stage[(lane * 4) * SP + r], v1 = stage[(lane * 4 + 1) * SP + r];
+                const float v2 = stage[(lane * 4 + 2) * SP + r], v3 = stage[(lane * 4 + 3) * SP + r];
+                float *dst = O + (size_t)jj * n + ii;
+                if (vec && ii + 3 < n) *reinterpret_cast<float4 *>(dst) = make_float4(v0, v1, v2, v3);
+                else {
+                    if (ii < n) dst[0] = v0;
+                    if (ii + 1 < n) dst[1] = v1;
+                    if (ii + 2 < n) dst[2] = v2;
+                    if (ii + 3 < n) dst[3] = v3;
+                }
             }
         }
     }
@@ -209,7 +220,9 @@ extern "C" int ssd3d_calc_square_dist(int b, int n, int c, const float *a, float
     SSD3D_REQUIRE(b >= 0 && n > 0 && c > 0, "calc_square_dist: bad shape b=%d n=%d c=%d", b, n, c);
     SSD3D_REQUIRE(a && out, "calc_square_dist: null pointer");
     if (b == 0) return 0;
-    const size_t smem128 = ((size_t)2 * c * SQ2_PITCH + 2 * SQ2_TILE) * sizeof(float);
+    size_t smem128 = ((size_t)2 * c * SQ2_PITCH + 2 * SQ2_TILE) * sizeof(float);
+    const size_t stage128 = (size_t)SQ2_TILE * (SQ2_TILE + 1) * sizeof(float);   // output staging reuses the slabs
+    if (smem128 < stage128) smem128 = stage128;
     if (n >= 256 && smem128 <= 200 * 1024) {
         cudaError_t e2 = cudaFuncSetAttribute((const void *)sqdist128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128);
         if (e2 != cudaSuccess) return cuda_status(e2, "calc_square_dist attr");

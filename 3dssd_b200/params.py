@@ -126,17 +126,28 @@ def fold(params, scope, bn, device):
     return FoldedConv(t(w), t(scale), t(shift))
 
 
+def _row_bytes(kp):
+    """Bytes per operand row in the fused kernel: 32 / 64 when the whole K fits one row (kp 16 / 32), else 128-byte
+    rows in 64-wide k-blocks (must match sf_row_bytes in csrc/sa_fused.cu)."""
+    return 32 if kp <= 16 else (64 if kp <= 32 else 128)
+
+
 def _swizzled_image(wt_bf16):
-    """[npad, kp] bf16 (W^T, K-major) -> bytes of the canonical UMMA K-major SWIZZLE_128B operand image:
-    k-blocks of [npad x 64] elements, rows of 128 bytes, 16-byte chunk j of row r stored at chunk j ^ (r % 8)."""
+    """[npad, kp] bf16 (W^T, K-major) -> the canonical UMMA K-major swizzled operand image: k-blocks of
+    [npad rows x rb bytes]; 16-byte chunk j of row r is stored at chunk j ^ ((r >> log2(128/rb)) & (rb/16 - 1)),
+    i.e. SWIZZLE_128B / _64B / _32B for rb = 128 / 64 / 32."""
     npad, kp = wt_bf16.shape
-    nkb = (kp + 63) // 64
-    full = torch.zeros((npad, nkb * 64), dtype=torch.bfloat16, device=wt_bf16.device)
+    rb = _row_bytes(kp)
+    epr = rb // 2                                   # elements per row
+    nc = rb // 16                                   # 16-byte chunks per row
+    sh = {128: 0, 64: 1, 32: 2}[rb]
+    nkb = (kp + epr - 1) // epr if rb == 128 else 1
+    full = torch.zeros((npad, nkb * epr), dtype=torch.bfloat16, device=wt_bf16.device)
     full[:, :kp] = wt_bf16
-    t = full.view(npad, nkb, 8, 8).permute(1, 0, 2, 3).contiguous()          # [kb, r, chunk, elem]
+    t = full.view(npad, nkb, nc, 8).permute(1, 0, 2, 3).contiguous()          # [kb, r, chunk, elem]
     r = torch.arange(npad, device=t.device).view(1, npad, 1, 1)
-    j = torch.arange(8, device=t.device).view(1, 1, 8, 1)
-    src = (j ^ (r % 8)).expand(nkb, npad, 8, 8)
+    j = torch.arange(nc, device=t.device).view(1, 1, nc, 1)
+    src = (j ^ ((r >> sh) & (nc - 1))).expand(nkb, npad, nc, 8)
     return torch.gather(t, 2, src).contiguous().view(-1)
 
 
