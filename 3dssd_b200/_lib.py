@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libssd3d.so")
+LIB_PATH = os.environ.get("SSD3D_LIB") or os.path.join(_HERE, "libssd3d.so")   # override: instrumented builds
 _lib = None
 
 c_int, c_long, c_float, c_void_p = ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_void_p
@@ -45,9 +45,12 @@ _SIGNATURES = {
     "ssd3d_group_point_grad": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "ssd3d_three_interpolate_grad": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ssd3d_bev_nms": [c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "ssd3d_farthest_point_sample_features": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "ssd3d_ffps_supported": [c_int, c_int],
     "ssd3d_tune_set_fps_cluster": [c_int],
     "ssd3d_tune_set_fps_variant": [c_int],
     "ssd3d_tune_set_fps_cluster_cap": [c_int],
+    "ssd3d_tune_set_fused": [c_int, c_int],
 }
 
 EXPORTS = sorted(list(_SIGNATURES) + ["ssd3d_last_error"])

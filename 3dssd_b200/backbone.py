@@ -20,7 +20,7 @@ class SABackbone:
     input buffer.
     """
 
-    def __init__(self, arch=None, params=None, in_channels=_cfg.INPUT_CHANNELS - 3, device="cuda", ffps_mode="matrix",
+    def __init__(self, arch=None, params=None, in_channels=_cfg.INPUT_CHANNELS - 3, device="cuda", ffps_mode="direct",
                  seed=0, mlp_mode="tc", fuse_scale=True, head=None):
         self.arch = _cfg.ARCH_3DSSD if arch is None else arch
         self.in_channels = in_channels

@@ -75,6 +75,14 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         "DONE_%=:\n\t}"
         ::"r"(bar), "r"(parity) : "memory");
 }
+// One lane of a converged warp (for single-thread instructions such as tcgen05.mma / commit issued from code the
+// whole warp runs, so that their operands stay in uniform registers).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // CTA-scope acquire: enough for data that lands in THIS CTA's shared memory (TMA, st.async from peers); a
 // cluster-scope acquire makes ptxas emit CCTL.IVALL (an L1 invalidate) on every wait -- 32% of the FPS round.
 __device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity)

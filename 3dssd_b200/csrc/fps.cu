@@ -448,6 +448,190 @@ fpsc_cluster_kernel(int n, int c, int m, const float *__restrict__ inp, int *__r
 }
 
 // ---------------------------------------------------------------------------------------------------
+// F-FPS without the distance matrix: farthest_point_sample_with_distance(m, calc_square_dist(feat)) evaluated row by
+// row, on the fly (layers_util.py:94-96 / :102-104 of the reference build the [B,N,N] matrix with a GEMM and then
+// read one row of it per round).  Bit-identical to the matrix route: the value used for point k in the round after
+// `old` was picked is exactly sqdist's entry  (sq[old] + sq[k]) - 2 * dot(old, k)  with the pinned fma chains.
+//
+// Every thread keeps the features of its P points in REGISTERS (P*CP <= 136 values); a copy of the CTA's rows lives
+// in shared memory so that warp 0 can attach the CTA candidate's whole feature row (+ its squared norm) to the
+// arg-max packet it pushes to the peers with st.async.  After the one mbarrier wait of the round every CTA therefore
+// already holds the winner's features locally: no second hop, no global memory, no [B,N,N] tensor (0.5 GB per step
+// at layer 2) and no kernel to produce it.
+// ---------------------------------------------------------------------------------------------------
+template <int CP>
+struct __align__(16) FfpsPacket {
+    uint32_t val, key;
+    float sq;
+    uint32_t pad;
+    float feat[CP];
+};
+
+template <int CL, int P, int CP>
+__global__ void __launch_bounds__(FPS_T, 1)
+ffps_cluster_kernel(int n, int ca, int cb, int m, const float *__restrict__ fa, const float *__restrict__ fb,
+                    int *__restrict__ out)
+{
+    constexpr int TT = CL * FPS_T, NL = P * FPS_T, NP = 1 + CP / 4;   // pieces of 16 bytes per packet
+    using Packet = FfpsPacket<CP>;
+    extern __shared__ float4 dyn_smem[];
+    float *featS = reinterpret_cast<float *>(dyn_smem);               // [NL][CP] rows of this CTA's points
+    float *sqS = featS + (size_t)NL * CP;                             // [NL]
+    Packet *cl_pk = reinterpret_cast<Packet *>(sqS + NL);             // [2][CL]
+    __shared__ uint32_t warp_val[2][FPS_NW], warp_key[2][FPS_NW];
+    __shared__ unsigned long long mbar[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+    const int scene = blockIdx.x / CL;
+    const int g = (int)rank * FPS_T + tid;
+    const int c = ca + cb;
+    const float *A = fa + (size_t)scene * n * ca;
+    const float *B = fb + (size_t)scene * n * cb;
+    int *idxs = out + (size_t)scene * m;
+
+    // ---- stage this CTA's rows: local point s = i*256 + t  <->  k = rank*256 + t + i*TT (zero rows beyond n)
+    for (int s = warp; s < NL; s += FPS_NW) {
+        const int k = (int)rank * FPS_T + (s % FPS_T) + (s / FPS_T) * TT;
+        for (int l = lane; l < CP; l += 32) {
+            float v = 0.0f;
+            if (k < n && l < c) v = l < ca ? __ldg(A + (size_t)k * ca + l) : __ldg(B + (size_t)k * cb + (l - ca));
+            featS[(size_t)s * CP + l] = v;
+        }
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(&mbar[0]), 1);
+        mbar_init(smem_u32(&mbar[1]), 1);
+        fence_mbar_init_cluster();
+    }
+    __syncthreads();
+    float f[P][CP], td[P], sq[P];
+    uint32_t key[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        const int k = g + i * TT;
+        const float4 *row = reinterpret_cast<const float4 *>(featS + (size_t)(i * FPS_T + tid) * CP);
+        float s2 = 0.0f;
+#pragma unroll
+        for (int l4 = 0; l4 < CP / 4; l4++) {
+            const float4 v = row[l4];
+            f[i][4 * l4 + 0] = v.x; f[i][4 * l4 + 1] = v.y; f[i][4 * l4 + 2] = v.z; f[i][4 * l4 + 3] = v.w;
+        }
+#pragma unroll
+        for (int l = 0; l < CP; l++) s2 = __fmaf_rn(f[i][l], f[i][l], s2);     // sqdist's squared-norm chain
+        sq[i] = s2;
+        sqS[i * FPS_T + tid] = s2;
+        td[i] = k < n ? 1e38f : -1.0f;
+        key[i] = fps_key(k);
+    }
+    // round 0 picks point 0: its row (owned by CTA 0, local point 0) is read from global memory by every CTA
+    {
+        Packet &p0 = cl_pk[0];
+        for (int l = tid; l < CP; l += FPS_T) {
+            float v = 0.0f;
+            if (l < c) v = l < ca ? __ldg(A + l) : __ldg(B + (l - ca));
+            p0.feat[l] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float s2 = 0.0f;
+            for (int l = 0; l < CP; l++) s2 = __fmaf_rn(p0.feat[l], p0.feat[l], s2);
+            p0.sq = s2;
+        }
+    }
+    __syncthreads();
+    if (CL > 1) cluster_sync_all();       // every CTA's barriers exist before any peer st.async targets them
+    if (g == 0) idxs[0] = 0;
+
+    const Packet *oldp = &cl_pk[0];
+    for (int j = 1; j < m; j++) {
+        const int par = j & 1;
+        // ---- row `old` of the distance matrix for this thread's points
+        float dot[P];
+#pragma unroll
+        for (int i = 0; i < P; i++) dot[i] = 0.0f;
+        const float4 *of4 = reinterpret_cast<const float4 *>(oldp->feat);
+#pragma unroll
+        for (int l4 = 0; l4 < CP / 4; l4++) {
+            const float4 o = of4[l4];
+#pragma unroll
+            for (int i = 0; i < P; i++) {
+                dot[i] = __fmaf_rn(o.x, f[i][4 * l4 + 0], dot[i]);
+                dot[i] = __fmaf_rn(o.y, f[i][4 * l4 + 1], dot[i]);
+                dot[i] = __fmaf_rn(o.z, f[i][4 * l4 + 2], dot[i]);
+                dot[i] = __fmaf_rn(o.w, f[i][4 * l4 + 3], dot[i]);
+            }
+        }
+        const float so = oldp->sq;
+        float best = -1.0f;
+        uint32_t bkey = KEY_INVALID;
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+            const float d = __fsub_rn(__fadd_rn(so, sq[i]), __fmul_rn(2.0f, dot[i]));
+            const float t = fminf(d, td[i]);
+            td[i] = t;
+            if (t > best || (t == best && key[i] < bkey)) { best = t; bkey = key[i]; }
+        }
+        // ---- CTA candidate
+        const uint32_t u = __float_as_uint(fmaxf(best, 0.0f));
+        uint32_t mx, kmin;
+        warp_argmax(u, best >= 0.0f ? bkey : KEY_INVALID, mx, kmin);
+        if (lane == 0) { warp_val[par][warp] = mx; warp_key[par][warp] = kmin; }
+        __syncthreads();
+        uint32_t win_key;
+        {
+            // every warp reduces the 8 warp candidates redundantly; warp w then pushes the CTA candidate's packet
+            // (header + feature row, one 16-byte piece per lane) to peer w -- no serial section in one warp
+            const uint32_t v = lane < FPS_NW ? warp_val[par][lane] : 0u;
+            const uint32_t kk = lane < FPS_NW ? warp_key[par][lane] : KEY_INVALID;
+            uint32_t m2, k2;
+            warp_argmax(v, kk, m2, k2);
+            // the candidate's row in this CTA's shared memory (k2 == KEY_INVALID: nothing valid left, send row 0)
+            const int kc = k2 != KEY_INVALID ? fps_key_to_k(k2) : (int)rank * FPS_T;
+            const int ls = ((kc - (int)rank * FPS_T) / TT) * FPS_T + ((kc - (int)rank * FPS_T) % TT);
+            const float4 *crow = reinterpret_cast<const float4 *>(featS + (size_t)ls * CP);
+            if (CL == 1) {
+                if (warp == 0) {
+                    Packet &dst = cl_pk[par];
+                    for (int e = lane; e < NP; e += 32) {
+                        const float4 v4 = e == 0 ? make_float4(__uint_as_float(m2), __uint_as_float(k2), sqS[ls], 0.0f) : crow[e - 1];
+                        reinterpret_cast<float4 *>(&dst)[e] = v4;
+                    }
+                }
+            } else {
+                if (tid == 0) mbar_arrive_expect_tx(smem_u32(&mbar[par]), CL * NP * 16);
+                for (int peer = warp; peer < CL; peer += FPS_NW) {
+                    const uint32_t dst = mapa(smem_u32(&cl_pk[par * CL + rank]), (uint32_t)peer);
+                    const uint32_t dbar = mapa(smem_u32(&mbar[par]), (uint32_t)peer);
+                    for (int piece = lane; piece < NP; piece += 32) {
+                        const float4 v4 = piece == 0 ? make_float4(__uint_as_float(m2), __uint_as_float(k2), sqS[ls], 0.0f) : crow[piece - 1];
+                        st_async_v4(dst + piece * 16, dbar,
+                                    make_uint4(__float_as_uint(v4.x), __float_as_uint(v4.y), __float_as_uint(v4.z), __float_as_uint(v4.w)));
+                    }
+                }
+            }
+            win_key = k2;
+        }
+        if (CL == 1) {
+            __syncthreads();
+            oldp = &cl_pk[par];
+            win_key = oldp->key;
+        } else {
+            mbar_wait_cta(smem_u32(&mbar[par]), ((j - 1) >> 1) & 1);
+            const uint32_t v = lane < CL ? cl_pk[par * CL + lane].val : 0u;
+            const uint32_t kk = lane < CL ? cl_pk[par * CL + lane].key : KEY_INVALID;
+            uint32_t m3, k3;
+            warp_argmax(v, kk, m3, k3);
+            const uint32_t bal = __ballot_sync(0xffffffffu, lane < CL && v == m3 && kk == k3);
+            oldp = &cl_pk[par * CL + (__ffs(bal) - 1)];
+            win_key = k3;
+        }
+        if (g == 0) idxs[j] = win_key != KEY_INVALID ? fps_key_to_k(win_key) : 0;
+    }
+    if (CL > 1) cluster_sync_all();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Fallback for shapes the on-chip kernels do not cover (very large n or c): one 1024-thread CTA per
 // scene, running distances in the caller's `temp` like the reference, warp-redux arg-max.
 // ---------------------------------------------------------------------------------------------------
@@ -705,4 +889,53 @@ extern "C" int ssd3d_farthest_point_sample_with_distance(int b, int n, int m, co
     SSD3D_REQUIRE(temp != nullptr, "farthest_point_sample_with_distance: n=%d needs the temp[b,n] workspace", n);
     fps_fallback_kernel<<<b, 1024, 0, st>>>(n, 0, m, nullptr, dist, temp, out);
     SSD3D_LAUNCH_CHECK("fps_fallback_kernel");
+}
+
+// ---- matrix-free F-FPS dispatch: CP = 68 (P = 2 points per thread) or 132 (P = 1); smallest cluster that holds n
+template <int CL, int P, int CP>
+static int launch_ffps_t(int b, int n, int ca, int cb, int m, const float *fa, const float *fb, int *out, cudaStream_t st)
+{
+    const size_t smem = (size_t)P * FPS_T * CP * 4 + (size_t)P * FPS_T * 4 + (size_t)2 * CL * sizeof(FfpsPacket<CP>);
+    void *args[] = { &n, &ca, &cb, &m, &fa, &fb, &out };
+    return (int)launch_cluster(ffps_cluster_kernel<CL, P, CP>, CL, b, smem, st, args);
+}
+static int ffps_cluster_for(int n, int c)
+{
+    const int per_cta = c <= 68 ? 2 * FPS_T : (c <= 132 ? FPS_T : 0);
+    if (per_cta == 0) return 0;
+    for (int cl = 1; cl <= 8; cl *= 2)
+        if (n <= cl * per_cta) return cl;
+    return 0;
+}
+
+// 1 when the matrix-free F-FPS kernel covers (n points, c = channels of the concatenated feature), else 0.
+extern "C" int ssd3d_ffps_supported(int n, int c) { return n > 0 && c > 0 && ffps_cluster_for(n, c) > 0 ? 1 : 0; }
+
+// farthest_point_sample_with_distance(m, calc_square_dist(concat[fa, fb])) without the [b,n,n] matrix; same indices.
+extern "C" int ssd3d_farthest_point_sample_features(int b, int n, int ca, int cb, int m, const float *fa, const float *fb,
+                                                    int *out, ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0 && ca > 0 && cb >= 0, "farthest_point_sample_features: bad shape b=%d n=%d m=%d c=%d+%d", b, n, m, ca, cb);
+    if (b == 0 || m == 0) return 0;
+    SSD3D_REQUIRE(fa && out && (fb || cb == 0), "farthest_point_sample_features: null pointer");
+    const int c = ca + cb;
+    const int cl = ffps_cluster_for(n, c);
+    if (cl == 0) {
+        set_error("farthest_point_sample_features: n=%d c=%d not covered (use calc_square_dist + farthest_point_sample_with_distance)", n, c);
+        return SSD3D_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (c <= 68) {
+        rc = cl == 1 ? launch_ffps_t<1, 2, 68>(b, n, ca, cb, m, fa, fb, out, st)
+           : cl == 2 ? launch_ffps_t<2, 2, 68>(b, n, ca, cb, m, fa, fb, out, st)
+           : cl == 4 ? launch_ffps_t<4, 2, 68>(b, n, ca, cb, m, fa, fb, out, st)
+                     : launch_ffps_t<8, 2, 68>(b, n, ca, cb, m, fa, fb, out, st);
+    } else {
+        rc = cl == 1 ? launch_ffps_t<1, 1, 132>(b, n, ca, cb, m, fa, fb, out, st)
+           : cl == 2 ? launch_ffps_t<2, 1, 132>(b, n, ca, cb, m, fa, fb, out, st)
+           : cl == 4 ? launch_ffps_t<4, 1, 132>(b, n, ca, cb, m, fa, fb, out, st)
+                     : launch_ffps_t<8, 1, 132>(b, n, ca, cb, m, fa, fb, out, st);
+    }
+    return cuda_status((cudaError_t)rc, "ffps launch");
 }

@@ -182,7 +182,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     __shared__ uint32_t tmem_base_smem;
     __shared__ float pool_xs[2 * 4 * 32];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int nkb = (p.kp + TC_BK - 1) / TC_BK;
 
@@ -232,8 +232,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp runs the loop (uniform control flow keeps descriptors in uniform registers
+        // and tcgen05.mma free of a per-instruction election loop), one elected lane issues =====
+        {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N = bn, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int it = 0, tcount = 0;
@@ -248,18 +249,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                     tc_fence_after();
                     const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
                     const int ksteps = min(TC_BK, p.kp - kb * TC_BK) / 16;
-                    for (int ks = 0; ks < ksteps; ks++) {
-                        const uint64_t a_hi = umma_desc(base + ks * 32);
-                        const uint64_t a_lo = umma_desc(base + TC_A_BYTES + ks * 32);
-                        const uint64_t b_hi = umma_desc(base + 2 * TC_A_BYTES + ks * 32);
-                        const uint64_t b_lo = umma_desc(base + 2 * TC_A_BYTES + b_bytes + ks * 32);
-                        umma_bf16(d_tmem, a_hi, b_hi, idesc, (kb | ks) ? 1u : 0u);
-                        umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
-                        umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+                    const uint64_t a_hi = umma_desc(base), a_lo = umma_desc(base + TC_A_BYTES);
+                    const uint64_t b_hi = umma_desc(base + 2 * TC_A_BYTES), b_lo = umma_desc(base + 2 * TC_A_BYTES + b_bytes);
+                    if (elect_one()) {
+                        for (int ks = 0; ks < ksteps; ks++) {          // +2 per k-step: 32 bytes in the address field
+                            umma_bf16(d_tmem, a_hi + 2 * ks, b_hi + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+                            umma_bf16(d_tmem, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+                            umma_bf16(d_tmem, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+                        }
+                        umma_commit(smem_u32(&empty_bar[s]));   // smem stage free once these MMAs retire
                     }
-                    umma_commit(smem_u32(&empty_bar[s]));       // smem stage free once these MMAs retire
+                    __syncwarp();
                 }
-                umma_commit(smem_u32(&tfull_bar[acc]));         // accumulator ready for the epilogue
+                if (elect_one()) umma_commit(smem_u32(&tfull_bar[acc]));   // accumulator ready for the epilogue
+                __syncwarp();
             }
         }
     } else if ((warp == 2 || warp == 3) && p.gather) {

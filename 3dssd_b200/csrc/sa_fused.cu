@@ -7,14 +7,18 @@
 // global memory; activations go TMEM -> registers -> shared memory (already split in bf16 hi/lo and already in the
 // 128B-swizzled K-major layout the next layer's UMMA descriptor expects).
 //
-// Per CTA (128 threads, thread t <-> row t of a 128-row tile = 128/K neighbour groups):
-//   weights of all layers (hi+lo images, pre-swizzled on the host) are bulk-copied to shared memory once;
-//   loop over tiles: gather+split -> [fence.proxy.async] -> layer-0 MMAs (one thread) -> epilogue (tcgen05.ld,
-//   scale/shift/ReLU, split) -> next layer's A operand in shared memory -> ... -> last layer: redux.sync max-pool.
-// Several CTAs per SM (layer1: ~30 KiB each) overlap each other's gather / MMA / epilogue phases.
+// Per CTA: S "slots" of 128 threads (thread t of a slot <-> row t of a 128-row tile = 128/K neighbour groups):
+//   weights of all layers (hi+lo images, pre-swizzled on the host) are bulk-copied to shared memory once and shared
+//   by the slots; each slot owns ONE operand buffer, one TMEM accumulator and one mbarrier and loops over tiles:
+//   gather+split -> [fence.proxy.async] -> layer-0 MMAs (one thread) -> epilogue (tcgen05.ld, scale/shift/ReLU,
+//   split) written IN PLACE over the operand the finished MMAs no longer need -> ... -> last layer: max-pool.
+// Small stacks (layer1: ~30 KiB) run S=1 with up to 6 CTAs per SM; stacks whose weights fill most of shared memory
+// (layer2: 68-92 KiB) run one CTA per SM with S=2..3 slots, so gather / MMA / epilogue phases still overlap.
 //
 // Precision: same bf16 hi/lo split and 3-MMA scheme as mlp_tc.cu.
 #include <cuda_bf16.h>
+#include <cstdio>
+#include <cstring>
 
 #include "common.cuh"
 #include "pool.cuh"
@@ -41,9 +45,11 @@ struct SfParams {
     const uint8_t *w_blob;
     const float *ss_blob;
     int sspad[SF_MAX_LAYERS];        // npad rounded up to 32 (scale/shift arrays are zero padded to this)
-    int rb[SF_MAX_LAYERS];           // bytes per operand row of layer l's A buffer: 32 / 64 (one block) or 128 (64-wide k-blocks)
-    uint32_t bufx_bytes, bufy_bytes;
-    uint32_t tmem_cols;
+    int nfull[SF_MAX_LAYERS];        // layer l's K = nfull 64-wide k-blocks (128-byte rows) + one tail block
+    int rbt[SF_MAX_LAYERS];          // bytes per row of the tail block: 0 (none), 32 (16 wide), 64 (32), 128 (48)
+    uint32_t abuf_bytes;             // operand buffer of one slot
+    uint32_t tmem_cols;              // accumulator columns of one slot
+    uint32_t tmem_alloc;             // power of two >= slots * tmem_cols
     float *out_f32; int ld_f32;
     __nv_bfloat16 *out_hi, *out_lo; int ld_split;
 };
@@ -93,15 +99,21 @@ __device__ __forceinline__ void sf_split_pair(float x0, float x1, uint32_t &hw, 
 }
 // byte offset of the 16-byte chunk holding columns [8*c16g, 8*c16g+8) of row r inside an A buffer laid out as
 // k-blocks of { hi tile | lo tile } (128 rows x rb bytes each), each tile in the canonical K-major swizzled layout
-// of span rb: chunk j of row r sits at chunk j ^ ((r >> log2(128/rb)) & (rb/16 - 1)).
-__device__ __forceinline__ uint32_t sf_a_chunk(int r, int c16g, int rb)
+// of span rb: chunk j of row r sits at chunk j ^ ((r >> log2(128/rb)) & (rb/16 - 1)).  The first nfull blocks are
+// 64 wide (rb = 128), the tail block is rbt bytes wide.  *lo_off receives the distance from the hi to the lo tile.
+__device__ __forceinline__ uint32_t sf_a_chunk(int r, int c16g, int nfull, int rbt, uint32_t *lo_off)
 {
+    const int kb = c16g >> 3;
+    const bool tail = kb >= nfull;
+    const int rb = tail ? rbt : 128;
+    const int c16 = tail ? c16g - nfull * 8 : (c16g & 7);
     const int nc = rb >> 4;                                  // chunks per row: 8 / 4 / 2
     const int sh = rb == 128 ? 0 : (rb == 64 ? 1 : 2);
-    const int kb = c16g / nc, c16 = c16g % nc;
-    return (uint32_t)kb * (uint32_t)(2 * 128 * rb) + (uint32_t)(r >> 3) * (uint32_t)(8 * rb) + (uint32_t)(r & 7) * (uint32_t)rb +
-           (uint32_t)((c16 ^ ((r >> sh) & (nc - 1))) << 4);
+    *lo_off = 128u * (uint32_t)rb;
+    return (uint32_t)(tail ? nfull : kb) * (2u * 128u * 128u) + (uint32_t)(r >> 3) * (uint32_t)(8 * rb) +
+           (uint32_t)(r & 7) * (uint32_t)rb + (uint32_t)((c16 ^ ((r >> sh) & (nc - 1))) << 4);
 }
+__device__ __forceinline__ void sf_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ uint32_t sf_f2ord(float x)
 {
     const uint32_t b = __float_as_uint(x);
@@ -109,9 +121,16 @@ __device__ __forceinline__ uint32_t sf_f2ord(float x)
 }
 __device__ __forceinline__ float sf_ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 
+#ifdef SF_PROFILE
+__device__ long long sf_prof[16];
+#define SF_T(i) do { if (prof_on) { const long long t_ = clock64(); sf_prof[i] += t_ - t_prev; t_prev = t_; } } while (0)
+#else
+#define SF_T(i) do { } while (0)
+#endif
+
 template <int POOL>
 __device__ __forceinline__ void sf_pool_store(const SfParams &p, float (&v)[32], int lane, int q, int tile,
-                                              int col0, int nout, float *xs)
+                                              int col0, int nout, float *xs, int wg_bar)
 {
     constexpr int GP = POOL >= 32 ? 32 : POOL;
     constexpr int KEEP = 32 / GP;
@@ -119,12 +138,12 @@ __device__ __forceinline__ void sf_pool_store(const SfParams &p, float (&v)[32],
     warp_colmax_transpose<GP>(v, lane);                   // lane owns columns (lane % GP) * KEEP + k in v[k]
     if (POOL > 32) {                                      // groups spanning 2 or 4 warps: combine through shared memory
         xs[q * 32 + lane] = v[0];
-        __syncthreads();
+        sf_bar_sync(wg_bar, 128);
         if ((q % WPG) == 0) {
 #pragma unroll
             for (int w = 1; w < WPG; w++) v[0] = fmaxf(v[0], xs[(q + w) * 32 + lane]);
         }
-        __syncthreads();
+        sf_bar_sync(wg_bar, 128);
         if ((q % WPG) != 0) return;
     }
     const int gg = tile * (128 / POOL) + (q * 32 + lane) / POOL;
@@ -144,113 +163,174 @@ __device__ __forceinline__ void sf_pool_store(const SfParams &p, float (&v)[32],
     }
 }
 
-__global__ void __launch_bounds__(SF_THREADS, 6)
+// SLOTS tiles in flight per CTA, WG warpgroups (128 threads) working on each: the warpgroups of a slot split the
+// 16-byte chunks of the gather and the 32-column chunks of every epilogue between them.
+template <int SLOTS, int WG>
+__global__ void __launch_bounds__(SF_THREADS * SLOTS * WG, SLOTS * WG == 1 ? 6 : 1)
 sa_fused_kernel(const SfParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *bufx = smem;                                // A operand of layers 0 and 2
-    uint8_t *bufy = bufx + p.bufx_bytes;                 // A operand of layer 1
-    uint8_t *wsm = bufy + p.bufy_bytes;                  // weight images (1024-aligned: buffers are multiples of 32 KiB)
+    uint8_t *wsm = smem + (size_t)SLOTS * p.abuf_bytes;  // weight images (1024-aligned: buffers are multiples of 1 KiB)
     float *ss = reinterpret_cast<float *>(wsm + p.w_total);
 
-    __shared__ unsigned long long w_bar, mma_bar;
+    __shared__ unsigned long long w_bar, mma_bar[SLOTS];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float xs[4 * 32];
+    __shared__ float xs_all[SLOTS * WG][4 * 32];
 
-    const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
+    constexpr int NT = SF_THREADS * SLOTS * WG, ST = SF_THREADS * WG;     // threads per CTA / per slot
+    constexpr int U = WG == 1 ? 4 : (WG == 2 ? 3 : 2);   // gather chunks in flight per thread
+    const int tid = threadIdx.x, lane = tid & 31, q = (tid >> 5) & 3;
+    const int slot = tid / ST, wg = (tid >> 7) % WG;
+    const int r = tid & 127;                             // row of the slot's tile this thread works on
+    // the slot's first warp issues the MMAs; its index is made provably warp-uniform (shfl) so that descriptors are
+    // computed on the uniform datapath and tcgen05.mma takes them without a per-operand R2UR "waterfall" loop
+    const int slot_u = __shfl_sync(0xffffffffu, slot, 0);
+    const bool issuer_warp = __shfl_sync(0xffffffffu, (tid % ST) >> 5, 0) == 0;
+    const int slot_bar = 1 + slot, wg_bar = 1 + SLOTS + slot * WG + wg;
+    uint8_t *buf = smem + (size_t)slot * p.abuf_bytes;   // the slot's operand buffer (every layer, in place)
+    float *xs = xs_all[slot * WG + wg];
 
     if (tid == 0) {
         mbar_init(smem_u32(&w_bar), 1);
-        mbar_init(smem_u32(&mma_bar), 1);
+#pragma unroll
+        for (int i = 0; i < SLOTS; i++) mbar_init(smem_u32(&mma_bar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_arrive_expect_tx(smem_u32(&w_bar), p.w_total);
         bulk_g2s(smem_u32(wsm), p.w_blob, p.w_total, smem_u32(&w_bar));
     }
-    if (q == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(p.tmem_cols) : "memory");
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(p.tmem_alloc) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (uint32_t i = tid; i < p.ss_total; i += SF_THREADS) ss[i] = __ldg(p.ss_blob + i);
+    for (uint32_t i = tid; i < p.ss_total; i += NT) ss[i] = __ldg(p.ss_blob + i);
     sf_fence_before();
     __syncthreads();
     sf_fence_after();
-    const uint32_t tmem = tmem_base_smem;
+    const uint32_t tmem = tmem_base_smem + (uint32_t)slot * p.tmem_cols;
+    const uint32_t bar = smem_u32(&mma_bar[slot]);
     mbar_wait_cta(smem_u32(&w_bar), 0);                  // weights landed (async proxy writes, read by UMMA only)
 
+#ifdef SF_PROFILE
+    const bool prof_on = blockIdx.x == 0 && (tid % ST) == 0 && slot == 0;
+    long long t_prev = clock64();
+#endif
     uint32_t mma_phase = 0;
-    const int r = tid;                                   // row of the tile this thread owns
     const int k0 = p.c + 3;
+    const bool vec = (p.c & 3) == 0;                     // feature rows are 16-byte aligned: float4 gathers
 
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-        // ---- gather + centre-subtract + concat + split -> bufx (layers_util.py:157-165)
+    const int tile0 = blockIdx.x * SLOTS + slot, tstep = gridDim.x * SLOTS;
+    // neighbour index of this thread's row, fetched one tile ahead (rows < 2^31: checked by the launcher)
+    int a_next = (tile0 < p.tiles && (long)tile0 * 128 + r < p.rows) ? __ldg(p.idx + (size_t)tile0 * 128u + r) : 0;
+    for (int tile = tile0; tile < p.tiles; tile += tstep) {
+        // ---- gather + centre-subtract + concat + split -> buf (layers_util.py:157-165)
         {
-            const uint32_t row = (uint32_t)tile * 128u + (uint32_t)r;  // rows < 2^31 (checked by the launcher)
+            const uint32_t row = (uint32_t)tile * 128u + (uint32_t)r;
             const bool ok = (long)row < p.rows;
             const uint32_t qi = ok ? row / (uint32_t)p.ns : 0u;        // == scene*m + query
             const uint32_t scene = qi / (uint32_t)p.m;
-            const int a = ok ? __ldg(p.idx + row) : 0;
+            const int a = a_next;
+            {
+                const long nrow = (long)(tile + tstep) * 128 + r;
+                a_next = (tile + tstep < p.tiles && nrow < p.rows) ? __ldg(p.idx + nrow) : 0;
+            }
             const float *src_f = p.points + ((size_t)scene * p.n + a) * p.c;
             const float *src_x = p.xyz + ((size_t)scene * p.n + a) * 3;
             const float *ctr = p.new_xyz + (size_t)qi * 3;
             const int nchunk = p.kp[0] >> 3;
-            for (int cg = 0; cg < nchunk; cg++) {
-                float f[8];
+            for (int cg0 = wg * U; cg0 < nchunk; cg0 += WG * U) {     // U chunks of 8 columns in flight per thread
+                float f[U][8];
 #pragma unroll
-                for (int e = 0; e < 8; e++) {
-                    const int k = cg * 8 + e;
-                    float val = 0.0f;
-                    if (ok) {
-                        if (k < p.c) val = __ldg(src_f + k);
-                        else if (k < k0) val = __ldg(src_x + (k - p.c)) - __ldg(ctr + (k - p.c));
+                for (int u = 0; u < U; u++) {
+                    const int kb = (cg0 + u) * 8;
+                    if (vec && ok && kb + 8 <= p.c) {
+                        const float4 lo4 = __ldg(reinterpret_cast<const float4 *>(src_f + kb));
+                        const float4 hi4 = __ldg(reinterpret_cast<const float4 *>(src_f + kb + 4));
+                        f[u][0] = lo4.x; f[u][1] = lo4.y; f[u][2] = lo4.z; f[u][3] = lo4.w;
+                        f[u][4] = hi4.x; f[u][5] = hi4.y; f[u][6] = hi4.z; f[u][7] = hi4.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            const int k = kb + e;
+                            float val = 0.0f;
+                            if (ok) {
+                                if (k < p.c) val = __ldg(src_f + k);
+                                else if (k < k0) val = __ldg(src_x + (k - p.c)) - __ldg(ctr + (k - p.c));
+                            }
+                            f[u][e] = val;
+                        }
                     }
-                    f[e] = val;
                 }
-                uint32_t hw[4], lw[4];
 #pragma unroll
-                for (int t = 0; t < 4; t++) sf_split_pair(f[2 * t], f[2 * t + 1], hw[t], lw[t]);
-                const uint32_t off = sf_a_chunk(r, cg, p.rb[0]);
-                *reinterpret_cast<uint4 *>(bufx + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4 *>(bufx + off + 128 * p.rb[0]) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                for (int u = 0; u < U; u++) {
+                    if (cg0 + u >= nchunk) break;
+                    uint32_t hw[4], lw[4], lo_off;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) sf_split_pair(f[u][2 * t], f[u][2 * t + 1], hw[t], lw[t]);
+                    const uint32_t off = sf_a_chunk(r, cg0 + u, p.nfull[0], p.rbt[0], &lo_off);
+                    *reinterpret_cast<uint4 *>(buf + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4 *>(buf + off + lo_off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
             }
         }
+        SF_T(0);                                                       // gather
         for (int l = 0; l < p.nl; l++) {
-            uint8_t *ain = (l & 1) ? bufy : bufx;
-            uint8_t *aout = (l & 1) ? bufx : bufy;
             // operand written with ordinary stores -> make it visible to the tensor-core (async) proxy
             sf_fence_async_smem();
             sf_fence_before();
-            __syncthreads();
-            if (tid == 0) {
+            sf_bar_sync(slot_bar, ST);
+            SF_T(1 + 4 * l);                                           // barrier
+            if (issuer_warp) {
                 sf_fence_after();
                 const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.npad[l] >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-                const uint32_t abase = smem_u32(ain);
-                const uint32_t wbase = smem_u32(wsm + p.w_off[l]);
-                const uint32_t wtile = (uint32_t)p.npad[l] * (uint32_t)p.rb[l];
-                const int nks = p.kp[l] >> 4;
-                const int rb = p.rb[l];
-                const uint32_t atile = 128u * (uint32_t)rb;
-                for (int ks = 0; ks < nks; ks++) {
-                    const int kb = ks >> 2, kin = ks & 3;            // A uses 64-wide k-blocks only when rb == 128 (else kb == 0)
-                    const uint64_t a_hi = sf_desc(abase + kb * (2 * atile) + kin * 32, rb);
-                    const uint64_t a_lo = sf_desc(abase + kb * (2 * atile) + atile + kin * 32, rb);
-                    const uint64_t b_hi = sf_desc(wbase + kb * wtile + kin * 32, rb);     // weights use the same row span
-                    const uint64_t b_lo = sf_desc(wbase + p.w_half[l] + kb * wtile + kin * 32, rb);
-                    sf_mma(tmem, a_hi, b_hi, idesc, ks ? 1u : 0u);
-                    sf_mma(tmem, a_lo, b_hi, idesc, 1u);
-                    sf_mma(tmem, a_hi, b_lo, idesc, 1u);
+                const uint32_t tmem_u = tmem_base_smem + (uint32_t)slot_u * p.tmem_cols;
+                const uint32_t abase = smem_u32(smem) + (uint32_t)slot_u * p.abuf_bytes;
+                const uint32_t wbase = smem_u32(wsm) + p.w_off[l];
+                const int nfull = p.nfull[l], rbt = p.rbt[l];
+                uint32_t acc = 0u;
+                // descriptors advance by (bytes >> 4) in their address field; shared memory < 256 KiB: no carry out of it
+                for (int kb = 0; kb < nfull; kb++) {
+                    const uint64_t a_hi = sf_desc(abase + (uint32_t)kb * (2u * 128u * 128u), 128);
+                    const uint64_t b_hi = sf_desc(wbase + (uint32_t)kb * ((uint32_t)p.npad[l] * 128u), 128);
+                    const uint64_t a_lo = a_hi + ((128u * 128u) >> 4), b_lo = b_hi + (p.w_half[l] >> 4);
+#pragma unroll
+                    for (int kin = 0; kin < 4; kin++) {
+                        if (elect_one()) {
+                            sf_mma(tmem_u, a_hi + 2 * kin, b_hi + 2 * kin, idesc, acc);
+                            sf_mma(tmem_u, a_lo + 2 * kin, b_hi + 2 * kin, idesc, 1u);
+                            sf_mma(tmem_u, a_hi + 2 * kin, b_lo + 2 * kin, idesc, 1u);
+                        }
+                        acc = 1u;
+                    }
                 }
-                sf_commit(smem_u32(&mma_bar));
+                if (rbt) {
+                    const uint64_t a_hi = sf_desc(abase + (uint32_t)nfull * (2u * 128u * 128u), rbt);
+                    const uint64_t b_hi = sf_desc(wbase + (uint32_t)nfull * ((uint32_t)p.npad[l] * 128u), rbt);
+                    const uint64_t a_lo = a_hi + ((128u * (uint32_t)rbt) >> 4), b_lo = b_hi + (p.w_half[l] >> 4);
+                    const int nt = rbt == 128 ? 3 : (rbt >> 5);              // 16-wide k-steps of the tail block
+                    for (int kin = 0; kin < nt; kin++) {
+                        if (elect_one()) {
+                            sf_mma(tmem_u, a_hi + 2 * kin, b_hi + 2 * kin, idesc, acc);
+                            sf_mma(tmem_u, a_lo + 2 * kin, b_hi + 2 * kin, idesc, 1u);
+                            sf_mma(tmem_u, a_hi + 2 * kin, b_lo + 2 * kin, idesc, 1u);
+                        }
+                        acc = 1u;
+                    }
+                }
+                if (elect_one()) sf_commit(smem_u32(&mma_bar[slot_u]));
+                __syncwarp();
             }
-            mbar_wait_cta(smem_u32(&mma_bar), mma_phase);
+            SF_T(2 + 4 * l);                                           // MMA issue
+            mbar_wait_cta(bar, mma_phase);                           // MMAs done: accumulator ready, operand buffer free
             mma_phase ^= 1u;
+            SF_T(3 + 4 * l);                                           // MMA wait
             sf_fence_after();
             // ---- epilogue of layer l
             const float *sc = ss + p.ss_off[l];
             const float *sh = sc + p.sspad[l];
             const bool last = l == p.nl - 1;
             const int nchunks = (p.npad[l] + 31) / 32;
-            for (int ci = 0; ci < nchunks; ci++) {
+            for (int ci = wg; ci < nchunks; ci += WG) {
                 const int c0 = ci * 32;
                 uint32_t rr[32];
                 sf_tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
@@ -268,33 +348,33 @@ sa_fused_kernel(const SfParams p)
 #pragma unroll
                     for (int j8 = 0; j8 < 32; j8 += 8) {
                         if (c0 + j8 >= p.kp[l + 1]) break;
-                        uint32_t hw[4], lw[4];
+                        uint32_t hw[4], lw[4], lo_off;
 #pragma unroll
                         for (int t = 0; t < 4; t++) sf_split_pair(v[j8 + 2 * t], v[j8 + 2 * t + 1], hw[t], lw[t]);
-                        const uint32_t off = sf_a_chunk(r, (c0 + j8) >> 3, p.rb[l + 1]);
-                        *reinterpret_cast<uint4 *>(aout + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                        *reinterpret_cast<uint4 *>(aout + off + 128 * p.rb[l + 1]) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        const uint32_t off = sf_a_chunk(r, (c0 + j8) >> 3, p.nfull[l + 1], p.rbt[l + 1], &lo_off);
+                        *reinterpret_cast<uint4 *>(buf + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        *reinterpret_cast<uint4 *>(buf + off + lo_off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     }
                 } else {
                     switch (p.ns) {
-                        case 8: sf_pool_store<8>(p, v, lane, q, tile, c0, p.nout[l], xs); break;
-                        case 16: sf_pool_store<16>(p, v, lane, q, tile, c0, p.nout[l], xs); break;
-                        case 32: sf_pool_store<32>(p, v, lane, q, tile, c0, p.nout[l], xs); break;
-                        case 64: sf_pool_store<64>(p, v, lane, q, tile, c0, p.nout[l], xs); break;
-                        default: sf_pool_store<128>(p, v, lane, q, tile, c0, p.nout[l], xs); break;
+                        case 8: sf_pool_store<8>(p, v, lane, q, tile, c0, p.nout[l], xs, wg_bar); break;
+                        case 16: sf_pool_store<16>(p, v, lane, q, tile, c0, p.nout[l], xs, wg_bar); break;
+                        case 32: sf_pool_store<32>(p, v, lane, q, tile, c0, p.nout[l], xs, wg_bar); break;
+                        case 64: sf_pool_store<64>(p, v, lane, q, tile, c0, p.nout[l], xs, wg_bar); break;
+                        default: sf_pool_store<128>(p, v, lane, q, tile, c0, p.nout[l], xs, wg_bar); break;
                     }
                 }
             }
             sf_fence_before();                                         // TMEM reads done before the next MMAs overwrite it
+            SF_T(4 + 4 * l);                                           // epilogue
         }
-        __syncthreads();                                               // bufx free for the next tile's gather
     }
 
     sf_fence_before();
     __syncthreads();
-    if (q == 0) {
+    if (tid < 32) {
         sf_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_smem), "r"(p.tmem_alloc) : "memory");
     }
 }
 
@@ -302,42 +382,86 @@ sa_fused_kernel(const SfParams p)
 
 using namespace ssd3d;
 
-// A-operand buffer of a layer with padded K = kp: { hi | lo } tiles of 128 rows; rows are 32 / 64 bytes when the
-// whole K fits (kp 16 / 32), else 128-byte rows in 64-wide k-blocks.  Rounded up to 1 KiB (descriptor alignment).
-static int sf_row_bytes(int kp) { return kp <= 16 ? 32 : (kp <= 32 ? 64 : 128); }
-static size_t sf_abuf_bytes(int kp)
+// Operand layout of a layer with padded K = kp: nfull 64-wide k-blocks of 128-byte rows + a tail block whose rows
+// are 32 / 64 / 128 bytes for a remainder of 16 / 32 / 48 columns (must match params._k_blocks).
+static void sf_k_blocks(int kp, int *nfull, int *rbt)
 {
-    const int rb = sf_row_bytes(kp);
-    const int nkb = rb == 128 ? (kp + 63) / 64 : 1;
-    return ((size_t)nkb * 2 * 128 * rb + 1023) / 1024 * 1024;
+    *nfull = kp / 64;
+    const int rem = kp % 64;
+    *rbt = rem == 0 ? 0 : (rem <= 16 ? 32 : (rem <= 32 ? 64 : 128));
+}
+static size_t sf_abuf_bytes(int kp)                       // { hi | lo } tiles of 128 rows per block, 1 KiB granular
+{
+    int nfull, rbt;
+    sf_k_blocks(kp, &nfull, &rbt);
+    return ((size_t)nfull * 2 * 128 * 128 + (size_t)2 * 128 * rbt + 1023) / 1024 * 1024;
+}
+static size_t sf_wimg_bytes(int kp, int npad)              // one half (hi or lo) of a layer's weight image
+{
+    int nfull, rbt;
+    sf_k_blocks(kp, &nfull, &rbt);
+    return (size_t)npad * (nfull * 128 + rbt);
+}
+
+struct SfPlan { size_t abuf, w, ssf; int maxn; };
+static bool sf_plan(int c, int nl, const int *nout, SfPlan *pl)
+{
+    if (nl < 1 || nl > SF_MAX_LAYERS) return false;
+    pl->abuf = 0; pl->w = 0; pl->ssf = 0; pl->maxn = 32;
+    int kp = (c + 3 + 15) / 16 * 16;
+    for (int l = 0; l < nl; l++) {
+        const int npad = (nout[l] + 15) / 16 * 16;
+        if (npad > 256) return false;
+        const size_t a = sf_abuf_bytes(kp);
+        if (a > pl->abuf) pl->abuf = a;
+        pl->w += 2 * sf_wimg_bytes(kp, npad);
+        pl->ssf += (size_t)2 * ((npad + 31) / 32 * 32);
+        if (npad > pl->maxn) pl->maxn = npad;
+        kp = npad;
+    }
+    return true;
+}
+static size_t sf_total(const SfPlan &pl, int slots) { return slots * pl.abuf + pl.w + pl.ssf * sizeof(float) + 1024; }
+constexpr size_t SF_SMEM_MAX = 226 * 1024;
+constexpr size_t SF_SMALL = 36 * 1024;                     // <= this: single-slot CTAs, up to 6 per SM
+
+static int g_sf_slots = 0, g_sf_wg = 0;                   // tuning override (0 = automatic)
+extern "C" void ssd3d_tune_set_fused(int slots, int wg) { g_sf_slots = slots; g_sf_wg = wg; }
+
+// Slots per CTA for a stack: 1 for small stacks (several CTAs per SM), else as many as fit one SM (<= 3).
+static int sf_slots(const SfPlan &pl)
+{
+    if (sf_total(pl, 1) <= SF_SMALL) return 1;
+    int cols = 32;
+    while (cols < pl.maxn) cols *= 2;
+    int s = g_sf_slots > 0 ? g_sf_slots : 3;
+    while (s > 1 && (sf_total(pl, s) > SF_SMEM_MAX || s * cols > 512)) s--;
+    return s;
 }
 
 // Shared-memory bytes of the fused kernel for a layer stack, or 0 when it cannot hold it.
 extern "C" size_t ssd3d_sa_fused_smem(int c, int nl, const int *nout)
 {
-    if (nl < 1 || nl > SF_MAX_LAYERS) return 0;
-    int kp[SF_MAX_LAYERS], npad[SF_MAX_LAYERS];
-    size_t w = 0, ssf = 0;
-    int kprev = (c + 3 + 15) / 16 * 16;
-    for (int l = 0; l < nl; l++) {
-        kp[l] = kprev;
-        npad[l] = (nout[l] + 15) / 16 * 16;
-        if (npad[l] > 256) return 0;
-        const int rbw = sf_row_bytes(kp[l]);
-        const int nkb = rbw == 128 ? (kp[l] + 63) / 64 : 1;
-        w += (size_t)2 * nkb * npad[l] * rbw;
-        ssf += (size_t)2 * ((npad[l] + 31) / 32 * 32);
-        kprev = npad[l];
-    }
-    const size_t a0 = sf_abuf_bytes(kp[0]), a1 = nl > 1 ? sf_abuf_bytes(kp[1]) : 0, a2 = nl > 2 ? sf_abuf_bytes(kp[2]) : 0;
-    const size_t bufx = a0 > a2 ? a0 : a2;
-    const size_t bufy = a1;
-    const size_t total = bufx + bufy + w + ssf * sizeof(float) + 1024;
-    return total <= 226 * 1024 ? total : 0;
+    SfPlan pl;
+    if (!sf_plan(c, nl, nout, &pl)) return 0;
+    const size_t total = sf_total(pl, sf_slots(pl));
+    return total <= SF_SMEM_MAX ? total : 0;
 }
 
-// w_blob: per layer { hi image | lo image }, each image = k-blocks of [npad x 64] bf16 in the canonical
-// K-major SWIZZLE_128B layout (built by params.FusedStack); ss_blob: per layer { scale[npad] | shift[npad] }.
+template <int SLOTS, int WG>
+static cudaError_t sf_launch(const SfParams &p, size_t smem, int per_sm, cudaStream_t stream)
+{
+    cudaError_t e = cudaFuncSetAttribute((const void *)sa_fused_kernel<SLOTS, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int ctas = (p.tiles + SLOTS - 1) / SLOTS;
+    int grid = kNumSMs * per_sm;
+    if (grid > ctas) grid = ctas;
+    sa_fused_kernel<SLOTS, WG><<<grid, SF_THREADS * SLOTS * WG, smem, stream>>>(p);
+    return cudaSuccess;
+}
+
+// w_blob: per layer { hi image | lo image }, each image = k-blocks of [npad x (64 | tail)] bf16 in the canonical
+// K-major swizzled layout (built by params.FusedStack); ss_blob: per layer { scale[sspad] | shift[sspad] }.
 extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
                                   const float *new_xyz, const int *idx, const int *pts_cnt, int nl, const int *nout,
                                   const void *w_blob, const float *ss_blob, float *out_f32, int ld_f32, void *out_hi,
@@ -349,8 +473,13 @@ extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const
     SSD3D_REQUIRE(xyz && new_xyz && idx && w_blob && ss_blob && (points || c == 0), "sa_mlp_fused: null pointer");
     SSD3D_REQUIRE(out_f32 || (out_hi && out_lo), "sa_mlp_fused: no output requested");
     SSD3D_REQUIRE((reinterpret_cast<uintptr_t>(w_blob) & 15u) == 0, "sa_mlp_fused: weight blob must be 16-byte aligned");
-    const size_t smem = ssd3d_sa_fused_smem(c, nl, nout);
-    if (smem == 0) { set_error("sa_mlp_fused: layer stack does not fit shared memory"); return SSD3D_ERR_UNSUPPORTED; }
+    SSD3D_REQUIRE(!points || (c & 3) || (reinterpret_cast<uintptr_t>(points) & 15u) == 0,
+                  "sa_mlp_fused: points must be 16-byte aligned when c is a multiple of 4");
+    SfPlan pl;
+    const bool planned = sf_plan(c, nl, nout, &pl);
+    const int slots = planned ? sf_slots(pl) : 0;
+    const size_t smem = planned ? sf_total(pl, slots) : 0;
+    if (!planned || smem > SF_SMEM_MAX) { set_error("sa_mlp_fused: layer stack does not fit shared memory"); return SSD3D_ERR_UNSUPPORTED; }
     SfParams p = {};
     p.n = n; p.c = c; p.m = m; p.ns = nsample;
     p.rows = (long)b * m * nsample;
@@ -361,43 +490,57 @@ extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const
     p.nl = nl;
     int kprev = (c + 3 + 15) / 16 * 16;
     uint32_t woff = 0, ssoff = 0;
-    int maxn = 32;
     for (int l = 0; l < nl; l++) {
         p.kp[l] = kprev;
         p.nout[l] = nout[l];
         p.npad[l] = (nout[l] + 15) / 16 * 16;
-        const int rbw = sf_row_bytes(p.kp[l]);
-        const int nkb = rbw == 128 ? (p.kp[l] + 63) / 64 : 1;
+        sf_k_blocks(p.kp[l], &p.nfull[l], &p.rbt[l]);
         p.w_off[l] = woff;
-        p.w_half[l] = (uint32_t)nkb * p.npad[l] * rbw;
+        p.w_half[l] = (uint32_t)sf_wimg_bytes(p.kp[l], p.npad[l]);
         woff += 2 * p.w_half[l];
         p.ss_off[l] = ssoff;
         p.sspad[l] = (p.npad[l] + 31) / 32 * 32;
         ssoff += 2 * p.sspad[l];
         kprev = p.npad[l];
-        if (p.npad[l] > maxn) maxn = p.npad[l];
     }
     p.w_total = woff; p.ss_total = ssoff;
     p.w_blob = (const uint8_t *)w_blob; p.ss_blob = ss_blob;
-    for (int l = 0; l < nl; l++) p.rb[l] = sf_row_bytes(p.kp[l]);
-    const size_t a0 = sf_abuf_bytes(p.kp[0]), a1 = nl > 1 ? sf_abuf_bytes(p.kp[1]) : 0, a2 = nl > 2 ? sf_abuf_bytes(p.kp[2]) : 0;
-    p.bufx_bytes = (uint32_t)(a0 > a2 ? a0 : a2);
-    p.bufy_bytes = (uint32_t)a1;
+    p.abuf_bytes = (uint32_t)pl.abuf;
     uint32_t cols = 32;
-    while ((int)cols < maxn) cols *= 2;
+    while ((int)cols < pl.maxn) cols *= 2;
     p.tmem_cols = cols;
+    uint32_t alloc = 32;
+    while (alloc < cols * (uint32_t)slots) alloc *= 2;
+    p.tmem_alloc = alloc;
     p.out_f32 = out_f32; p.ld_f32 = ld_f32;
     p.out_hi = (__nv_bfloat16 *)out_hi; p.out_lo = (__nv_bfloat16 *)out_lo; p.ld_split = ld_split;
 
-    cudaError_t e = cudaFuncSetAttribute((const void *)sa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // resident CTAs per SM: bounded by shared memory, TMEM columns (512 per SM) and, for single-slot CTAs, registers
+    int per_sm = 1;
+    if (slots == 1) {
+        per_sm = (int)((227 * 1024) / (smem + 1024));
+        if (per_sm > (int)(512 / alloc)) per_sm = 512 / alloc;
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 6) per_sm = 6;                                   // 6 x 128 threads x 80 registers
+    }
+    const int wg = slots == 1 ? 1 : (g_sf_wg > 0 ? g_sf_wg : 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = slots == 1 ? sf_launch<1, 1>(p, smem, per_sm, st)
+                  : slots == 2 ? (wg == 4 ? sf_launch<2, 4>(p, smem, per_sm, st) : wg == 1 ? sf_launch<2, 1>(p, smem, per_sm, st)
+                                                                                           : sf_launch<2, 2>(p, smem, per_sm, st))
+                               : (wg == 1 ? sf_launch<3, 1>(p, smem, per_sm, st) : sf_launch<3, 2>(p, smem, per_sm, st));
     if (e != cudaSuccess) return cuda_status(e, "sa_mlp_fused attr");
-    // resident CTAs per SM: bounded by shared memory and by TMEM columns (512 per SM)
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm > (int)(512 / cols)) per_sm = 512 / cols;
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 6) per_sm = 6;                                       // register file: 6 x 128 threads x 80 registers
-    int grid = kNumSMs * per_sm;
-    if (grid > p.tiles) grid = p.tiles;
-    sa_fused_kernel<<<grid, SF_THREADS, smem, (cudaStream_t)stream>>>(p);
+#ifdef SF_PROFILE
+    {
+        long long h[16];
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(h, sf_prof, sizeof(h));
+        fprintf(stderr, "sf_prof slots=%d tiles=%d:", slots, p.tiles);
+        for (int i = 0; i < 13; i++) fprintf(stderr, " %lld", h[i]);
+        fprintf(stderr, "\n");
+        memset(h, 0, sizeof(h));
+        cudaMemcpyToSymbol(sf_prof, h, sizeof(h));
+    }
+#endif
     SSD3D_LAUNCH_CHECK("sa_fused_kernel");
 }

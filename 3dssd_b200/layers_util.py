@@ -45,21 +45,30 @@ def _arange_idx(bs, npoint, device):
 
 def ffps_indices(npoint, xyz, points, mode):
     """F-FPS on concat[xyz, points] (layers_util.py:94-96, :102-104).
+    mode 'direct': one kernel, no [B,N,N] tensor, the SAME indices as 'matrix' (each round evaluates the picked point's
+                   matrix row on chip with calc_square_dist's arithmetic); falls back to 'matrix' for uncovered shapes;
     mode 'matrix': calc_square_dist + farthest_point_sample_with_distance, the reference's route;
     mode 'fused' : matrix-free -- the generic-c FPS kernel evaluates the feature distance on the fly (no
                    [B,N,N] tensor); identical to the reference's own farthest_point_sample on the features."""
+    if mode == "direct":
+        c = xyz.shape[2] + points.shape[2]
+        # the 132-channel variant walks a 131-long dependent fma chain per round: at layer-3 sizes (512 points) the
+        # small matrix is faster, so 'direct' is used where the matrix is the expensive part (c <= 68, layer 2)
+        if c <= 68 and tf_ops.ffps_supported(xyz.shape[1], c):
+            return tf_ops.farthest_point_sample_features(npoint, xyz, points)
+        mode = "matrix"
     feats = torch.cat([xyz, points], dim=-1).contiguous()
     if mode == "matrix":
         return tf_ops.farthest_point_sample_with_distance(npoint, tf_ops.calc_square_dist(feats))
     if mode == "fused":
         return tf_ops.farthest_point_sample(npoint, feats)
-    raise ValueError("ffps_mode must be 'matrix' or 'fused'")
+    raise ValueError("ffps_mode must be 'direct', 'matrix' or 'fused'")
 
 
 def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_training, bn_decay, bn,
                            fps_sample_range_list, fps_method_list, npoint_list, former_fps_idx, use_attention, scope,
                            dilated_group, vote_ctr=None, aggregation_channel=None, debugging=False, epsilon=1e-5, *,
-                           params, ffps_mode="matrix", aggregation=None, return_debug=False, mlp_mode="tc",
+                           params, ffps_mode="direct", aggregation=None, return_debug=False, mlp_mode="tc",
                            fuse_scale=True, gather_in_kernel=False):
     """PointNet++ SA module with multi-scale grouping; returns (new_xyz, new_points, fps_idx)."""
     if is_training:

@@ -13,7 +13,7 @@ import torch
 
 from . import config as _cfg
 
-FUSED_SMEM_LIMIT = 110 * 1024
+FUSED_SMEM_LIMIT = 226 * 1024
 BN_EPS = 1e-3  # tf.contrib.layers.batch_norm default epsilon (tf_util.py:439-444 does not override it)
 
 
@@ -126,29 +126,38 @@ def fold(params, scope, bn, device):
     return FoldedConv(t(w), t(scale), t(shift))
 
 
-def _row_bytes(kp):
-    """Bytes per operand row in the fused kernel: 32 / 64 when the whole K fits one row (kp 16 / 32), else 128-byte
-    rows in 64-wide k-blocks (must match sf_row_bytes in csrc/sa_fused.cu)."""
-    return 32 if kp <= 16 else (64 if kp <= 32 else 128)
+def _k_blocks(kp):
+    """Operand layout of the fused kernel for a padded K: (nfull, rbt) = number of 64-wide k-blocks (128-byte rows) and
+    the row bytes of the tail block -- 0 / 32 / 64 / 128 for a remainder of 0 / 16 / 32 / 48 columns (must match
+    sf_k_blocks in csrc/sa_fused.cu)."""
+    rem = kp % 64
+    return kp // 64, 0 if rem == 0 else (32 if rem <= 16 else (64 if rem <= 32 else 128))
+
+
+def _swizzle_block(blk, rb):
+    """[npad, rb/2] bf16 -> canonical UMMA K-major image with swizzle span rb: 16-byte chunk j of row r is stored at
+    chunk j ^ ((r >> log2(128/rb)) & (rb/16 - 1)), i.e. SWIZZLE_128B / _64B / _32B for rb = 128 / 64 / 32."""
+    npad = blk.shape[0]
+    nc = rb // 16
+    sh = {128: 0, 64: 1, 32: 2}[rb]
+    t = blk.reshape(npad, nc, 8)
+    r = torch.arange(npad, device=blk.device).view(npad, 1, 1)
+    j = torch.arange(nc, device=blk.device).view(1, nc, 1)
+    src = (j ^ ((r >> sh) & (nc - 1))).expand(npad, nc, 8)
+    return torch.gather(t, 1, src).contiguous().view(-1)
 
 
 def _swizzled_image(wt_bf16):
-    """[npad, kp] bf16 (W^T, K-major) -> the canonical UMMA K-major swizzled operand image: k-blocks of
-    [npad rows x rb bytes]; 16-byte chunk j of row r is stored at chunk j ^ ((r >> log2(128/rb)) & (rb/16 - 1)),
-    i.e. SWIZZLE_128B / _64B / _32B for rb = 128 / 64 / 32."""
+    """[npad, kp] bf16 (W^T, K-major) -> the fused kernel's operand image: nfull blocks of [npad x 128 bytes] followed
+    by the tail block of [npad x rbt bytes] (zero padded), each block swizzled over its own row span."""
     npad, kp = wt_bf16.shape
-    rb = _row_bytes(kp)
-    epr = rb // 2                                   # elements per row
-    nc = rb // 16                                   # 16-byte chunks per row
-    sh = {128: 0, 64: 1, 32: 2}[rb]
-    nkb = (kp + epr - 1) // epr if rb == 128 else 1
-    full = torch.zeros((npad, nkb * epr), dtype=torch.bfloat16, device=wt_bf16.device)
-    full[:, :kp] = wt_bf16
-    t = full.view(npad, nkb, nc, 8).permute(1, 0, 2, 3).contiguous()          # [kb, r, chunk, elem]
-    r = torch.arange(npad, device=t.device).view(1, npad, 1, 1)
-    j = torch.arange(nc, device=t.device).view(1, 1, nc, 1)
-    src = (j ^ ((r >> sh) & (nc - 1))).expand(nkb, npad, nc, 8)
-    return torch.gather(t, 2, src).contiguous().view(-1)
+    nfull, rbt = _k_blocks(kp)
+    parts = [_swizzle_block(wt_bf16[:, 64 * i: 64 * (i + 1)].contiguous(), 128) for i in range(nfull)]
+    if rbt:
+        tail = torch.zeros((npad, rbt // 2), dtype=torch.bfloat16, device=wt_bf16.device)
+        tail[:, : kp - 64 * nfull] = wt_bf16[:, 64 * nfull:]
+        parts.append(_swizzle_block(tail, rbt))
+    return torch.cat(parts)
 
 
 class FusedStack:
@@ -205,8 +214,8 @@ class PreparedParams:
             convs = [self.conv(sc, bn) for sc in scopes]
             nout = (ctypes.c_int * len(convs))(*[f.cout for f in convs])
             need = lib().ssd3d_sa_fused_smem(cin - 3, len(convs), ctypes.cast(nout, ctypes.c_void_p)) if len(convs) <= 3 else 0
-            # the fused kernel runs its phases (gather, MMA, epilogue) back to back per tile and relies on several
-            # co-resident CTAs per SM to overlap them: only worth it while >= 2 CTAs fit (layer-1 sized stacks)
+            # the fused kernel keeps every layer's weights in shared memory; stacks that do not fit (layer3/4 sized)
+            # return None and take the layer-by-layer tensor-core path
             fits = 0 < need <= limit
             self._cache[key] = FusedStack(convs, cin) if fits else None
         return self._cache[key]

@@ -74,6 +74,29 @@ def farthest_point_sample_with_distance(npoint, dist):
     return out
 
 
+def ffps_supported(n, c):
+    """True when the matrix-free F-FPS kernel covers n points with c concatenated channels."""
+    return bool(lib().ssd3d_ffps_supported(int(n), int(c)))
+
+
+def farthest_point_sample_features(npoint, xyz, points=None):
+    """F-FPS on concat[xyz, points] without the distance matrix: the same indices as
+    farthest_point_sample_with_distance(npoint, calc_square_dist(concat[xyz, points])) (layers_util.py:94-96)."""
+    xyz = _req(xyz, "xyz", torch.float32, 3)
+    b, n, ca = xyz.shape
+    cb = 0
+    if points is not None:
+        points = _req(points, "points", torch.float32, 3)
+        if points.shape[:2] != (b, n):
+            raise ValueError("points must be (batch, n, c) like xyz")
+        cb = points.shape[2]
+    npoint = int(npoint)
+    out = torch.empty((b, npoint), dtype=torch.int32, device=xyz.device)
+    check(lib().ssd3d_farthest_point_sample_features(b, n, ca, cb, npoint, _p(xyz), _p(points), _p(out), _stream()),
+          "farthest_point_sample_features")
+    return out
+
+
 def _gather_point_fwd(inp, idx):
     b, n, c = inp.shape
     m = idx.shape[1]

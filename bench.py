@@ -139,7 +139,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ffps-mode", default="matrix", choices=["matrix", "fused"])
+    ap.add_argument("--ffps-mode", default="direct", choices=["direct", "matrix", "fused"])
     ap.add_argument("--mlp-mode", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu captures)")
     ap.add_argument("--pipeline", type=int, default=8, help="steps in flight (independent CUDA graphs on separate streams)")

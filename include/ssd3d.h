@@ -51,6 +51,17 @@ int ssd3d_fps_needs_temp(int n, int c);
 int ssd3d_farthest_point_sample_with_distance(int b, int n, int m, const float *dist, float *temp, int *out,
                                               ssd3d_stream_t stream);
 
+/* The F-FPS branch of the SA layer in one call (lib/utils/layers_util.py:94-96 and :102-104):
+ *   farthest_point_sample_with_distance(m, calc_square_dist(concat[fa, fb]))
+ * without materialising the [b,n,n] matrix -- each round evaluates the picked point's matrix row on the fly from
+ * feature rows kept on chip.  fa[b,n,ca] (xyz, ca = 3 in the model), fb[b,n,cb] (features; may be NULL when cb = 0).
+ * Same indices as the two-call route (same pinned fp32 arithmetic as ssd3d_calc_square_dist).  Covers
+ * ca+cb <= 68 with n <= 4096 and ca+cb <= 132 with n <= 2048 (ssd3d_ffps_supported); other shapes return
+ * SSD3D_ERR_UNSUPPORTED and the caller takes the two-call route. */
+int ssd3d_farthest_point_sample_features(int b, int n, int ca, int cb, int m, const float *fa, const float *fb,
+                                         int *out, ssd3d_stream_t stream);
+int ssd3d_ffps_supported(int n, int c);
+
 /* replaces gatherpointLauncher(b,n,m,c,inp,idx,out)
  *   sampling/tf_sampling.cpp:235, sampling/tf_sampling_g.cu:403-407, kernel :320-331.
  * out[b,m,c] = inp[b, idx[b,m], c] */
@@ -194,6 +205,9 @@ void ssd3d_tune_set_fps_variant(int variant);
 /* Throughput mode: cap the heuristic FPS cluster size (0 = no cap).  FPS is latency-bound, so a smaller cluster
  * costs little time per scene and leaves SMs to concurrently running work. */
 void ssd3d_tune_set_fps_cluster_cap(int cluster_size);
+/* Fused SA kernel shape for stacks too big for several CTAs per SM: tiles in flight per CTA (2..3) and warpgroups
+ * working on each tile (1, 2 or 4); 0 = automatic. */
+void ssd3d_tune_set_fused(int slots, int warpgroups);
 
 #ifdef __cplusplus
 }

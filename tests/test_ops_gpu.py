@@ -396,6 +396,54 @@ def test_linear_tc_large_gemm_matches_fp32_path(pkg, cuda):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# matrix-free F-FPS == calc_square_dist + farthest_point_sample_with_distance, index for index
+# ---------------------------------------------------------------------------------------------------------
+FFPS_CASES = [  # b, n, c_feat, m
+    (8, 4096, 64, 512),     # 3DSSD layer 2 (cluster of 8, 2 points per thread)
+    (8, 512, 128, 256),     # 3DSSD layer 3 (cluster of 2, 1 point per thread, 131 channels)
+    (3, 3000, 29, 300),     # n not a multiple of anything, partial last CTA
+    (2, 200, 64, 200),      # single CTA, every point picked (m == n)
+    (2, 1500, 100, 64),     # 103 channels: the 132-wide variant with a cluster of 8
+    (1, 700, 0, 40),        # xyz only
+]
+
+
+@pytest.mark.parametrize("b,n,c,m", FFPS_CASES)
+def test_ffps_matrix_free_matches_matrix_route(pkg, oracle_ops, cuda, b, n, c, m):
+    rng = np.random.default_rng(n + c)
+    xyz = rng.uniform(-3, 3, (b, n, 3)).astype(np.float32)
+    feats = np.maximum(rng.standard_normal((b, n, c)), 0).astype(np.float32) if c else None   # post-ReLU like the model's
+    if c:
+        feats[:, n // 2] = feats[:, n // 3]; xyz[:, n // 2] = xyz[:, n // 3]                   # exact duplicates: ties
+    assert pkg.ffps_supported(n, c + 3)
+    tx, tf = T(xyz, cuda), (T(feats, cuda) if c else None)
+    got = pkg.farthest_point_sample_features(m, tx, tf)
+    cat = torch.cat([tx, tf], -1).contiguous() if c else tx
+    ref = pkg.farthest_point_sample_with_distance(m, pkg.calc_square_dist(cat))
+    assert torch.equal(got, ref)
+    if n <= 700:    # and against the CPU oracle's own two-step route
+        exp = oracle_ops.farthest_point_sample_with_distance(m, oracle_ops.calc_square_dist(N(cat)))
+        np.testing.assert_array_equal(N(got), exp)
+
+
+def test_ffps_quantised_features_ties(pkg, cuda):
+    """Heavily quantised features: many exactly equal distances, the tie-break must follow the matrix route."""
+    rng = np.random.default_rng(5)
+    xyz = (rng.integers(0, 4, (4, 2048, 3)) * 0.5).astype(np.float32)
+    feats = rng.integers(0, 3, (4, 2048, 13)).astype(np.float32)
+    tx, tf = T(xyz, cuda), T(feats, cuda)
+    got = pkg.farthest_point_sample_features(256, tx, tf)
+    ref = pkg.farthest_point_sample_with_distance(256, pkg.calc_square_dist(torch.cat([tx, tf], -1).contiguous()))
+    assert torch.equal(got, ref)
+
+
+def test_ffps_unsupported_shape_is_loud(pkg, cuda):
+    assert not pkg.ffps_supported(8192, 67) and not pkg.ffps_supported(1024, 200)
+    with pytest.raises(RuntimeError):
+        pkg.farthest_point_sample_features(16, torch.zeros((1, 8192, 3), device=cuda), torch.zeros((1, 8192, 64), device=cuda))
+
+
+# ---------------------------------------------------------------------------------------------------------
 # whole SA scale in one kernel (gather + concat + conv stack + max-pool + mask)
 # ---------------------------------------------------------------------------------------------------------
 FUSED_CASES = [  # b, n, c, m, nsample, mlp
@@ -406,6 +454,9 @@ FUSED_CASES = [  # b, n, c, m, nsample, mlp
     (3, 300, 29, 33, 16, [48, 32]),          # two layers, nsample 16, odd channel counts
     (2, 300, 5, 17, 8, [16]),                # one layer, nsample 8
     (1, 400, 8, 9, 128, [32, 32, 64]),       # nsample 128: group = whole tile
+    (2, 900, 45, 130, 16, [112, 80, 64]),    # K = 48 / 112 / 80: every tail-block width (128 / 128 / 32-byte rows)
+    (4, 2000, 64, 512, 32, [64, 64, 128]),   # layer-2 shape, several tiles per slot (3 slots per CTA)
+    (2, 2000, 64, 300, 64, [64, 96, 128]),   # 2 slots per CTA, last tile partial
 ]
 
 

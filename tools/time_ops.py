@@ -83,6 +83,9 @@ def main(out_path):
         except Exception as e:  # noqa: BLE001
             res["ffps_fused_L2_cl%d_ms" % cl] = "ERR " + str(e)
     pkg.lib().ssd3d_tune_set_fps_cluster(0)
+    res["ffps_direct_L2_ms"] = timeit(lambda: pkg.farthest_point_sample_features(512, f2[..., :3].contiguous(), f2[..., 3:].contiguous()))
+    x2c, p2c = f2[..., :3].contiguous(), f2[..., 3:].contiguous()
+    res["ffps_direct_L2_ms"] = timeit(lambda: pkg.farthest_point_sample_features(512, x2c, p2c))
     if have_ref:
         res["ref_fpsdist_L2_ms"] = timeit(lambda: ref_ops.farthest_point_sample_with_distance(512, d2, sync=False), 1, 3)
         res["ref_fps_generic_L2_ms"] = timeit(lambda: ref_ops.farthest_point_sample(512, f2, sync=False), 1, 3)
@@ -92,6 +95,8 @@ def main(out_path):
     d3 = pkg.calc_square_dist(f3)
     res["fpsdist_L3_ms"] = timeit(lambda: pkg.farthest_point_sample_with_distance(256, d3))
     res["ffps_fused_L3_ms"] = timeit(lambda: pkg.farthest_point_sample(256, f3))
+    x3c, p3c = f3[..., :3].contiguous(), f3[..., 3:].contiguous()
+    res["ffps_direct_L3_ms"] = timeit(lambda: pkg.farthest_point_sample_features(256, x3c, p3c))
 
     # ---- ball query layer 1: 3 dilated shells
     lows, highs, ks = [0.0, 0.2, 0.4], [0.2, 0.4, 0.8], [32, 32, 64]
