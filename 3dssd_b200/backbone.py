@@ -21,7 +21,7 @@ class SABackbone:
     """
 
     def __init__(self, arch=None, params=None, in_channels=_cfg.INPUT_CHANNELS - 3, device="cuda", ffps_mode="direct",
-                 seed=0, mlp_mode="tc", fuse_scale=True, head=None):
+                 seed=0, mlp_mode="tc", fuse_scale=True, head=None, gather_in_kernel=True):
         self.arch = _cfg.ARCH_3DSSD if arch is None else arch
         self.in_channels = in_channels
         self.device = torch.device(device)
@@ -30,6 +30,7 @@ class SABackbone:
         self.params = prepare(params, self.device).prepare_all()
         self.ffps_mode = ffps_mode
         self.mlp_mode = mlp_mode
+        self.gather_in_kernel = gather_in_kernel
         self.fuse_scale = fuse_scale
         self.head = head                      # optional head.DetectionHead: real detections instead of the stand-in block
         self._graph = None
@@ -50,7 +51,8 @@ class SABackbone:
                 r = L.pointnet_sa_module_msg(xyz_list[xyz_i[0]], feat_list[feat_i[0]], radius, nsample, mlps, False,
                                              None, bn, rng, method, npoint, former_idx, attn, scope, dilated, vote_ctr,
                                              agg, params=self.params, ffps_mode=self.ffps_mode, return_debug=True,
-                                             mlp_mode=self.mlp_mode, fuse_scale=self.fuse_scale)
+                                             mlp_mode=self.mlp_mode, fuse_scale=self.fuse_scale,
+                                             gather_in_kernel=self.gather_in_kernel)
                 xyz_list.append(r[0]); feat_list.append(r[1]); fps_list.append(r[2]); dbg.append(r[3])
             elif ltype == "Vote_Layer":
                 nx, nf, off = L.vote_layer(xyz_list[xyz_i[0]], feat_list[feat_i[0]], mlps, False, None, bn, scope,

@@ -141,9 +141,11 @@ ball_query_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2
                 // one vote per step in the common case (no candidate of this step is inside any query's largest ball)
                 if (!__any_sync(0xffffffffu, near_any && in)) continue;
                 const int k = base + local;
-                bool all_full = true;
 #pragma unroll
                 for (int q = 0; q < BQ_QW; q++) {
+                    // most slow steps concern ONE of the warp's queries: a single vote skips the others' shells
+                    const bool nearq = in && (DILATED ? (tt[q] < p.t_max) : !(tt[q] >= p.t_max));
+                    if (!__any_sync(0xffffffffu, nearq)) continue;
 #pragma unroll
                     for (int s = 0; s < NS; s++) {
                         const bool hit = in && (DILATED ? (tt[q] == 0.0f || (tt[q] >= p.t_lo[s] && tt[q] < p.t_hi[s]))
@@ -157,9 +159,13 @@ ball_query_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2
                             if (hit && pos < ns) row[pos] = k;
                             cnt[q][s] = min(ns, c0 + __popc(hs));
                         }
-                        all_full = all_full && (cnt[q][s] >= ns);
                     }
                 }
+                bool all_full = true;
+#pragma unroll
+                for (int q = 0; q < BQ_QW; q++)
+#pragma unroll
+                    for (int s = 0; s < NS; s++) all_full = all_full && (cnt[q][s] >= p.nsample[s]);
                 if (all_full) { warp_done = true; break; }
             }
         }

@@ -27,7 +27,9 @@ namespace ssd3d {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int TC_EPI_WARP0 = 4;           // warps 4..11 are the epilogue (warp%4 selects the TMEM lane quarter)
+constexpr int TC_PROD_WARP0 = 2;          // warps 2..5: A-operand producers of the gather mode (one tile row per thread)
+constexpr int TC_PROD_WARPS = 4;
+constexpr int TC_EPI_WARP0 = TC_PROD_WARP0 + TC_PROD_WARPS;   // warps 6..13: epilogue (warp%4 selects the TMEM lane quarter)
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARP0 + TC_EPI_WARPS) * 32;
 constexpr int TC_MAX_STAGES = 4;
@@ -117,11 +119,9 @@ __device__ __forceinline__ float ord2f(uint32_t u)
 }
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t &hw, uint32_t &lw)
 {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-    const float2 hf = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
-    hw = *reinterpret_cast<const uint32_t *>(&h);
-    lw = *reinterpret_cast<const uint32_t *>(&l);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hw) : "f"(x1), "f"(x0));       // {x1 : x0} like two adjacent bf16
+    const float h0 = __uint_as_float(hw << 16), h1 = __uint_as_float(hw & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lw) : "f"(x1 - h1), "f"(x0 - h0));
 }
 
 // Max-pool of one 32-column chunk over runs of POOL rows (tf.reduce_max(axis=2), layers_util.py:178) + mask (:180).
@@ -172,7 +172,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     // carve: [stages] x { A_hi | A_lo | B_hi | B_lo }, per-warp output blocks (4 KiB each), then scale/shift
     const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
     const uint32_t stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1 KiB alignment by pointer arithmetic on the __shared__ array (an integer round-trip would demote every access
+    // through these pointers to generic LD/ST with 64-bit address math)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int ncov = p.n_tiles * p.bn + 32;
     uint8_t *out_stage = smem + (size_t)p.stages * stage_bytes;          // [8 warps][4 KiB], 4 KiB aligned
     float *s_scale = reinterpret_cast<float *>(out_stage + (p.tma_store ? TC_EPI_WARPS * 4096 : 0));
@@ -188,7 +190,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
 
     if (threadIdx.x == 0) {
         // full barrier: the TMA thread's expect_tx arrival (+ one arrival per producer warp in gather mode)
-        for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&full_bar[s]), p.gather ? 3 : 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&full_bar[s]), p.gather ? 1 + TC_PROD_WARPS : 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
         for (int a = 0; a < 2; a++) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -265,68 +267,67 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                 __syncwarp();
             }
         }
-    } else if ((warp == 2 || warp == 3) && p.gather) {
-        // ===== A-operand producers (gather mode): 64 threads, two rows of the tile each.  A row's source features
-        // are one contiguous run (16-byte loads when c % 4 == 0); values are split into bf16 hi/lo and stored as
-        // 16-byte chunks in the K-major SWIZZLE_128B layout the UMMA descriptor expects.
-        const int pt = threadIdx.x - 64;
-        const uint32_t rps = (uint32_t)p.g_m * (uint32_t)p.g_ns;
-        const bool vec4 = (p.g_c % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.g_points) & 15u) == 0);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int mt = tile / p.n_tiles;
-            const float *src_f[2], *src_x[2], *ctr[2];
-            bool ok[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t row = (uint32_t)mt * TC_BM + (uint32_t)(pt + 64 * h);
-                ok[h] = (long)row < p.rows;
-                const uint32_t rr = ok[h] ? row : 0u;
+    } else if (warp >= TC_PROD_WARP0 && warp < TC_EPI_WARP0) {
+        // ===== A-operand producers (gather mode): 128 threads, one row of the tile each.  A row's source features are
+        // one contiguous run (16-byte loads when c % 4 == 0); all loads of a 64-wide k-block are issued before the
+        // values are split into bf16 hi/lo and stored as 16-byte chunks in the K-major SWIZZLE_128B layout the UMMA
+        // descriptor expects.
+        if (p.gather) {
+            const int r = threadIdx.x - TC_PROD_WARP0 * 32;
+            const uint32_t rps = (uint32_t)p.g_m * (uint32_t)p.g_ns;
+            const bool vec4 = (p.g_c % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.g_points) & 15u) == 0);
+            const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / p.n_tiles;
+                const uint32_t row = (uint32_t)mt * TC_BM + (uint32_t)r;
+                const bool ok = (long)row < p.rows;
+                const uint32_t rr = ok ? row : 0u;
                 const uint32_t scene = rr / rps, q = rr / (uint32_t)p.g_ns;
                 const int a = __ldg(p.g_idx + rr);
-                src_f[h] = p.g_points + ((size_t)scene * p.g_n + a) * p.g_c;
-                src_x[h] = p.g_xyz + ((size_t)scene * p.g_n + a) * 3;
-                ctr[h] = p.g_new_xyz + (size_t)q * 3;
-            }
-            for (int kb = 0; kb < nkb; kb++, it++) {
-                const int s = it % p.stages;
-                mbar_wait_cta(smem_u32(&empty_bar[s]), ((uint32_t)(it / p.stages) & 1u) ^ 1u);
-                uint8_t *abase = smem + (size_t)s * stage_bytes;
+                const float *src_f = p.g_points + ((size_t)scene * p.g_n + a) * p.g_c;
+                const float *src_x = p.g_xyz + ((size_t)scene * p.g_n + a) * 3;
+                const float *ctr = p.g_new_xyz + (size_t)q * 3;
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % p.stages;
+                    float f[8][8];
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int r = pt + 64 * h;
-                    uint8_t *rowp = abase + (r >> 3) * 1024 + (r & 7) * 128;
                     for (int c16 = 0; c16 < 8; c16++) {
                         const int k0 = kb * TC_BK + c16 * 8;
-                        if (k0 >= p.kp) break;
-                        float f[8];
-                        if (vec4 && ok[h] && k0 + 8 <= p.g_c) {
-                            const float4 u0 = __ldg(reinterpret_cast<const float4 *>(src_f[h] + k0));
-                            const float4 u1 = __ldg(reinterpret_cast<const float4 *>(src_f[h] + k0 + 4));
-                            f[0] = u0.x; f[1] = u0.y; f[2] = u0.z; f[3] = u0.w; f[4] = u1.x; f[5] = u1.y; f[6] = u1.z; f[7] = u1.w;
+                        if (vec4 && ok && k0 + 8 <= p.g_c) {
+                            const float4 u0 = __ldg(reinterpret_cast<const float4 *>(src_f + k0));
+                            const float4 u1 = __ldg(reinterpret_cast<const float4 *>(src_f + k0 + 4));
+                            f[c16][0] = u0.x; f[c16][1] = u0.y; f[c16][2] = u0.z; f[c16][3] = u0.w;
+                            f[c16][4] = u1.x; f[c16][5] = u1.y; f[c16][6] = u1.z; f[c16][7] = u1.w;
                         } else {
 #pragma unroll
                             for (int e = 0; e < 8; e++) {
                                 const int k = k0 + e;
                                 float val = 0.0f;
-                                if (ok[h]) {
-                                    if (k < p.g_c) val = __ldg(src_f[h] + k);
-                                    else if (k < p.g_c + 3) val = __ldg(src_x[h] + (k - p.g_c)) - __ldg(ctr[h] + (k - p.g_c));
+                                if (ok && k < p.kp) {
+                                    if (k < p.g_c) val = __ldg(src_f + k);
+                                    else if (k < p.g_c + 3) val = __ldg(src_x + (k - p.g_c)) - __ldg(ctr + (k - p.g_c));
                                 }
-                                f[e] = val;
+                                f[c16][e] = val;
                             }
                         }
+                    }
+                    mbar_wait_cta(smem_u32(&empty_bar[s]), ((uint32_t)(it / p.stages) & 1u) ^ 1u);   // loads already in flight
+                    uint8_t *rowp = smem + (size_t)s * stage_bytes + row_off;
+#pragma unroll
+                    for (int c16 = 0; c16 < 8; c16++) {
+                        if (kb * TC_BK + c16 * 8 >= p.kp) break;
                         uint32_t hw[4], lw[4];
 #pragma unroll
-                        for (int t = 0; t < 4; t++) split_pair(f[2 * t], f[2 * t + 1], hw[t], lw[t]);
+                        for (int t = 0; t < 4; t++) split_pair(f[c16][2 * t], f[c16][2 * t + 1], hw[t], lw[t]);
                         const uint32_t off = (uint32_t)((c16 ^ (r & 7)) << 4);
                         *reinterpret_cast<uint4 *>(rowp + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                         *reinterpret_cast<uint4 *>(rowp + TC_A_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     }
+                    fence_async_smem();                                   // generic-proxy stores -> visible to the tensor core
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
                 }
-                fence_async_smem();                                   // generic-proxy stores -> visible to the tensor core
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
             }
         }
     } else if (warp >= TC_EPI_WARP0) {

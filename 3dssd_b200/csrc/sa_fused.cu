@@ -89,30 +89,44 @@ __device__ __forceinline__ void sf_tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi); two values per call, packed {x1 : x0} like two adjacent bf16
 __device__ __forceinline__ void sf_split_pair(float x0, float x1, uint32_t &hw, uint32_t &lw)
 {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-    const float2 hf = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
-    hw = *reinterpret_cast<const uint32_t *>(&h);
-    lw = *reinterpret_cast<const uint32_t *>(&l);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hw) : "f"(x1), "f"(x0));
+    const float h0 = __uint_as_float(hw << 16), h1 = __uint_as_float(hw & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lw) : "f"(x1 - h1), "f"(x0 - h0));
 }
-// byte offset of the 16-byte chunk holding columns [8*c16g, 8*c16g+8) of row r inside an A buffer laid out as
-// k-blocks of { hi tile | lo tile } (128 rows x rb bytes each), each tile in the canonical K-major swizzled layout
-// of span rb: chunk j of row r sits at chunk j ^ ((r >> log2(128/rb)) & (rb/16 - 1)).  The first nfull blocks are
-// 64 wide (rb = 128), the tail block is rbt bytes wide.  *lo_off receives the distance from the hi to the lo tile.
-__device__ __forceinline__ uint32_t sf_a_chunk(int r, int c16g, int nfull, int rbt, uint32_t *lo_off)
-{
-    const int kb = c16g >> 3;
-    const bool tail = kb >= nfull;
-    const int rb = tail ? rbt : 128;
-    const int c16 = tail ? c16g - nfull * 8 : (c16g & 7);
-    const int nc = rb >> 4;                                  // chunks per row: 8 / 4 / 2
-    const int sh = rb == 128 ? 0 : (rb == 64 ? 1 : 2);
-    *lo_off = 128u * (uint32_t)rb;
-    return (uint32_t)(tail ? nfull : kb) * (2u * 128u * 128u) + (uint32_t)(r >> 3) * (uint32_t)(8 * rb) +
-           (uint32_t)(r & 7) * (uint32_t)rb + (uint32_t)((c16 ^ ((r >> sh) & (nc - 1))) << 4);
-}
+// Where row r of a 128-row operand tile lives.  An A buffer is laid out as k-blocks of { hi tile | lo tile }
+// (128 rows x rb bytes each), each tile in the canonical K-major swizzled layout of span rb: 16-byte chunk j of
+// row r sits at chunk j ^ ((r >> log2(128/rb)) & (rb/16 - 1)).  The first nfull blocks are 64 wide (rb = 128),
+// the tail block is rbt bytes wide.  Built once per (thread, layer); chunk() is then a handful of integer ops.
+struct SfRowMap {
+    uint32_t row_f, xor_f;            // full blocks: byte offset of the row inside a tile, swizzle mask
+    uint32_t base_t, row_t, xor_t;    // tail block: byte offset of the block, of the row, swizzle mask
+    uint32_t lo_t;                    // hi -> lo tile distance in the tail block (full blocks: 16 KiB)
+    int full8;                        // nfull * 8: first 16-byte chunk index of the tail block
+    __device__ __forceinline__ SfRowMap(int r, int nfull, int rbt)
+    {
+        row_f = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        xor_f = (uint32_t)(r & 7);
+        const int sh = rbt == 128 ? 0 : (rbt == 64 ? 1 : 2);
+        base_t = (uint32_t)nfull * (2u * 128u * 128u);
+        row_t = (uint32_t)(r >> 3) * (uint32_t)(8 * rbt) + (uint32_t)(r & 7) * (uint32_t)rbt;
+        xor_t = (uint32_t)((r >> sh) & ((rbt >> 4) - 1));
+        lo_t = 128u * (uint32_t)rbt;
+        full8 = nfull * 8;
+    }
+    // byte offset of the 16-byte chunk holding columns [8*c16g, 8*c16g+8); *lo_off = distance to the lo tile
+    __device__ __forceinline__ uint32_t chunk(int c16g, uint32_t *lo_off) const
+    {
+        if (c16g < full8) {
+            *lo_off = 128u * 128u;
+            return (uint32_t)(c16g >> 3) * (2u * 128u * 128u) + row_f + ((((uint32_t)c16g & 7u) ^ xor_f) << 4);
+        }
+        *lo_off = lo_t;
+        return base_t + row_t + (((uint32_t)(c16g - full8) ^ xor_t) << 4);
+    }
+};
 __device__ __forceinline__ void sf_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ uint32_t sf_f2ord(float x)
 {
@@ -154,11 +168,12 @@ __device__ __forceinline__ void sf_pool_store(const SfParams &p, float (&v)[32],
         const int col = col0 + (lane % GP) * KEEP + k;
         if (col >= nout) continue;
         const float mx = masked ? 0.0f : v[k];
-        if (p.out_f32) p.out_f32[(size_t)gg * p.ld_f32 + col] = mx;
+        if (p.out_f32) asm volatile("st.global.f32 [%0], %1;" ::"l"(p.out_f32 + (size_t)gg * p.ld_f32 + col), "f"(mx) : "memory");
         if (p.out_hi) {
             const __nv_bfloat16 hb = __float2bfloat16_rn(mx);
-            p.out_hi[(size_t)gg * p.ld_split + col] = hb;
-            p.out_lo[(size_t)gg * p.ld_split + col] = __float2bfloat16_rn(mx - __bfloat162float(hb));
+            const __nv_bfloat16 lb = __float2bfloat16_rn(mx - __bfloat162float(hb));
+            asm volatile("st.global.b16 [%0], %1;" ::"l"(p.out_hi + (size_t)gg * p.ld_split + col), "h"(__bfloat16_as_ushort(hb)) : "memory");
+            asm volatile("st.global.b16 [%0], %1;" ::"l"(p.out_lo + (size_t)gg * p.ld_split + col), "h"(__bfloat16_as_ushort(lb)) : "memory");
         }
     }
 }
@@ -169,8 +184,14 @@ template <int SLOTS, int WG>
 __global__ void __launch_bounds__(SF_THREADS * SLOTS * WG, SLOTS * WG == 1 ? 6 : 1)
 sa_fused_kernel(const SfParams p)
 {
+    // pointers inside the by-value parameter struct carry no address space: tell the compiler they are global
+    __builtin_assume(__isGlobal(p.xyz)); __builtin_assume(__isGlobal(p.new_xyz)); __builtin_assume(__isGlobal(p.idx));
+    __builtin_assume(p.points == nullptr || __isGlobal(p.points)); __builtin_assume(p.cnt == nullptr || __isGlobal(p.cnt));
+    __builtin_assume(__isGlobal(p.w_blob)); __builtin_assume(__isGlobal(p.ss_blob));
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1 KiB alignment by pointer arithmetic on the __shared__ array (an integer round-trip would demote every access
+    // through these pointers to generic LD/ST with 64-bit address math)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *wsm = smem + (size_t)SLOTS * p.abuf_bytes;  // weight images (1024-aligned: buffers are multiples of 1 KiB)
     float *ss = reinterpret_cast<float *>(wsm + p.w_total);
 
@@ -238,6 +259,7 @@ sa_fused_kernel(const SfParams p)
             const float *src_x = p.xyz + ((size_t)scene * p.n + a) * 3;
             const float *ctr = p.new_xyz + (size_t)qi * 3;
             const int nchunk = p.kp[0] >> 3;
+            const SfRowMap map0(r, p.nfull[0], p.rbt[0]);
             for (int cg0 = wg * U; cg0 < nchunk; cg0 += WG * U) {     // U chunks of 8 columns in flight per thread
                 float f[U][8];
 #pragma unroll
@@ -267,7 +289,7 @@ sa_fused_kernel(const SfParams p)
                     uint32_t hw[4], lw[4], lo_off;
 #pragma unroll
                     for (int t = 0; t < 4; t++) sf_split_pair(f[u][2 * t], f[u][2 * t + 1], hw[t], lw[t]);
-                    const uint32_t off = sf_a_chunk(r, cg0 + u, p.nfull[0], p.rbt[0], &lo_off);
+                    const uint32_t off = map0.chunk(cg0 + u, &lo_off);
                     *reinterpret_cast<uint4 *>(buf + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                     *reinterpret_cast<uint4 *>(buf + off + lo_off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 }
@@ -329,6 +351,7 @@ sa_fused_kernel(const SfParams p)
             const float *sc = ss + p.ss_off[l];
             const float *sh = sc + p.sspad[l];
             const bool last = l == p.nl - 1;
+            const SfRowMap mapn(r, last ? 0 : p.nfull[l + 1], last ? 32 : p.rbt[l + 1]);
             const int nchunks = (p.npad[l] + 31) / 32;
             for (int ci = wg; ci < nchunks; ci += WG) {
                 const int c0 = ci * 32;
@@ -351,7 +374,7 @@ sa_fused_kernel(const SfParams p)
                         uint32_t hw[4], lw[4], lo_off;
 #pragma unroll
                         for (int t = 0; t < 4; t++) sf_split_pair(v[j8 + 2 * t], v[j8 + 2 * t + 1], hw[t], lw[t]);
-                        const uint32_t off = sf_a_chunk(r, (c0 + j8) >> 3, p.nfull[l + 1], p.rbt[l + 1], &lo_off);
+                        const uint32_t off = mapn.chunk((c0 + j8) >> 3, &lo_off);
                         *reinterpret_cast<uint4 *>(buf + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                         *reinterpret_cast<uint4 *>(buf + off + lo_off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     }

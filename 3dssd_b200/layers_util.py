@@ -69,7 +69,7 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                            fps_sample_range_list, fps_method_list, npoint_list, former_fps_idx, use_attention, scope,
                            dilated_group, vote_ctr=None, aggregation_channel=None, debugging=False, epsilon=1e-5, *,
                            params, ffps_mode="direct", aggregation=None, return_debug=False, mlp_mode="tc",
-                           fuse_scale=True, gather_in_kernel=False):
+                           fuse_scale=True, gather_in_kernel=True):
     """PointNet++ SA module with multi-scale grouping; returns (new_xyz, new_points, fps_idx)."""
     if is_training:
         raise NotImplementedError("training-mode BatchNorm / backward ops are out of scope (inference only)")
