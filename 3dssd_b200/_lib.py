@@ -32,6 +32,9 @@ _SIGNATURES = {
     "ssd3d_rowgroup_max": [c_long, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "ssd3d_linear_tc": [c_long, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                         c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    "ssd3d_linear_tc_hoisted": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
+                                c_void_p, c_void_p, c_int, c_void_p],
     "ssd3d_linear_tc_gather": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                c_int, c_void_p],

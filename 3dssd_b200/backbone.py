@@ -21,7 +21,7 @@ class SABackbone:
     """
 
     def __init__(self, arch=None, params=None, in_channels=_cfg.INPUT_CHANNELS - 3, device="cuda", ffps_mode="direct",
-                 seed=0, mlp_mode="tc", fuse_scale=True, head=None, gather_in_kernel=True):
+                 seed=0, mlp_mode="tc", fuse_scale=True, head=None, gather_in_kernel=True, hoist_first=True):
         self.arch = _cfg.ARCH_3DSSD if arch is None else arch
         self.in_channels = in_channels
         self.device = torch.device(device)
@@ -31,6 +31,7 @@ class SABackbone:
         self.ffps_mode = ffps_mode
         self.mlp_mode = mlp_mode
         self.gather_in_kernel = gather_in_kernel
+        self.hoist_first = hoist_first
         self.fuse_scale = fuse_scale
         self.head = head                      # optional head.DetectionHead: real detections instead of the stand-in block
         self._graph = None
@@ -52,7 +53,7 @@ class SABackbone:
                                              None, bn, rng, method, npoint, former_idx, attn, scope, dilated, vote_ctr,
                                              agg, params=self.params, ffps_mode=self.ffps_mode, return_debug=True,
                                              mlp_mode=self.mlp_mode, fuse_scale=self.fuse_scale,
-                                             gather_in_kernel=self.gather_in_kernel)
+                                             gather_in_kernel=self.gather_in_kernel, hoist_first=self.hoist_first)
                 xyz_list.append(r[0]); feat_list.append(r[1]); fps_list.append(r[2]); dbg.append(r[3])
             elif ltype == "Vote_Layer":
                 nx, nf, off = L.vote_layer(xyz_list[xyz_i[0]], feat_list[feat_i[0]], mlps, False, None, bn, scope,

@@ -49,8 +49,12 @@ struct TcParams {
     int tma_store;   // non-pooled outputs leave through per-warp shared-memory blocks + TMA tensor stores
     // gather mode (first layer of an SA scale): the A operand is not read from memory but BUILT by two producer warps:
     // x[row] = concat(points[scene, idx[row], :], xyz[scene, idx[row], :] - new_xyz[scene, row/ns, :])  (layers_util.py:160-165)
-    int gather, g_n, g_c, g_m, g_ns;
-    const float *g_xyz, *g_points, *g_new_xyz;
+    // gather == 2 ("hoisted first layer"): the operand of THIS layer is the OUTPUT of the scale's first conv, rebuilt per
+    // grouped row from a per-point table instead of being computed per row:  with W1 = [Wf ; Wx] split by input rows,
+    //   relu((concat(f_j, x_j - c_i) . W1) * s + t) = relu(z[j] + (x_j - c_i) . (Wx * s)),   z = (f . Wf) * s + t  [per point]
+    // g_points = z (row pitch g_ldz, this scale's columns), g_c = first-layer width (= K of this layer), g_wx = Wx*s [3][g_c]
+    int gather, g_n, g_c, g_m, g_ns, g_ldz;
+    const float *g_xyz, *g_points, *g_new_xyz, *g_wx;
     const int *g_idx;
 };
 
@@ -179,6 +183,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     uint8_t *out_stage = smem + (size_t)p.stages * stage_bytes;          // [8 warps][4 KiB], 4 KiB aligned
     float *s_scale = reinterpret_cast<float *>(out_stage + (p.tma_store ? TC_EPI_WARPS * 4096 : 0));
     float *s_shift = s_scale + ncov;
+    float *s_wx = s_shift + ncov;                                        // [3][kp] (hoisted mode only)
 
     __shared__ unsigned long long full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
@@ -202,6 +207,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
         s_scale[i] = i < p.n ? __ldg(p.scale + i) : 0.0f;
         s_shift[i] = i < p.n ? __ldg(p.shift + i) : 0.0f;
     }
+    if (p.gather == 2)
+        for (int i = threadIdx.x; i < 3 * p.kp; i += TC_THREADS) {
+            const int a = i / p.kp, k = i - a * p.kp;
+            s_wx[i] = k < p.g_c ? __ldg(p.g_wx + a * p.g_c + k) : 0.0f;
+        }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -275,7 +285,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
         if (p.gather) {
             const int r = threadIdx.x - TC_PROD_WARP0 * 32;
             const uint32_t rps = (uint32_t)p.g_m * (uint32_t)p.g_ns;
-            const bool vec4 = (p.g_c % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.g_points) & 15u) == 0);
+            const bool hoisted = p.gather == 2;
+            const int src_pitch = hoisted ? p.g_ldz : p.g_c;
+            const bool vec4 = (p.g_c % 4 == 0) && (src_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.g_points) & 15u) == 0);
             const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -285,9 +297,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                 const uint32_t rr = ok ? row : 0u;
                 const uint32_t scene = rr / rps, q = rr / (uint32_t)p.g_ns;
                 const int a = __ldg(p.g_idx + rr);
-                const float *src_f = p.g_points + ((size_t)scene * p.g_n + a) * p.g_c;
+                const float *src_f = p.g_points + ((size_t)scene * p.g_n + a) * src_pitch;
                 const float *src_x = p.g_xyz + ((size_t)scene * p.g_n + a) * 3;
                 const float *ctr = p.g_new_xyz + (size_t)q * 3;
+                float dx = 0.0f, dy = 0.0f, dz = 0.0f;
+                if (hoisted && ok) {
+                    dx = __ldg(src_x) - __ldg(ctr); dy = __ldg(src_x + 1) - __ldg(ctr + 1); dz = __ldg(src_x + 2) - __ldg(ctr + 2);
+                }
                 for (int kb = 0; kb < nkb; kb++, it++) {
                     const int s = it % p.stages;
                     float f[8][8];
@@ -306,7 +322,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                                 float val = 0.0f;
                                 if (ok && k < p.kp) {
                                     if (k < p.g_c) val = __ldg(src_f + k);
-                                    else if (k < p.g_c + 3) val = __ldg(src_x + (k - p.g_c)) - __ldg(ctr + (k - p.g_c));
+                                    else if (!hoisted && k < p.g_c + 3) val = __ldg(src_x + (k - p.g_c)) - __ldg(ctr + (k - p.g_c));
                                 }
                                 f[c16][e] = val;
                             }
@@ -316,7 +332,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                     uint8_t *rowp = smem + (size_t)s * stage_bytes + row_off;
 #pragma unroll
                     for (int c16 = 0; c16 < 8; c16++) {
-                        if (kb * TC_BK + c16 * 8 >= p.kp) break;
+                        const int k0 = kb * TC_BK + c16 * 8;
+                        if (k0 >= p.kp) break;
+                        if (hoisted) {                                   // relu(z + d . Wx'); rows beyond the tensor stay 0
+#pragma unroll
+                            for (int e4 = 0; e4 < 8; e4 += 4) {
+                                const float4 w0 = *reinterpret_cast<const float4 *>(s_wx + k0 + e4);
+                                const float4 w1 = *reinterpret_cast<const float4 *>(s_wx + p.kp + k0 + e4);
+                                const float4 w2 = *reinterpret_cast<const float4 *>(s_wx + 2 * p.kp + k0 + e4);
+                                f[c16][e4 + 0] = fmaxf(fmaf(dz, w2.x, fmaf(dy, w1.x, fmaf(dx, w0.x, f[c16][e4 + 0]))), 0.0f);
+                                f[c16][e4 + 1] = fmaxf(fmaf(dz, w2.y, fmaf(dy, w1.y, fmaf(dx, w0.y, f[c16][e4 + 1]))), 0.0f);
+                                f[c16][e4 + 2] = fmaxf(fmaf(dz, w2.z, fmaf(dy, w1.z, fmaf(dx, w0.z, f[c16][e4 + 2]))), 0.0f);
+                                f[c16][e4 + 3] = fmaxf(fmaf(dz, w2.w, fmaf(dy, w1.w, fmaf(dx, w0.w, f[c16][e4 + 3]))), 0.0f);
+                            }
+                        }
                         uint32_t hw[4], lw[4];
 #pragma unroll
                         for (int t = 0; t < 4; t++) split_pair(f[c16][2 * t], f[c16][2 * t + 1], hw[t], lw[t]);
@@ -605,7 +634,7 @@ static int make_out_map(CUtensorMap *map, const void *ptr, long nrows, int ncols
 
 using namespace ssd3d;
 
-struct TcGather { int b, n, c, m, ns; const float *xyz, *points, *new_xyz; const int *idx; };
+struct TcGather { int b, n, c, m, ns; const float *xyz, *points, *new_xyz; const int *idx; int ldz; const float *wx; };
 
 static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const void *a_lo, const TcGather *g,
                             const void *b_hi, const void *b_lo, const float *scale, const float *shift, int relu, int pool,
@@ -629,8 +658,9 @@ static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const vo
     TcParams p = {};
     p.rows = rows; p.kp = kp; p.n = n;
     if (g) {
-        p.gather = 1; p.g_n = g->n; p.g_c = g->c; p.g_m = g->m; p.g_ns = g->ns;
+        p.gather = g->wx ? 2 : 1; p.g_n = g->n; p.g_c = g->c; p.g_m = g->m; p.g_ns = g->ns;
         p.g_xyz = g->xyz; p.g_points = g->points; p.g_new_xyz = g->new_xyz; p.g_idx = g->idx;
+        p.g_ldz = g->ldz; p.g_wx = g->wx;
     }
     const int n16 = (n + 15) / 16 * 16;
     // when split outputs are requested the tile must also cover (and zero) the padding columns n..ld_split-1
@@ -647,7 +677,8 @@ static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const vo
     p.m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
     const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)p.bn * TC_BK * 2;
     const size_t budget = 224 * 1024 - 1024;   // 227 KiB per CTA minus static barriers and the 1 KiB alignment slack
-    const size_t pool_bytes = 2 * ((size_t)p.n_tiles * p.bn + 32) * sizeof(float) + (tma_store ? TC_EPI_WARPS * 4096 : 0);
+    const size_t pool_bytes = 2 * ((size_t)p.n_tiles * p.bn + 32) * sizeof(float) + (tma_store ? TC_EPI_WARPS * 4096 : 0) +
+                              (g && g->wx ? (size_t)3 * kp * sizeof(float) : 0);
     SSD3D_REQUIRE((size_t)p.n_tiles * p.bn <= 4096, "linear_tc: n=%d too wide for the staged scale/shift", n);
     int stages = (int)((budget - pool_bytes) / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -700,8 +731,25 @@ extern "C" int ssd3d_linear_tc_gather(int b, int n, int c, int m, int nsample, c
 {
     SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0 && c >= 0 && nsample > 0, "linear_tc_gather: bad shape");
     SSD3D_REQUIRE(xyz && new_xyz && idx && (points || c == 0), "linear_tc_gather: null pointer");
-    TcGather g = {b, n, c, m, nsample, xyz, points, new_xyz, idx};
+    TcGather g = {b, n, c, m, nsample, xyz, points, new_xyz, idx, 0, nullptr};
     const int kp = (c + 3 + 15) / 16 * 16;
+    return linear_tc_launch((long)b * m * nsample, kp, nout, nullptr, nullptr, &g, b_hi, b_lo, scale, shift, relu, pool,
+                            rowmask, out_f32, ld_f32, out_hi, out_lo, ld_split, (cudaStream_t)stream);
+}
+
+// Second layer of an SA scale fed by the HOISTED first layer (see TcParams): z[b,n,ldz] holds (f . Wf) * s1 + t1 per
+// point (this scale's n1 columns start at z), wx = Wx * s1 as [3][n1]; the operand row of grouped element (i,j) is
+// relu(z[idx] + (xyz[idx] - new_xyz[i]) . wx), built by the producer warps.  K of this layer = n1 (kp = round16).
+extern "C" int ssd3d_linear_tc_hoisted(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
+                                       const float *wx, const float *new_xyz, const int *idx, int nout, const void *b_hi,
+                                       const void *b_lo, const float *scale, const float *shift, int relu, int pool,
+                                       const int *rowmask, float *out_f32, int ld_f32, void *out_hi, void *out_lo,
+                                       int ld_split, ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0 && n1 > 0 && nsample > 0 && ldz >= n1, "linear_tc_hoisted: bad shape");
+    SSD3D_REQUIRE(xyz && new_xyz && idx && z && wx, "linear_tc_hoisted: null pointer");
+    TcGather g = {b, n, n1, m, nsample, xyz, z, new_xyz, idx, ldz, wx};
+    const int kp = (n1 + 15) / 16 * 16;
     return linear_tc_launch((long)b * m * nsample, kp, nout, nullptr, nullptr, &g, b_hi, b_lo, scale, shift, relu, pool,
                             rowmask, out_f32, ld_f32, out_hi, out_lo, ld_split, (cudaStream_t)stream);
 }

@@ -69,7 +69,7 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                            fps_sample_range_list, fps_method_list, npoint_list, former_fps_idx, use_attention, scope,
                            dilated_group, vote_ctr=None, aggregation_channel=None, debugging=False, epsilon=1e-5, *,
                            params, ffps_mode="direct", aggregation=None, return_debug=False, mlp_mode="tc",
-                           fuse_scale=True, gather_in_kernel=True):
+                           fuse_scale=True, gather_in_kernel=True, hoist_first=True):
     """PointNet++ SA module with multi-scale grouping; returns (new_xyz, new_points, fps_idx)."""
     if is_training:
         raise NotImplementedError("training-mode BatchNorm / backward ops are out of scope (inference only)")
@@ -166,12 +166,24 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                 cat_hi = mk((bs, m_q, ldc), dtype=torch.bfloat16, device=xyz.device)
                 cat_lo = mk((bs, m_q, ldc), dtype=torch.bfloat16, device=xyz.device)
             off = 0
+            c_feat = points.shape[-1]
+            stacks = [pp.fused_stack(["%s/conv%d_%d" % (scope, i, j) for j in range(len(mlp_list[i]))], bn, c_feat + 3)
+                      if fuse_scale else None for i in range(nscale)]
+            # scales that run layer by layer: their first conv is hoisted out of the grouped domain -- its feature part
+            # becomes ONE per-point GEMM for all such scales (z), its xyz part is re-applied per grouped row inside the
+            # second conv's operand producer (ssd3d_linear_tc_hoisted)
+            hoist = [i for i in range(nscale) if stacks[i] is None and len(mlp_list[i]) >= 2] if (gather_in_kernel and hoist_first) else []
+            z = zoffs = wxs = None
+            if hoist:
+                zconv, wxs, n1s = pp.hoisted(["%s/conv%d_0" % (scope, i) for i in hoist], bn, c_feat)
+                p_hi, p_lo = tf_ops.split_rows(points)
+                z, _ = tf_ops.linear_tc(p_hi, p_lo, zconv, relu=False, want_f32=True, want_split=False)
+                zoffs = [sum(n1s[:t]) for t in range(len(hoist))]
             for i in range(nscale):
                 idx, cnt = idx_list[i], cnt_list[i]
                 debug["idx"].append(idx); debug["cnt"].append(cnt)
                 nl = len(mlp_list[i])
-                stack = pp.fused_stack(["%s/conv%d_%d" % (scope, i, j) for j in range(nl)], bn, points.shape[-1] + 3) \
-                    if fuse_scale else None
+                stack = stacks[i]
                 if stack is not None:                                              # whole scale in one kernel
                     tf_ops.sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=(concat, off),
                                         out_split=(cat_hi, cat_lo, off) if use_agg else None)
@@ -182,6 +194,16 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                     f = pp.conv("%s/conv%d_%d" % (scope, i, j), bn)
                     last_kw = dict(pool=nsample_list[i], rowmask=cnt, out_f32=(concat, off),
                                    out_split=(cat_hi, cat_lo, off) if use_agg else None)   # :167-180 conv+BN+ReLU+max+mask
+                    if i in hoist:
+                        if j == 0:
+                            continue                  # folded into z and into the next conv's operand producer
+                        if j == 1:
+                            t = hoist.index(i)
+                            if nl == 2:
+                                tf_ops.linear_tc_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, f, want_split=False, **last_kw)
+                            else:
+                                _, (hi, lo) = tf_ops.linear_tc_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, f)
+                            continue
                     if j == 0 and gather_in_kernel:   # :160-165 inside the kernel's operand load (no [B,M,K,C] tensor)
                         if nl == 1:
                             tf_ops.linear_tc_gather(xyz, points, new_xyz, idx, f, want_split=False, **last_kw)

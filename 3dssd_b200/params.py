@@ -220,6 +220,22 @@ class PreparedParams:
             self._cache[key] = FusedStack(convs, cin) if fits else None
         return self._cache[key]
 
+    def hoisted(self, scopes, bn, c):
+        """First convs of the scales of one SA layer (scopes), hoisted: returns (FoldedConv for the per-point table
+        z = (f . [Wf_1 | Wf_2 | ...]) * s + t over all scales, [Wx_i * s_i as (3, n1_i) per scale], [n1_i]).
+        c = feature channels (the convs take c + 3 inputs: features first, then xyz - centre)."""
+        key = ("hoisted",) + tuple(scopes) + (bool(bn), c)
+        if key not in self._cache:
+            convs = [self.conv(sc, bn) for sc in scopes]
+            for f in convs:
+                if f.cin != c + 3:
+                    raise ValueError("hoisted: conv expects %d inputs, got c + 3 = %d" % (f.cin, c + 3))
+            wf = torch.cat([f.w[:c] for f in convs], dim=1).contiguous()
+            zconv = FoldedConv(wf, torch.cat([f.scale for f in convs]).contiguous(), torch.cat([f.shift for f in convs]).contiguous())
+            wxs = [(f.w[c:c + 3].double() * f.scale.double().unsqueeze(0)).float().contiguous() for f in convs]
+            self._cache[key] = (zconv, wxs, [f.cout for f in convs])
+        return self._cache[key]
+
     def prepare_all(self):
         for k in self.raw:
             if k.endswith("/weights"):

@@ -500,6 +500,35 @@ def linear_tc_gather(xyz, points, new_xyz, idx, f, relu=True, pool=1, rowmask=No
     return y, sp
 
 
+def linear_tc_hoisted(xyz, z, zoff, wx, new_xyz, idx, f, relu=True, pool=1, rowmask=None, want_f32=False, want_split=True,
+                      out_f32=None, out_split=None):
+    """Second conv of an SA scale fed by the hoisted first conv (include/ssd3d.h, ssd3d_linear_tc_hoisted).
+    z: (b, n, ldz) fp32 per-point table = (features . Wf) * s1 + t1 for all scales of the layer, this scale's
+    columns start at zoff; wx: (3, n1) fp32 = Wx * s1; f: params.FoldedConv of the second conv (cin == n1)."""
+    xyz = _req(xyz, "xyz", torch.float32, 3, 3)
+    new_xyz = _req(new_xyz, "new_xyz", torch.float32, 3, 3)
+    idx = _req(idx, "idx", torch.int32, 3)
+    z = _req(z, "z", torch.float32, 3)
+    wx = _req(wx, "wx", torch.float32, 2)
+    b, n, _ = xyz.shape
+    n1 = wx.shape[1]
+    if z.shape[:2] != (b, n) or wx.shape[0] != 3 or zoff < 0 or zoff + n1 > z.shape[2]:
+        raise ValueError("z must be (b, n, ldz) with zoff + n1 <= ldz and wx (3, n1)")
+    if f.cin != n1:
+        raise ValueError("second conv expects %d inputs, the hoisted first conv has %d outputs" % (f.cin, n1))
+    _, m, ns = idx.shape
+    pool = int(pool)
+    if pool > 1 and (pool != ns or pool not in (8, 16, 32, 64, 128)):
+        raise ValueError("pool must equal nsample and be one of 8, 16, 32, 64, 128")
+    lead = (b, m) if pool > 1 else (b, m, ns)
+    y, pf, ldf, sp, ph, pl, lds = _tc_outputs(lead, f.cout, pool, xyz.device, want_f32, want_split, out_f32, out_split)
+    vp = ctypes.c_void_p
+    check(lib().ssd3d_linear_tc_hoisted(b, n, n1, m, ns, _p(xyz), vp(z.data_ptr() + 4 * zoff), z.shape[2], _p(wx), _p(new_xyz),
+                                        _p(idx), f.cout, _p(f.b_hi), _p(f.b_lo), _p(f.scale), _p(f.shift), 1 if relu else 0,
+                                        pool, _p(rowmask), vp(pf), ldf, vp(ph), vp(pl), lds, _stream()), "linear_tc_hoisted")
+    return y, sp
+
+
 def sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=None, out_split=None):
     """One SA scale in one kernel: gather + concat + conv stack + max-pool + mask (layers_util.py:157-180).
     stack: params.FusedStack.  out_f32=(buffer, col_offset) / out_split=(hi, lo, col_offset) as linear_tc;

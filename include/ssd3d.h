@@ -148,6 +148,18 @@ int ssd3d_linear_tc_gather(int b, int n, int c, int m, int nsample, const float 
                            const float *new_xyz, const int *idx, int nout, const void *b_hi, const void *b_lo,
                            const float *scale, const float *shift, int relu, int pool, const int *rowmask,
                            float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream);
+
+/* "Hoisted first layer": with the first conv of an SA scale split by input rows, W1 = [Wf ; Wx],
+ *   relu((concat(f_j, x_j - c_i) . W1) * s1 + t1) = relu(z[j] + (x_j - c_i) . (Wx * s1)),   z = (f . Wf) * s1 + t1,
+ * the feature part is one small per-POINT GEMM (ssd3d_linear_tc on the [b*n, c] features, no ReLU) instead of a
+ * per-grouped-row one, and this call runs the SECOND conv of the scale with its operand rebuilt on the fly from z
+ * (z[b,n,ldz], this scale's n1 columns start at the pointer; wx = Wx*s1 as [3][n1]).  Replaces conv #1 and #2 of
+ * layers_util.py:167-176 plus the grouping of :157-165; outputs as ssd3d_linear_tc. */
+int ssd3d_linear_tc_hoisted(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
+                            const float *wx, const float *new_xyz, const int *idx, int nout, const void *b_hi,
+                            const void *b_lo, const float *scale, const float *shift, int relu, int pool,
+                            const int *rowmask, float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split,
+                            ssd3d_stream_t stream);
 /* hi/lo[row, 0:kp] = split(x[row, 0:c]), zero padded (kp % 8 == 0). */
 int ssd3d_split_rows(long rows, int c, const float *x, int ldx, void *hi, void *lo, int kp, ssd3d_stream_t stream);
 /* ssd3d_group_concat fused with the split: hi/lo [b*m*nsample, kp] bf16. */

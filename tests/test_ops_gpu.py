@@ -592,3 +592,49 @@ def test_linear_tc_gather_equals_materialised_path(pkg, oracle_ops, cuda, b, n, 
         _, (h1, l1) = pkg.linear_tc_gather(t(xyz), t(feats), t(new_xyz), t(idx), f)
         assert torch.equal(h0, h1) and torch.equal(l0, l1)
         assert rel_err(N(h1.float() + l1.float())[..., :cout], exp) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------
+# hoisted first conv: per-point table + second conv with the operand rebuilt per grouped row
+# ---------------------------------------------------------------------------------------------------------
+HOIST_CASES = [  # b, n, c, m, nsample, mlp
+    (2, 600, 128, 70, 32, [128, 128, 256]),      # layer-3 shape, rows not a multiple of 128
+    (2, 400, 256, 40, 16, [256, 512, 1024]),     # layer-4 scale: second conv has two 256-wide n-tiles
+    (3, 300, 29, 33, 8, [48, 40]),               # two layers only (second conv pools), odd widths (n1 = 48 -> kp 48)
+    (1, 500, 64, 50, 64, [72, 96, 64]),          # n1 = 72: K padded to 80, z row pitch not a multiple of 16 bytes... (72*4 ok)
+]
+
+
+@pytest.mark.parametrize("b,n,c,m,k,mlp", HOIST_CASES)
+def test_hoisted_first_conv_matches_oracle_and_gather_path(pkg, oracle_ops, cuda, b, n, c, m, k, mlp):
+    rng = np.random.default_rng(n + c + k)
+    xyz = rng.uniform(0, 70, (b, n, 3)).astype(np.float32)          # KITTI-sized coordinates: the xyz part cancels
+    feats = np.maximum(rng.standard_normal((b, n, c)), 0).astype(np.float32)
+    new_xyz = np.array(xyz[:, :m], copy=True)
+    idx = rng.integers(0, n, (b, m, k)).astype(np.int32)
+    xyz[np.arange(b)[:, None, None], idx] = new_xyz[:, :, None, :] + rng.uniform(-2, 2, (b, m, k, 3)).astype(np.float32)
+    cnt = rng.integers(0, 3, (b, m)).astype(np.int32)
+    P = importlib.import_module("3dssd_b200.params")
+    prm, scopes, cin = {}, [], c + 3
+    for j, cout in enumerate(mlp):
+        P._conv_init(rng, prm, "s/conv0_%d" % j, cin, cout, True)
+        prm["s/conv0_%d/biases" % j] = rng.standard_normal(cout).astype(np.float32)
+        scopes.append("s/conv0_%d" % j)
+        cin = cout
+    pp = P.prepare(prm, cuda)
+    g = np.concatenate([oracle_ops.group_point(feats, idx), oracle_ops.group_point(xyz, idx) - new_xyz[:, :, None]], -1)
+    for sc in scopes:
+        bnp = tuple(prm[sc + "/bn/" + kk] for kk in ("gamma", "beta", "moving_mean", "moving_variance"))
+        g = oracle_ops.linear_bn_relu(g, prm[sc + "/weights"], prm[sc + "/biases"], bnp, True)
+    exp = g.max(axis=2) * (cnt > 0)[..., None]
+    tx, tf, tn, ti, tc = T(xyz, cuda), T(feats, cuda), T(new_xyz, cuda), T(idx, cuda), T(cnt, cuda)
+    zconv, wxs, n1s = pp.hoisted([scopes[0]], True, c)
+    p_hi, p_lo = pkg.split_rows(tf)
+    z, _ = pkg.linear_tc(p_hi, p_lo, zconv, relu=False, want_f32=True, want_split=False)
+    f1 = pp.conv(scopes[1], True)
+    if len(mlp) == 2:
+        y, _ = pkg.linear_tc_hoisted(tx, z, 0, wxs[0], tn, ti, f1, pool=k, rowmask=tc, want_f32=True, want_split=False)
+    else:
+        _, (hi, lo) = pkg.linear_tc_hoisted(tx, z, 0, wxs[0], tn, ti, f1)
+        y, _ = pkg.linear_tc(hi, lo, pp.conv(scopes[2], True), pool=k, rowmask=tc, want_f32=True, want_split=False)
+    assert y.shape == (b, m, mlp[-1]) and rel_err(N(y), exp) < 1e-4
