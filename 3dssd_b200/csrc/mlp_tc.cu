@@ -33,6 +33,7 @@ constexpr int TC_EPI_WARP0 = TC_PROD_WARP0 + TC_PROD_WARPS;   // warps 6..13: ep
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARP0 + TC_EPI_WARPS) * 32;
 constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_AKB = 4;            // A-stationary mode: k-blocks of an m-tile resident at once (K <= 256)
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;   // one A tile (hi or lo): 16 KiB
 
 struct TcParams {
@@ -53,6 +54,10 @@ struct TcParams {
     // grouped row from a per-point table instead of being computed per row:  with W1 = [Wf ; Wx] split by input rows,
     //   relu((concat(f_j, x_j - c_i) . W1) * s + t) = relu(z[j] + (x_j - c_i) . (Wx * s)),   z = (f . Wf) * s + t  [per point]
     // g_points = z (row pitch g_ldz, this scale's columns), g_c = first-layer width (= K of this layer), g_wx = Wx*s [3][g_c]
+    // astat ("A-stationary", gather modes): the produced A tile of an m-tile (all its k-blocks) stays in shared memory
+    // while the CTA sweeps that m-tile's n-tiles, so the producers build it once instead of once per n-tile; only the
+    // weights travel through the ring.  Tiles are then enumerated m-major per CTA.
+    int astat;
     int gather, g_n, g_c, g_m, g_ns, g_ldz;
     const float *g_xyz, *g_points, *g_new_xyz, *g_wx;
     const int *g_idx;
@@ -175,27 +180,43 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages] x { A_hi | A_lo | B_hi | B_lo }, per-warp output blocks (4 KiB each), then scale/shift
     const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
-    const uint32_t stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+    const int nkb = (p.kp + TC_BK - 1) / TC_BK;
+    const uint32_t a_region = p.astat ? (uint32_t)nkb * 2u * TC_A_BYTES : 0u;       // [nkb] x { A_hi | A_lo }
+    const uint32_t stage_bytes = (p.astat ? 0u : 2 * TC_A_BYTES) + 2 * b_bytes;     // ring stage
+    const uint32_t b_off = p.astat ? 0u : 2 * TC_A_BYTES;                           // B_hi inside a stage
     // 1 KiB alignment by pointer arithmetic on the __shared__ array (an integer round-trip would demote every access
     // through these pointers to generic LD/ST with 64-bit address math)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int ncov = p.n_tiles * p.bn + 32;
-    uint8_t *out_stage = smem + (size_t)p.stages * stage_bytes;          // [8 warps][4 KiB], 4 KiB aligned
+    uint8_t *ring = smem + a_region;
+    uint8_t *out_stage = ring + (size_t)p.stages * stage_bytes;          // [8 warps][4 KiB], 4 KiB aligned
     float *s_scale = reinterpret_cast<float *>(out_stage + (p.tma_store ? TC_EPI_WARPS * 4096 : 0));
     float *s_shift = s_scale + ncov;
     float *s_wx = s_shift + ncov;                                        // [3][kp] (hoisted mode only)
 
     __shared__ unsigned long long full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ unsigned long long afull_bar[TC_MAX_AKB], aempty_bar[TC_MAX_AKB];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float pool_xs[2 * 4 * 32];
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
-    const int total_tiles = p.m_tiles * p.n_tiles;
-    const int nkb = (p.kp + TC_BK - 1) / TC_BK;
+    // local tile i of this CTA -> (mt, nt): n-major round robin over all tiles, or (astat) every n-tile of an m-tile
+    auto tile_at = [&](int i, int &mt, int &nt) -> bool {
+        if (p.astat) {
+            mt = (int)blockIdx.x + (i / p.n_tiles) * (int)gridDim.x;
+            nt = i % p.n_tiles;
+            return mt < p.m_tiles;
+        }
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        mt = tile / p.n_tiles;
+        nt = tile - mt * p.n_tiles;
+        return tile < p.m_tiles * p.n_tiles;
+    };
 
     if (threadIdx.x == 0) {
         // full barrier: the TMA thread's expect_tx arrival (+ one arrival per producer warp in gather mode)
-        for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&full_bar[s]), p.gather ? 1 + TC_PROD_WARPS : 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&full_bar[s]), (p.gather && !p.astat) ? 1 + TC_PROD_WARPS : 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        for (int k = 0; k < TC_MAX_AKB; k++) { mbar_init(smem_u32(&afull_bar[k]), TC_PROD_WARPS); mbar_init(smem_u32(&aempty_bar[k]), 1); }
         for (int a = 0; a < 2; a++) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -224,22 +245,21 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_alo) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bhi) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+            int it = 0, mt, nt;
+            for (int i = 0; tile_at(i, mt, nt); i++) {
                 for (int kb = 0; kb < nkb; kb++, it++) {
                     const int s = it % p.stages;
                     const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                     mbar_wait_cta(smem_u32(&empty_bar[s]), ph ^ 1u);
-                    const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t base = smem_u32(ring + (size_t)s * stage_bytes);
                     const uint32_t fb = smem_u32(&full_bar[s]);
                     mbar_arrive_expect_tx(fb, p.gather ? 2 * b_bytes : stage_bytes);
                     if (!p.gather) {
                         tma_load_2d(base, &map_ahi, kb * TC_BK, mt * TC_BM, fb);
                         tma_load_2d(base + TC_A_BYTES, &map_alo, kb * TC_BK, mt * TC_BM, fb);
                     }
-                    tma_load_2d(base + 2 * TC_A_BYTES, &map_bhi, kb * TC_BK, nt * p.bn, fb);
-                    tma_load_2d(base + 2 * TC_A_BYTES + b_bytes, &map_blo, kb * TC_BK, nt * p.bn, fb);
+                    tma_load_2d(base + b_off, &map_bhi, kb * TC_BK, nt * p.bn, fb);
+                    tma_load_2d(base + b_off + b_bytes, &map_blo, kb * TC_BK, nt * p.bn, fb);
                 }
             }
         }
@@ -249,32 +269,37 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
         {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N = bn, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            int it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+            int it = 0, tcount = 0, mi = 0, mt, nt;
+            for (int i = 0; tile_at(i, mt, nt); i++, tcount++) {
                 const int acc = tcount & 1;
                 mbar_wait_cta(smem_u32(&tempty_bar[acc]), (((uint32_t)(tcount >> 1)) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
+                const bool last_nt = nt == p.n_tiles - 1;
                 for (int kb = 0; kb < nkb; kb++, it++) {
                     const int s = it % p.stages;
+                    if (p.astat && nt == 0) mbar_wait_cta(smem_u32(&afull_bar[kb]), (uint32_t)mi & 1u);   // this m-tile's A k-block
                     mbar_wait_cta(smem_u32(&full_bar[s]), (uint32_t)(it / p.stages) & 1u);
                     tc_fence_after();
-                    const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t base = smem_u32(ring + (size_t)s * stage_bytes);
+                    const uint32_t abase = p.astat ? smem_u32(smem) + (uint32_t)kb * 2u * TC_A_BYTES : base;
                     const int ksteps = min(TC_BK, p.kp - kb * TC_BK) / 16;
-                    const uint64_t a_hi = umma_desc(base), a_lo = umma_desc(base + TC_A_BYTES);
-                    const uint64_t b_hi = umma_desc(base + 2 * TC_A_BYTES), b_lo = umma_desc(base + 2 * TC_A_BYTES + b_bytes);
+                    const uint64_t a_hi = umma_desc(abase), a_lo = umma_desc(abase + TC_A_BYTES);
+                    const uint64_t b_hi = umma_desc(base + b_off), b_lo = umma_desc(base + b_off + b_bytes);
                     if (elect_one()) {
                         for (int ks = 0; ks < ksteps; ks++) {          // +2 per k-step: 32 bytes in the address field
                             umma_bf16(d_tmem, a_hi + 2 * ks, b_hi + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
                             umma_bf16(d_tmem, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
                             umma_bf16(d_tmem, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
                         }
-                        umma_commit(smem_u32(&empty_bar[s]));   // smem stage free once these MMAs retire
+                        umma_commit(smem_u32(&empty_bar[s]));   // ring stage free once these MMAs retire
+                        if (p.astat && last_nt) umma_commit(smem_u32(&aempty_bar[kb]));   // A k-block free for the next m-tile
                     }
                     __syncwarp();
                 }
                 if (elect_one()) umma_commit(smem_u32(&tfull_bar[acc]));   // accumulator ready for the epilogue
                 __syncwarp();
+                if (last_nt) mi++;
             }
         }
     } else if (warp >= TC_PROD_WARP0 && warp < TC_EPI_WARP0) {
@@ -289,9 +314,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
             const int src_pitch = hoisted ? p.g_ldz : p.g_c;
             const bool vec4 = (p.g_c % 4 == 0) && (src_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.g_points) & 15u) == 0);
             const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / p.n_tiles;
+            int it = 0, mi = 0, mt, nt;
+            for (int i = 0; tile_at(i, mt, nt); i++) {
+                if (p.astat && nt != 0) continue;                 // A-stationary: the tile built for nt == 0 serves every n-tile
                 const uint32_t row = (uint32_t)mt * TC_BM + (uint32_t)r;
                 const bool ok = (long)row < p.rows;
                 const uint32_t rr = ok ? row : 0u;
@@ -328,8 +353,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                             }
                         }
                     }
-                    mbar_wait_cta(smem_u32(&empty_bar[s]), ((uint32_t)(it / p.stages) & 1u) ^ 1u);   // loads already in flight
-                    uint8_t *rowp = smem + (size_t)s * stage_bytes + row_off;
+                    // (loads already in flight) wait for the slot: ring stage, or this k-block of the resident A tile
+                    if (p.astat) mbar_wait_cta(smem_u32(&aempty_bar[kb]), ((uint32_t)mi & 1u) ^ 1u);
+                    else mbar_wait_cta(smem_u32(&empty_bar[s]), ((uint32_t)(it / p.stages) & 1u) ^ 1u);
+                    uint8_t *rowp = (p.astat ? smem + (size_t)kb * 2 * TC_A_BYTES : ring + (size_t)s * stage_bytes) + row_off;
 #pragma unroll
                     for (int c16 = 0; c16 < 8; c16++) {
                         const int k0 = kb * TC_BK + c16 * 8;
@@ -355,8 +382,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                     }
                     fence_async_smem();                                   // generic-proxy stores -> visible to the tensor core
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
+                    if (lane == 0) mbar_arrive(smem_u32(p.astat ? &afull_bar[kb] : &full_bar[s]));
                 }
+                mi++;
             }
         }
     } else if (warp >= TC_EPI_WARP0) {
@@ -364,9 +392,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
         const int q = warp & 3;
         const int h = (warp - TC_EPI_WARP0) >> 2;
         const int nchunks = (p.bn + 31) / 32;
-        int tcount = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
-            const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        int tcount = 0, mt, nt;
+        for (int i = 0; tile_at(i, mt, nt); i++, tcount++) {
             const int acc = tcount & 1;
             mbar_wait_cta(smem_u32(&tfull_bar[acc]), ((uint32_t)(tcount >> 1)) & 1u);
             tc_fence_after();
@@ -671,16 +698,40 @@ static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const vo
     bool tma_store = pool <= 1 && (want_f32 != want_split);
     if (tma_store && want_f32) tma_store = (ld_f32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out_f32) & 15u) == 0);
     p.tma_store = tma_store ? 1 : 0;
-    const int bn_cap = tma_store ? 128 : 256;
-    p.bn = ncover < bn_cap ? ncover : bn_cap;
+    const size_t budget = 224 * 1024 - 1024;   // 227 KiB per CTA minus static barriers and the 1 KiB alignment slack
+    const int nkb = (kp + TC_BK - 1) / TC_BK;
+    auto misc_bytes = [&](int bn) {            // scale/shift (+ hoisted Wx) + per-warp store blocks
+        const int nt = (ncover + bn - 1) / bn;
+        return 2 * ((size_t)nt * bn + 32) * sizeof(float) + (tma_store ? TC_EPI_WARPS * 4096 : 0) +
+               (g && g->wx ? (size_t)3 * kp * sizeof(float) : 0);
+    };
+    // gather modes keep the produced A tile resident (A-stationary) when all its k-blocks fit next to a >= 2-stage
+    // weight ring: the producers then build it once per m-tile, not once per (m, n) tile
+    int bn = 0, stages = 0;
+    p.astat = 0;
+    if (g && nkb <= TC_MAX_AKB) {
+        const size_t a_region = (size_t)nkb * 2 * TC_A_BYTES;
+        for (int cand = tma_store ? 128 : 256; cand >= 64 && !bn; cand /= 2) {
+            const int b = ncover < cand ? ncover : cand;
+            const size_t need = a_region + misc_bytes(b);
+            if (need + 2 * (size_t)(2 * b * TC_BK * 2) <= budget) {
+                bn = b;
+                stages = (int)((budget - need) / (size_t)(2 * b * TC_BK * 2));
+                p.astat = 1;
+            }
+        }
+    }
+    if (!bn) {
+        const int bn_cap = tma_store ? 128 : 256;
+        bn = ncover < bn_cap ? ncover : bn_cap;
+        stages = (int)((budget - misc_bytes(bn)) / (2 * (size_t)TC_A_BYTES + 2 * (size_t)bn * TC_BK * 2));
+    }
+    p.bn = bn;
     p.n_tiles = (ncover + p.bn - 1) / p.bn;
     p.m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
-    const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + 2 * (size_t)p.bn * TC_BK * 2;
-    const size_t budget = 224 * 1024 - 1024;   // 227 KiB per CTA minus static barriers and the 1 KiB alignment slack
-    const size_t pool_bytes = 2 * ((size_t)p.n_tiles * p.bn + 32) * sizeof(float) + (tma_store ? TC_EPI_WARPS * 4096 : 0) +
-                              (g && g->wx ? (size_t)3 * kp * sizeof(float) : 0);
+    const size_t stage_bytes = (p.astat ? 0 : 2 * (size_t)TC_A_BYTES) + 2 * (size_t)p.bn * TC_BK * 2;
+    const size_t pool_bytes = misc_bytes(p.bn) + (p.astat ? (size_t)nkb * 2 * TC_A_BYTES : 0);
     SSD3D_REQUIRE((size_t)p.n_tiles * p.bn <= 4096, "linear_tc: n=%d too wide for the staged scale/shift", n);
-    int stages = (int)((budget - pool_bytes) / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     SSD3D_REQUIRE(stages >= 2, "linear_tc: tile does not fit shared memory");
     p.stages = stages;
@@ -707,7 +758,7 @@ static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const vo
     const size_t smem = stages * stage_bytes + pool_bytes + 1024;
     cudaError_t e = cudaFuncSetAttribute((const void *)linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e, "linear_tc attr");
-    const int total = p.m_tiles * p.n_tiles;
+    const int total = p.astat ? p.m_tiles : p.m_tiles * p.n_tiles;    // A-stationary CTAs own whole m-tiles
     const int grid = total < kNumSMs ? total : kNumSMs;
     linear_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mah, mal, mbh, mbl, moh, mol, mof, p);
     SSD3D_LAUNCH_CHECK("linear_tc_kernel");
