@@ -54,6 +54,8 @@ _SIGNATURES = {
     "ssd3d_tune_set_fps_variant": [c_int],
     "ssd3d_tune_set_fps_cluster_cap": [c_int],
     "ssd3d_tune_set_fused": [c_int, c_int],
+    "ssd3d_tune_set_mma_split": [c_int],
+    "ssd3d_tune_set_fused_mma_split": [c_int],
 }
 
 EXPORTS = sorted(list(_SIGNATURES) + ["ssd3d_last_error"])

@@ -220,6 +220,10 @@ void ssd3d_tune_set_fps_cluster_cap(int cluster_size);
 /* Fused SA kernel shape for stacks too big for several CTAs per SM: tiles in flight per CTA (2..3) and warpgroups
  * working on each tile (1, 2 or 4); 0 = automatic. */
 void ssd3d_tune_set_fused(int slots, int warpgroups);
+/* Tensor-core layer kernel: issue every tile-wide MMA as `nsplit` narrower MMAs into adjacent accumulator columns
+ * (independent dependency chains); 0 = automatic. */
+void ssd3d_tune_set_mma_split(int nsplit);
+void ssd3d_tune_set_fused_mma_split(int nsplit);   /* same for the fused SA kernel */
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,7 @@ def main():
     sel = [int(a) for a in sys.argv[1:] if "=" not in a] or range(len(CASES))
     kv = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
     pkg.lib().ssd3d_tune_set_fused(int(kv.get("slots", 0)), int(kv.get("wg", 0)))
+    pkg.lib().ssd3d_tune_set_fused_mma_split(int(kv.get("nsplit", 0)))
     rng = np.random.default_rng(0)
     B = 8
     pts = torch.from_numpy(synth.kitti_like(B, 16384, seed=1000)).to(dev)
