@@ -21,6 +21,9 @@ SHAPES = [  # rows, cin, cout, pool, mode
     (1048576, 16, 32, 32, "pool"),
     (524288, 67, 64, 1, "split"),        # L2
     (131072, 128, 128, 1, "f32"),
+    (131072, 128, 128, 1, "hoist"),      # 9: L3 scale 1 second conv fed by the hoisted first conv (n1 = cin)
+    (131072, 128, 256, 1, "hoist"),      # 10: L3 scale 3
+    (65536, 256, 512, 1, "hoist"),       # 11: L4 scale 2
 ]
 
 
@@ -36,14 +39,26 @@ def main():
         P._conv_init(rng, prm, "s", cin, cout, True)
         f = P.fold(prm, "s", True, dev)
         shape = (rows // pool, pool, cin) if pool > 1 else (rows, cin)
-        x = torch.randn(shape, device=dev)
-        hi, lo = pkg.split_rows(x)
         kw = dict(pool=pool) if pool > 1 else {}
         if mode == "split":
             kw.update(want_f32=False, want_split=True)
+        if mode == "hoist":
+            B, ns, npts = 8, 32, 1024
+            m = rows // (B * ns)
+            xyz = torch.rand((B, npts, 3), device=dev) * 40
+            new_xyz = xyz[:, :m].contiguous()
+            idx = torch.randint(0, npts, (B, m, ns), device=dev, dtype=torch.int32)
+            z = torch.randn((B, npts, cin), device=dev)
+            wx = torch.randn((3, cin), device=dev)
 
-        def run():
-            return pkg.linear_tc(hi, lo, f, **kw)
+            def run():
+                return pkg.linear_tc_hoisted(xyz, z, 0, wx, new_xyz, idx, f)
+        else:
+            x = torch.randn(shape, device=dev)
+            hi, lo = pkg.split_rows(x)
+
+            def run():
+                return pkg.linear_tc(hi, lo, f, **kw)
         for _ in range(3):
             run()
         torch.cuda.synchronize()
