@@ -10,7 +10,7 @@ from .layers_util import (pointnet_fp_module, pointnet_sa_module, pointnet_sa_mo
 from .tf_ops import (bev_nms, calc_square_dist, farthest_point_sample, farthest_point_sample_with_distance,  # noqa: F401
                      farthest_point_sample_features, ffps_supported,
                      furthest_point_sample, gather_point, gather_point_grad, group_point_grad, three_interpolate_grad, group_concat, group_concat_split, group_point, linear_bn_relu,
-                     linear_tc, linear_tc_gather, linear_tc_hoisted, sa_mlp_fused, split_rows,
+                     linear_tc, linear_tc_gather, linear_tc_hoisted, sa_mlp_fused, sa_mlp_fused_hoisted, split_rows,
                      query_ball_point, query_ball_point_dilated, query_ball_point_multi, three_interpolate,
                      three_nn)
 

@@ -34,6 +34,11 @@ struct SfParams {
     int tiles;
     const float *xyz, *points, *new_xyz;
     const int *idx, *cnt;
+    // hoisted first conv (see ssd3d_linear_tc_hoisted in include/ssd3d.h): `points` is the per-point table z (row pitch
+    // ldz, c = its width n1), the operand row is relu(z[idx] + (xyz[idx] - new_xyz) . wx) with wx = [3][c], and the
+    // stack starts at the scale's SECOND conv (K = c, no xyz columns appended)
+    int hoist, ldz;
+    const float *wx;
     int nl;
     int kp[SF_MAX_LAYERS];           // K of layer l padded to 16
     int npad[SF_MAX_LAYERS];         // N of layer l padded to 16
@@ -195,6 +200,7 @@ sa_fused_kernel(const SfParams p)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *wsm = smem + (size_t)SLOTS * p.abuf_bytes;  // weight images (1024-aligned: buffers are multiples of 1 KiB)
     float *ss = reinterpret_cast<float *>(wsm + p.w_total);
+    float *wxs = ss + p.ss_total;                        // [3][kp0] hoisted mode: Wx * s1, zero beyond c
 
     __shared__ unsigned long long w_bar, mma_bar[SLOTS];
     __shared__ uint32_t tmem_base_smem;
@@ -226,6 +232,11 @@ sa_fused_kernel(const SfParams p)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (uint32_t i = tid; i < p.ss_total; i += NT) ss[i] = __ldg(p.ss_blob + i);
+    if (p.hoist)
+        for (int i = tid; i < 3 * p.kp[0]; i += NT) {
+            const int a3 = i / p.kp[0], k = i - a3 * p.kp[0];
+            wxs[i] = k < p.c ? __ldg(p.wx + a3 * p.c + k) : 0.0f;
+        }
     sf_fence_before();
     __syncthreads();
     sf_fence_after();
@@ -238,8 +249,9 @@ sa_fused_kernel(const SfParams p)
     long long t_prev = clock64();
 #endif
     uint32_t mma_phase = 0;
-    const int k0 = p.c + 3;
-    const bool vec = (p.c & 3) == 0;                     // feature rows are 16-byte aligned: float4 gathers
+    const int k0 = p.hoist ? p.c : p.c + 3;              // valid operand columns
+    const int pitch = p.hoist ? p.ldz : p.c;
+    const bool vec = (p.c & 3) == 0 && (pitch & 3) == 0; // source rows are 16-byte aligned: float4 gathers
 
     const int tile0 = blockIdx.x * SLOTS + slot, tstep = gridDim.x * SLOTS;
     // neighbour index of this thread's row, fetched one tile ahead (rows < 2^31: checked by the launcher)
@@ -256,11 +268,15 @@ sa_fused_kernel(const SfParams p)
                 const long nrow = (long)(tile + tstep) * 128 + r;
                 a_next = (tile + tstep < p.tiles && nrow < p.rows) ? __ldg(p.idx + nrow) : 0;
             }
-            const float *src_f = p.points + ((size_t)scene * p.n + a) * p.c;
+            const float *src_f = p.points + ((size_t)scene * p.n + a) * pitch;
             const float *src_x = p.xyz + ((size_t)scene * p.n + a) * 3;
             const float *ctr = p.new_xyz + (size_t)qi * 3;
             const int nchunk = p.kp[0] >> 3;
             const SfRowMap map0(r, p.nfull[0], p.rbt[0]);
+            float dx = 0.0f, dy = 0.0f, dz = 0.0f;
+            if (p.hoist && ok) {
+                dx = __ldg(src_x) - __ldg(ctr); dy = __ldg(src_x + 1) - __ldg(ctr + 1); dz = __ldg(src_x + 2) - __ldg(ctr + 2);
+            }
             for (int cg0 = wg * U; cg0 < nchunk; cg0 += WG * U) {     // U chunks of 8 columns in flight per thread
                 float f[U][8];
 #pragma unroll
@@ -278,7 +294,7 @@ sa_fused_kernel(const SfParams p)
                             float val = 0.0f;
                             if (ok) {
                                 if (k < p.c) val = __ldg(src_f + k);
-                                else if (k < k0) val = __ldg(src_x + (k - p.c)) - __ldg(ctr + (k - p.c));
+                                else if (k < k0) val = __ldg(src_x + (k - p.c)) - __ldg(ctr + (k - p.c));   // never in hoisted mode
                             }
                             f[u][e] = val;
                         }
@@ -287,6 +303,19 @@ sa_fused_kernel(const SfParams p)
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     if (cg0 + u >= nchunk) break;
+                    if (p.hoist) {                                     // relu(z + d . Wx'); padded columns and rows stay 0
+                        const float *w = wxs + (cg0 + u) * 8;
+#pragma unroll
+                        for (int e4 = 0; e4 < 8; e4 += 4) {
+                            const float4 w0 = *reinterpret_cast<const float4 *>(w + e4);
+                            const float4 w1 = *reinterpret_cast<const float4 *>(w + p.kp[0] + e4);
+                            const float4 w2 = *reinterpret_cast<const float4 *>(w + 2 * p.kp[0] + e4);
+                            f[u][e4 + 0] = fmaxf(fmaf(dz, w2.x, fmaf(dy, w1.x, fmaf(dx, w0.x, f[u][e4 + 0]))), 0.0f);
+                            f[u][e4 + 1] = fmaxf(fmaf(dz, w2.y, fmaf(dy, w1.y, fmaf(dx, w0.y, f[u][e4 + 1]))), 0.0f);
+                            f[u][e4 + 2] = fmaxf(fmaf(dz, w2.z, fmaf(dy, w1.z, fmaf(dx, w0.z, f[u][e4 + 2]))), 0.0f);
+                            f[u][e4 + 3] = fmaxf(fmaf(dz, w2.w, fmaf(dy, w1.w, fmaf(dx, w0.w, f[u][e4 + 3]))), 0.0f);
+                        }
+                    }
                     uint32_t hw[4], lw[4], lo_off;
 #pragma unroll
                     for (int t = 0; t < 4; t++) sf_split_pair(f[u][2 * t], f[u][2 * t + 1], hw[t], lw[t]);
@@ -434,11 +463,12 @@ static size_t sf_wimg_bytes(int kp, int npad)              // one half (hi or lo
 }
 
 struct SfPlan { size_t abuf, w, ssf; int maxn; };
-static bool sf_plan(int c, int nl, const int *nout, SfPlan *pl)
+static bool sf_plan(int k_in, int nl, const int *nout, SfPlan *pl)      // k_in: columns of the first operand
 {
     if (nl < 1 || nl > SF_MAX_LAYERS) return false;
     pl->abuf = 0; pl->w = 0; pl->ssf = 0; pl->maxn = 32;
-    int kp = (c + 3 + 15) / 16 * 16;
+    int kp = (k_in + 15) / 16 * 16;
+    pl->ssf = 3 * (size_t)kp;                               // room for the hoisted mode's Wx table
     for (int l = 0; l < nl; l++) {
         const int npad = (nout[l] + 15) / 16 * 16;
         if (npad > 256) return false;
@@ -474,7 +504,7 @@ static int sf_slots(const SfPlan &pl)
 extern "C" size_t ssd3d_sa_fused_smem(int c, int nl, const int *nout)
 {
     SfPlan pl;
-    if (!sf_plan(c, nl, nout, &pl)) return 0;
+    if (!sf_plan(c + 3, nl, nout, &pl)) return 0;
     const size_t total = sf_total(pl, sf_slots(pl));
     return total <= SF_SMEM_MAX ? total : 0;
 }
@@ -493,21 +523,25 @@ static cudaError_t sf_launch(const SfParams &p, size_t smem, int per_sm, cudaStr
 
 // w_blob: per layer { hi image | lo image }, each image = k-blocks of [npad x (64 | tail)] bf16 in the canonical
 // K-major swizzled layout (built by params.FusedStack); ss_blob: per layer { scale[sspad] | shift[sspad] }.
-extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
-                                  const float *new_xyz, const int *idx, const int *pts_cnt, int nl, const int *nout,
-                                  const void *w_blob, const float *ss_blob, float *out_f32, int ld_f32, void *out_hi,
-                                  void *out_lo, int ld_split, ssd3d_stream_t stream)
+// wx != NULL selects the hoisted mode: `points` is the per-point table z (pitch ldz), c its width.
+static int sa_mlp_fused_impl(int b, int n, int c, int m, int nsample, const float *xyz, const float *points, int ldz,
+                             const float *wx, const float *new_xyz, const int *idx, const int *pts_cnt, int nl,
+                             const int *nout, const void *w_blob, const float *ss_blob, float *out_f32, int ld_f32,
+                             void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream)
 {
+    const bool hoist = wx != nullptr;
     SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0 && c >= 0, "sa_mlp_fused: bad shape");
     SSD3D_REQUIRE(nsample == 8 || nsample == 16 || nsample == 32 || nsample == 64 || nsample == 128,
                   "sa_mlp_fused: nsample=%d must be one of 8, 16, 32, 64, 128", nsample);
     SSD3D_REQUIRE(xyz && new_xyz && idx && w_blob && ss_blob && (points || c == 0), "sa_mlp_fused: null pointer");
+    SSD3D_REQUIRE(!hoist || (c > 0 && ldz >= c), "sa_mlp_fused_hoisted: bad table shape n1=%d ldz=%d", c, ldz);
     SSD3D_REQUIRE(out_f32 || (out_hi && out_lo), "sa_mlp_fused: no output requested");
     SSD3D_REQUIRE((reinterpret_cast<uintptr_t>(w_blob) & 15u) == 0, "sa_mlp_fused: weight blob must be 16-byte aligned");
-    SSD3D_REQUIRE(!points || (c & 3) || (reinterpret_cast<uintptr_t>(points) & 15u) == 0,
+    SSD3D_REQUIRE(!points || (c & 3) || (hoist && (ldz & 3)) || (reinterpret_cast<uintptr_t>(points) & 15u) == 0,
                   "sa_mlp_fused: points must be 16-byte aligned when c is a multiple of 4");
+    const int k_in = hoist ? c : c + 3;
     SfPlan pl;
-    const bool planned = sf_plan(c, nl, nout, &pl);
+    const bool planned = sf_plan(k_in, nl, nout, &pl);
     const int slots = planned ? sf_slots(pl) : 0;
     const size_t smem = planned ? sf_total(pl, slots) : 0;
     if (!planned || smem > SF_SMEM_MAX) { set_error("sa_mlp_fused: layer stack does not fit shared memory"); return SSD3D_ERR_UNSUPPORTED; }
@@ -518,8 +552,9 @@ extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const
     SSD3D_REQUIRE(p.rows < (1L << 31) - 128, "sa_mlp_fused: too many grouped rows (%ld)", p.rows);
     p.tiles = (int)((p.rows + 127) / 128);
     p.xyz = xyz; p.points = points; p.new_xyz = new_xyz; p.idx = idx; p.cnt = pts_cnt;
+    p.hoist = hoist ? 1 : 0; p.ldz = ldz; p.wx = wx;
     p.nl = nl;
-    int kprev = (c + 3 + 15) / 16 * 16;
+    int kprev = (k_in + 15) / 16 * 16;
     uint32_t woff = 0, ssoff = 0;
     for (int l = 0; l < nl; l++) {
         p.kp[l] = kprev;
@@ -579,4 +614,25 @@ extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const
     }
 #endif
     SSD3D_LAUNCH_CHECK("sa_fused_kernel");
+}
+
+extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
+                                  const float *new_xyz, const int *idx, const int *pts_cnt, int nl, const int *nout,
+                                  const void *w_blob, const float *ss_blob, float *out_f32, int ld_f32, void *out_hi,
+                                  void *out_lo, int ld_split, ssd3d_stream_t stream)
+{
+    return sa_mlp_fused_impl(b, n, c, m, nsample, xyz, points, c, nullptr, new_xyz, idx, pts_cnt, nl, nout, w_blob, ss_blob,
+                             out_f32, ld_f32, out_hi, out_lo, ld_split, stream);
+}
+
+// The fused SA scale with its first conv hoisted (see ssd3d_linear_tc_hoisted): z[b,n,ldz] per-point table (this scale's
+// n1 columns start at z), wx = Wx*s1 as [3][n1]; the stack (w_blob / ss_blob / nout) starts at the scale's SECOND conv.
+extern "C" int ssd3d_sa_mlp_fused_hoisted(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
+                                          const float *wx, const float *new_xyz, const int *idx, const int *pts_cnt, int nl,
+                                          const int *nout, const void *w_blob, const float *ss_blob, float *out_f32,
+                                          int ld_f32, void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(z && wx, "sa_mlp_fused_hoisted: null table pointer");
+    return sa_mlp_fused_impl(b, n, n1, m, nsample, xyz, z, ldz, wx, new_xyz, idx, pts_cnt, nl, nout, w_blob, ss_blob,
+                             out_f32, ld_f32, out_hi, out_lo, ld_split, stream);
 }

@@ -69,7 +69,7 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                            fps_sample_range_list, fps_method_list, npoint_list, former_fps_idx, use_attention, scope,
                            dilated_group, vote_ctr=None, aggregation_channel=None, debugging=False, epsilon=1e-5, *,
                            params, ffps_mode="direct", aggregation=None, return_debug=False, mlp_mode="tc",
-                           fuse_scale=True, gather_in_kernel=True, hoist_first=True):
+                           fuse_scale=True, gather_in_kernel=True, hoist_first=2):
     """PointNet++ SA module with multi-scale grouping; returns (new_xyz, new_points, fps_idx)."""
     if is_training:
         raise NotImplementedError("training-mode BatchNorm / backward ops are out of scope (inference only)")
@@ -169,24 +169,35 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
             c_feat = points.shape[-1]
             stacks = [pp.fused_stack(["%s/conv%d_%d" % (scope, i, j) for j in range(len(mlp_list[i]))], bn, c_feat + 3)
                       if fuse_scale else None for i in range(nscale)]
-            # scales that run layer by layer: their first conv is hoisted out of the grouped domain -- its feature part
-            # becomes ONE per-point GEMM for all such scales (z), its xyz part is re-applied per grouped row inside the
-            # second conv's operand producer (ssd3d_linear_tc_hoisted)
-            hoist = [i for i in range(nscale) if stacks[i] is None and len(mlp_list[i]) >= 2] if (gather_in_kernel and hoist_first) else []
+            # The first conv of every scale with >= 2 convs is hoisted out of the grouped domain: its feature part becomes
+            # ONE per-point GEMM for all scales of the layer (z), its xyz part is re-applied per grouped row while the
+            # operand of the second conv is built (in the fused kernel's gather, or in the producer warps of
+            # ssd3d_linear_tc_hoisted for the scales that run layer by layer).
+            hoist = [i for i in range(nscale) if len(mlp_list[i]) >= 2 and (int(hoist_first) >= 2 or stacks[i] is None)] \
+                if (gather_in_kernel and hoist_first) else []   # hoist_first: 0 off, 1 layer-by-layer scales only, 2 all
             z = zoffs = wxs = None
+            hstacks = {}
             if hoist:
                 zconv, wxs, n1s = pp.hoisted(["%s/conv%d_0" % (scope, i) for i in hoist], bn, c_feat)
                 p_hi, p_lo = tf_ops.split_rows(points)
                 z, _ = tf_ops.linear_tc(p_hi, p_lo, zconv, relu=False, want_f32=True, want_split=False)
                 zoffs = [sum(n1s[:t]) for t in range(len(hoist))]
+                for t, i in enumerate(hoist):
+                    if stacks[i] is not None:    # remaining convs of a fused scale
+                        hstacks[i] = pp.fused_stack(["%s/conv%d_%d" % (scope, i, j) for j in range(1, len(mlp_list[i]))], bn, n1s[t])
             for i in range(nscale):
                 idx, cnt = idx_list[i], cnt_list[i]
                 debug["idx"].append(idx); debug["cnt"].append(cnt)
                 nl = len(mlp_list[i])
                 stack = stacks[i]
                 if stack is not None:                                              # whole scale in one kernel
-                    tf_ops.sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=(concat, off),
-                                        out_split=(cat_hi, cat_lo, off) if use_agg else None)
+                    if hstacks.get(i) is not None:
+                        t = hoist.index(i)
+                        tf_ops.sa_mlp_fused_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, cnt, hstacks[i], out_f32=(concat, off),
+                                                    out_split=(cat_hi, cat_lo, off) if use_agg else None)
+                    else:
+                        tf_ops.sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=(concat, off),
+                                            out_split=(cat_hi, cat_lo, off) if use_agg else None)
                     off += mlp_list[i][-1]
                     continue
                 hi = lo = None

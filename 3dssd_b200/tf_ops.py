@@ -565,6 +565,42 @@ def sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=None, out_split=
     return y
 
 
+def sa_mlp_fused_hoisted(xyz, z, zoff, wx, new_xyz, idx, cnt, stack, out_f32=None, out_split=None):
+    """sa_mlp_fused with the scale's first conv hoisted into the per-point table z (see linear_tc_hoisted): `stack` is the
+    params.FusedStack of the REMAINING convs (its input width == wx.shape[1])."""
+    xyz = _req(xyz, "xyz", torch.float32, 3, 3)
+    new_xyz = _req(new_xyz, "new_xyz", torch.float32, 3, 3)
+    idx = _req(idx, "idx", torch.int32, 3)
+    z = _req(z, "z", torch.float32, 3)
+    wx = _req(wx, "wx", torch.float32, 2)
+    b, n, _ = xyz.shape
+    n1 = wx.shape[1]
+    if z.shape[:2] != (b, n) or wx.shape[0] != 3 or zoff < 0 or zoff + n1 > z.shape[2]:
+        raise ValueError("z must be (b, n, ldz) with zoff + n1 <= ldz and wx (3, n1)")
+    if n1 != stack.cin:
+        raise ValueError("hoisted width (%d) does not match the stack's input width (%d)" % (n1, stack.cin))
+    _, m, ns = idx.shape
+    n3 = stack.nout[-1]
+    y = None
+    pf, ldf = 0, 0
+    if out_f32 is not None:
+        buf, off = out_f32
+        ldf, pf, y = buf.shape[-1], buf.data_ptr() + 4 * off, buf
+    elif out_split is None:
+        y = torch.empty((b, m, n3), dtype=torch.float32, device=xyz.device)
+        pf, ldf = y.data_ptr(), n3
+    ph = pl = lds = 0
+    if out_split is not None:
+        hb, lb, off = out_split
+        lds, ph, pl = hb.shape[-1], hb.data_ptr() + 2 * off, lb.data_ptr() + 2 * off
+    nout = (ctypes.c_int * len(stack.nout))(*stack.nout)
+    vp = ctypes.c_void_p
+    check(lib().ssd3d_sa_mlp_fused_hoisted(b, n, n1, m, ns, _p(xyz), vp(z.data_ptr() + 4 * zoff), z.shape[2], _p(wx), _p(new_xyz),
+                                           _p(idx), _p(cnt), len(stack.nout), ctypes.cast(nout, vp), _p(stack.w_blob),
+                                           _p(stack.ss_blob), vp(pf), ldf, vp(ph), vp(pl), lds, _stream()), "sa_mlp_fused_hoisted")
+    return y
+
+
 def bev_nms(boxes, scores, iou_threshold, max_output, cls_id=0):
     """Greedy BEV NMS per scene (postprocessor.py:76-88): boxes (b,n,7) = (x,y,z,l,h,w,ry), scores (b,n) ->
     block (b,max_output,9) = (box7, score, class) zero padded, count (b,) int32."""

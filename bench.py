@@ -142,7 +142,7 @@ def main():
     ap.add_argument("--ffps-mode", default="direct", choices=["direct", "matrix", "fused"])
     ap.add_argument("--mlp-mode", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--gather-in-kernel", type=int, default=1, help="1: first conv of unfused SA scales gathers its operand itself")
-    ap.add_argument("--hoist-first", type=int, default=1, help="1: first conv of unfused SA scales evaluated per point (hoisted), not per grouped row")
+    ap.add_argument("--hoist-first", type=int, default=2, help="first conv of an SA scale evaluated per point (hoisted), not per grouped row: 0 off, 1 layer-by-layer scales, 2 all")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu captures)")
     ap.add_argument("--pipeline", type=int, default=8, help="steps in flight (independent CUDA graphs on separate streams)")
     ap.add_argument("--fps-cluster", type=int, default=0, help="tuning: force the FPS cluster size (0 = heuristic)")
@@ -185,7 +185,7 @@ def main():
     # detection head + decode + GPU BEV-NMS produce the per-scene detection block that is gathered / copied to the host
     head = pkg.DetectionHead(params=head_params, device=dev)
     net = pkg.SABackbone(arch, params, in_channels=1, device=dev, ffps_mode=args.ffps_mode, mlp_mode=args.mlp_mode, head=head,
-                         gather_in_kernel=bool(args.gather_in_kernel), hoist_first=bool(args.hoist_first))
+                         gather_in_kernel=bool(args.gather_in_kernel), hoist_first=args.hoist_first)
     pts = torch.from_numpy(pts_np).to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 

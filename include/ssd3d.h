@@ -160,6 +160,12 @@ int ssd3d_linear_tc_hoisted(int b, int n, int n1, int m, int nsample, const floa
                             const void *b_lo, const float *scale, const float *shift, int relu, int pool,
                             const int *rowmask, float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split,
                             ssd3d_stream_t stream);
+/* Same idea for a scale that fits the fused kernel (ssd3d_sa_mlp_fused): the stack passed here starts at the scale's
+ * SECOND conv, the first operand row is relu(z[idx] + (xyz[idx] - new_xyz) . wx), built during the gather. */
+int ssd3d_sa_mlp_fused_hoisted(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
+                               const float *wx, const float *new_xyz, const int *idx, const int *pts_cnt, int nl,
+                               const int *nout, const void *w_blob, const float *ss_blob, float *out_f32, int ld_f32,
+                               void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream);
 /* hi/lo[row, 0:kp] = split(x[row, 0:c]), zero padded (kp % 8 == 0). */
 int ssd3d_split_rows(long rows, int c, const float *x, int ldx, void *hi, void *lo, int kp, ssd3d_stream_t stream);
 /* ssd3d_group_concat fused with the split: hi/lo [b*m*nsample, kp] bf16. */

@@ -638,3 +638,41 @@ def test_hoisted_first_conv_matches_oracle_and_gather_path(pkg, oracle_ops, cuda
         _, (hi, lo) = pkg.linear_tc_hoisted(tx, z, 0, wxs[0], tn, ti, f1)
         y, _ = pkg.linear_tc(hi, lo, pp.conv(scopes[2], True), pool=k, rowmask=tc, want_f32=True, want_split=False)
     assert y.shape == (b, m, mlp[-1]) and rel_err(N(y), exp) < 1e-4
+
+
+@pytest.mark.parametrize("b,n,c,m,k,mlp", [
+    (2, 700, 1, 96, 32, [16, 16, 32]),       # layer-1 scale 1: one feature channel, n1 = 16
+    (2, 700, 1, 70, 64, [32, 32, 64]),       # layer-1 scale 3
+    (4, 2000, 64, 512, 32, [64, 64, 128]),   # layer-2 (3 slots per CTA)
+    (2, 2000, 64, 300, 64, [64, 96, 128]),   # layer-2 scale 3
+    (3, 300, 29, 33, 16, [48, 32]),          # two convs: the fused stack is a single conv
+])
+def test_sa_mlp_fused_hoisted_vs_oracle(pkg, oracle_ops, cuda, b, n, c, m, k, mlp):
+    rng = np.random.default_rng(n + c + k + 1)
+    xyz = rng.uniform(0, 70, (b, n, 3)).astype(np.float32)
+    feats = np.maximum(rng.standard_normal((b, n, c)), 0).astype(np.float32)
+    new_xyz = np.array(xyz[:, :m], copy=True)
+    idx = rng.integers(0, n, (b, m, k)).astype(np.int32)
+    cnt = rng.integers(0, 3, (b, m)).astype(np.int32)
+    P = importlib.import_module("3dssd_b200.params")
+    prm, scopes, cin = {}, [], c + 3
+    for j, cout in enumerate(mlp):
+        P._conv_init(rng, prm, "s/conv0_%d" % j, cin, cout, True)
+        prm["s/conv0_%d/biases" % j] = rng.standard_normal(cout).astype(np.float32)
+        scopes.append("s/conv0_%d" % j)
+        cin = cout
+    pp = P.prepare(prm, cuda)
+    g = np.concatenate([oracle_ops.group_point(feats, idx), oracle_ops.group_point(xyz, idx) - new_xyz[:, :, None]], -1)
+    for sc in scopes:
+        bnp = tuple(prm[sc + "/bn/" + kk] for kk in ("gamma", "beta", "moving_mean", "moving_variance"))
+        g = oracle_ops.linear_bn_relu(g, prm[sc + "/weights"], prm[sc + "/biases"], bnp, True)
+    exp = g.max(axis=2) * (cnt > 0)[..., None]
+    tx, tf, tn, ti, tc = T(xyz, cuda), T(feats, cuda), T(new_xyz, cuda), T(idx, cuda), T(cnt, cuda)
+    zconv, wxs, n1s = pp.hoisted([scopes[0]], True, c)
+    p_hi, p_lo = pkg.split_rows(tf)
+    z, _ = pkg.linear_tc(p_hi, p_lo, zconv, relu=False, want_f32=True, want_split=False)
+    stack = pp.fused_stack(scopes[1:], True, n1s[0], limit=0)
+    assert stack is not None
+    y = pkg.sa_mlp_fused_hoisted(tx, z, 0, wxs[0], tn, ti, tc, stack)
+    # absolute coordinates up to 70 m: |(x_j - c_i) . Wx| is compared on the scale of the layer's outputs
+    assert y.shape == (b, m, mlp[-1]) and rel_err(N(y), exp) < 1e-4
