@@ -725,7 +725,9 @@ static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const vo
     p.astat = 0;
     if (g && nkb <= TC_MAX_AKB) {
         const size_t a_region = (size_t)nkb * 2 * TC_A_BYTES;
-        for (int cand = tma_store ? 128 : 256; cand >= 64 && !bn; cand /= 2) {
+        const int cands[4] = {256, 128, 96, 64};            // widest tile first: a tcgen05.mma has a fixed cost per instruction
+        for (int ci = tma_store ? 1 : 0; ci < 4 && !bn; ci++) {
+            const int cand = cands[ci];
             const int b = ncover < cand ? ncover : cand;
             const size_t need = a_region + misc_bytes(b);
             if (need + 2 * (size_t)(2 * b * TC_BK * 2) <= budget) {
