@@ -116,16 +116,13 @@ ball_query_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2
 
         if (!warp_done) {
             const int nsteps = (npts + 31) >> 5;
-            for (int step = 0; step < nsteps; step++) {
-                const int local = step * 32 + lane;
-                const bool in = local < npts;                       // false only in the last, partial step of a scene
-                const int li = in ? local : 0;
+            // squared distances of one candidate (32 per step, one per lane) to the warp's 4 queries.  Packed fp32
+            // (FADD2 / FMUL2 / FFMA2, sm_100): two queries per instruction, each lane-half an independent IEEE operation
+            // -> same bits as the reference recipe t = dy*dy ; t = fma(dx,dx,t) ; t = fma(dz,dz,t)
+            auto dist4 = [&](int li, float (&tt)[BQ_QW]) -> bool {
                 const float cx = pts[li * 3], cy = pts[li * 3 + 1], cz = pts[li * 3 + 2];
-                float tt[BQ_QW];
-                bool near_any = false;
-                // packed fp32 (FADD2 / FMUL2 / FFMA2, sm_100): two queries per instruction, each lane-half an independent
-                // IEEE operation -> same bits as the reference recipe t = dy*dy ; t = fma(dx,dx,t) ; t = fma(dz,dz,t)
                 const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
+                bool near_any = false;
 #pragma unroll
                 for (int q = 0; q < BQ_QW; q += 2) {
                     const float2 dx = __fadd2_rn(make_float2(qx[q], qx[q + 1]), ncx);
@@ -138,35 +135,53 @@ ball_query_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2
                     near_any = near_any || (DILATED ? (t.x < p.t_max) : !(t.x >= p.t_max)) ||
                                (DILATED ? (t.y < p.t_max) : !(t.y >= p.t_max));
                 }
-                // one vote per step in the common case (no candidate of this step is inside any query's largest ball)
-                if (!__any_sync(0xffffffffu, near_any && in)) continue;
-                const int k = base + local;
+                return near_any;
+            };
+            for (int step2 = 0; step2 < nsteps; step2 += 2) {
+                // two steps (64 candidates) per vote: in the common case neither holds a candidate inside any query's
+                // largest ball and one __any_sync dismisses both
+                float tta[BQ_QW], ttb[BQ_QW];
+                const int la = step2 * 32 + lane, lb = la + 32;
+                const bool ina = la < npts, inb = lb < npts;             // false only at the ragged end of a scene
+                const bool neara = dist4(ina ? la : 0, tta) && ina;
+                const bool nearb = dist4(inb ? lb : 0, ttb) && inb;
+                if (!__any_sync(0xffffffffu, neara || nearb)) continue;
+                bool full2 = false;
 #pragma unroll
-                for (int q = 0; q < BQ_QW; q++) {
-                    // most slow steps concern ONE of the warp's queries: a single vote skips the others' shells
-                    const bool nearq = in && (DILATED ? (tt[q] < p.t_max) : !(tt[q] >= p.t_max));
-                    if (!__any_sync(0xffffffffu, nearq)) continue;
+                for (int half = 0; half < 2 && !full2; half++) {
+                    const float (&tt)[BQ_QW] = half ? ttb : tta;
+                    const bool in = half ? inb : ina;
+                    const int local = half ? lb : la;
+                    if (!__any_sync(0xffffffffu, half ? nearb : neara)) continue;
+                    const int k = base + local;
 #pragma unroll
-                    for (int s = 0; s < NS; s++) {
-                        const bool hit = in && (DILATED ? (tt[q] == 0.0f || (tt[q] >= p.t_lo[s] && tt[q] < p.t_hi[s]))
-                                                        : !(tt[q] >= p.t_hi[s]));
-                        const uint32_t hs = __ballot_sync(0xffffffffu, hit);
-                        const int c0 = cnt[q][s];
-                        const int ns = p.nsample[s];
-                        if (hs != 0u && c0 < ns) {
-                            int *row = my_stage + q * p.ktot + p.koff[s];
-                            const int pos = c0 + __popc(hs & ((1u << lane) - 1u));
-                            if (hit && pos < ns) row[pos] = k;
-                            cnt[q][s] = min(ns, c0 + __popc(hs));
+                    for (int q = 0; q < BQ_QW; q++) {
+                        // most slow steps concern ONE of the warp's queries: a single vote skips the others' shells
+                        const bool nearq = in && (DILATED ? (tt[q] < p.t_max) : !(tt[q] >= p.t_max));
+                        if (!__any_sync(0xffffffffu, nearq)) continue;
+#pragma unroll
+                        for (int s = 0; s < NS; s++) {
+                            const bool hit = in && (DILATED ? (tt[q] == 0.0f || (tt[q] >= p.t_lo[s] && tt[q] < p.t_hi[s]))
+                                                            : !(tt[q] >= p.t_hi[s]));
+                            const uint32_t hs = __ballot_sync(0xffffffffu, hit);
+                            const int c0 = cnt[q][s];
+                            const int ns = p.nsample[s];
+                            if (hs != 0u && c0 < ns) {
+                                int *row = my_stage + q * p.ktot + p.koff[s];
+                                const int pos = c0 + __popc(hs & ((1u << lane) - 1u));
+                                if (hit && pos < ns) row[pos] = k;
+                                cnt[q][s] = min(ns, c0 + __popc(hs));
+                            }
                         }
                     }
+                    bool all_full = true;
+#pragma unroll
+                    for (int q = 0; q < BQ_QW; q++)
+#pragma unroll
+                        for (int s = 0; s < NS; s++) all_full = all_full && (cnt[q][s] >= p.nsample[s]);
+                    if (all_full) { warp_done = true; full2 = true; }
                 }
-                bool all_full = true;
-#pragma unroll
-                for (int q = 0; q < BQ_QW; q++)
-#pragma unroll
-                    for (int s = 0; s < NS; s++) all_full = all_full && (cnt[q][s] >= p.nsample[s]);
-                if (all_full) { warp_done = true; break; }
+                if (full2) break;
             }
         }
         // everyone is done with this stage -> refill it; stop streaming when every warp is full
