@@ -132,6 +132,49 @@ def cpu_baseline(arch, params, pts_np, max_scenes=2):
                       % (sample.shape[0], pts_np.shape[0], dt)}
 
 
+def ncu_dram_bytes(name):
+    """dram read+write bytes per launch from a committed ncu export (profiles/<name>), or None."""
+    path = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(path):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, seen = 0.0, 0
+    for line in open(path):
+        parts = line.split()
+        if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and parts[2] in unit:
+            tot += float(parts[1]) * unit[parts[2]]
+            seen += 1
+    return tot if seen == 2 else None
+
+
+def tensor_roofline(torch, pkg, dev, peaks):
+    """Largest GEMM of the step (layer 4, scale 2, last conv: 65536 x 512 -> 1024, max-pooled over 32 neighbours) timed
+    alone: achieved = bf16 MMA flops actually issued (3 per logical MMA, hi/lo split) / time, against the measured
+    cuBLAS bf16 peak."""
+    P = pkg.params
+    rng = np.random.default_rng(1)
+    prm = {}
+    P._conv_init(rng, prm, "s", 512, 1024, True)
+    f = P.fold(prm, "s", True, dev)
+    x = torch.randn((2048, 32, 512), device=dev)
+    hi, lo = pkg.split_rows(x)
+    for _ in range(3):
+        pkg.linear_tc(hi, lo, f, pool=32)
+    torch.cuda.synchronize()
+    ev = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); pkg.linear_tc(hi, lo, f, pool=32); e1.record()
+        ev.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    peak = float(peaks.get("bf16_tflops", peaks.get("bf16_tfs", 1700.0))) if peaks else 1700.0
+    ach = 3 * 2.0 * 65536 * 512 * 1024 / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": ncu_dram_bytes("r01_ncu_tc_l4_pooled.txt"),
+            "kernel": "linear_tc_kernel (layer 4 scale 2 last conv, 65536x512x1024, pooled)", "kernel_ms": ms,
+            "note": "bf16 MMA flops issued = 3 per logical fp32-grade MMA (hi.hi + lo.hi + hi.lo); fp32-equivalent rate = achieved / 3"}
+
+
 # ----------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -339,12 +382,13 @@ def main():
             "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "kernel": "fps3_direct_kernel (D-FPS layer 1, 16384->4096, B=8, cluster of %d CTAs per scene)" % (min(8, args.fps_cluster_cap) if args.fps_cluster_cap else 8),
+                         "traffic": ncu_dram_bytes("r01_ncu_fps_l1.txt"), "kernel": "fps3_direct_kernel (D-FPS layer 1, 16384->4096, B=8, cluster of %d CTAs per scene)" % (min(8, args.fps_cluster_cap) if args.fps_cluster_cap else 8),
                          "kernel_ms": k_ms,
                          "note": "effective-stream bytes B*(M-1)*N*16 (what the reference streams per round, SURVEY 8d); "
                                  "the kernel keeps them on-chip, so frac can exceed 1 and DRAM traffic is ~2 MB; peak = "
                                  + ("MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)")},
         }
+        line["roofline_tensor"] = tensor_roofline(torch, pkg, dev, peaks)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(arch, params, pts_np, args.cpu_scenes)
         print(json.dumps(line))

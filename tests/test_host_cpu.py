@@ -125,3 +125,31 @@ def test_gather_detections_world2_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, "rank %d failed:\n%s" % (r, o)
         assert "ok" in o
+
+
+def test_first_conv_hoisting_algebra_matches_literal_conv():
+    """relu((concat(f_j, x_j - c_i) . W1 + b) folded with BN) == relu(z[j] + (x_j - c_i) . Wx') with the per-point table
+    z = (f . Wf) * s + t  -- the identity behind ssd3d_linear_tc_hoisted / ssd3d_sa_mlp_fused_hoisted, checked on the CPU
+    against the oracle's literal first conv with KITTI-sized coordinates."""
+    import importlib
+    from oracle import ops as oops
+    P = importlib.import_module("3dssd_b200.params")
+    rng = np.random.default_rng(3)
+    b, n, c, m, k, n1 = 2, 300, 29, 20, 16, 48
+    xyz = rng.uniform(0, 70, (b, n, 3)).astype(np.float32)
+    feats = np.maximum(rng.standard_normal((b, n, c)), 0).astype(np.float32)
+    new_xyz = np.array(xyz[:, :m], copy=True)
+    idx = rng.integers(0, n, (b, m, k)).astype(np.int32)
+    prm = {}
+    P._conv_init(rng, prm, "s/conv0_0", c + 3, n1, True)
+    prm["s/conv0_0/biases"] = rng.standard_normal(n1).astype(np.float32)
+    g = np.concatenate([oops.group_point(feats, idx), oops.group_point(xyz, idx) - new_xyz[:, :, None]], -1)
+    bnp = tuple(prm["s/conv0_0/bn/" + kk] for kk in ("gamma", "beta", "moving_mean", "moving_variance"))
+    exp = oops.linear_bn_relu(g, prm["s/conv0_0/weights"], prm["s/conv0_0/biases"], bnp, True)
+    zconv, wxs, n1s = P.prepare(prm, "cpu").hoisted(["s/conv0_0"], True, c)
+    assert n1s == [n1] and tuple(wxs[0].shape) == (3, n1)
+    z = (feats.reshape(-1, c).astype(np.float64) @ zconv.w.numpy().astype(np.float64)) * zconv.scale.numpy() + zconv.shift.numpy()
+    z = z.reshape(b, n, n1).astype(np.float32)
+    d = oops.group_point(xyz, idx) - new_xyz[:, :, None]                                  # exact fp32 subtraction first
+    got = np.maximum(oops.group_point(z, idx) + d @ wxs[0].numpy(), 0)
+    assert np.abs(got - exp).max() <= 1e-4 * np.abs(exp).max()
