@@ -67,6 +67,20 @@ def test_backbone_small_vs_oracle(pkg, oracle_ops, cuda, ffps_mode, mlp_mode, fu
     assert out[1][-1].shape == (2, 32, 512)
 
 
+@pytest.mark.parametrize("gather,hoist", [(False, 0), (True, 0), (True, 1), (True, 2)])
+def test_backbone_mlp_route_variants_vs_oracle(pkg, oracle_ops, cuda, gather, hoist):
+    """Every route of the grouped MLP (materialised operand, operand built in the kernel, first conv hoisted for the
+    layer-by-layer scales only / for all scales) reproduces the oracle's literal conv stack."""
+    from oracle import layers as olayers
+    arch = scaled_arch(pkg, 8)
+    params = pkg.params.init_params(arch, 1, seed=6, random_bias=True)
+    pts = compact_scene(2, 2048, seed=41)
+    net = pkg.SABackbone(arch, params, in_channels=1, device=cuda, gather_in_kernel=gather, hoist_first=hoist)
+    out = net.forward(torch.from_numpy(pts).to(cuda), return_debug=True)
+    exp = olayers.backbone_forward(arch, pts, params, return_debug=True)
+    check_backbone(pkg, out, exp, len(arch))
+
+
 def test_single_sa_layer_plain_query_vs_oracle(pkg, oracle_ops, cuda):
     """BASELINE configs[0]: one SA layer N=4096 -> 1024, plain ball query r=0.4, K=32, C=64, MLP [64,64,128]."""
     from oracle import layers as olayers
