@@ -150,6 +150,36 @@ def calc_square_dist(a):
     return out
 
 
+def farthest_point_sample_features(npoint, xyz, points=None):
+    """Row-by-row restatement of the product's matrix-free F-FPS (include/ssd3d.h,
+    ssd3d_farthest_point_sample_features): the value used for point k in the round after `old` was picked is the
+    matrix entry (sq[old] + sq[k]) - 2*dot(old, k) of calc_square_dist, evaluated on the fly -- so the result must equal
+    farthest_point_sample_with_distance(npoint, calc_square_dist(concat[xyz, points])) index for index
+    (lib/utils/layers_util.py:94-96 of the reference).  Pure numpy/python, small inputs only."""
+    f = np.ascontiguousarray(xyz if points is None else np.concatenate([xyz, points], -1), dtype=np.float32)
+    b, n, c = f.shape
+    out = np.zeros((b, npoint), np.int32)
+    key = (np.arange(n) % 1024).astype(np.int64) * (1 << 21) + np.arange(n) // 1024     # tie-break of the reference scan
+    for s in range(b):
+        fs = f[s]
+        sq = np.zeros(n, np.float32)
+        for l in range(c):                                   # sequential fp32 fma chain; products of fp32 are exact in f64
+            sq = (sq.astype(np.float64) + fs[:, l].astype(np.float64) * fs[:, l].astype(np.float64)).astype(np.float32)
+        td = np.full(n, 1e38, np.float32)
+        old = 0
+        for j in range(1, npoint):
+            dot = np.zeros(n, np.float32)
+            for l in range(c):
+                dot = (dot.astype(np.float64) + np.float64(fs[old, l]) * fs[:, l].astype(np.float64)).astype(np.float32)
+            d = (np.float32(sq[old]) + sq) - np.float32(2.0) * dot
+            td = np.minimum(d, td)
+            best = td.max()
+            cand = np.flatnonzero(td == best)
+            old = int(cand[np.argmin(key[cand])])
+            out[s, j] = old
+    return out
+
+
 def linear_bn_relu(x, w, bias=None, bn=None, relu=True):
     """conv(1x1)+BN+ReLU over the last axis; bn = (gamma, beta, moving_mean, moving_var) or None."""
     x, px = _f(x)

@@ -235,3 +235,19 @@ def test_oracle_bev_nms_hand_case():
     np.testing.assert_array_equal(blk[0, 0, :7], b[0, 0])
     np.testing.assert_array_equal(blk[0, 1, :7], b[0, 2])
     assert (blk[0, 2:] == 0).all()
+
+
+def test_matrix_free_ffps_restatement_equals_matrix_route(oracle_ops):
+    """The on-the-fly evaluation the CUDA kernel performs (oracle.ops.farthest_point_sample_features, numpy) picks the same
+    indices as the reference's two-op route on the CPU oracle: calc_square_dist + farthest_point_sample_with_distance."""
+    rng = np.random.default_rng(8)
+    xyz = rng.uniform(-3, 3, (2, 90, 3)).astype(np.float32)
+    feats = np.maximum(rng.standard_normal((2, 90, 13)), 0).astype(np.float32)
+    feats[:, 40] = feats[:, 7]; xyz[:, 40] = xyz[:, 7]                     # an exact duplicate: ties
+    cat = np.concatenate([xyz, feats], -1)
+    exp = oracle_ops.farthest_point_sample_with_distance(30, oracle_ops.calc_square_dist(cat))
+    got = oracle_ops.farthest_point_sample_features(30, xyz, feats)
+    np.testing.assert_array_equal(got, exp)
+    q = (rng.integers(0, 3, (1, 70, 5)) * 0.5).astype(np.float32)        # quantised: many equal distances
+    np.testing.assert_array_equal(oracle_ops.farthest_point_sample_features(25, q),
+                                  oracle_ops.farthest_point_sample_with_distance(25, oracle_ops.calc_square_dist(q)))
