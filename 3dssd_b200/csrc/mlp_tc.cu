@@ -12,11 +12,15 @@
 // split (two bf16 matrices, row-major == K-major), so every operand tile is a plain TMA box in the 128B-swizzled
 // canonical UMMA layout and no conversion happens on the load path.
 //
-// Kernel shape: 384 threads; warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warp 2 = TMEM
-// allocator, warps 4-11 = epilogue (TMEM -> registers -> scale/shift/ReLU -> fp32 / split-bf16 / pooled store;
-// two warps per TMEM lane quarter share the 32-column chunks; max-pool = redux.sync across the lanes of a group).
+// Kernel shape: 448 threads; warp 0 = TMA producer, warp 1 = MMA issuer (whole warp runs the loop, one elect.sync lane
+// issues), warps 2-5 = operand producers of the gather modes (warp 2 also allocates TMEM), warps 6-13 = epilogue
+// (TMEM -> registers -> scale/shift/ReLU -> fp32 / split-bf16 through TMA tensor stores, or max-pool as a shuffle
+// reduce-and-transpose butterfly; two warps per TMEM lane quarter share the 32-column chunks).
 // Tile 128 rows x BN<=256 columns, K streamed in 64-element blocks through a multi-stage mbarrier ring;
 // two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
+// Gather modes (TcParams::gather): the operand tile is not read from memory but built in shared memory by the
+// producer warps from neighbour indices (1: concat(features, xyz - centre); 2: the hoisted first conv) and kept
+// resident across the n-tiles of its m-tile (TcParams::astat).
 #include <cuda.h>
 #include <cuda_bf16.h>
 

@@ -7,13 +7,17 @@
 // global memory; activations go TMEM -> registers -> shared memory (already split in bf16 hi/lo and already in the
 // 128B-swizzled K-major layout the next layer's UMMA descriptor expects).
 //
-// Per CTA: S "slots" of 128 threads (thread t of a slot <-> row t of a 128-row tile = 128/K neighbour groups):
+// Per CTA: S "slots" of 128*WG threads (a slot works on one 128-row tile = 128/K neighbour groups; its WG warpgroups
+// split the 16-byte chunks of the gather and the 32-column chunks of every epilogue):
 //   weights of all layers (hi+lo images, pre-swizzled on the host) are bulk-copied to shared memory once and shared
 //   by the slots; each slot owns ONE operand buffer, one TMEM accumulator and one mbarrier and loops over tiles:
 //   gather+split -> [fence.proxy.async] -> layer-0 MMAs (one thread) -> epilogue (tcgen05.ld, scale/shift/ReLU,
 //   split) written IN PLACE over the operand the finished MMAs no longer need -> ... -> last layer: max-pool.
 // Small stacks (layer1: ~30 KiB) run S=1 with up to 6 CTAs per SM; stacks whose weights fill most of shared memory
 // (layer2: 68-92 KiB) run one CTA per SM with S=2..3 slots, so gather / MMA / epilogue phases still overlap.
+// Hoisted mode (SfParams::hoist): the scale's first conv has been moved to a per-point table z (include/ssd3d.h,
+// ssd3d_sa_mlp_fused_hoisted); the gather then builds relu(z[idx] + (xyz[idx] - centre) . Wx') and the stack starts at
+// the second conv.
 //
 // Precision: same bf16 hi/lo split and 3-MMA scheme as mlp_tc.cu.
 #include <cuda_bf16.h>
