@@ -153,3 +153,35 @@ def test_first_conv_hoisting_algebra_matches_literal_conv():
     d = oops.group_point(xyz, idx) - new_xyz[:, :, None]                                  # exact fp32 subtraction first
     got = np.maximum(oops.group_point(z, idx) + d @ wxs[0].numpy(), 0)
     assert np.abs(got - exp).max() <= 1e-4 * np.abs(exp).max()
+
+
+def test_c_abi_argument_validation_needs_no_gpu(pkg):
+    """The attribute / shape checks of the reference's OpKernel::Compute (OP_REQUIRES -> InvalidArgument,
+    tf_sampling.cpp:136-142, tf_grouping.cpp:275-288) live in the C ABI in front of any CUDA call: they answer with
+    SSD3D_ERR_INVALID_ARGUMENT (-1) or SSD3D_ERR_UNSUPPORTED (-2) and a message, also on a machine without a GPU."""
+    import ctypes
+    L = pkg.lib()
+    null = ctypes.c_void_p(None)
+    one = ctypes.c_void_p(16)                                  # a non-null, never dereferenced address
+
+    def err():
+        return L.ssd3d_last_error().decode()
+
+    assert L.ssd3d_farthest_point_sample(1, 0, 3, 4, one, null, one, null) == -1 and "bad shape" in err()
+    assert L.ssd3d_farthest_point_sample(1, 8, 3, 4, null, null, one, null) == -1 and "null" in err()
+    assert L.ssd3d_farthest_point_sample_features(1, 100, 3, 0, 4, null, null, one, null) == -1
+    assert L.ssd3d_farthest_point_sample_features(1, 8192, 3, 64, 16, one, one, one, null) == -2 and "not covered" in err()
+    assert L.ssd3d_ffps_supported(4096, 67) == 1 and L.ssd3d_ffps_supported(8192, 67) == 0 and L.ssd3d_ffps_supported(512, 131) == 1
+    r = (ctypes.c_float * 1)(-1.0)
+    k = (ctypes.c_int * 1)(16)
+    ptrs = (ctypes.c_void_p * 1)(16)
+    assert L.ssd3d_query_ball_point_multi(1, 8, 4, 1, 0, ctypes.cast(r, ctypes.c_void_p), ctypes.cast(r, ctypes.c_void_p),
+                                          ctypes.cast(k, ctypes.c_void_p), one, one, ctypes.cast(ptrs, ctypes.c_void_p),
+                                          ctypes.cast(ptrs, ctypes.c_void_p), null) == -1 and "positive radius" in err()
+    nout = (ctypes.c_int * 3)(128, 128, 256)
+    assert L.ssd3d_sa_mlp_fused(1, 64, 128, 8, 32, one, one, one, one, null, 3, ctypes.cast(nout, ctypes.c_void_p), one, one,
+                                one, 256, null, null, 0, null) == -2 and "does not fit" in err()
+    assert L.ssd3d_sa_mlp_fused(1, 64, 1, 8, 7, one, one, one, one, null, 3, ctypes.cast(nout, ctypes.c_void_p), one, one,
+                                one, 256, null, null, 0, null) == -1 and "nsample" in err()
+    assert L.ssd3d_linear_tc(128, 20, 16, one, one, one, one, one, one, 1, 1, null, one, 16, null, null, 0, null) == -1 and "multiple of 16" in err()
+    assert L.ssd3d_version() > 0
