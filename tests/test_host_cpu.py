@@ -185,3 +185,17 @@ def test_c_abi_argument_validation_needs_no_gpu(pkg):
                                 one, 256, null, null, 0, null) == -1 and "nsample" in err()
     assert L.ssd3d_linear_tc(128, 20, 16, one, one, one, one, one, one, 1, 1, null, one, 16, null, null, 0, null) == -1 and "multiple of 16" in err()
     assert L.ssd3d_version() > 0
+
+
+def test_header_is_plain_c():
+    """include/ssd3d.h is the drop-in boundary: it must compile as C99 and as C++ with nothing but the standard
+    headers (no torch / CUDA types in any signature)."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "ssd3d.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", hdr])
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)          # declarations only, comments stripped
+    assert "torch" not in code.lower() and "cudaStream_t" not in code and "#include <cuda" not in code
