@@ -251,3 +251,26 @@ def test_matrix_free_ffps_restatement_equals_matrix_route(oracle_ops):
     q = (rng.integers(0, 3, (1, 70, 5)) * 0.5).astype(np.float32)        # quantised: many equal distances
     np.testing.assert_array_equal(oracle_ops.farthest_point_sample_features(25, q),
                                   oracle_ops.farthest_point_sample_with_distance(25, oracle_ops.calc_square_dist(q)))
+
+
+def test_oracle_on_real_lidar_scene(oracle_ops):
+    """Domain invariants of the CPU oracle on the committed real scan (tests/golden/realscan_16384.npz): D-FPS picks
+    4096 distinct points starting at index 0 with non-increasing pick distances; every dilated-shell neighbour list is
+    ascending up to its count, back-filled with the first hit, and its members lie inside the shell."""
+    pts = np.load(os.path.join(GOLDEN, "realscan_16384.npz"))["points"][None, :, :3].astype(np.float32)
+    idx = oracle_ops.farthest_point_sample(4096, pts)[0]
+    assert idx[0] == 0 and len(set(idx.tolist())) == 4096
+    sel = pts[0, idx].astype(np.float64)
+    # distance of pick j to the picks before it is non-increasing in j (the defining property of FPS), checked on a prefix
+    mind = [np.min(((sel[:j] - sel[j]) ** 2).sum(-1)) for j in range(1, 400)]
+    assert all(mind[j] <= mind[j - 1] * (1 + 1e-5) for j in range(1, len(mind)))
+    q = np.ascontiguousarray(pts[:, idx[:512]])
+    nbr, cnt = oracle_ops.query_ball_point_dilated(0.4, 0.8, 64, pts, q)
+    assert cnt.min() >= 1 and cnt.max() <= 64
+    d = np.sqrt(((pts[0, nbr[0]].astype(np.float64) - q[0][:, None, :]) ** 2).sum(-1))
+    for i in range(512):
+        c = cnt[0, i]
+        row = nbr[0, i]
+        assert (np.diff(row[:c]) > 0).all() and (row[c:] == row[0]).all()
+        ok = (d[i, :c] == 0) | ((d[i, :c] >= 0.4 - 1e-5) & (d[i, :c] < 0.8 + 1e-5))
+        assert ok.all()
