@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SSD3D_LIB") or os.path.join(_HERE, "libssd3d.so")   # override: instrumented builds
 _lib = None
 
-c_int, c_long, c_float, c_void_p = ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_void_p
+c_int, c_long, c_float, c_void_p, c_longlong = ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong
 
 # name -> argtypes, exactly the prototypes of include/ssd3d.h
 _SIGNATURES = {
@@ -53,12 +53,21 @@ _SIGNATURES = {
     "ssd3d_bev_nms": [c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "ssd3d_farthest_point_sample_features": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "ssd3d_ffps_supported": [c_int, c_int],
-    "ssd3d_tune_set_fps_cluster": [c_int],
-    "ssd3d_tune_set_fps_variant": [c_int],
-    "ssd3d_tune_set_fps_cluster_cap": [c_int],
-    "ssd3d_tune_set_fused": [c_int, c_int],
-    "ssd3d_tune_set_mma_split": [c_int],
-    "ssd3d_tune_set_fused_mma_split": [c_int],
+    "ssd3d_farthest_point_sample_ex": [c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int,
+                                       c_int, c_int, c_int, c_int, c_void_p],
+    "ssd3d_fps_supports_rounds": [c_int, c_int],
+    "ssd3d_farthest_point_sample_with_distance_ex": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                                     c_void_p],
+    "ssd3d_farthest_point_sample_features_ex": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p,
+                                                c_longlong, c_void_p, c_int, c_int, c_void_p],
+    "ssd3d_gather_point_ex": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "ssd3d_concat_rows": [c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "ssd3d_split_points": [c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "ssd3d_iota_idx": [c_int, c_int, c_int, c_void_p, c_int, c_void_p],
+    "ssd3d_concat_cols": [c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p],
+    "ssd3d_vote_translate": [c_long, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_void_p, c_void_p],
+    "ssd3d_decode_dist_anchor_free": [c_long, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                      c_void_p],
 }
 
 EXPORTS = sorted(list(_SIGNATURES) + ["ssd3d_last_error"])
@@ -75,8 +84,7 @@ def lib():
         for name, argtypes in _SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = argtypes
-            fn.restype = (None if name.startswith("ssd3d_tune_set") else
-                          ctypes.c_size_t if name == "ssd3d_sa_fused_smem" else c_int)
+            fn.restype = ctypes.c_size_t if name == "ssd3d_sa_fused_smem" else c_int
         l.ssd3d_last_error.restype = ctypes.c_char_p
         l.ssd3d_last_error.argtypes = []
         _lib = l

@@ -9,6 +9,7 @@ import torch
 
 from . import config as _cfg
 from . import layers_util as L
+from . import tf_ops
 from .params import init_params, prepare
 
 
@@ -21,7 +22,12 @@ class SABackbone:
     """
 
     def __init__(self, arch=None, params=None, in_channels=_cfg.INPUT_CHANNELS - 3, device="cuda", ffps_mode="direct",
-                 seed=0, mlp_mode="tc", fuse_scale=True, head=None, gather_in_kernel=True, hoist_first=2):
+                 seed=0, mlp_mode="tc", fuse_scale=True, head=None, gather_in_kernel=True, hoist_first=2, fps_cluster=0,
+                 latency_mode=False, fps_parts=(0.34, 0.28, 0.22, 0.16)):
+        """fps_cluster: CTAs per scene of the D-FPS kernels (0 heuristic, < 0 cap; see tf_ops.farthest_point_sample).
+        latency_mode: minimise the time of ONE step instead of the throughput of many in flight -- every SA layer
+        consumes its sampling in parts (pointnet_sa_module_msg `fps_parts`): a lone D-FPS (layer 1) is cut into
+        resumable launches with the given round fractions, fusion-sampling layers hand over their halves separately."""
         self.arch = _cfg.ARCH_3DSSD if arch is None else arch
         self.in_channels = in_channels
         self.device = torch.device(device)
@@ -33,14 +39,17 @@ class SABackbone:
         self.gather_in_kernel = gather_in_kernel
         self.hoist_first = hoist_first
         self.fuse_scale = fuse_scale
+        self.fps_cluster = fps_cluster
+        self.latency_mode = latency_mode
+        self.fps_parts = list(fps_parts)
         self.head = head                      # optional head.DetectionHead: real detections instead of the stand-in block
         self._graph = None
 
     def forward(self, points, return_debug=False):
         if points.dim() != 3 or points.shape[-1] != 3 + self.in_channels:
             raise ValueError("points must be [B, N, %d], got %s" % (3 + self.in_channels, tuple(points.shape)))
-        xyz_list = [points[..., :3].contiguous()]
-        feat_list = [points[..., 3:].contiguous()]
+        xyz0, feat0 = tf_ops.split_points(points)                  # single_stage_detector.py:116-117
+        xyz_list, feat_list = [xyz0], [feat0]
         fps_list = [None]
         dbg = []
         for spec in self.arch:
@@ -49,11 +58,15 @@ class SABackbone:
             former_idx = fps_list[former] if former != -1 else None
             vote_ctr = xyz_list[vote_idx] if vote_idx != -1 else None
             if ltype == "SA_Layer":
+                parts = None
+                if self.latency_mode and len(radius) and vote_ctr is None:
+                    parts = self.fps_parts if (len(npoint) == 1 and method[0] == "D-FPS") else True
                 r = L.pointnet_sa_module_msg(xyz_list[xyz_i[0]], feat_list[feat_i[0]], radius, nsample, mlps, False,
                                              None, bn, rng, method, npoint, former_idx, attn, scope, dilated, vote_ctr,
                                              agg, params=self.params, ffps_mode=self.ffps_mode, return_debug=True,
                                              mlp_mode=self.mlp_mode, fuse_scale=self.fuse_scale,
-                                             gather_in_kernel=self.gather_in_kernel, hoist_first=self.hoist_first)
+                                             gather_in_kernel=self.gather_in_kernel, hoist_first=self.hoist_first,
+                                             fps_cluster=self.fps_cluster, fps_parts=parts)
                 xyz_list.append(r[0]); feat_list.append(r[1]); fps_list.append(r[2]); dbg.append(r[3])
             elif ltype == "Vote_Layer":
                 nx, nf, off = L.vote_layer(xyz_list[xyz_i[0]], feat_list[feat_i[0]], mlps, False, None, bn, scope,
@@ -78,13 +91,17 @@ class SABackbone:
 
     __call__ = forward
 
-    # ---- per-scene detection block (stand-in until the head/NMS rows of SURVEY.md section 8f exist) -------
-    def detections(self, xyz_list, feat_list):
+    # ---- per-scene detection block ---------------------------------------------------------------------------
+    def detections(self, xyz_list, feat_list, out=None):
         """Per-scene detection block [B,100,9] + count [B]: the detection head + decode + BEV NMS when a head is
-        attached, otherwise the stand-in derived from the CG layer."""
+        attached, otherwise the stand-in derived from the CG layer.  out=(block, count) preallocated outputs."""
         if self.head is not None:
-            return self.head(xyz_list, feat_list)
-        return self.detection_block(xyz_list, feat_list)
+            return self.head(xyz_list, feat_list, out=out)
+        blk, cnt = self.detection_block(xyz_list, feat_list)
+        if out is not None:
+            out[0].copy_(blk); out[1].copy_(cnt)
+            return out
+        return blk, cnt
 
     @staticmethod
     def detection_block(xyz_list, feat_list, max_output=100):
@@ -107,20 +124,31 @@ class SABackbone:
         return blk, cnt
 
     # ---- CUDA graph ---------------------------------------------------------------------------------------
-    def capture(self, example_points, warmup=2):
+    def capture(self, example_points, warmup=2, gather=None):
+        """Record forward + detections (+ the multi-GPU all-gather when `gather`, a dist.DetectionGather, is given: the
+        NMS writes into its send buffer and ncclAllGather is captured with the kernels) into one CUDA graph.  Returns
+        replay(points=None) -> (forward outputs, (block, count)); with `gather` the pair holds this rank's views of the
+        send buffer and gather.result() / gather.raw hold all ranks' detections after the replay."""
         static_in = example_points.clone()
+        out_buf = gather.out() if gather is not None else None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
                 out = self.forward(static_in)
-                blk = self.detections(out[0], out[1])
+                blk = self.detections(out[0], out[1], out=out_buf)
+                if gather is not None:
+                    gather.gather()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # thread_local: NCCL's watchdog thread polls its events while this thread captures
+        kw = {"capture_error_mode": "thread_local"} if (gather is not None and gather.world > 1) else {}
+        with torch.cuda.graph(g, **kw):
             out = self.forward(static_in)
-            blk = self.detections(out[0], out[1])
+            blk = self.detections(out[0], out[1], out=out_buf)
+            if gather is not None:
+                gather.gather()
         self._graph = (g, static_in, out, blk)
 
         def replay(points=None):

@@ -20,7 +20,8 @@ int cuda_status(cudaError_t e, const char *what);
         }                                                          \
     } while (0)
 
-#define SSD3D_LAUNCH_CHECK(what) return ::ssd3d::cuda_status(cudaPeekAtLastError(), what)
+// cudaGetLastError (capture-safe) reports a failed launch once AND clears it, so later calls do not inherit it
+#define SSD3D_LAUNCH_CHECK(what) return ::ssd3d::cuda_status(cudaGetLastError(), what)
 
 constexpr int kNumSMs = 148;  // B200
 

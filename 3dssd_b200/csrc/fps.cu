@@ -26,6 +26,18 @@ constexpr int FPS_T = 256;  // threads per CTA
 constexpr int FPS_NW = FPS_T / 32;
 constexpr uint32_t KEY_INVALID = 0x7FFFFFFFu;
 
+// Where a launch reads and writes (the *_ex entry points of include/ssd3d.h): scene strides of the inputs in
+// elements (so a [:, a:b] slice of a dense [b,N,c] tensor needs no copy), row stride + value offset of the index
+// output (so the segments of a fusion-sampling layer land directly in the concatenated fps_idx tensor with the
+// segment offset already added, layers_util.py:109-111), and -- fps3_direct_kernel only -- the range of rounds
+// [j0, j1) this launch runs, the running distances travelling through `temp` between launches.
+struct FpsIO {
+    long long sa, sb;   // scene stride of inp / fa (sa) and fb (sb), in floats
+    int ldo, ioff;      // out row stride (ints), offset added to every stored index
+    int j0, j1;         // rounds [j0, j1) of 0..m (round 0 = "sample point 0")
+    float *temp;        // [b, n] running distances (resume state; NULL when j0 == 0 && j1 == m)
+};
+
 __device__ __forceinline__ uint32_t fps_key(int k) { return ((uint32_t)(k & 1023) << 21) | (uint32_t)(k >> 10); }
 __device__ __forceinline__ int fps_key_to_k(uint32_t key) { return (int)(((key & 0x1FFFFFu) << 10) | (key >> 21)); }
 
@@ -164,7 +176,7 @@ __device__ __forceinline__ void fps_shared_init(FpsShared<CL> &sh)
 // ---------------------------------------------------------------------------------------------------
 template <int CL, int P>
 __global__ void __launch_bounds__(FPS_T, 1)
-fps3_cluster_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out)
+fps3_cluster_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out, const FpsIO io)
 {
     using Map = FpsMap<CL * FPS_T, P>;
     extern __shared__ float4 own_pts[];  // [P][FPS_T] xyz of this CTA's points (lookup by the round winner)
@@ -174,8 +186,8 @@ fps3_cluster_kernel(int n, int m, const float *__restrict__ inp, int *__restrict
     const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
     const int scene = blockIdx.x / CL;
     const int g = (int)rank * FPS_T + tid;
-    const float *data = inp + (size_t)scene * n * 3;
-    int *idxs = out + (size_t)scene * m;
+    const float *data = inp + (size_t)scene * io.sa;
+    int *idxs = out + (size_t)scene * io.ldo;
 
     float px[P], py[P], pz[P], td[P];
 #pragma unroll
@@ -193,7 +205,7 @@ fps3_cluster_kernel(int n, int m, const float *__restrict__ inp, int *__restrict
     fps_shared_init<CL>(sh);
 
     float ox = data[0], oy = data[1], oz = data[2];  // first sample is point 0 (:131-133)
-    if (g == 0) idxs[0] = 0;
+    if (g == 0) idxs[0] = io.ioff;
 
     for (int j = 1; j < m; j++) {
         float best = -1.0f;
@@ -211,7 +223,7 @@ fps3_cluster_kernel(int n, int m, const float *__restrict__ inp, int *__restrict
         const float4 c = own_pts[bi * FPS_T + tid];
         uint32_t wkey;
         fps_exchange<CL, true>(sh, j, rank, best, fps_key(Map::k_of(g, bi)), c.x, c.y, c.z, wkey, ox, oy, oz);
-        if (g == 0) idxs[j] = fps_key_to_k(wkey);
+        if (g == 0) idxs[j] = fps_key_to_k(wkey) + io.ioff;
     }
     if (CL > 1) cluster_sync_all();  // peers may still be storing into this CTA's shared memory
 }
@@ -224,7 +236,7 @@ fps3_cluster_kernel(int n, int m, const float *__restrict__ inp, int *__restrict
 // ---------------------------------------------------------------------------------------------------
 template <int CL, int P>
 __global__ void __launch_bounds__(FPS_T, 1)
-fps3_direct_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out)
+fps3_direct_kernel(int n, int m, const float *__restrict__ inp, int *__restrict__ out, const FpsIO io)
 {
     using Map = FpsMap<CL * FPS_T, P>;
     constexpr int NSLOT = CL * FPS_NW;                   // packets received per round
@@ -237,8 +249,13 @@ fps3_direct_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
     const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
     const int scene = blockIdx.x / CL;
     const int g = (int)rank * FPS_T + tid;
-    const float *data = inp + (size_t)scene * n * 3;
-    int *idxs = out + (size_t)scene * m;
+    const float *data = inp + (size_t)scene * io.sa;
+    int *idxs = out + (size_t)scene * io.ldo;
+    // Resumable: this launch runs rounds [jbeg, jend) of 1..m-1.  A launch that does not start at round 0 reloads the
+    // running distances from io.temp and the last winner from the index output; one that stops before m saves them.
+    const int jbeg = io.j0 > 1 ? io.j0 : 1, jend = io.j1 < m ? io.j1 : m;
+    const bool resume = io.j0 > 0, save = io.j1 < m;
+    float *tsave = io.temp + (size_t)scene * n;
 
     if (tid == 0) {
         mbar_init(smem_u32(&mbar[0]), 1);
@@ -255,16 +272,21 @@ fps3_direct_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
 #pragma unroll
     for (int i = 0; i < P; i++) {
         const int k = Map::k_of(g, i);
-        if (k < n) { px[i] = sxyz[3 * k]; py[i] = sxyz[3 * k + 1]; pz[i] = sxyz[3 * k + 2]; td[i] = 1e38f; }
-        else { px[i] = py[i] = pz[i] = 0.0f; td[i] = -1.0f; }
+        if (k < n) {
+            px[i] = sxyz[3 * k]; py[i] = sxyz[3 * k + 1]; pz[i] = sxyz[3 * k + 2];
+            td[i] = resume ? tsave[k] : 1e38f;
+        } else { px[i] = py[i] = pz[i] = 0.0f; td[i] = -1.0f; }
     }
     if (CL > 1) cluster_sync_all();                      // all peers' barriers are initialised
 
-    float ox = sxyz[0], oy = sxyz[1], oz = sxyz[2];
-    if (g == 0) idxs[0] = 0;
+    int old0 = 0;
+    if (resume) old0 = idxs[jbeg - 1] - io.ioff;         // written by the previous launch of this scene
+    else if (g == 0) idxs[0] = io.ioff;
+    float ox = sxyz[3 * old0], oy = sxyz[3 * old0 + 1], oz = sxyz[3 * old0 + 2];
 
-    for (int j = 1; j < m; j++) {
-        const int par = j & 1;
+    for (int j = jbeg; j < jend; j++) {
+        const int r = j - jbeg + 1;                      // 1-based round of THIS launch: slot parity / barrier phase
+        const int par = r & 1;
         if (tid == 0) mbar_arrive_expect_tx(smem_u32(&mbar[par]), NSLOT * 8);
         float best = -1.0f;
         int bi = 0;
@@ -303,7 +325,7 @@ fps3_direct_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
             st_async_b64(mapa(smem_u32(&slots[par][rank * FPS_NW + warp]), (uint32_t)lane),
                          mapa(smem_u32(&mbar[par]), (uint32_t)lane), pk);
         }
-        mbar_wait_cta(smem_u32(&mbar[par]), ((j - 1) >> 1) & 1);
+        mbar_wait_cta(smem_u32(&mbar[par]), ((r - 1) >> 1) & 1);
         // reduce the NSLOT packets: value desc, key asc
         unsigned long long a = lane < NSLOT ? slots[par][lane] : 0x00000000ffffffffull;
 #pragma unroll
@@ -316,7 +338,14 @@ fps3_direct_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
         warp_argmax((uint32_t)(a >> 32), (uint32_t)a, m3, k3);
         const int old = fps_key_to_k(k3);
         ox = sxyz[3 * old]; oy = sxyz[3 * old + 1]; oz = sxyz[3 * old + 2];
-        if (g == 0) idxs[j] = old;
+        if (g == 0) idxs[j] = old + io.ioff;
+    }
+    if (save) {
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+            const int k = Map::k_of(g, i);
+            if (k < n) tsave[k] = td[i];
+        }
     }
     if (CL > 1) cluster_sync_all();
 }
@@ -326,7 +355,7 @@ fps3_direct_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
 // ---------------------------------------------------------------------------------------------------
 template <int CL, int P>
 __global__ void __launch_bounds__(FPS_T, 1)
-fpsdist_cluster_kernel(int n, int m, const float *__restrict__ dist, int *__restrict__ out)
+fpsdist_cluster_kernel(int n, int m, const float *__restrict__ dist, int *__restrict__ out, const FpsIO io)
 {
     using Map = FpsMap<CL * FPS_T, P>;
     __shared__ FpsShared<CL> sh;
@@ -334,8 +363,8 @@ fpsdist_cluster_kernel(int n, int m, const float *__restrict__ dist, int *__rest
     const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
     const int scene = blockIdx.x / CL;
     const int g = (int)rank * FPS_T + tid;
-    const float *mat = dist + (size_t)scene * n * n;
-    int *idxs = out + (size_t)scene * m;
+    const float *mat = dist + (size_t)scene * io.sa;
+    int *idxs = out + (size_t)scene * io.ldo;
 
     float td[P];
     int kk[P];
@@ -346,7 +375,7 @@ fpsdist_cluster_kernel(int n, int m, const float *__restrict__ dist, int *__rest
     }
     fps_shared_init<CL>(sh);
     int old = 0;
-    if (g == 0) idxs[0] = 0;
+    if (g == 0) idxs[0] = io.ioff;
     for (int j = 1; j < m; j++) {
         const float *row = mat + (size_t)old * n;
         float dv[P];
@@ -364,7 +393,7 @@ fpsdist_cluster_kernel(int n, int m, const float *__restrict__ dist, int *__rest
         float ux, uy, uz;
         fps_exchange<CL, false>(sh, j, rank, best, fps_key(Map::k_of(g, bi)), 0.f, 0.f, 0.f, wkey, ux, uy, uz, mat, n);
         old = fps_key_to_k(wkey);
-        if (g == 0) idxs[j] = old;
+        if (g == 0) idxs[j] = old + io.ioff;
     }
     if (CL > 1) cluster_sync_all();
 }
@@ -376,7 +405,7 @@ fpsdist_cluster_kernel(int n, int m, const float *__restrict__ dist, int *__rest
 // ---------------------------------------------------------------------------------------------------
 template <int CL, int P>
 __global__ void __launch_bounds__(FPS_T, 1)
-fpsc_cluster_kernel(int n, int c, int m, const float *__restrict__ inp, int *__restrict__ out)
+fpsc_cluster_kernel(int n, int c, int m, const float *__restrict__ inp, int *__restrict__ out, const FpsIO io)
 {
     using Map = FpsMap<CL * FPS_T, P>;
     constexpr int NL = P * FPS_T;
@@ -390,8 +419,8 @@ fpsc_cluster_kernel(int n, int c, int m, const float *__restrict__ inp, int *__r
     const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
     const int scene = blockIdx.x / CL;
     const int g = (int)rank * FPS_T + tid;
-    const float *data = inp + (size_t)scene * n * c;
-    int *idxs = out + (size_t)scene * m;
+    const float *data = inp + (size_t)scene * io.sa;
+    int *idxs = out + (size_t)scene * io.ldo;
 
     float td[P];
 #pragma unroll
@@ -404,7 +433,7 @@ fpsc_cluster_kernel(int n, int c, int m, const float *__restrict__ inp, int *__r
     }
     for (int l = tid; l < c; l += FPS_T) old_f[l] = data[l];  // first sample is point 0
     fps_shared_init<CL>(sh);  // contains __syncthreads
-    if (g == 0) idxs[0] = 0;
+    if (g == 0) idxs[0] = io.ioff;
 
     for (int j = 1; j < m; j++) {
         float d[P];
@@ -431,7 +460,7 @@ fpsc_cluster_kernel(int n, int c, int m, const float *__restrict__ inp, int *__r
         float ux, uy, uz;
         fps_exchange<CL, false>(sh, j, rank, best, fps_key(Map::k_of(g, bi)), 0.f, 0.f, 0.f, wkey, ux, uy, uz);
         const int old = fps_key_to_k(wkey);
-        if (g == 0) idxs[j] = old;
+        if (g == 0) idxs[j] = old + io.ioff;
         // fetch the winner's feature vector from its owner CTA (all threads passed the __syncthreads inside
         // fps_exchange, so nobody still reads old_f of this round)
         int og, oi;
@@ -470,7 +499,7 @@ struct __align__(16) FfpsPacket {
 template <int CL, int P, int CP>
 __global__ void __launch_bounds__(FPS_T, 1)
 ffps_cluster_kernel(int n, int ca, int cb, int m, const float *__restrict__ fa, const float *__restrict__ fb,
-                    int *__restrict__ out)
+                    int *__restrict__ out, const FpsIO io)
 {
     constexpr int TT = CL * FPS_T, NL = P * FPS_T, NP = 1 + CP / 4;   // pieces of 16 bytes per packet
     using Packet = FfpsPacket<CP>;
@@ -486,9 +515,9 @@ ffps_cluster_kernel(int n, int ca, int cb, int m, const float *__restrict__ fa, 
     const int scene = blockIdx.x / CL;
     const int g = (int)rank * FPS_T + tid;
     const int c = ca + cb;
-    const float *A = fa + (size_t)scene * n * ca;
-    const float *B = fb + (size_t)scene * n * cb;
-    int *idxs = out + (size_t)scene * m;
+    const float *A = fa + (size_t)scene * io.sa;
+    const float *B = fb + (size_t)scene * io.sb;
+    int *idxs = out + (size_t)scene * io.ldo;
 
     // ---- stage this CTA's rows: local point s = i*256 + t  <->  k = rank*256 + t + i*TT (zero rows beyond n)
     for (int s = warp; s < NL; s += FPS_NW) {
@@ -541,7 +570,7 @@ ffps_cluster_kernel(int n, int ca, int cb, int m, const float *__restrict__ fa, 
     }
     __syncthreads();
     if (CL > 1) cluster_sync_all();       // every CTA's barriers exist before any peer st.async targets them
-    if (g == 0) idxs[0] = 0;
+    if (g == 0) idxs[0] = io.ioff;
 
     const Packet *oldp = &cl_pk[0];
     for (int j = 1; j < m; j++) {
@@ -626,7 +655,7 @@ ffps_cluster_kernel(int n, int ca, int cb, int m, const float *__restrict__ fa, 
             oldp = &cl_pk[par * CL + (__ffs(bal) - 1)];
             win_key = k3;
         }
-        if (g == 0) idxs[j] = win_key != KEY_INVALID ? fps_key_to_k(win_key) : 0;
+        if (g == 0) idxs[j] = (win_key != KEY_INVALID ? fps_key_to_k(win_key) : 0) + io.ioff;
     }
     if (CL > 1) cluster_sync_all();
 }
@@ -637,18 +666,18 @@ ffps_cluster_kernel(int n, int ca, int cb, int m, const float *__restrict__ fa, 
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 fps_fallback_kernel(int n, int c, int m, const float *__restrict__ inp, const float *__restrict__ dist,
-                    float *__restrict__ temp, int *__restrict__ out)
+                    float *__restrict__ temp, int *__restrict__ out, const FpsIO io)
 {
     __shared__ uint32_t s_val[32], s_key[32];
     __shared__ int s_old;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int scene = blockIdx.x;
-    const float *data = inp ? inp + (size_t)scene * n * c : nullptr;
-    const float *mat = dist ? dist + (size_t)scene * n * n : nullptr;
+    const float *data = inp ? inp + (size_t)scene * io.sa : nullptr;
+    const float *mat = dist ? dist + (size_t)scene * io.sa : nullptr;
     float *td = temp + (size_t)scene * n;
-    int *idxs = out + (size_t)scene * m;
+    int *idxs = out + (size_t)scene * io.ldo;
     for (int k = tid; k < n; k += 1024) td[k] = 1e38f;
-    if (tid == 0) idxs[0] = 0;
+    if (tid == 0) idxs[0] = io.ioff;
     int old = 0;
     __syncthreads();
     for (int j = 1; j < m; j++) {
@@ -677,7 +706,7 @@ fps_fallback_kernel(int n, int c, int m, const float *__restrict__ inp, const fl
         if (warp == 0) {
             uint32_t m2, k2;
             warp_argmax(s_val[lane], s_key[lane], m2, k2);
-            if (lane == 0) { s_old = fps_key_to_k(k2); idxs[j] = s_old; }
+            if (lane == 0) { s_old = fps_key_to_k(k2); idxs[j] = s_old + io.ioff; }
         }
         __syncthreads();
         old = s_old;
@@ -727,29 +756,26 @@ static int pick_p(int n, int cl)
     return p;
 }
 
-static int g_fps_cluster_override = 0;  // test / tuning hook (ssd3d_tune_set)
-static int g_fps_variant = 0;           // 0 = auto (direct when it fits), 1 = force the packet-with-xyz kernel
-static int g_fps_cluster_cap = 0;       // > 0: upper bound on the heuristic cluster size (throughput mode: FPS is
-                                        // latency-bound, so fewer SMs per scene cost little time and free SMs for
-                                        // other work running concurrently)
-
-static int cap_cl(int cl, int n)
+// Cluster-size request of one call (the `cluster` argument of the *_ex entry points): 0 = heuristic, > 0 = exactly
+// that many CTAs per scene, < 0 = heuristic capped at -cluster (throughput mode: FPS is latency-bound, so fewer SMs
+// per scene cost little time and free SMs for work running concurrently).
+static int cap_cl(int cl, int n, int hint)
 {
-    if (g_fps_cluster_cap > 0)
-        while (cl > g_fps_cluster_cap && cl > 1 && (n + (cl / 2) * FPS_T - 1) / ((cl / 2) * FPS_T) <= 16) cl /= 2;
+    if (hint < 0)
+        while (cl > -hint && cl > 1 && (n + (cl / 2) * FPS_T - 1) / ((cl / 2) * FPS_T) <= 16) cl /= 2;
     return cl;
 }
 
-static int pick_cl_xyz(int n)
+static int pick_cl_xyz(int n, int hint)
 {
-    if (g_fps_cluster_override > 0) return g_fps_cluster_override;
+    if (hint > 0) return hint;
     int cl;
     if (n <= 1024) cl = 1;
     else if (n <= 2048) cl = 2;
     else if (n <= 4096) cl = 4;
     else if (n <= 32768) cl = 8;
     else cl = 16;
-    return cap_cl(cl, n);
+    return cap_cl(cl, n, hint);
 }
 
 }  // namespace ssd3d
@@ -799,31 +825,31 @@ using namespace ssd3d;
         return (int)e;                                                                                    \
     } while (0)
 
-static int launch_fps3(int b, int n, int m, int cl, const float *inp, int *out, cudaStream_t st)
+static int launch_fps3(int b, int n, int m, int cl, const float *inp, int *out, const FpsIO &io, cudaStream_t st)
 {
-    void *args[] = {&n, &m, (void *)&inp, (void *)&out};
+    void *args[] = {&n, &m, (void *)&inp, (void *)&out, (void *)&io};
     SSD3D_FPS_SWITCH(fps3_cluster_kernel, (size_t)p * FPS_T * sizeof(float4));
 }
-static int launch_fps3_direct(int b, int n, int m, int cl, const float *inp, int *out, cudaStream_t st)
+static int launch_fps3_direct(int b, int n, int m, int cl, const float *inp, int *out, const FpsIO &io, cudaStream_t st)
 {
-    void *args[] = {&n, &m, (void *)&inp, (void *)&out};
+    void *args[] = {&n, &m, (void *)&inp, (void *)&out, (void *)&io};
     SSD3D_FPS_SWITCH(fps3_direct_kernel, (size_t)n * 12 + 16);
 }
-static int launch_fpsdist(int b, int n, int m, int cl, const float *dist, int *out, cudaStream_t st)
+static int launch_fpsdist(int b, int n, int m, int cl, const float *dist, int *out, const FpsIO &io, cudaStream_t st)
 {
-    void *args[] = {&n, &m, (void *)&dist, (void *)&out};
+    void *args[] = {&n, &m, (void *)&dist, (void *)&out, (void *)&io};
     SSD3D_FPS_SWITCH(fpsdist_cluster_kernel, (size_t)0);
 }
-static int launch_fpsc(int b, int n, int c, int m, int cl, const float *inp, int *out, cudaStream_t st)
+static int launch_fpsc(int b, int n, int c, int m, int cl, const float *inp, int *out, const FpsIO &io, cudaStream_t st)
 {
-    void *args[] = {&n, &c, &m, (void *)&inp, (void *)&out};
+    void *args[] = {&n, &c, &m, (void *)&inp, (void *)&out, (void *)&io};
     SSD3D_FPS_SWITCH(fpsc_cluster_kernel, ((size_t)c * (p * FPS_T + 1) + c) * sizeof(float) + 16);
 }
 
 // cluster size for the generic-c kernel: smallest CL whose per-CTA feature slab fits in shared memory
-static int pick_cl_generic(int n, int c)
+static int pick_cl_generic(int n, int c, int hint)
 {
-    if (g_fps_cluster_override > 0) return g_fps_cluster_override;
+    if (hint > 0) return hint;
     const size_t budget = 200 * 1024;
     for (int cl = 1; cl <= 16; cl *= 2) {
         const int p = pick_p(n, cl);
@@ -840,63 +866,103 @@ static int pick_cl_generic(int n, int c)
 extern "C" int ssd3d_fps_needs_temp(int n, int c)
 {
     if (c == 3) return pick_p(n, 16) > 16;
-    return pick_cl_generic(n, c) == 0;
+    return pick_cl_generic(n, c, 0) == 0;
 }
 
-extern "C" void ssd3d_tune_set_fps_cluster(int cl) { g_fps_cluster_override = cl; }
-extern "C" void ssd3d_tune_set_fps_variant(int v) { g_fps_variant = v; }
-extern "C" void ssd3d_tune_set_fps_cluster_cap(int cl) { g_fps_cluster_cap = cl; }
+// (c == 3) does the resumable direct kernel cover n?  It needs the scene resident in one CTA's shared memory.
+static bool fps3_direct_fits(int n, int cl, const float *inp, long long sa)
+{
+    return cl >= 2 && (size_t)n * 12 + 16 <= 200 * 1024 && (n % 4) == 0 &&
+           (reinterpret_cast<uintptr_t>(inp) & 15u) == 0 && (sa % 4) == 0 && pick_p(n, cl) <= 16;
+}
 
-extern "C" int ssd3d_farthest_point_sample(int b, int n, int c, int m, const float *inp, float *temp, int *out,
-                                           ssd3d_stream_t stream)
+extern "C" int ssd3d_fps_supports_rounds(int n, int c)
+{
+    if (c != 3) return 0;
+    int cl = pick_cl_xyz(n, 0);
+    while (cl < 16 && pick_p(n, cl) > 16) cl *= 2;
+    return cl >= 2 && (size_t)n * 12 + 16 <= 200 * 1024 && (n % 4) == 0 && pick_p(n, cl) <= 16;
+}
+
+extern "C" int ssd3d_farthest_point_sample_ex(int b, int n, int c, int m, const float *inp, long long in_stride,
+                                              float *temp, int *out, int ldo, int idx_offset, int j0, int j1,
+                                              int cluster, int flags, ssd3d_stream_t stream)
 {
     SSD3D_REQUIRE(b >= 0 && n > 0 && c > 0 && m >= 0, "farthest_point_sample: bad shape b=%d n=%d c=%d m=%d", b, n, c, m);
-    if (b == 0 || m == 0) return 0;  // tf_sampling_g.cu:126-127
+    SSD3D_REQUIRE(ldo >= m && in_stride >= (long long)n * c, "farthest_point_sample: strides smaller than a row (ldo=%d, in_stride=%lld)", ldo, in_stride);
+    SSD3D_REQUIRE(0 <= j0 && j0 <= j1 && j1 <= m, "farthest_point_sample: rounds [%d,%d) outside [0,%d]", j0, j1, m);
+    SSD3D_REQUIRE(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16 ||
+                  cluster == -1 || cluster == -2 || cluster == -4 || cluster == -8 || cluster == -16,
+                  "farthest_point_sample: cluster must be 0, +-1, +-2, +-4, +-8 or +-16, got %d", cluster);
+    if (b == 0 || m == 0 || j0 == j1) return 0;  // tf_sampling_g.cu:126-127
     SSD3D_REQUIRE(inp && out, "farthest_point_sample: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    const bool partial = j0 > 0 || j1 < m;
+    FpsIO io = {in_stride, 0, ldo, idx_offset, j0, j1, temp};
     int rc = -100;
     if (c == 3) {
-        int cl = pick_cl_xyz(n);
+        int cl = pick_cl_xyz(n, cluster);
         while (cl < 16 && pick_p(n, cl) > 16) cl *= 2;
         // direct variant: whole scene resident in every CTA (bulk copy needs 16-byte aligned source and size)
-        const bool direct_ok = g_fps_variant != 1 && cl >= 2 && (size_t)n * 12 + 16 <= 200 * 1024 && (n % 4) == 0 &&
-                               (reinterpret_cast<uintptr_t>(inp) & 15u) == 0 && pick_p(n, cl) <= 16;
-        if (direct_ok) rc = launch_fps3_direct(b, n, m, cl, inp, out, st);
-        else if (pick_p(n, cl) <= 16) rc = launch_fps3(b, n, m, cl, inp, out, st);
+        const bool direct_ok = (flags & 1) == 0 && fps3_direct_fits(n, cl, inp, in_stride);
+        if (partial) {
+            SSD3D_REQUIRE(direct_ok, "farthest_point_sample: a partial range of rounds needs the resident-scene kernel "
+                          "(c == 3, n %% 4 == 0, n <= 17000, 16-byte aligned input); see ssd3d_fps_supports_rounds");
+            SSD3D_REQUIRE(temp != nullptr, "farthest_point_sample: a partial range of rounds carries its state in temp[b,n]");
+        }
+        if (direct_ok) rc = launch_fps3_direct(b, n, m, cl, inp, out, io, st);
+        else if (pick_p(n, cl) <= 16) rc = launch_fps3(b, n, m, cl, inp, out, io, st);
     } else {
-        const int cl = pick_cl_generic(n, c);
-        if (cl > 0) rc = launch_fpsc(b, n, c, m, cl, inp, out, st);
+        SSD3D_REQUIRE(!partial, "farthest_point_sample: a partial range of rounds is only built for c == 3");
+        const int cl = pick_cl_generic(n, c, cluster);
+        if (cl > 0) rc = launch_fpsc(b, n, c, m, cl, inp, out, io, st);
     }
     if (rc == -100) {
         SSD3D_REQUIRE(temp != nullptr, "farthest_point_sample: n=%d c=%d needs the temp[b,n] workspace", n, c);
-        fps_fallback_kernel<<<b, 1024, 0, st>>>(n, c, m, inp, nullptr, temp, out);
+        fps_fallback_kernel<<<b, 1024, 0, st>>>(n, c, m, inp, nullptr, temp, out, io);
         SSD3D_LAUNCH_CHECK("fps_fallback_kernel");
     }
     return cuda_status((cudaError_t)rc, "farthest_point_sample launch");
 }
 
-extern "C" int ssd3d_farthest_point_sample_with_distance(int b, int n, int m, const float *dist, float *temp,
-                                                         int *out, ssd3d_stream_t stream)
+extern "C" int ssd3d_farthest_point_sample(int b, int n, int c, int m, const float *inp, float *temp, int *out,
+                                           ssd3d_stream_t stream)
+{
+    return ssd3d_farthest_point_sample_ex(b, n, c, m, inp, (long long)n * c, temp, out, m, 0, 0, m, 0, 0, stream);
+}
+
+extern "C" int ssd3d_farthest_point_sample_with_distance_ex(int b, int n, int m, const float *dist, float *temp,
+                                                            int *out, int ldo, int idx_offset, int cluster,
+                                                            ssd3d_stream_t stream)
 {
     SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0, "farthest_point_sample_with_distance: bad shape b=%d n=%d m=%d", b, n, m);
+    SSD3D_REQUIRE(ldo >= m, "farthest_point_sample_with_distance: ldo=%d smaller than m=%d", ldo, m);
     if (b == 0 || m == 0) return 0;
     SSD3D_REQUIRE(dist && out, "farthest_point_sample_with_distance: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    FpsIO io = {(long long)n * n, 0, ldo, idx_offset, 0, m, nullptr};
     // the per-round row read is a DRAM-latency-bound gather: more CTAs per scene = more loads in flight
-    int cl = g_fps_cluster_override > 0 ? g_fps_cluster_override : cap_cl(n <= 1024 ? 1 : (n <= 2048 ? 4 : 8), n);
+    int cl = cluster > 0 ? cluster : cap_cl(n <= 1024 ? 1 : (n <= 2048 ? 4 : 8), n, cluster);
     while (cl < 16 && pick_p(n, cl) > 16) cl *= 2;
-    if (pick_p(n, cl) <= 16) return cuda_status((cudaError_t)launch_fpsdist(b, n, m, cl, dist, out, st), "fpsdist launch");
+    if (pick_p(n, cl) <= 16) return cuda_status((cudaError_t)launch_fpsdist(b, n, m, cl, dist, out, io, st), "fpsdist launch");
     SSD3D_REQUIRE(temp != nullptr, "farthest_point_sample_with_distance: n=%d needs the temp[b,n] workspace", n);
-    fps_fallback_kernel<<<b, 1024, 0, st>>>(n, 0, m, nullptr, dist, temp, out);
+    fps_fallback_kernel<<<b, 1024, 0, st>>>(n, 0, m, nullptr, dist, temp, out, io);
     SSD3D_LAUNCH_CHECK("fps_fallback_kernel");
+}
+
+extern "C" int ssd3d_farthest_point_sample_with_distance(int b, int n, int m, const float *dist, float *temp,
+                                                         int *out, ssd3d_stream_t stream)
+{
+    return ssd3d_farthest_point_sample_with_distance_ex(b, n, m, dist, temp, out, m, 0, 0, stream);
 }
 
 // ---- matrix-free F-FPS dispatch: CP = 68 (P = 2 points per thread) or 132 (P = 1); smallest cluster that holds n
 template <int CL, int P, int CP>
-static int launch_ffps_t(int b, int n, int ca, int cb, int m, const float *fa, const float *fb, int *out, cudaStream_t st)
+static int launch_ffps_t(int b, int n, int ca, int cb, int m, const float *fa, const float *fb, int *out, const FpsIO &io,
+                         cudaStream_t st)
 {
     const size_t smem = (size_t)P * FPS_T * CP * 4 + (size_t)P * FPS_T * 4 + (size_t)2 * CL * sizeof(FfpsPacket<CP>);
-    void *args[] = { &n, &ca, &cb, &m, &fa, &fb, &out };
+    void *args[] = { &n, &ca, &cb, &m, &fa, &fb, &out, (void *)&io };
     return (int)launch_cluster(ffps_cluster_kernel<CL, P, CP>, CL, b, smem, st, args);
 }
 static int ffps_cluster_for(int n, int c)
@@ -912,10 +978,13 @@ static int ffps_cluster_for(int n, int c)
 extern "C" int ssd3d_ffps_supported(int n, int c) { return n > 0 && c > 0 && ffps_cluster_for(n, c) > 0 ? 1 : 0; }
 
 // farthest_point_sample_with_distance(m, calc_square_dist(concat[fa, fb])) without the [b,n,n] matrix; same indices.
-extern "C" int ssd3d_farthest_point_sample_features(int b, int n, int ca, int cb, int m, const float *fa, const float *fb,
-                                                    int *out, ssd3d_stream_t stream)
+extern "C" int ssd3d_farthest_point_sample_features_ex(int b, int n, int ca, int cb, int m, const float *fa,
+                                                       long long fa_stride, const float *fb, long long fb_stride,
+                                                       int *out, int ldo, int idx_offset, ssd3d_stream_t stream)
 {
     SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0 && ca > 0 && cb >= 0, "farthest_point_sample_features: bad shape b=%d n=%d m=%d c=%d+%d", b, n, m, ca, cb);
+    SSD3D_REQUIRE(ldo >= m && fa_stride >= (long long)n * ca && fb_stride >= (long long)n * cb,
+                  "farthest_point_sample_features: strides smaller than a row");
     if (b == 0 || m == 0) return 0;
     SSD3D_REQUIRE(fa && out && (fb || cb == 0), "farthest_point_sample_features: null pointer");
     const int c = ca + cb;
@@ -925,17 +994,25 @@ extern "C" int ssd3d_farthest_point_sample_features(int b, int n, int ca, int cb
         return SSD3D_ERR_UNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    const FpsIO io = {fa_stride, fb_stride, ldo, idx_offset, 0, m, nullptr};
     int rc;
     if (c <= 68) {
-        rc = cl == 1 ? launch_ffps_t<1, 2, 68>(b, n, ca, cb, m, fa, fb, out, st)
-           : cl == 2 ? launch_ffps_t<2, 2, 68>(b, n, ca, cb, m, fa, fb, out, st)
-           : cl == 4 ? launch_ffps_t<4, 2, 68>(b, n, ca, cb, m, fa, fb, out, st)
-                     : launch_ffps_t<8, 2, 68>(b, n, ca, cb, m, fa, fb, out, st);
+        rc = cl == 1 ? launch_ffps_t<1, 2, 68>(b, n, ca, cb, m, fa, fb, out, io, st)
+           : cl == 2 ? launch_ffps_t<2, 2, 68>(b, n, ca, cb, m, fa, fb, out, io, st)
+           : cl == 4 ? launch_ffps_t<4, 2, 68>(b, n, ca, cb, m, fa, fb, out, io, st)
+                     : launch_ffps_t<8, 2, 68>(b, n, ca, cb, m, fa, fb, out, io, st);
     } else {
-        rc = cl == 1 ? launch_ffps_t<1, 1, 132>(b, n, ca, cb, m, fa, fb, out, st)
-           : cl == 2 ? launch_ffps_t<2, 1, 132>(b, n, ca, cb, m, fa, fb, out, st)
-           : cl == 4 ? launch_ffps_t<4, 1, 132>(b, n, ca, cb, m, fa, fb, out, st)
-                     : launch_ffps_t<8, 1, 132>(b, n, ca, cb, m, fa, fb, out, st);
+        rc = cl == 1 ? launch_ffps_t<1, 1, 132>(b, n, ca, cb, m, fa, fb, out, io, st)
+           : cl == 2 ? launch_ffps_t<2, 1, 132>(b, n, ca, cb, m, fa, fb, out, io, st)
+           : cl == 4 ? launch_ffps_t<4, 1, 132>(b, n, ca, cb, m, fa, fb, out, io, st)
+                     : launch_ffps_t<8, 1, 132>(b, n, ca, cb, m, fa, fb, out, io, st);
     }
     return cuda_status((cudaError_t)rc, "ffps launch");
+}
+
+extern "C" int ssd3d_farthest_point_sample_features(int b, int n, int ca, int cb, int m, const float *fa, const float *fb,
+                                                    int *out, ssd3d_stream_t stream)
+{
+    return ssd3d_farthest_point_sample_features_ex(b, n, ca, cb, m, fa, (long long)n * ca, fb, (long long)n * cb, out, m, 0,
+                                                   stream);
 }

@@ -11,14 +11,15 @@ namespace ssd3d {
 
 // out[row, :] = src[scene(row), idx[row], :]   rows = b*rows_per_scene, c % 4 == 0, 16-byte aligned
 __global__ void gather_rows_v4_kernel(long rows, long rows_per_scene, int n, int c4, const float4 *__restrict__ src,
-                                      const int *__restrict__ idx, float4 *__restrict__ out, int neg_is_zero)
+                                      const int *__restrict__ idx, float4 *__restrict__ out, int neg_is_zero,
+                                      long idx_scene_stride)
 {
     const long total = rows * c4;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         const long row = e / c4;
         const int v = (int)(e - row * c4);
         const long scene = row / rows_per_scene;
-        const int a = __ldg(idx + row);
+        const int a = __ldg(idx + scene * idx_scene_stride + (row - scene * rows_per_scene));
         float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!(neg_is_zero && a == -1)) val = __ldg(src + ((size_t)scene * n + a) * c4 + v);
         out[e] = val;
@@ -26,14 +27,15 @@ __global__ void gather_rows_v4_kernel(long rows, long rows_per_scene, int n, int
 }
 
 __global__ void gather_rows_kernel(long rows, long rows_per_scene, int n, int c, const float *__restrict__ src,
-                                   const int *__restrict__ idx, float *__restrict__ out, int neg_is_zero)
+                                   const int *__restrict__ idx, float *__restrict__ out, int neg_is_zero,
+                                   long idx_scene_stride)
 {
     const long total = rows * c;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         const long row = e / c;
         const int ch = (int)(e - row * c);
         const long scene = row / rows_per_scene;
-        const int a = __ldg(idx + row);
+        const int a = __ldg(idx + scene * idx_scene_stride + (row - scene * rows_per_scene));
         float val = 0.0f;
         if (!(neg_is_zero && a == -1)) val = __ldg(src + ((size_t)scene * n + a) * c + ch);
         out[e] = val;
@@ -41,8 +43,9 @@ __global__ void gather_rows_kernel(long rows, long rows_per_scene, int n, int c,
 }
 
 static int launch_gather(long rows, long rows_per_scene, int n, int c, const float *src, const int *idx, float *out,
-                         int neg_is_zero, cudaStream_t st, const char *what)
+                         int neg_is_zero, cudaStream_t st, const char *what, long idx_scene_stride = -1)
 {
+    if (idx_scene_stride < 0) idx_scene_stride = rows_per_scene;
     if (rows == 0 || c == 0) return 0;
     const bool vec = (c % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) &&
                      ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
@@ -52,9 +55,9 @@ static int launch_gather(long rows, long rows_per_scene, int n, int c, const flo
                                                                                   : (long)kNumSMs * 16);
     if (vec)
         gather_rows_v4_kernel<<<blocks, threads, 0, st>>>(rows, rows_per_scene, n, c / 4, (const float4 *)src, idx,
-                                                          (float4 *)out, neg_is_zero);
+                                                          (float4 *)out, neg_is_zero, idx_scene_stride);
     else
-        gather_rows_kernel<<<blocks, threads, 0, st>>>(rows, rows_per_scene, n, c, src, idx, out, neg_is_zero);
+        gather_rows_kernel<<<blocks, threads, 0, st>>>(rows, rows_per_scene, n, c, src, idx, out, neg_is_zero, idx_scene_stride);
     SSD3D_LAUNCH_CHECK(what);
 }
 
@@ -138,6 +141,15 @@ extern "C" int ssd3d_gather_point(int b, int n, int m, int c, const float *inp, 
     SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0 && c >= 0, "gather_point: bad shape b=%d n=%d m=%d c=%d", b, n, m, c);
     SSD3D_REQUIRE(inp && idx && out, "gather_point: null pointer");
     return launch_gather((long)b * m, m, n, c, inp, idx, out, 0, (cudaStream_t)stream, "gather_point");
+}
+
+// gather_point reading idx rows ld_idx ints apart (a column block of a wider [b, L] index tensor)
+extern "C" int ssd3d_gather_point_ex(int b, int n, int m, int c, const float *inp, const int *idx, int ld_idx, float *out,
+                                     ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0 && c >= 0 && ld_idx >= m, "gather_point: bad shape b=%d n=%d m=%d c=%d ld_idx=%d", b, n, m, c, ld_idx);
+    SSD3D_REQUIRE(inp && idx && out, "gather_point: null pointer");
+    return launch_gather((long)b * m, m, n, c, inp, idx, out, 0, (cudaStream_t)stream, "gather_point", ld_idx);
 }
 
 extern "C" int ssd3d_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx,

@@ -62,11 +62,6 @@ struct TcParams {
     // while the CTA sweeps that m-tile's n-tiles, so the producers build it once instead of once per n-tile; only the
     // weights travel through the ring.  Tiles are then enumerated m-major per CTA.
     int astat;
-    // nsplit (experiment, default 1): issue each logical MMA of width bn as nsplit MMAs of width bn/nsplit into adjacent
-    // accumulator columns.  MEASURED SLOWER on B200 (65536x512x1024: 157 -> 197 -> 215 us for 1 / 2 / 4): the cost of a
-    // tcgen05.mma is not a dependent-chain latency that independent chains could hide but ~N/2 cycles plus a fixed
-    // ~20-45 cycles per instruction, so narrower MMAs only add overhead.  Kept behind ssd3d_tune_set_mma_split.
-    int nsplit;
     int gather, g_n, g_c, g_m, g_ns, g_ldz;
     const float *g_xyz, *g_points, *g_new_xyz, *g_wx;
     const int *g_idx;
@@ -277,9 +272,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
         // and tcgen05.mma free of a per-instruction election loop), one elected lane issues =====
         {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N = bn, M = 128
-            const int bnh = p.bn / p.nsplit;                                   // columns per issued MMA
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bnh >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            const uint32_t bstep = (uint32_t)(bnh * 128) >> 4;                 // descriptor units between column groups of B
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int it = 0, tcount = 0, mi = 0, mt, nt;
             for (int i = 0; tile_at(i, mt, nt); i++, tcount++) {
                 const int acc = tcount & 1;
@@ -300,12 +293,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                     if (elect_one()) {
                         for (int ks = 0; ks < ksteps; ks++) {          // +2 per k-step: 32 bytes in the address field
                             const uint32_t first = (kb | ks) ? 1u : 0u;
-                            for (int c = 0; c < p.nsplit; c++)
-                                umma_bf16(d_tmem + c * bnh, a_hi + 2 * ks, b_hi + 2 * ks + c * bstep, idesc, first);
-                            for (int c = 0; c < p.nsplit; c++)
-                                umma_bf16(d_tmem + c * bnh, a_lo + 2 * ks, b_hi + 2 * ks + c * bstep, idesc, 1u);
-                            for (int c = 0; c < p.nsplit; c++)
-                                umma_bf16(d_tmem + c * bnh, a_hi + 2 * ks, b_lo + 2 * ks + c * bstep, idesc, 1u);
+                            umma_bf16(d_tmem, a_hi + 2 * ks, b_hi + 2 * ks, idesc, first);
+                            umma_bf16(d_tmem, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+                            umma_bf16(d_tmem, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
                         }
                         umma_commit(smem_u32(&empty_bar[s]));   // ring stage free once these MMAs retire
                         if (p.astat && last_nt) umma_commit(smem_u32(&aempty_bar[kb]));   // A k-block free for the next m-tile
@@ -676,8 +666,6 @@ static int make_out_map(CUtensorMap *map, const void *ptr, long nrows, int ncols
 
 using namespace ssd3d;
 
-static int g_tc_nsplit = 0;                // tuning override (0 = automatic)
-extern "C" void ssd3d_tune_set_mma_split(int nsplit) { g_tc_nsplit = nsplit; }
 
 struct TcGather { int b, n, c, m, ns; const float *xyz, *points, *new_xyz; const int *idx; int ldz; const float *wx; };
 
@@ -755,11 +743,6 @@ static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const vo
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     SSD3D_REQUIRE(stages >= 2, "linear_tc: tile does not fit shared memory");
     p.stages = stages;
-    {   // independent accumulator chains per tile: widths stay multiples of 16 (M = 128 MMA shapes)
-        int ns = g_tc_nsplit > 0 ? g_tc_nsplit : 1;
-        while (ns > 1 && (p.bn % (16 * ns)) != 0) ns /= 2;
-        p.nsplit = ns;
-    }
     p.scale = scale; p.shift = shift; p.relu = relu; p.pool = pool; p.rowmask = rowmask;
     p.out_f32 = out_f32; p.ld_f32 = ld_f32;
     p.out_hi = (__nv_bfloat16 *)out_hi; p.out_lo = (__nv_bfloat16 *)out_lo; p.ld_split = ld_split;

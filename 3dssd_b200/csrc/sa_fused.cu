@@ -57,7 +57,6 @@ struct SfParams {
     int nfull[SF_MAX_LAYERS];        // layer l's K = nfull 64-wide k-blocks (128-byte rows) + one tail block
     int rbt[SF_MAX_LAYERS];          // bytes per row of the tail block: 0 (none), 32 (16 wide), 64 (32), 128 (48)
     uint32_t abuf_bytes;             // operand buffer of one slot
-    int nsplit[SF_MAX_LAYERS];       // layer l's MMAs are issued as nsplit column groups (independent accumulator chains)
     uint32_t tmem_cols;              // accumulator columns of one slot
     uint32_t tmem_alloc;             // power of two >= slots * tmem_cols
     float *out_f32; int ld_f32;
@@ -338,11 +337,9 @@ sa_fused_kernel(const SfParams p)
             SF_T(1 + 4 * l);                                           // barrier
             if (issuer_warp) {
                 sf_fence_after();
-                // nsplit > 1 (experiment, ssd3d_tune_set_fused_mma_split): issue every logical MMA as nsplit MMAs of
-                // npad/nsplit columns into adjacent accumulator columns.  Measured slower (a tcgen05.mma costs ~N/2 cycles
-                // plus a fixed per-instruction part; there is no dependent-chain latency to hide), default 1.
-                const int ns = p.nsplit[l], nh = p.npad[l] / ns;
-                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nh >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                // one MMA per k-step covers the whole layer width: a tcgen05.mma costs ~N/2 cycles plus a fixed
+                // per-instruction part, so narrower MMAs only add overhead (measured in round 1)
+                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.npad[l] >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
                 const uint32_t tmem_u = tmem_base_smem + (uint32_t)slot_u * p.tmem_cols;
                 const uint32_t abase = smem_u32(smem) + (uint32_t)slot_u * p.abuf_bytes;
                 const uint32_t wbase = smem_u32(wsm) + p.w_off[l];
@@ -353,13 +350,12 @@ sa_fused_kernel(const SfParams p)
                     const uint64_t a_hi = sf_desc(abase + (uint32_t)kb * (2u * 128u * 128u), 128);
                     const uint64_t b_hi = sf_desc(wbase + (uint32_t)kb * ((uint32_t)p.npad[l] * 128u), 128);
                     const uint64_t a_lo = a_hi + ((128u * 128u) >> 4), b_lo = b_hi + (p.w_half[l] >> 4);
-                    const uint32_t bstep = (uint32_t)(nh * 128) >> 4;
 #pragma unroll
                     for (int kin = 0; kin < 4; kin++) {
                         if (elect_one()) {
-                            for (int c = 0; c < ns; c++) sf_mma(tmem_u + c * nh, a_hi + 2 * kin, b_hi + 2 * kin + c * bstep, idesc, acc);
-                            for (int c = 0; c < ns; c++) sf_mma(tmem_u + c * nh, a_lo + 2 * kin, b_hi + 2 * kin + c * bstep, idesc, 1u);
-                            for (int c = 0; c < ns; c++) sf_mma(tmem_u + c * nh, a_hi + 2 * kin, b_lo + 2 * kin + c * bstep, idesc, 1u);
+                            sf_mma(tmem_u, a_hi + 2 * kin, b_hi + 2 * kin, idesc, acc);
+                            sf_mma(tmem_u, a_lo + 2 * kin, b_hi + 2 * kin, idesc, 1u);
+                            sf_mma(tmem_u, a_hi + 2 * kin, b_lo + 2 * kin, idesc, 1u);
                         }
                         acc = 1u;
                     }
@@ -368,13 +364,12 @@ sa_fused_kernel(const SfParams p)
                     const uint64_t a_hi = sf_desc(abase + (uint32_t)nfull * (2u * 128u * 128u), rbt);
                     const uint64_t b_hi = sf_desc(wbase + (uint32_t)nfull * ((uint32_t)p.npad[l] * 128u), rbt);
                     const uint64_t a_lo = a_hi + ((128u * (uint32_t)rbt) >> 4), b_lo = b_hi + (p.w_half[l] >> 4);
-                    const uint32_t bstep = (uint32_t)(nh * rbt) >> 4;
                     const int nt = rbt == 128 ? 3 : (rbt >> 5);              // 16-wide k-steps of the tail block
                     for (int kin = 0; kin < nt; kin++) {
                         if (elect_one()) {
-                            for (int c = 0; c < ns; c++) sf_mma(tmem_u + c * nh, a_hi + 2 * kin, b_hi + 2 * kin + c * bstep, idesc, acc);
-                            for (int c = 0; c < ns; c++) sf_mma(tmem_u + c * nh, a_lo + 2 * kin, b_hi + 2 * kin + c * bstep, idesc, 1u);
-                            for (int c = 0; c < ns; c++) sf_mma(tmem_u + c * nh, a_hi + 2 * kin, b_lo + 2 * kin + c * bstep, idesc, 1u);
+                            sf_mma(tmem_u, a_hi + 2 * kin, b_hi + 2 * kin, idesc, acc);
+                            sf_mma(tmem_u, a_lo + 2 * kin, b_hi + 2 * kin, idesc, 1u);
+                            sf_mma(tmem_u, a_hi + 2 * kin, b_lo + 2 * kin, idesc, 1u);
                         }
                         acc = 1u;
                     }
@@ -489,9 +484,14 @@ static size_t sf_total(const SfPlan &pl, int slots) { return slots * pl.abuf + p
 constexpr size_t SF_SMEM_MAX = 226 * 1024;
 constexpr size_t SF_SMALL = 36 * 1024;                     // <= this: single-slot CTAs, up to 6 per SM
 
-static int g_sf_slots = 0, g_sf_wg = 0, g_sf_nsplit = 0;  // tuning overrides (0 = automatic)
-extern "C" void ssd3d_tune_set_fused(int slots, int wg) { g_sf_slots = slots; g_sf_wg = wg; }
-extern "C" void ssd3d_tune_set_fused_mma_split(int nsplit) { g_sf_nsplit = nsplit; }
+// Developer build only (-DSSD3D_DEV_HOOKS, csrc/ssd3d_dev.h): override the slot / warpgroup shape from a probe script.
+// The shipped library has no such state.
+#ifdef SSD3D_DEV_HOOKS
+static int g_sf_slots = 0, g_sf_wg = 0;
+extern "C" void ssd3d_dev_set_fused(int slots, int wg) { g_sf_slots = slots; g_sf_wg = wg; }
+#else
+constexpr int g_sf_slots = 0, g_sf_wg = 0;
+#endif
 
 // Slots per CTA for a stack: 1 for small stacks (several CTAs per SM), else as many as fit one SM (<= 3).
 static int sf_slots(const SfPlan &pl)
@@ -565,11 +565,6 @@ static int sa_mlp_fused_impl(int b, int n, int c, int m, int nsample, const floa
         p.nout[l] = nout[l];
         p.npad[l] = (nout[l] + 15) / 16 * 16;
         sf_k_blocks(p.kp[l], &p.nfull[l], &p.rbt[l]);
-        {   // column groups stay multiples of 16 (M = 128 MMA shapes); sub-tiles of the weight image start on 8-row groups
-            int ns = g_sf_nsplit > 0 ? g_sf_nsplit : 1;
-            while (ns > 1 && (p.npad[l] % (16 * ns)) != 0) ns /= 2;
-            p.nsplit[l] = ns;
-        }
         p.w_off[l] = woff;
         p.w_half[l] = (uint32_t)sf_wimg_bytes(p.kp[l], p.npad[l]);
         woff += 2 * p.w_half[l];

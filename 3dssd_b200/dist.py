@@ -5,11 +5,19 @@ the path shards by scene with no activation exchange: rank r of G processes scen
 only collective is ONE all-gather per step of the fixed-size per-scene detection block ([100, 9] fp32 + a
 count word); at <= 64 scenes x 3.6 KB it is latency-bound, so a single NCCL call is the right tool.
 The reference has no inference sharding (evaluation is single-GPU bs=1, lib/core/evaluator.py:145-147).
+
+DetectionGather keeps the whole exchange inside the captured step: the NMS kernel writes its block and count
+straight into a preallocated send buffer, ncclAllGather on that buffer is captured into the step's CUDA graph, and the
+gathered result is read through views of the receive buffer -- no pack / unpack kernels and no host work per step
+beyond graph.replay().
 """
 import os
 
 import torch
 import torch.distributed as dist
+
+MAX_OUTPUT_NUM = 100
+BLOCK_COLS = 9
 
 
 def init_from_env(backend=None):
@@ -38,25 +46,75 @@ def shard_batch(batch, rank, world):
     return batch[lo:hi]
 
 
-def gather_detections(block, count, total_scenes=None):
-    """All-gather the per-scene detection blocks: block [b_local, 100, 9] fp32, count [b_local] int32 ->
-    ([B, 100, 9], [B]) on every rank.  One collective: the count travels as a 10th column."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+def _world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+class DetectionGather:
+    """Send / receive buffers of the per-step all-gather, owned by one step pipeline.
+
+    total_scenes scenes are sharded with shard_bounds; every rank sends b_max = ceil(total / world) slots (unused
+    slots stay zero).  Layout of a rank's slice (bytes): [b_max * 100 * 9 fp32 block | b_max int32 count].
+      out()      -> (block [b_local,100,9] fp32, count [b_local] int32) views of the SEND buffer: hand them to the NMS
+      gather()   -> enqueue the all-gather on the current stream (CUDA-graph capturable; a no-op for one rank)
+      result()   -> (blocks [total,100,9], counts [total]) of all scenes, assembled from views of the RECEIVE buffer
+      raw        -> the receive buffer itself (uint8), what a host reads back in one copy
+    group: the process group (= NCCL communicator) to use.  Step pipelines that run concurrently on different streams
+    must not share one -- collectives of one communicator may not overlap -- so each pipeline passes its own group."""
+
+    def __init__(self, total_scenes, device, group=None, max_output=MAX_OUTPUT_NUM):
+        self.world, self.rank = _world(group)
+        self.group = group
+        self.total = int(total_scenes)
+        self.max_output = int(max_output)
+        lo, hi = shard_bounds(self.total, self.rank, self.world)
+        self.b_local = hi - lo
+        self.b_max = (self.total + self.world - 1) // self.world
+        self.block_bytes = self.b_max * self.max_output * BLOCK_COLS * 4
+        self.slice_bytes = self.block_bytes + self.b_max * 4
+        self.send = torch.zeros((self.slice_bytes,), dtype=torch.uint8, device=device)
+        self.raw = self.send if self.world == 1 else torch.zeros((self.world * self.slice_bytes,), dtype=torch.uint8,
+                                                                 device=device)
+
+    def _views(self, buf):
+        blk = buf[: self.block_bytes].view(torch.float32).view(self.b_max, self.max_output, BLOCK_COLS)
+        cnt = buf[self.block_bytes: self.slice_bytes].view(torch.int32)
+        return blk, cnt
+
+    def out(self):
+        blk, cnt = self._views(self.send)
+        return blk[: self.b_local], cnt[: self.b_local]
+
+    def gather(self):
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.raw, self.send, group=self.group)
+
+    def result(self):
+        blocks, counts = [], []
+        for r in range(self.world):
+            lo, hi = shard_bounds(self.total, r, self.world)
+            blk, cnt = self._views(self.raw[r * self.slice_bytes: (r + 1) * self.slice_bytes])
+            blocks.append(blk[: hi - lo]); counts.append(cnt[: hi - lo])
+        if self.world == 1:
+            return blocks[0], counts[0]
+        return torch.cat(blocks, dim=0), torch.cat(counts, dim=0)
+
+
+def gather_detections(block, count, total_scenes, group=None):
+    """One-shot form: all-gather per-scene detection blocks block [b_local, 100, 9] fp32 / count [b_local] int32 of a
+    batch of `total_scenes` scenes sharded with shard_bounds -> ([total, 100, 9], [total]) on every rank.
+    total_scenes is required: with uneven shards the ranks cannot derive a common slot count from their own b_local."""
+    world, rank = _world(group)
+    if world == 1:
         return block, count
-    world = dist.get_world_size()
-    b_local = block.shape[0]
-    if total_scenes is None:
-        total_scenes = b_local * world
-    b_max = (total_scenes + world - 1) // world
-    packed = torch.zeros((b_max, block.shape[1], block.shape[2] + 1), dtype=torch.float32, device=block.device)
-    packed[:b_local, :, : block.shape[2]] = block
-    packed[:b_local, 0, block.shape[2]] = count.to(torch.float32)
-    out = torch.empty((world * b_max,) + tuple(packed.shape[1:]), dtype=torch.float32, device=block.device)
-    dist.all_gather_into_tensor(out, packed)
-    pieces, counts = [], []
-    for r in range(world):
-        lo, hi = shard_bounds(total_scenes, r, world)
-        seg = out[r * b_max: r * b_max + (hi - lo)]
-        pieces.append(seg[:, :, : block.shape[2]])
-        counts.append(seg[:, 0, block.shape[2]].to(torch.int32))
-    return torch.cat(pieces, dim=0), torch.cat(counts, dim=0)
+    lo, hi = shard_bounds(int(total_scenes), rank, world)
+    if block.shape[0] != hi - lo or count.shape[0] != hi - lo:
+        raise ValueError("rank %d holds %d scenes but shard_bounds(%d, %d, %d) assigns it %d"
+                         % (rank, block.shape[0], total_scenes, rank, world, hi - lo))
+    g = DetectionGather(total_scenes, block.device, group=group, max_output=block.shape[1])
+    b, c = g.out()
+    b.copy_(block); c.copy_(count)
+    g.gather()
+    return g.result()

@@ -93,22 +93,29 @@ class DetectionHead:
         self.cls_num = cls_num
         self.params = prepare(params, device)
 
-    def forward(self, xyz_list, feature_list, return_raw=False):
-        xyz = torch.cat([xyz_list[i] for i in self.xyz_index], dim=1)             # head_builder.py:82-85
-        feat = torch.cat([feature_list[i] for i in self.feature_index], dim=1).contiguous()
+    def forward(self, xyz_list, feature_list, return_raw=False, out=None):
+        """out=(block, count): preallocated outputs of the NMS (the send buffer of the multi-GPU gather)."""
+        xs = [xyz_list[i] for i in self.xyz_index]                                 # head_builder.py:82-85
+        fs = [feature_list[i] for i in self.feature_index]
+        xyz = xs[0] if len(xs) == 1 else torch.cat(xs, dim=1)
+        feat = (fs[0] if len(fs) == 1 else torch.cat(fs, dim=1)).contiguous()
         hi, lo = tf_ops.split_rows(feat)
         y = feat
         for i, ch in enumerate(self.mlp_list):                                    # :93-95
             y, (hi, lo) = tf_ops.linear_tc(hi, lo, self.params.conv(_scope(self.scope, "conv1d_%d" % i), self.bn),
                                            want_f32=True, want_split=True)
-        cls, off, acls, ares = box_regression_head(y, self.cls_num, 1, REG_CHANNELS, self.bn, False,
-                                                   params=self.params, scope=self.scope)
-        boxes = decode_dist_anchor_free(xyz, off[:, :, 0], acls[:, :, 0], ares[:, :, 0]).unsqueeze(2)   # (bs,n,1,7)
-        score = torch.sigmoid(cls)                                                # single_stage_detector.py:210-211
-        block, cnt = postprocess(boxes, score)
+        pp, sc = self.params, self.scope
+        cls = _conv_chain(pp, hi, lo, [(_scope(sc, "pred_cls_base"), self.bn, True), (_scope(sc, "pred_cls"), False, False)])
+        reg = _conv_chain(pp, hi, lo, [(_scope(sc, "pred_reg_base"), self.bn, True), (_scope(sc, "pred_reg"), False, False)])
+        # decode_dist_anchor_free + sigmoid (anchor_decoder.py:86-112, single_stage_detector.py:210-211): one kernel
+        boxes, score = tf_ops.decode_dist_anchor_free(xyz, reg, cls, ANGLE_CLS_NUM)
+        block, cnt = tf_ops.bev_nms(boxes, score, NMS_THRESH, MAX_OUTPUT_NUM, cls_id=0, out=out)   # postprocessor.py:52-120
         if return_raw:
-            return block, cnt, {"boxes": boxes, "score": score, "cls": cls, "offset": off, "angle_cls": acls,
-                                "angle_res": ares, "feat": y}
+            bs, n, _ = reg.shape
+            r4 = reg.view(bs, n, 1, REG_CHANNELS + 2 * ANGLE_CLS_NUM)
+            return block, cnt, {"boxes": boxes.unsqueeze(2), "score": score.unsqueeze(-1), "cls": cls,
+                                "offset": r4[..., :REG_CHANNELS], "angle_cls": r4[..., REG_CHANNELS:REG_CHANNELS + ANGLE_CLS_NUM],
+                                "angle_res": r4[..., REG_CHANNELS + ANGLE_CLS_NUM:], "feat": y}
         return block, cnt
 
     __call__ = forward

@@ -32,225 +32,352 @@ def _const(values, device):
 _SIDE_STREAMS = {}
 
 
-def _side_stream(device):
-    key = str(device)
+def _side_stream(device, i=0):
+    key = (str(device), i)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]
 
 
-def _arange_idx(bs, npoint, device):
-    return torch.arange(npoint, dtype=torch.int32, device=device).unsqueeze(0).repeat(bs, 1)
-
-
-def ffps_indices(npoint, xyz, points, mode):
+def ffps_indices(npoint, xyz, points, mode, out=None, idx_offset=0):
     """F-FPS on concat[xyz, points] (layers_util.py:94-96, :102-104).
     mode 'direct': one kernel, no [B,N,N] tensor, the SAME indices as 'matrix' (each round evaluates the picked point's
                    matrix row on chip with calc_square_dist's arithmetic); falls back to 'matrix' for uncovered shapes;
     mode 'matrix': calc_square_dist + farthest_point_sample_with_distance, the reference's route;
     mode 'fused' : matrix-free -- the generic-c FPS kernel evaluates the feature distance on the fly (no
-                   [B,N,N] tensor); identical to the reference's own farthest_point_sample on the features."""
+                   [B,N,N] tensor); identical to the reference's own farthest_point_sample on the features.
+    xyz / points may be [:, a:b] slices of dense tensors (read in place); out=(buffer, col) / idx_offset as in
+    tf_ops.farthest_point_sample."""
     if mode == "direct":
         c = xyz.shape[2] + points.shape[2]
         # the 132-channel variant walks a 131-long dependent fma chain per round: at layer-3 sizes (512 points) the
         # small matrix is faster, so 'direct' is used where the matrix is the expensive part (c <= 68, layer 2)
         if c <= 68 and tf_ops.ffps_supported(xyz.shape[1], c):
-            return tf_ops.farthest_point_sample_features(npoint, xyz, points)
+            return tf_ops.farthest_point_sample_features(npoint, xyz, points, out=out, idx_offset=idx_offset)
         mode = "matrix"
-    feats = torch.cat([xyz, points], dim=-1).contiguous()
+    feats = tf_ops.concat_cols(xyz, points) if points.shape[2] else xyz
     if mode == "matrix":
-        return tf_ops.farthest_point_sample_with_distance(npoint, tf_ops.calc_square_dist(feats))
+        return tf_ops.farthest_point_sample_with_distance(npoint, tf_ops.calc_square_dist(feats), out=out,
+                                                          idx_offset=idx_offset)
     if mode == "fused":
-        return tf_ops.farthest_point_sample(npoint, feats)
+        return tf_ops.farthest_point_sample(npoint, feats, out=out, idx_offset=idx_offset)
     raise ValueError("ffps_mode must be 'direct', 'matrix' or 'fused'")
+
+
+def _part_bounds(npoint, fps_parts):
+    """Round ranges of a D-FPS consumed in parts: fps_parts = number of equal parts or a list of fractions."""
+    if isinstance(fps_parts, int):
+        fr = [1.0 / fps_parts] * fps_parts
+    else:
+        fr = [float(f) for f in fps_parts]
+    cuts, acc = [0], 0.0
+    for f in fr[:-1]:
+        acc += f
+        c = int(round(acc / sum(fr) * npoint / 128.0)) * 128          # parts are whole 128-row tiles of every scale
+        cuts.append(min(max(c, cuts[-1]), npoint))
+    cuts.append(npoint)
+    return [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]]
+
+
+class _Hoisted:
+    """The per-point table of the hoisted first convs of a layer (see pointnet_sa_module_msg)."""
+    __slots__ = ("scales", "z", "zoffs", "wxs", "stacks")
+
+
+def _prepare_hoist(pp, scope, mlp_list, bn, c_feat, stacks, gather_in_kernel, hoist_first):
+    nscale = len(mlp_list)
+    h = _Hoisted()
+    # hoist_first: 0 off, 1 layer-by-layer scales only, 2 all.  An xyz-only cloud (c_feat == 0) has no feature part to
+    # hoist: the first conv then runs in the grouped domain (linear_tc_gather / sa_mlp_fused accept c = 0).
+    h.scales = [i for i in range(nscale) if len(mlp_list[i]) >= 2 and (int(hoist_first) >= 2 or stacks[i] is None)] \
+        if (gather_in_kernel and hoist_first and c_feat > 0) else []
+    h.z = h.zoffs = h.wxs = None
+    h.stacks = {}
+    return h
+
+
+def _compute_hoist(h, pp, scope, mlp_list, bn, points, stacks):
+    if not h.scales:
+        return
+    c_feat = points.shape[-1]
+    zconv, h.wxs, n1s = pp.hoisted(["%s/conv%d_0" % (scope, i) for i in h.scales], bn, c_feat)
+    p_hi, p_lo = tf_ops.split_rows(points)
+    h.z, _ = tf_ops.linear_tc(p_hi, p_lo, zconv, relu=False, want_f32=True, want_split=False)
+    h.zoffs = [sum(n1s[:t]) for t in range(len(h.scales))]
+    for t, i in enumerate(h.scales):
+        if stacks[i] is not None:    # remaining convs of a fused scale
+            h.stacks[i] = pp.fused_stack(["%s/conv%d_%d" % (scope, i, j) for j in range(1, len(mlp_list[i]))], bn, n1s[t])
+
+
+def _group_and_mlp(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, mlp_list, bn, dilated_group, use_agg,
+                   mlp_mode, stacks, hoist, gather_in_kernel, debug):
+    """Everything of pointnet_sa_module_msg after the sampling, for one block of query points new_xyz (b, m_q, 3):
+    ball queries (:137-145), grouping + MLP + max-pool + mask per scale (:157-180), concat + aggregation (:182-185)."""
+    bs = xyz.shape[0]
+    nscale = len(radius_list)
+    min_r = [0.0 if (i == 0 or not dilated_group) else radius_list[i - 1] for i in range(nscale)]   # :137-141
+    if nscale <= 4:   # one pass over the candidates for all shells
+        idx_list, cnt_list = tf_ops.query_ball_point_multi(min_r, radius_list, nsample_list, xyz, new_xyz, dilated_group)
+    else:
+        idx_list, cnt_list = [], []
+        for i in range(nscale):
+            if dilated_group:
+                a, c = tf_ops.query_ball_point_dilated(min_r[i], radius_list[i], nsample_list[i], xyz, new_xyz)
+            else:
+                a, c = tf_ops.query_ball_point(radius_list[i], nsample_list[i], xyz, new_xyz)
+            idx_list.append(a); cnt_list.append(c)
+    debug["idx"].append(idx_list); debug["cnt"].append(cnt_list)
+    # tensor-core path needs pooling widths the epilogue covers and 16-byte aligned column slices of the concat buffers
+    tc = (mlp_mode == "tc" and all(k in (8, 16, 32, 64, 128) for k in nsample_list)
+          and all(m[-1] % 8 == 0 for m in mlp_list))
+    if tc:
+        # tensor-core path: every scale pools straight into its slice of the concat buffer (fp32 for the
+        # caller, split bf16 for the aggregation conv), activations stay split between layers
+        m_q = new_xyz.shape[1]
+        ctot = sum(m[-1] for m in mlp_list)
+        concat = torch.empty((bs, m_q, ctot), dtype=torch.float32, device=xyz.device)
+        cat_hi = cat_lo = None
+        if use_agg:
+            ldc = tf_ops.round16(ctot)
+            mk = torch.zeros if ldc != ctot else torch.empty
+            cat_hi = mk((bs, m_q, ldc), dtype=torch.bfloat16, device=xyz.device)
+            cat_lo = mk((bs, m_q, ldc), dtype=torch.bfloat16, device=xyz.device)
+        off = 0
+        z, zoffs, wxs, hstacks, hscales = hoist.z, hoist.zoffs, hoist.wxs, hoist.stacks, hoist.scales
+        for i in range(nscale):
+            idx, cnt = idx_list[i], cnt_list[i]
+            nl = len(mlp_list[i])
+            stack = stacks[i]
+            if stack is not None:                                              # whole scale in one kernel
+                if hstacks.get(i) is not None:
+                    t = hscales.index(i)
+                    tf_ops.sa_mlp_fused_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, cnt, hstacks[i], out_f32=(concat, off),
+                                                out_split=(cat_hi, cat_lo, off) if use_agg else None)
+                else:
+                    tf_ops.sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=(concat, off),
+                                        out_split=(cat_hi, cat_lo, off) if use_agg else None)
+                off += mlp_list[i][-1]
+                continue
+            hi = lo = None
+            for j in range(nl):
+                f = pp.conv("%s/conv%d_%d" % (scope, i, j), bn)
+                last_kw = dict(pool=nsample_list[i], rowmask=cnt, out_f32=(concat, off),
+                               out_split=(cat_hi, cat_lo, off) if use_agg else None)   # :167-180 conv+BN+ReLU+max+mask
+                if i in hscales:
+                    if j == 0:
+                        continue                  # folded into z and into the next conv's operand producer
+                    if j == 1:
+                        t = hscales.index(i)
+                        if nl == 2:
+                            tf_ops.linear_tc_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, f, want_split=False, **last_kw)
+                        else:
+                            _, (hi, lo) = tf_ops.linear_tc_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, f)
+                        continue
+                if j == 0 and gather_in_kernel:   # :160-165 inside the kernel's operand load (no [B,M,K,C] tensor)
+                    if nl == 1:
+                        tf_ops.linear_tc_gather(xyz, points, new_xyz, idx, f, want_split=False, **last_kw)
+                    else:
+                        _, (hi, lo) = tf_ops.linear_tc_gather(xyz, points, new_xyz, idx, f)
+                    continue
+                if j == 0:                        # :160-165 fused with the split, materialised once in bf16 hi/lo
+                    hi, lo = tf_ops.group_concat_split(xyz, points, new_xyz, idx)
+                if j < nl - 1:
+                    _, (hi, lo) = tf_ops.linear_tc(hi, lo, f, want_f32=False, want_split=True)
+                else:
+                    tf_ops.linear_tc(hi, lo, f, **last_kw)
+            off += mlp_list[i][-1]
+        new_points = concat
+        if use_agg:                                                            # :183-185
+            new_points, _ = tf_ops.linear_tc(cat_hi, cat_lo, pp.conv(scope + "/ensemble", bn))
+        return new_points
+    outs = []
+    for i in range(nscale):
+        idx, cnt = idx_list[i], cnt_list[i]
+        # rows with cnt == 0 come back zero-filled, which is what idx * (cnt > 0) produces (:157-159)
+        g = tf_ops.group_concat(xyz, points, new_xyz, idx)                    # :160-165 fused
+        nl = len(mlp_list[i])
+        for j in range(nl):
+            lastl = j == nl - 1
+            g = _conv(pp, "%s/conv%d_%d" % (scope, i, j), g, bn=bn,
+                      pool=nsample_list[i] if lastl else 1, rowmask=cnt if lastl else None)   # :167-180
+        outs.append(g)
+    new_points = outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
+    if use_agg:
+        new_points = _conv(pp, scope + "/ensemble", new_points, bn=bn)        # :183-185
+    return new_points
 
 
 def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_training, bn_decay, bn,
                            fps_sample_range_list, fps_method_list, npoint_list, former_fps_idx, use_attention, scope,
                            dilated_group, vote_ctr=None, aggregation_channel=None, debugging=False, epsilon=1e-5, *,
                            params, ffps_mode="direct", aggregation=None, return_debug=False, mlp_mode="tc",
-                           fuse_scale=True, gather_in_kernel=True, hoist_first=2):
-    """PointNet++ SA module with multi-scale grouping; returns (new_xyz, new_points, fps_idx)."""
+                           fuse_scale=True, gather_in_kernel=True, hoist_first=2, fps_cluster=0, fps_parts=None):
+    """PointNet++ SA module with multi-scale grouping; returns (new_xyz, new_points, fps_idx).
+
+    Keyword extensions (none changes a result):
+      fps_cluster  CTAs per scene of the D-FPS kernels (tf_ops.farthest_point_sample `cluster`);
+      fps_parts    latency mode.  FPS emits its samples in order, and a sample is final once its round is done, so the
+                   layer consumes the sampling IN PARTS: a lone D-FPS runs as resumable launches of rounds (an int =
+                   that many equal parts, or a list of fractions), a fusion-sampling layer hands over its F-FPS and
+                   D-FPS halves separately; ball query + grouped MLP + aggregation of a part run on a side stream
+                   while the sampling of the next part continues, and the per-part results are joined at the end.
+                   Captured in a CUDA graph this is a plain dependency graph -- nothing polls."""
     if is_training:
         raise NotImplementedError("training-mode BatchNorm / backward ops are out of scope (inference only)")
     if use_attention:
         raise NotImplementedError("query_ball_point_withidx (use_attention) is unused by the shipped 3DSSD configs")
+    if mlp_mode not in ("tc", "fp32"):
+        raise ValueError("mlp_mode must be 'tc' or 'fp32'")
     pp = prepare(params, xyz.device)
     aggregation = _cfg.AGGREGATION_SA_FEATURE if aggregation is None else aggregation
     bs, n, _ = xyz.shape
+    dev = xyz.device
+    nscale = len(radius_list)
+    main = torch.cuda.current_stream()
+    in_parts = bool(fps_parts) and nscale > 0 and former_fps_idx is None
+    keep = []                                  # temporaries shared between streams stay alive until the final join
 
-    cur, last = [], 0
-    join_side = False
+    # ---- hoisted first convs: the feature part of conv0 of every scale, once per POINT (independent of the sampling)
+    c_feat = points.shape[-1]
+    stacks = hoist = None
+    if nscale:
+        tc_ok = mlp_mode == "tc" and all(k in (8, 16, 32, 64, 128) for k in nsample_list) and all(m[-1] % 8 == 0 for m in mlp_list)
+        stacks = [pp.fused_stack(["%s/conv%d_%d" % (scope, i, j) for j in range(len(mlp_list[i]))], bn, c_feat + 3)
+                  if (fuse_scale and tc_ok) else None for i in range(nscale)]
+        hoist = _prepare_hoist(pp, scope, mlp_list, bn, c_feat, stacks, gather_in_kernel and tc_ok, hoist_first)
+        if in_parts and hoist.scales:          # overlaps the first rounds of the sampling
+            zs = _side_stream(dev, 7)
+            zs.wait_stream(main)
+            with torch.cuda.stream(zs):
+                _compute_hoist(hoist, pp, scope, mlp_list, bn, points, stacks)
+            z_ready = torch.cuda.Event()
+            z_ready.record(zs)
+
+    # ---- sampling (:84-111): every segment writes its indices, segment offset included, straight into fps_idx
+    segs, last = [], 0
     for rng, method, npoint in zip(fps_sample_range_list, fps_method_list, npoint_list):
         end = n if rng == -1 else last + rng                      # tf.slice size -1 (:86-87)
-        tmp_xyz = xyz[:, last:end].contiguous()
-        tmp_points = points[:, last:end]
         if npoint == 0:                                           # :88-90
             last += rng
             continue
         if vote_ctr is not None:                                  # :91-93
-            npoint = vote_ctr.shape[1]
-            fps_idx = _arange_idx(bs, npoint, xyz.device)
+            kind, width = "iota", vote_ctr.shape[1]
         elif method == "FS":                                      # :94-99 fusion sampling
-            # F-FPS and D-FPS are independent latency-bound chains on a handful of SMs each: run them concurrently
-            side = _side_stream(xyz.device)
-            cur_s = torch.cuda.current_stream()
-            side.wait_stream(cur_s)
-            tmp_xyz.record_stream(side)
-            with torch.cuda.stream(side):
-                d_idx = tf_ops.farthest_point_sample(npoint, tmp_xyz)
-            f_idx = ffps_indices(npoint, tmp_xyz, tmp_points, ffps_mode)
-            cur_s.wait_stream(side)
-            d_idx.record_stream(cur_s)
-            fps_idx = torch.cat([f_idx, d_idx], dim=-1)
-        elif npoint == tmp_xyz.shape[1]:                          # :100-101
-            fps_idx = _arange_idx(bs, npoint, xyz.device)
+            kind, width = "FS", 2 * npoint
+        elif npoint == end - last:                                # :100-101
+            kind, width = "iota", npoint
         elif method == "F-FPS":                                   # :102-105
-            fps_idx = ffps_indices(npoint, tmp_xyz, tmp_points, ffps_mode)
-        elif len(npoint_list) > 1:                                # D-FPS segment next to other segments: side stream
-            side = _side_stream(xyz.device)
-            cur_s = torch.cuda.current_stream()
-            side.wait_stream(cur_s)
-            tmp_xyz.record_stream(side)
-            with torch.cuda.stream(side):
-                fps_idx = tf_ops.farthest_point_sample(npoint, tmp_xyz)
-                if last:
-                    fps_idx = fps_idx + last
-            fps_idx.record_stream(cur_s)
-            cur.append(fps_idx)
-            last += rng
-            join_side = True
-            continue
+            kind, width = "F", npoint
         else:                                                     # D-FPS :106-107
-            fps_idx = tf_ops.farthest_point_sample(npoint, tmp_xyz)
-        cur.append(fps_idx + last if last else fps_idx)           # :109
+            kind, width = "D", npoint
+        segs.append((kind, last, end, npoint, width))
         last += rng
-    if join_side:
-        torch.cuda.current_stream().wait_stream(_side_stream(xyz.device))
-    fps_idx = cur[0] if len(cur) == 1 else torch.cat(cur, dim=-1)
-    if former_fps_idx is not None:
-        fps_idx = torch.cat([fps_idx, former_fps_idx], dim=-1)    # :113-114
-    fps_idx = fps_idx.contiguous()
-    new_xyz = tf_ops.gather_point(vote_ctr if vote_ctr is not None else xyz, fps_idx)   # :116-119
+    mtot = sum(sg[4] for sg in segs)
+    fps_idx = torch.empty((bs, mtot), dtype=torch.int32, device=dev)
+    parts = []                                 # (col0, col1, event): fps_idx[:, col0:col1] is complete at `event`
+    col, nside = 0, 0
 
+    def on_side(fn):
+        nonlocal nside
+        side = _side_stream(dev, nside)
+        nside += 1
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            fn()
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return ev
+
+    def ev_main():
+        ev = torch.cuda.Event()
+        ev.record(main)
+        return ev
+
+    lone = len(segs) == 1
+    for kind, lo, hi, npoint, width in segs:
+        tmp_xyz, tmp_points = xyz[:, lo:hi], points[:, lo:hi]     # read in place (scene-strided)
+        if kind == "iota":
+            tf_ops.iota_idx(bs, width, dev, out=(fps_idx, col), start=lo)
+            parts.append((col, col + width, ev_main() if in_parts else None))
+        elif kind == "FS":
+            # F-FPS and D-FPS are independent latency-bound chains on a handful of SMs each: run them concurrently
+            c0 = col
+            ev_d = on_side(lambda: tf_ops.farthest_point_sample(npoint, tmp_xyz, out=(fps_idx, c0 + npoint), idx_offset=lo,
+                                                                cluster=fps_cluster))
+            ffps_indices(npoint, tmp_xyz, tmp_points, ffps_mode, out=(fps_idx, col), idx_offset=lo)
+            parts.append((col, col + npoint, ev_main() if in_parts else None))
+            parts.append((col + npoint, col + 2 * npoint, ev_d))
+        elif kind == "F":
+            ffps_indices(npoint, tmp_xyz, tmp_points, ffps_mode, out=(fps_idx, col), idx_offset=lo)
+            parts.append((col, col + npoint, ev_main() if in_parts else None))
+        elif not lone:                                            # D-FPS segment next to other segments: side stream
+            c0 = col
+            ev_d = on_side(lambda: tf_ops.farthest_point_sample(npoint, tmp_xyz, out=(fps_idx, c0), idx_offset=lo,
+                                                                cluster=fps_cluster))
+            parts.append((col, col + npoint, ev_d))
+        elif in_parts and not isinstance(fps_parts, bool) and tf_ops.fps_supports_rounds(hi - lo, 3):
+            temp = torch.empty((bs, hi - lo), dtype=torch.float32, device=dev)
+            keep.append(temp)
+            for j0, j1 in _part_bounds(npoint, fps_parts):
+                tf_ops.farthest_point_sample(npoint, tmp_xyz, out=(fps_idx, col), idx_offset=lo, rounds=(j0, j1), temp=temp,
+                                             cluster=fps_cluster)
+                parts.append((col + j0, col + j1, ev_main()))
+        else:
+            tf_ops.farthest_point_sample(npoint, tmp_xyz, out=(fps_idx, col), idx_offset=lo, cluster=fps_cluster)
+            parts.append((col, col + npoint, ev_main() if in_parts else None))
+        col += width
+
+    src_xyz = vote_ctr if vote_ctr is not None else xyz
+    use_agg = bool(aggregation and aggregation_channel is not None and aggregation_channel != -1)
     debug = {"idx": [], "cnt": []}
-    outs = []
-    nscale = len(radius_list)
-    if nscale:
-        min_r = [0.0 if (i == 0 or not dilated_group) else radius_list[i - 1] for i in range(nscale)]   # :137-141
-        if nscale <= 4:   # one pass over the candidates for all shells
-            idx_list, cnt_list = tf_ops.query_ball_point_multi(min_r, radius_list, nsample_list, xyz, new_xyz,
-                                                               dilated_group)
+
+    if not in_parts:
+        for _, _, ev in parts:
+            if ev is not None:
+                main.wait_event(ev)
+        if former_fps_idx is not None:
+            fps_idx = torch.cat([fps_idx, former_fps_idx], dim=-1).contiguous()    # :113-114
+        new_xyz = tf_ops.gather_point(src_xyz, fps_idx)                            # :116-119
+        if nscale:
+            _compute_hoist(hoist, pp, scope, mlp_list, bn, points, stacks)
+            new_points = _group_and_mlp(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, mlp_list, bn,
+                                        dilated_group, use_agg, mlp_mode, stacks, hoist, gather_in_kernel, debug)
+            debug = {"idx": debug["idx"][0], "cnt": debug["cnt"][0]}
         else:
-            idx_list, cnt_list = [], []
-            for i in range(nscale):
-                if dilated_group:
-                    a, c = tf_ops.query_ball_point_dilated(min_r[i], radius_list[i], nsample_list[i], xyz, new_xyz)
-                else:
-                    a, c = tf_ops.query_ball_point(radius_list[i], nsample_list[i], xyz, new_xyz)
-                idx_list.append(a); cnt_list.append(c)
-        use_agg = bool(aggregation and aggregation_channel is not None and aggregation_channel != -1)
-        tc = mlp_mode == "tc" and all(k in (8, 16, 32, 64, 128) for k in nsample_list)
-        if mlp_mode not in ("tc", "fp32"):
-            raise ValueError("mlp_mode must be 'tc' or 'fp32'")
-        if tc:
-            # tensor-core path: every scale pools straight into its slice of the concat buffer (fp32 for the
-            # caller, split bf16 for the aggregation conv), activations stay split between layers
-            m_q = new_xyz.shape[1]
-            ctot = sum(m[-1] for m in mlp_list)
-            concat = torch.empty((bs, m_q, ctot), dtype=torch.float32, device=xyz.device)
-            cat_hi = cat_lo = None
-            if use_agg:
-                ldc = tf_ops.round16(ctot)
-                mk = torch.zeros if ldc != ctot else torch.empty
-                cat_hi = mk((bs, m_q, ldc), dtype=torch.bfloat16, device=xyz.device)
-                cat_lo = mk((bs, m_q, ldc), dtype=torch.bfloat16, device=xyz.device)
-            off = 0
-            c_feat = points.shape[-1]
-            stacks = [pp.fused_stack(["%s/conv%d_%d" % (scope, i, j) for j in range(len(mlp_list[i]))], bn, c_feat + 3)
-                      if fuse_scale else None for i in range(nscale)]
-            # The first conv of every scale with >= 2 convs is hoisted out of the grouped domain: its feature part becomes
-            # ONE per-point GEMM for all scales of the layer (z), its xyz part is re-applied per grouped row while the
-            # operand of the second conv is built (in the fused kernel's gather, or in the producer warps of
-            # ssd3d_linear_tc_hoisted for the scales that run layer by layer).
-            hoist = [i for i in range(nscale) if len(mlp_list[i]) >= 2 and (int(hoist_first) >= 2 or stacks[i] is None)] \
-                if (gather_in_kernel and hoist_first) else []   # hoist_first: 0 off, 1 layer-by-layer scales only, 2 all
-            z = zoffs = wxs = None
-            hstacks = {}
-            if hoist:
-                zconv, wxs, n1s = pp.hoisted(["%s/conv%d_0" % (scope, i) for i in hoist], bn, c_feat)
-                p_hi, p_lo = tf_ops.split_rows(points)
-                z, _ = tf_ops.linear_tc(p_hi, p_lo, zconv, relu=False, want_f32=True, want_split=False)
-                zoffs = [sum(n1s[:t]) for t in range(len(hoist))]
-                for t, i in enumerate(hoist):
-                    if stacks[i] is not None:    # remaining convs of a fused scale
-                        hstacks[i] = pp.fused_stack(["%s/conv%d_%d" % (scope, i, j) for j in range(1, len(mlp_list[i]))], bn, n1s[t])
-            for i in range(nscale):
-                idx, cnt = idx_list[i], cnt_list[i]
-                debug["idx"].append(idx); debug["cnt"].append(cnt)
-                nl = len(mlp_list[i])
-                stack = stacks[i]
-                if stack is not None:                                              # whole scale in one kernel
-                    if hstacks.get(i) is not None:
-                        t = hoist.index(i)
-                        tf_ops.sa_mlp_fused_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, cnt, hstacks[i], out_f32=(concat, off),
-                                                    out_split=(cat_hi, cat_lo, off) if use_agg else None)
-                    else:
-                        tf_ops.sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=(concat, off),
-                                            out_split=(cat_hi, cat_lo, off) if use_agg else None)
-                    off += mlp_list[i][-1]
-                    continue
-                hi = lo = None
-                for j in range(nl):
-                    f = pp.conv("%s/conv%d_%d" % (scope, i, j), bn)
-                    last_kw = dict(pool=nsample_list[i], rowmask=cnt, out_f32=(concat, off),
-                                   out_split=(cat_hi, cat_lo, off) if use_agg else None)   # :167-180 conv+BN+ReLU+max+mask
-                    if i in hoist:
-                        if j == 0:
-                            continue                  # folded into z and into the next conv's operand producer
-                        if j == 1:
-                            t = hoist.index(i)
-                            if nl == 2:
-                                tf_ops.linear_tc_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, f, want_split=False, **last_kw)
-                            else:
-                                _, (hi, lo) = tf_ops.linear_tc_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, f)
-                            continue
-                    if j == 0 and gather_in_kernel:   # :160-165 inside the kernel's operand load (no [B,M,K,C] tensor)
-                        if nl == 1:
-                            tf_ops.linear_tc_gather(xyz, points, new_xyz, idx, f, want_split=False, **last_kw)
-                        else:
-                            _, (hi, lo) = tf_ops.linear_tc_gather(xyz, points, new_xyz, idx, f)
-                        continue
-                    if j == 0:                        # :160-165 fused with the split, materialised once in bf16 hi/lo
-                        hi, lo = tf_ops.group_concat_split(xyz, points, new_xyz, idx)
-                    if j < nl - 1:
-                        _, (hi, lo) = tf_ops.linear_tc(hi, lo, f, want_f32=False, want_split=True)
-                    else:
-                        tf_ops.linear_tc(hi, lo, f, **last_kw)
-                off += mlp_list[i][-1]
-            new_points = concat
-            if use_agg:                                                            # :183-185
-                new_points, _ = tf_ops.linear_tc(cat_hi, cat_lo, pp.conv(scope + "/ensemble", bn))
-        else:
-            for i in range(nscale):
-                idx, cnt = idx_list[i], cnt_list[i]
-                # rows with cnt == 0 come back zero-filled, which is what idx * (cnt > 0) produces (:157-159)
-                debug["idx"].append(idx); debug["cnt"].append(cnt)
-                g = tf_ops.group_concat(xyz, points, new_xyz, idx)                    # :160-165 fused
-                nl = len(mlp_list[i])
-                for j in range(nl):
-                    lastl = j == nl - 1
-                    g = _conv(pp, "%s/conv%d_%d" % (scope, i, j), g, bn=bn,
-                              pool=nsample_list[i] if lastl else 1, rowmask=cnt if lastl else None)   # :167-180
-                outs.append(g)
-            new_points = outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
-            if use_agg:
-                new_points = _conv(pp, scope + "/ensemble", new_points, bn=bn)        # :183-185
+            new_points = tf_ops.gather_point(points.contiguous(), fps_idx)         # :186-187
     else:
-        new_points = tf_ops.gather_point(points.contiguous(), fps_idx)           # :186-187
+        # ---- one consumer chain per part, each on its own stream, joined at the end
+        xyz_parts, pts_parts, done = [], [], []
+        for pi, (c0, c1, ev) in enumerate(parts):
+            st = _side_stream(dev, 8 + pi)
+            st.wait_event(ev)
+            if hoist.scales:
+                st.wait_event(z_ready)
+            with torch.cuda.stream(st):
+                nx = tf_ops.gather_point(src_xyz, fps_idx[:, c0:c1])
+                npnts = _group_and_mlp(pp, scope, xyz, points, nx, radius_list, nsample_list, mlp_list, bn, dilated_group,
+                                       use_agg, mlp_mode, stacks, hoist, gather_in_kernel, debug)
+                e2 = torch.cuda.Event()
+                e2.record(st)
+            xyz_parts.append(nx); pts_parts.append(npnts); done.append(e2)
+        for e2 in done:
+            main.wait_event(e2)
+        for i in range(nside):
+            main.wait_stream(_side_stream(dev, i))
+        new_xyz = tf_ops.concat_rows(xyz_parts)
+        new_points = tf_ops.concat_rows(pts_parts)
+        keep.extend(xyz_parts + pts_parts)
+        if return_debug:
+            debug = {"idx": [torch.cat([d[i] for d in debug["idx"]], dim=1) for i in range(nscale)],
+                     "cnt": [torch.cat([d[i] for d in debug["cnt"]], dim=1) for i in range(nscale)]}
+        _KEEPALIVE.append((keep, debug if not return_debug else None, hoist))
+        del _KEEPALIVE[:-8]
     if return_debug:
         return new_xyz, new_points, fps_idx, debug
     return new_xyz, new_points, fps_idx
+
+
+_KEEPALIVE = []   # latency mode: the last layers' cross-stream temporaries (freed a few calls later, long after their use)
 
 
 def pointnet_sa_module(xyz, points, mlp, is_training, bn_decay, bn, scope, *, params):
@@ -297,6 +424,4 @@ def vote_layer(xyz, points, mlp_list, is_training, bn_decay, bn, scope, *, param
         for i in range(len(mlp_list)):
             points = _conv(pp, "%s/vote_layer_%d" % (scope, i), points, bn=bn)
         off = _conv(pp, scope + "/vote_offsets", points, bn=False, relu=False)
-    lo = _const(tuple(max_translate_range), xyz.device).view(1, 1, 3)
-    lim = torch.minimum(torch.maximum(off, lo), -lo)
-    return xyz + lim, points, off
+    return tf_ops.vote_translate(xyz, off, max_translate_range), points, off                       # :20-23

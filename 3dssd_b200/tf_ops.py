@@ -39,39 +39,89 @@ def _req(t, name, dtype, rank, last=None):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def farthest_point_sample(npoint, inp):
+def _scene_strided(t, name, rank=3, last=None):
+    """A float32 CUDA tensor (b, n, c) whose rows are dense but whose scenes may be strided (a [:, a:b] slice of a
+    dense tensor): returns (tensor, scene stride in floats) without copying; anything else is made contiguous."""
+    if not isinstance(t, torch.Tensor):
+        raise ValueError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (there is no CPU path)" % name)
+    if t.dtype != torch.float32:
+        raise ValueError("%s must be %s, got %s" % (name, torch.float32, t.dtype))
+    if t.dim() != rank:
+        raise ValueError("%s must have rank %d, got shape %s" % (name, rank, tuple(t.shape)))
+    if last is not None and t.shape[-1] != last:
+        raise ValueError("%s must have last dimension %d, got shape %s" % (name, last, tuple(t.shape)))
+    b, n, c = t.shape
+    if c > 0 and n > 0 and t.stride(2) == 1 and t.stride(1) == c and (b <= 1 or t.stride(0) >= n * c):
+        return t, (t.stride(0) if b > 1 else n * c)
+    t = t.contiguous()
+    return t, n * c
+
+
+def _idx_out(out, b, npoint, device):
+    """Resolve the optional (buffer, column) output placement of the sampling ops -> (tensor to return, ptr, ldo)."""
+    if out is None:
+        o = torch.empty((b, npoint), dtype=torch.int32, device=device)
+        return o, o.data_ptr(), npoint
+    buf, col = out
+    if buf.dtype != torch.int32 or buf.dim() != 2 or not buf.is_contiguous() or buf.shape[0] != b or col < 0 or col + npoint > buf.shape[1]:
+        raise ValueError("out must be (int32 contiguous (b, >= col + npoint) buffer, col)")
+    return buf[:, col:col + npoint], buf.data_ptr() + 4 * col, buf.shape[1]
+
+
+def farthest_point_sample(npoint, inp, *, out=None, idx_offset=0, rounds=None, temp=None, cluster=0, packet_kernel=False):
     """inp: (batch, ndataset, c) float32 -> (batch, npoint) int32.  tf_sampling.py:43-51; shape check
-    tf_sampling.cpp:142 (rank 3)."""
-    inp = _req(inp, "inp", torch.float32, 3)
+    tf_sampling.cpp:142 (rank 3).
+
+    Keyword extensions (include/ssd3d.h, ssd3d_farthest_point_sample_ex; none changes the sampled indices):
+      out=(buffer, col)   write into columns [col, col+npoint) of an int32 (batch, L) buffer and return that view;
+      idx_offset          added to every index (segment offset of a fusion-sampling layer, layers_util.py:109);
+      rounds=(j0, j1), temp   run only rounds [j0, j1); `temp` (batch, n) float32 carries the running distances
+                          between the calls (j0 == 0 starts fresh); the output must be the same buffer in every call;
+      cluster             CTAs per scene: 0 heuristic, >0 exact, <0 heuristic capped at -cluster;
+      packet_kernel       use the general cluster kernel even where the resident-scene one applies (tests)."""
+    inp, stride = _scene_strided(inp, "inp")
     npoint = int(npoint)
     if npoint < 0:
         raise ValueError("npoint must be non-negative")
     b, n, c = inp.shape
-    out = torch.empty((b, npoint), dtype=torch.int32, device=inp.device)
-    temp = None
-    if lib().ssd3d_fps_needs_temp(n, c):
+    o, optr, ldo = _idx_out(out, b, npoint, inp.device)
+    j0, j1 = (0, npoint) if rounds is None else (int(rounds[0]), int(rounds[1]))
+    if temp is None and (lib().ssd3d_fps_needs_temp(n, c) or (j0, j1) != (0, npoint)):
+        if (j0, j1) != (0, npoint):
+            raise ValueError("a partial range of rounds needs the caller's temp (batch, n) float32 buffer")
         temp = torch.empty((b, n), dtype=torch.float32, device=inp.device)
-    check(lib().ssd3d_farthest_point_sample(b, n, c, npoint, _p(inp), _p(temp), _p(out), _stream()),
+    if temp is not None and (temp.dtype != torch.float32 or not temp.is_contiguous() or temp.numel() < b * n):
+        raise ValueError("temp must be a contiguous float32 buffer of at least batch * n elements")
+    check(lib().ssd3d_farthest_point_sample_ex(b, n, c, npoint, _p(inp), stride, _p(temp), ctypes.c_void_p(optr), ldo,
+                                               int(idx_offset), j0, j1, int(cluster), 1 if packet_kernel else 0, _stream()),
           "farthest_point_sample")
-    return out
+    return o
 
 
 furthest_point_sample = farthest_point_sample  # spelling used by BASELINE.json's north star
 
 
-def farthest_point_sample_with_distance(npoint, dist):
+def fps_supports_rounds(n, c=3):
+    """True when farthest_point_sample(..., rounds=...) is available for n points of c channels."""
+    return bool(lib().ssd3d_fps_supports_rounds(int(n), int(c)))
+
+
+def farthest_point_sample_with_distance(npoint, dist, *, out=None, idx_offset=0, cluster=0):
     """dist: (batch, n, n) float32 distance matrix -> (batch, npoint) int32.  tf_sampling.py:54-62; the
-    square-matrix check is tf_sampling.cpp:175."""
+    square-matrix check is tf_sampling.cpp:175.  Keyword extensions as farthest_point_sample."""
     dist = _req(dist, "dist", torch.float32, 3)
     b, n, n2 = dist.shape
     if n != n2:
         raise ValueError("FarthestPointSampleWithDistance expects (batch_size,num_points,num_points) inp shape")
     npoint = int(npoint)
-    out = torch.empty((b, npoint), dtype=torch.int32, device=dist.device)
+    o, optr, ldo = _idx_out(out, b, npoint, dist.device)
     temp = torch.empty((b, n), dtype=torch.float32, device=dist.device) if n > 65536 else None
-    check(lib().ssd3d_farthest_point_sample_with_distance(b, n, npoint, _p(dist), _p(temp), _p(out), _stream()),
+    check(lib().ssd3d_farthest_point_sample_with_distance_ex(b, n, npoint, _p(dist), _p(temp), ctypes.c_void_p(optr), ldo,
+                                                             int(idx_offset), int(cluster), _stream()),
           "farthest_point_sample_with_distance")
-    return out
+    return o
 
 
 def ffps_supported(n, c):
@@ -79,29 +129,35 @@ def ffps_supported(n, c):
     return bool(lib().ssd3d_ffps_supported(int(n), int(c)))
 
 
-def farthest_point_sample_features(npoint, xyz, points=None):
+def farthest_point_sample_features(npoint, xyz, points=None, *, out=None, idx_offset=0):
     """F-FPS on concat[xyz, points] without the distance matrix: the same indices as
-    farthest_point_sample_with_distance(npoint, calc_square_dist(concat[xyz, points])) (layers_util.py:94-96)."""
-    xyz = _req(xyz, "xyz", torch.float32, 3)
+    farthest_point_sample_with_distance(npoint, calc_square_dist(concat[xyz, points])) (layers_util.py:94-96).
+    Keyword extensions as farthest_point_sample."""
+    xyz, sa = _scene_strided(xyz, "xyz")
     b, n, ca = xyz.shape
-    cb = 0
-    if points is not None:
-        points = _req(points, "points", torch.float32, 3)
+    cb, sb = 0, 0
+    if points is not None and points.shape[-1] > 0:
+        points, sb = _scene_strided(points, "points")
         if points.shape[:2] != (b, n):
             raise ValueError("points must be (batch, n, c) like xyz")
         cb = points.shape[2]
+    else:
+        points = None
     npoint = int(npoint)
-    out = torch.empty((b, npoint), dtype=torch.int32, device=xyz.device)
-    check(lib().ssd3d_farthest_point_sample_features(b, n, ca, cb, npoint, _p(xyz), _p(points), _p(out), _stream()),
+    o, optr, ldo = _idx_out(out, b, npoint, xyz.device)
+    check(lib().ssd3d_farthest_point_sample_features_ex(b, n, ca, cb, npoint, _p(xyz), sa, _p(points), sb,
+                                                        ctypes.c_void_p(optr), ldo, int(idx_offset), _stream()),
           "farthest_point_sample_features")
-    return out
+    return o
 
 
 def _gather_point_fwd(inp, idx):
     b, n, c = inp.shape
     m = idx.shape[1]
     out = torch.empty((b, m, c), dtype=torch.float32, device=inp.device)
-    check(lib().ssd3d_gather_point(b, n, m, c, _p(inp), _p(idx), _p(out), _stream()), "gather_point")
+    # idx may be a column block of a wider contiguous (b, L) tensor: read in place
+    check(lib().ssd3d_gather_point_ex(b, n, m, c, _p(inp), _p(idx), idx.stride(0) if b > 1 else m, _p(out), _stream()),
+          "gather_point")
     return out
 
 
@@ -132,7 +188,9 @@ def gather_point(inp, idx):
     """inp (batch, ndataset, c) float32, idx (batch, npoints) int32 -> (batch, npoints, c).  tf_sampling.py:24-32.
     Differentiable w.r.t. inp (the reference registers GatherPoint's gradient, tf_sampling.py:37-42)."""
     inp = _req(inp, "inp", torch.float32, 3)
-    idx = _req(idx, "idx", torch.int32, 2)
+    if not (isinstance(idx, torch.Tensor) and idx.is_cuda and idx.dtype == torch.int32 and idx.dim() == 2
+            and idx.stride(1) == 1 and idx.stride(0) >= idx.shape[1]):
+        idx = _req(idx, "idx", torch.int32, 2)
     if idx.shape[0] != inp.shape[0]:
         raise ValueError("GatherPoint expects (batch_size,num_result) idx shape")
     if inp.requires_grad and torch.is_grad_enabled():
@@ -601,16 +659,106 @@ def sa_mlp_fused_hoisted(xyz, z, zoff, wx, new_xyz, idx, cnt, stack, out_f32=Non
     return y
 
 
-def bev_nms(boxes, scores, iou_threshold, max_output, cls_id=0):
+def bev_nms(boxes, scores, iou_threshold, max_output, cls_id=0, out=None):
     """Greedy BEV NMS per scene (postprocessor.py:76-88): boxes (b,n,7) = (x,y,z,l,h,w,ry), scores (b,n) ->
-    block (b,max_output,9) = (box7, score, class) zero padded, count (b,) int32."""
+    block (b,max_output,9) = (box7, score, class) zero padded, count (b,) int32.  out=(block, count) writes into
+    preallocated contiguous tensors (the send buffer of the multi-GPU gather)."""
     boxes = _req(boxes, "boxes", torch.float32, 3, 7)
     scores = _req(scores, "scores", torch.float32, 2)
     b, n, _ = boxes.shape
     if scores.shape != (b, n):
         raise ValueError("scores must be (b, n)")
-    block = torch.empty((b, int(max_output), 9), dtype=torch.float32, device=boxes.device)
-    cnt = torch.empty((b,), dtype=torch.int32, device=boxes.device)
+    if out is None:
+        block = torch.empty((b, int(max_output), 9), dtype=torch.float32, device=boxes.device)
+        cnt = torch.empty((b,), dtype=torch.int32, device=boxes.device)
+    else:
+        block, cnt = out
+        if (block.dtype != torch.float32 or tuple(block.shape) != (b, int(max_output), 9) or not block.is_contiguous()
+                or cnt.dtype != torch.int32 or tuple(cnt.shape) != (b,) or not cnt.is_contiguous()):
+            raise ValueError("out must be (float32 (b, max_output, 9), int32 (b,)) contiguous tensors")
     check(lib().ssd3d_bev_nms(b, n, _p(boxes), _p(scores), float(iou_threshold), int(max_output), int(cls_id),
                               _p(block), _p(cnt), _stream()), "bev_nms")
     return block, cnt
+
+
+# ---- the small elementwise stages (csrc/misc.cu): one kernel each, so a captured step holds no framework kernels ----
+
+def split_points(points):
+    """(b, n, 3 + c) -> xyz (b, n, 3), features (b, n, c): single_stage_detector.py:116-117."""
+    points = _req(points, "points", torch.float32, 3)
+    b, n, c = points.shape
+    if c < 3:
+        raise ValueError("points must have at least 3 channels")
+    xyz = torch.empty((b, n, 3), dtype=torch.float32, device=points.device)
+    feat = torch.empty((b, n, c - 3), dtype=torch.float32, device=points.device)
+    check(lib().ssd3d_split_points(b * n, c, _p(points), _p(xyz), _p(feat) if c > 3 else ctypes.c_void_p(0), _stream()),
+          "split_points")
+    return xyz, feat
+
+
+def iota_idx(b, npoint, device, *, out=None, start=0):
+    """tf.tile(tf.range(npoint)) + start: the identity sampling of layers_util.py:91-92, :100-101."""
+    o, optr, ldo = _idx_out(out, b, int(npoint), device)
+    check(lib().ssd3d_iota_idx(b, int(npoint), int(start), ctypes.c_void_p(optr), ldo, _stream()), "iota_idx")
+    return o
+
+
+def concat_cols(a, bsrc):
+    """tf.concat([a, bsrc], -1) for (b, n, ca) / (b, n, cb) float32 tensors whose scenes may be strided."""
+    a, sa = _scene_strided(a, "a")
+    bsrc, sb = _scene_strided(bsrc, "bsrc")
+    b, n, ca = a.shape
+    if bsrc.shape[:2] != (b, n):
+        raise ValueError("concat_cols: leading shapes differ")
+    cb = bsrc.shape[2]
+    out = torch.empty((b, n, ca + cb), dtype=torch.float32, device=a.device)
+    check(lib().ssd3d_concat_cols(b, n, ca, cb, _p(a), sa, _p(bsrc), sb, _p(out), _stream()), "concat_cols")
+    return out
+
+
+def vote_translate(xyz, offsets, min_range):
+    """xyz + min(max(offsets, min_range), -min_range) (layers_util.py:20-23); offsets (b, n, >= 3)."""
+    xyz = _req(xyz, "xyz", torch.float32, 3, 3)
+    offsets = _req(offsets, "offsets", torch.float32, 3)
+    if offsets.shape[:2] != xyz.shape[:2] or offsets.shape[2] < 3:
+        raise ValueError("offsets must be (b, n, >= 3) like xyz")
+    out = torch.empty_like(xyz)
+    check(lib().ssd3d_vote_translate(xyz.shape[0] * xyz.shape[1], _p(xyz), _p(offsets), offsets.shape[2], float(min_range[0]),
+                                     float(min_range[1]), float(min_range[2]), _p(out), _stream()), "vote_translate")
+    return out
+
+
+def decode_dist_anchor_free(center_xyz, pred_reg, pred_cls, angle_bins=12):
+    """anchor_decoder.decode_dist_anchor_free + decode_class2angle + sigmoid in one kernel: center_xyz (b, n, 3),
+    pred_reg (b, n, 6 + 2*angle_bins), pred_cls (b, n, >= 1) -> boxes (b, n, 7), scores (b, n)."""
+    center_xyz = _req(center_xyz, "center_xyz", torch.float32, 3, 3)
+    pred_reg = _req(pred_reg, "pred_reg", torch.float32, 3)
+    pred_cls = _req(pred_cls, "pred_cls", torch.float32, 3)
+    b, n, _ = center_xyz.shape
+    if pred_reg.shape[:2] != (b, n) or pred_cls.shape[:2] != (b, n) or pred_reg.shape[2] < 6 + 2 * angle_bins:
+        raise ValueError("pred_reg must be (b, n, >= 6 + 2*angle_bins) and pred_cls (b, n, >= 1)")
+    boxes = torch.empty((b, n, 7), dtype=torch.float32, device=center_xyz.device)
+    scores = torch.empty((b, n), dtype=torch.float32, device=center_xyz.device)
+    check(lib().ssd3d_decode_dist_anchor_free(b * n, int(angle_bins), _p(center_xyz), _p(pred_reg), pred_reg.shape[2],
+                                              _p(pred_cls), pred_cls.shape[2], _p(boxes), _p(scores), _stream()),
+          "decode_dist_anchor_free")
+    return boxes, scores
+
+
+def concat_rows(parts):
+    """tf.concat(parts, axis=1) for contiguous float32 (b, m_i, c) tensors (at most 8) in one kernel."""
+    parts = [_req(t, "part", torch.float32, 3) for t in parts]
+    if len(parts) == 1:
+        return parts[0]
+    if len(parts) > 8:
+        raise ValueError("concat_rows joins at most 8 parts")
+    b, _, c = parts[0].shape
+    if any(t.shape[0] != b or t.shape[2] != c for t in parts):
+        raise ValueError("concat_rows: parts must agree in batch and channel size")
+    ms = [t.shape[1] for t in parts]
+    out = torch.empty((b, sum(ms), c), dtype=torch.float32, device=parts[0].device)
+    src = (ctypes.c_void_p * len(parts))(*[t.data_ptr() for t in parts])
+    marr = (ctypes.c_int * len(parts))(*ms)
+    check(lib().ssd3d_concat_rows(b, len(parts), ctypes.cast(src, ctypes.c_void_p), ctypes.cast(marr, ctypes.c_void_p), c,
+                                  _p(out), _stream()), "concat_rows")
+    return out

@@ -45,11 +45,32 @@ int ssd3d_farthest_point_sample(int b, int n, int c, int m, const float *inp, fl
                                 ssd3d_stream_t stream);
 int ssd3d_fps_needs_temp(int n, int c);
 
+/* The same operator with explicit placement -- what lets an SA layer run its sampling without any copy / add /
+ * concat kernels around it (lib/utils/layers_util.py:84-111):
+ *   in_stride   floats between consecutive scenes of inp (>= n*c): a [:, a:b] slice of a dense [b,N,c] tensor;
+ *   ldo         ints between consecutive rows of out (>= m): a column block of the concatenated fps_idx tensor;
+ *   idx_offset  added to every stored index (the `+ last_fps_end_index` of :109);
+ *   j0, j1      run only rounds [j0, j1) of 0..m; the running distances travel through temp[b,n] between the launches
+ *               (required when the range is partial).  A sample is final as soon as its round is done, so work on the
+ *               first samples can overlap the remaining rounds.  Partial ranges need ssd3d_fps_supports_rounds(n, c);
+ *   cluster     CTAs per scene: 0 = heuristic, 1/2/4/8/16 = exactly that, negative = heuristic capped at -cluster
+ *               (FPS is latency-bound: fewer CTAs cost little time and leave SMs to concurrent work);
+ *   flags       bit 0: use the general cluster kernel (coordinates travel in the packets) even where the
+ *               resident-scene kernel applies.
+ * No state is kept in the library: every choice is an argument. */
+int ssd3d_farthest_point_sample_ex(int b, int n, int c, int m, const float *inp, long long in_stride, float *temp,
+                                   int *out, int ldo, int idx_offset, int j0, int j1, int cluster, int flags,
+                                   ssd3d_stream_t stream);
+int ssd3d_fps_supports_rounds(int n, int c);
+
 /* replaces farthestpointsamplingwithdistLauncher(b,n,m,inp,temp,out)
  *   sampling/tf_sampling.cpp:164, sampling/tf_sampling_g.cu:396-398, kernel :181-230.
  * F-FPS over a precomputed distance matrix dist[b,n,n]. */
 int ssd3d_farthest_point_sample_with_distance(int b, int n, int m, const float *dist, float *temp, int *out,
                                               ssd3d_stream_t stream);
+/* ... with explicit output placement and cluster request (see ssd3d_farthest_point_sample_ex). */
+int ssd3d_farthest_point_sample_with_distance_ex(int b, int n, int m, const float *dist, float *temp, int *out, int ldo,
+                                                 int idx_offset, int cluster, ssd3d_stream_t stream);
 
 /* The F-FPS branch of the SA layer in one call (lib/utils/layers_util.py:94-96 and :102-104):
  *   farthest_point_sample_with_distance(m, calc_square_dist(concat[fa, fb]))
@@ -60,6 +81,10 @@ int ssd3d_farthest_point_sample_with_distance(int b, int n, int m, const float *
  * SSD3D_ERR_UNSUPPORTED and the caller takes the two-call route. */
 int ssd3d_farthest_point_sample_features(int b, int n, int ca, int cb, int m, const float *fa, const float *fb,
                                          int *out, ssd3d_stream_t stream);
+/* ... with scene strides of fa / fb in floats and explicit output placement (see ssd3d_farthest_point_sample_ex). */
+int ssd3d_farthest_point_sample_features_ex(int b, int n, int ca, int cb, int m, const float *fa, long long fa_stride,
+                                            const float *fb, long long fb_stride, int *out, int ldo, int idx_offset,
+                                            ssd3d_stream_t stream);
 int ssd3d_ffps_supported(int n, int c);
 
 /* replaces gatherpointLauncher(b,n,m,c,inp,idx,out)
@@ -67,6 +92,9 @@ int ssd3d_ffps_supported(int n, int c);
  * out[b,m,c] = inp[b, idx[b,m], c] */
 int ssd3d_gather_point(int b, int n, int m, int c, const float *inp, const int *idx, float *out,
                        ssd3d_stream_t stream);
+/* ... reading idx rows ld_idx ints apart (a column block of a wider [b, L] index tensor). */
+int ssd3d_gather_point_ex(int b, int n, int m, int c, const float *inp, const int *idx, int ld_idx, float *out,
+                          ssd3d_stream_t stream);
 
 /* ---- grouping ------------------------------------------------------------------------------ */
 
@@ -216,20 +244,30 @@ int ssd3d_bev_nms(int b, int n, const float *boxes, const float *scores, float i
 int ssd3d_rowgroup_max(long groups, int pool, int c, const float *y, int ldy, const int *rowmask, float *out,
                        ssd3d_stream_t stream);
 
-/* Tuning hook (tests/benchmarks only): force the FPS cluster size (1,2,4,8,16); 0 restores the heuristic. */
-void ssd3d_tune_set_fps_cluster(int cluster_size);
-/* 0 = automatic D-FPS kernel choice, 1 = force the general (coordinates-in-packet) cluster kernel. */
-void ssd3d_tune_set_fps_variant(int variant);
-/* Throughput mode: cap the heuristic FPS cluster size (0 = no cap).  FPS is latency-bound, so a smaller cluster
- * costs little time per scene and leaves SMs to concurrently running work. */
-void ssd3d_tune_set_fps_cluster_cap(int cluster_size);
-/* Fused SA kernel shape for stacks too big for several CTAs per SM: tiles in flight per CTA (2..3) and warpgroups
- * working on each tile (1, 2 or 4); 0 = automatic. */
-void ssd3d_tune_set_fused(int slots, int warpgroups);
-/* Tensor-core layer kernel: issue every tile-wide MMA as `nsplit` narrower MMAs into adjacent accumulator columns
- * (independent dependency chains); 0 = automatic. */
-void ssd3d_tune_set_mma_split(int nsplit);
-void ssd3d_tune_set_fused_mma_split(int nsplit);   /* same for the fused SA kernel */
+/* ---- the small elementwise stages of the path (csrc/misc.cu) --------------------------------- */
+
+/* points[rows, c] -> xyz[rows, 3], feat[rows, c-3]: the tf.slice pair of
+ * lib/modeling/single_stage_detector.py:116-117.  feat may be NULL when c == 3. */
+int ssd3d_split_points(long rows, int c, const float *points, float *xyz, float *feat, ssd3d_stream_t stream);
+/* out[s*ldo + j] = start + j, s < b, j < m: tf.tile(tf.range(npoint)) of lib/utils/layers_util.py:91-92, :100-101. */
+int ssd3d_iota_idx(int b, int m, int start, int *out, int ldo, ssd3d_stream_t stream);
+/* out[b,n,ca+cb] = concat(a[b,n,ca], bsrc[b,n,cb]) with scene strides in floats: tf.concat([xyz, points], -1) in
+ * front of calc_square_dist (lib/utils/layers_util.py:94, :102). */
+int ssd3d_concat_cols(int b, int n, int ca, int cb, const float *a, long long a_stride, const float *bsrc,
+                      long long b_stride, float *out, ssd3d_stream_t stream);
+/* out[b, sum(m), c] = concat along axis 1 of parts src[i][b, m[i], c] (i < parts <= 8; src / m are HOST arrays of
+ * device pointers / row counts): joins the per-part results of an SA layer whose sampling was consumed in parts. */
+int ssd3d_concat_rows(int b, int parts, const float *const *src, const int *m, int c, float *out, ssd3d_stream_t stream);
+/* out[r, 0:3] = xyz[r, 0:3] + min(max(offsets[r, 0:3], min_xyz), -min_xyz): the clamp + add of vote_layer,
+ * lib/utils/layers_util.py:20-23 (min_xyz = MODEL.MAX_TRANSLATE_RANGE, negative). */
+int ssd3d_vote_translate(long rows, const float *xyz, const float *offsets, int ld_offsets, float min_x, float min_y,
+                         float min_z, float *out, ssd3d_stream_t stream);
+/* decode_dist_anchor_free + decode_class2angle + the score sigmoid (lib/utils/anchor_decoder.py:86-112, :6-14,
+ * lib/modeling/single_stage_detector.py:210-211) in one pass.  pred_reg[rows, ld_reg] = [6 face distances |
+ * angle_bins logits | angle_bins residuals], pred_cls[rows, ld_cls] (column 0 = the class logit), center_xyz[rows,3]
+ * -> boxes[rows,7] = (x, y, z, l, h, w, ry), scores[rows]. */
+int ssd3d_decode_dist_anchor_free(long rows, int angle_bins, const float *center_xyz, const float *pred_reg, int ld_reg,
+                                  const float *pred_cls, int ld_cls, float *boxes, float *scores, ssd3d_stream_t stream);
 
 #ifdef __cplusplus
 }

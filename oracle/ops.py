@@ -239,3 +239,15 @@ def three_interpolate_grad(points_shape, idx, weight, grad_out):
     g = np.empty((b, m, c), np.float32)
     lib().oracle_three_interpolate_grad(b, n, c, m, p, q, w, g.ctypes.data_as(_f32p))
     return g
+
+
+def bev_nms(boxes, scores, iou_threshold=0.1, max_output=100, cls_id=0):
+    """C twin of oracle/head.py:bev_nms (the reference runs this stage on the CPU: postprocessor.py:76-88)."""
+    boxes, pb = _f(boxes)
+    scores, ps = _f(scores)
+    b, n, _ = boxes.shape
+    block = np.zeros((b, int(max_output), 9), np.float32)
+    cnt = np.zeros((b,), np.int32)
+    lib().oracle_bev_nms(b, n, pb, ps, ctypes.c_float(iou_threshold), int(max_output), int(cls_id),
+                         block.ctypes.data_as(_f32p), cnt.ctypes.data_as(_i32p))
+    return block, cnt

@@ -120,3 +120,35 @@ def backbone_forward(arch, points_in, params, cache=None):
         else:
             raise ValueError("reference arm covers the 3DSSD backbone layer types only, got %r" % (ltype,))
     return xyz_list, feat_list
+
+
+def head_forward(xyz, feat, params, cache=None, mlp=(128,), bn=True, scope="", angle_bins=12, max_output=100,
+                 nms_threshold=0.1):
+    """Detection head + decode + post-processing as the reference runs them (lib/modeling/head_builder.py:81-114,
+    lib/utils/head_util.py:26-59, lib/utils/anchor_decoder.py:6-14, :86-112, single_stage_detector.py:210-211,
+    lib/builder/postprocessor.py:52-120): conv1d stacks and the decode as eager fp32 ops one-for-one on the GPU, then
+    -- like tf.image.non_max_suppression in the reference -- the greedy BEV NMS on the CPU (oracle C twin), which
+    puts a device->host sync in the step.  Returns (block [B,100,9], count [B]) numpy."""
+    import math
+
+    from . import ops
+    cache = {} if cache is None else cache
+    pre = "" if scope == "" else scope + "/"
+    y = feat
+    for i in range(len(mlp)):
+        y = _conv(params, "%sconv1d_%d" % (pre, i), y, bn, True, cache)
+    cls = _conv(params, pre + "pred_cls", _conv(params, pre + "pred_cls_base", y, bn, True, cache), False, False, cache)
+    reg = _conv(params, pre + "pred_reg", _conv(params, pre + "pred_reg_base", y, bn, True, cache), False, False, cache)
+    off, acls, ares = reg[..., :6], reg[..., 6:6 + angle_bins], reg[..., 6 + angle_bins:]
+    bins = torch.argmax(acls, dim=-1)
+    res = torch.gather(ares, -1, bins.unsqueeze(-1)).squeeze(-1)
+    angle = ((bins.to(torch.float32) + res + 0.0) * (2 * math.pi / angle_bins)).unsqueeze(-1)
+    translate, half = off[..., :3], off[..., 3:6]
+    ctr = xyz + translate
+    pad = torch.zeros_like(half)
+    pad[..., 1] = half[..., 1]
+    ctr = ctr + pad
+    lhw = torch.clamp_min(half * 2.0, 0.1)
+    boxes = torch.cat([ctr, lhw, angle], dim=-1)
+    score = torch.sigmoid(cls)[..., 0]
+    return ops.bev_nms(boxes.cpu().numpy(), score.cpu().numpy(), nms_threshold, max_output)

@@ -426,3 +426,60 @@ void oracle_three_interpolate_grad(int b, int n, int c, int m, const float *grad
     for (size_t i = 0; i < total; i++) grad_points[i] = (float)acc[i];
     free(acc);
 }
+
+/* ---- greedy BEV NMS (C twin of oracle/head.py:bev_nms; TensorFlow's non_max_suppression semantics) ----------------
+ * Follows /root/reference/lib/builder/postprocessor.py:76-88 with lib/utils/box_3d_utils.py:25-58 (box_3d_to_anchor)
+ * and lib/utils/anchors_util.py:11-48 (project_to_bev): candidates in descending score order (ties: lower index), a
+ * candidate is dropped when its axis-aligned BEV IoU with a kept box is > thr, at most max_out kept.  Used by the
+ * `--impl reference` arm of bench.py (the reference runs this stage on the CPU) and by the CPU baseline. */
+typedef struct { float s; int i; } nms_key;
+static int nms_cmp(const void *a, const void *b)
+{
+    const nms_key *x = (const nms_key *)a, *y = (const nms_key *)b;
+    if (x->s > y->s) return -1;
+    if (x->s < y->s) return 1;
+    return x->i - y->i;
+}
+void oracle_bev_nms(int b, int n, const float *boxes, const float *scores, float thr, int max_out, int cls_id,
+                    float *out_block, int *out_cnt)
+{
+    nms_key *keys = (nms_key *)malloc(sizeof(nms_key) * (size_t)(n > 0 ? n : 1));
+    float *rect = (float *)malloc(sizeof(float) * 5 * (size_t)(n > 0 ? n : 1));
+    int *kept = (int *)malloc(sizeof(int) * (size_t)(max_out > 0 ? max_out : 1));
+    for (int s = 0; s < b; s++) {
+        const float *bx = boxes + (size_t)s * n * 7, *sc = scores + (size_t)s * n;
+        float *blk = out_block + (size_t)s * max_out * 9;
+        memset(blk, 0, sizeof(float) * (size_t)max_out * 9);
+        for (int i = 0; i < n; i++) {
+            const float c = fabsf(cosf(bx[i * 7 + 6])), sn = fabsf(sinf(bx[i * 7 + 6]));
+            const float dimx = bx[i * 7 + 3] * c + bx[i * 7 + 5] * sn, dimz = bx[i * 7 + 5] * c + bx[i * 7 + 3] * sn;
+            rect[i * 5 + 0] = bx[i * 7 + 0] - dimx * 0.5f; rect[i * 5 + 1] = bx[i * 7 + 2] - dimz * 0.5f;
+            rect[i * 5 + 2] = bx[i * 7 + 0] + dimx * 0.5f; rect[i * 5 + 3] = bx[i * 7 + 2] + dimz * 0.5f;
+            rect[i * 5 + 4] = (rect[i * 5 + 2] - rect[i * 5 + 0]) * (rect[i * 5 + 3] - rect[i * 5 + 1]);
+            keys[i].s = sc[i]; keys[i].i = i;
+        }
+        qsort(keys, (size_t)n, sizeof(nms_key), nms_cmp);
+        int nk = 0;
+        for (int t = 0; t < n && nk < max_out; t++) {
+            const int i = keys[t].i;
+            int ok = 1;
+            for (int u = 0; u < nk && ok; u++) {
+                const int j = kept[u];
+                if (rect[i * 5 + 4] <= 0 || rect[j * 5 + 4] <= 0) continue;
+                float iw = fminf(rect[i * 5 + 2], rect[j * 5 + 2]) - fmaxf(rect[i * 5 + 0], rect[j * 5 + 0]);
+                float ih = fminf(rect[i * 5 + 3], rect[j * 5 + 3]) - fmaxf(rect[i * 5 + 1], rect[j * 5 + 1]);
+                iw = iw > 0 ? iw : 0; ih = ih > 0 ? ih : 0;
+                const float inter = iw * ih;
+                if (inter / (rect[i * 5 + 4] + rect[j * 5 + 4] - inter) > thr) ok = 0;
+            }
+            if (ok) kept[nk++] = i;
+        }
+        for (int u = 0; u < nk; u++) {
+            for (int e = 0; e < 7; e++) blk[u * 9 + e] = bx[kept[u] * 7 + e];
+            blk[u * 9 + 7] = sc[kept[u]];
+            blk[u * 9 + 8] = (float)cls_id;
+        }
+        out_cnt[s] = nk;
+    }
+    free(keys); free(rect); free(kept);
+}

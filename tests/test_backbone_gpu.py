@@ -13,8 +13,17 @@ synth = importlib.import_module("3dssd_b200.synth")
 TOL = 1e-3   # BASELINE.json north star: grouped-MLP features within 1e-3 relative fp32
 
 
-def rel_err(got, exp):
-    return float(np.abs(got.astype(np.float64) - exp.astype(np.float64)).max() / max(1e-12, np.abs(exp).max()))
+def rel_err(got, exp, rtol=1e-3, atol_frac=2e-5):
+    """max|got-exp| / max|exp| (the global norm the tolerances are quoted in), after ALSO asserting the elementwise
+    bound |got - exp| <= rtol*|exp| + atol_frac*max|exp|: a small-magnitude feature may not hide behind a large one."""
+    g, e = got.astype(np.float64), exp.astype(np.float64)
+    scale = max(1e-12, np.abs(e).max())
+    excess = np.abs(g - e) - (rtol * np.abs(e) + atol_frac * scale)
+    if excess.size and excess.max() > 0:
+        k = np.unravel_index(np.argmax(excess), excess.shape)
+        raise AssertionError("elementwise bound exceeded at %s: got %r expected %r (max|exp| %g, %d of %d elements over)"
+                             % (k, g[k], e[k], scale, int((excess > 0).sum()), excess.size))
+    return float(np.abs(g - e).max() / scale)
 
 
 def scaled_arch(pkg, div):
@@ -49,6 +58,38 @@ def check_backbone(pkg, net_out, oracle_out, nlayers):
             e = rel_err(xyz_l[li].cpu().numpy(), oxyz[li])
             assert e < TOL, "xyz of layer %d: rel err %g" % (li, e)
         e = rel_err(feat_l[li].cpu().numpy(), ofeat[li])
+        assert e < TOL, "features of layer %d: rel err %g" % (li, e)
+
+
+def check_backbone_layerwise(pkg, arch, params, net_out, ffps_mode="matrix"):
+    """Teacher-forced parity: every layer of the oracle is fed the GPU's OWN outputs of the layers before it, so its
+    indices (FPS -- incl. F-FPS, which reads features --, ball query) must match bit for bit BY CONSTRUCTION of the
+    arithmetic, not because no near-tie happened to flip under the ~1e-5 feature differences of the layers before."""
+    from oracle import layers as olayers
+    xyz_l, feat_l, fps_l, dbg = net_out
+    npy = lambda t: None if t is None else t.cpu().numpy()
+    for li, spec in enumerate(arch, start=1):
+        (xyz_i, feat_i, radius, nsample, mlps, bn, rng, method, npoint, former, attn, ltype, scope, dilated,
+         vote_idx, agg) = spec
+        xin, fin = npy(xyz_l[xyz_i[0]]), npy(feat_l[feat_i[0]])
+        if ltype == "SA_Layer":
+            former_idx = npy(fps_l[former]) if former != -1 else None
+            vote_ctr = npy(xyz_l[vote_idx]) if vote_idx != -1 else None
+            ex, ef, ei, ed = olayers.pointnet_sa_module_msg(xin, fin, radius, nsample, mlps, False, None, bn, rng, method,
+                                                            npoint, former_idx, attn, scope, dilated, vote_ctr, agg,
+                                                            params=params, ffps_mode=ffps_mode, return_debug=True)
+            np.testing.assert_array_equal(npy(fps_l[li]), ei, err_msg="fps_idx of layer %d" % li)
+            for sc, (a, b) in enumerate(zip(dbg[li - 1].get("idx", []), ed.get("idx", []))):
+                np.testing.assert_array_equal(npy(a), b, err_msg="ball-query idx layer %d scale %d" % (li, sc))
+            for sc, (a, b) in enumerate(zip(dbg[li - 1].get("cnt", []), ed.get("cnt", []))):
+                np.testing.assert_array_equal(npy(a), b, err_msg="pts_cnt layer %d scale %d" % (li, sc))
+            np.testing.assert_array_equal(npy(xyz_l[li]), ex, err_msg="new_xyz of layer %d" % li)
+        elif ltype == "Vote_Layer":
+            ex, ef, _ = olayers.vote_layer(xin, fin, mlps, False, None, bn, scope, params=params)
+            assert rel_err(npy(xyz_l[li]), ex) < TOL, "vote xyz of layer %d" % li
+        else:
+            continue
+        e = rel_err(npy(feat_l[li]), ef)
         assert e < TOL, "features of layer %d: rel err %g" % (li, e)
 
 
@@ -148,8 +189,42 @@ def test_backbone_full_size_one_scene_vs_oracle(pkg, oracle_ops, cuda):
     pts = synth.kitti_like(1, 16384, seed=1000)
     net = pkg.SABackbone(arch, params, in_channels=1, device=cuda)
     out = net.forward(torch.from_numpy(pts).to(cuda), return_debug=True)
-    exp = olayers.backbone_forward(arch, pts, params, return_debug=True)
-    check_backbone(pkg, out, exp, len(arch))
+    check_backbone_layerwise(pkg, arch, params, out)          # robust: teacher-forced, layer by layer
+    # latency mode (sampling consumed in parts, resumable layer-1 FPS) is the same function: identical outputs
+    net_l = pkg.SABackbone(arch, params, in_channels=1, device=cuda, latency_mode=True)
+    out_l = net_l.forward(torch.from_numpy(pts).to(cuda), return_debug=True)
+    for li in range(1, len(arch) + 1):
+        if out[2][li] is not None:
+            assert torch.equal(out_l[2][li], out[2][li]), "latency-mode fps_idx of layer %d" % li
+        if out[0][li] is not None:
+            assert torch.equal(out_l[0][li], out[0][li]), "latency-mode xyz of layer %d" % li
+        assert torch.equal(out_l[1][li], out[1][li]), "latency-mode features of layer %d" % li
+        for a, b in zip(out_l[3][li - 1].get("idx", []), out[3][li - 1].get("idx", [])):
+            assert torch.equal(a, b)
+    exp = olayers.backbone_forward(arch, pts, params, return_debug=True)   # end to end (indices may legitimately fork
+    check_backbone(pkg, out, exp, len(arch))                               # at a near-tie; this seed does not)
+
+
+@pytest.mark.parametrize("parts", [2, [0.5, 0.25, 0.25]])
+def test_backbone_latency_mode_small_equals_default(pkg, cuda, parts):
+    """Sampling consumed in parts (side streams, resumable D-FPS) is bit-identical to the plain schedule, eager and
+    captured."""
+    arch = scaled_arch(pkg, 4)                                    # 4096 -> 1024 -> 256 -> 128
+    params = pkg.params.init_params(arch, 1, seed=9, random_bias=True)
+    pts = torch.from_numpy(compact_scene(3, 4096, seed=44)).to(cuda)
+    a = pkg.SABackbone(arch, params, in_channels=1, device=cuda).forward(pts, return_debug=True)
+    net = pkg.SABackbone(arch, params, in_channels=1, device=cuda, latency_mode=True, fps_parts=parts)
+    b = net.forward(pts, return_debug=True)
+    replay = net.capture(pts)
+    c, _ = replay()
+    torch.cuda.synchronize()
+    for li in range(1, len(arch) + 1):
+        for o in (b, c):
+            assert torch.equal(o[1][li], a[1][li]), "features of layer %d" % li
+            if a[2][li] is not None:
+                assert torch.equal(o[2][li], a[2][li]), "fps_idx of layer %d" % li
+        for x, y in zip(b[3][li - 1].get("idx", []), a[3][li - 1].get("idx", [])):
+            assert torch.equal(x, y)
 
 
 def test_backbone_full_size_properties_and_graph_replay(pkg, cuda):

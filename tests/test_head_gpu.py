@@ -9,8 +9,17 @@ pytestmark = pytest.mark.gpu
 synth = importlib.import_module("3dssd_b200.synth")
 
 
-def rel_err(got, exp):
-    return float(np.abs(got.astype(np.float64) - exp.astype(np.float64)).max() / max(1e-12, np.abs(exp).max()))
+def rel_err(got, exp, rtol=1e-3, atol_frac=2e-5):
+    """max|got-exp| / max|exp| (the global norm the tolerances are quoted in), after ALSO asserting the elementwise
+    bound |got - exp| <= rtol*|exp| + atol_frac*max|exp|: a small-magnitude feature may not hide behind a large one."""
+    g, e = got.astype(np.float64), exp.astype(np.float64)
+    scale = max(1e-12, np.abs(e).max())
+    excess = np.abs(g - e) - (rtol * np.abs(e) + atol_frac * scale)
+    if excess.size and excess.max() > 0:
+        k = np.unravel_index(np.argmax(excess), excess.shape)
+        raise AssertionError("elementwise bound exceeded at %s: got %r expected %r (max|exp| %g, %d of %d elements over)"
+                             % (k, g[k], e[k], scale, int((excess > 0).sum()), excess.size))
+    return float(np.abs(g - e).max() / scale)
 
 
 def random_boxes(rng, b, n, spread=20.0):

@@ -105,6 +105,19 @@ lo, hi = d.shard_bounds(total, rank, world)
 blk, c = d.gather_detections(full[lo:hi].clone(), cnt[lo:hi].clone(), total_scenes=total)
 assert torch.equal(blk, full), "gathered blocks differ"
 assert torch.equal(c, cnt), "gathered counts differ"
+# the in-step form: the producer writes into views of the send buffer, one collective, result read through views
+g = d.DetectionGather(total, "cpu")
+ob, oc = g.out()
+assert ob.shape == (hi - lo, 100, 9) and oc.shape == (hi - lo,) and g.b_max == 3
+ob.copy_(full[lo:hi]); oc.copy_(cnt[lo:hi])
+g.gather()
+rb, rc = g.result()
+assert torch.equal(rb, full) and torch.equal(rc, cnt) and g.raw.numel() == world * g.slice_bytes
+try:
+    d.gather_detections(full[:1], cnt[:1], total_scenes=total)
+    raise SystemExit("a wrong local shard size must be rejected")
+except ValueError:
+    pass
 assert torch.equal(d.shard_batch(full, rank, world), full[lo:hi])
 dist.barrier()
 print("rank", rank, "ok")
@@ -185,6 +198,57 @@ def test_c_abi_argument_validation_needs_no_gpu(pkg):
                                 one, 256, null, null, 0, null) == -1 and "nsample" in err()
     assert L.ssd3d_linear_tc(128, 20, 16, one, one, one, one, one, one, 1, 1, null, one, 16, null, null, 0, null) == -1 and "multiple of 16" in err()
     assert L.ssd3d_version() > 0
+    # the explicit-placement entry points (round 2): strides, round ranges and the cluster request are validated up front
+    ll = ctypes.c_longlong
+    fps_ex = L.ssd3d_farthest_point_sample_ex
+    assert fps_ex(1, 64, 3, 8, one, ll(64 * 3), null, one, 4, 0, 0, 8, 0, 0, null) == -1 and "strides" in err()      # ldo < m
+    assert fps_ex(1, 64, 3, 8, one, ll(10), null, one, 8, 0, 0, 8, 0, 0, null) == -1 and "strides" in err()          # scene stride < n*c
+    assert fps_ex(1, 64, 3, 8, one, ll(192), null, one, 8, 0, 5, 3, 0, 0, null) == -1 and "rounds" in err()
+    assert fps_ex(1, 64, 3, 8, one, ll(192), null, one, 8, 0, 0, 8, 3, 0, null) == -1 and "cluster" in err()
+    assert fps_ex(1, 4096, 3, 8, one, ll(4096 * 3), null, one, 8, 0, 0, 4, 0, 0, null) == -1 and "temp" in err()   # partial range, no state buffer
+    assert fps_ex(1, 64, 3, 8, one, ll(192), one, one, 8, 0, 0, 4, 0, 0, null) == -1 and "resident-scene" in err()  # too small for a cluster
+    assert fps_ex(1, 64, 7, 8, one, ll(64 * 7), one, one, 8, 0, 0, 4, 0, 0, null) == -1 and "c == 3" in err()
+    assert fps_ex(1, 64, 3, 8, one, ll(192), one, one, 8, 0, 4, 4, 0, 0, null) == 0                                   # empty range: nothing to do
+    assert L.ssd3d_fps_supports_rounds(16384, 3) == 1 and L.ssd3d_fps_supports_rounds(65536, 3) == 0 and L.ssd3d_fps_supports_rounds(4096, 4) == 0
+    assert L.ssd3d_iota_idx(2, 8, 0, one, 4, null) == -1 and "ldo" in err()
+    assert L.ssd3d_decode_dist_anchor_free(4, 12, one, one, 20, one, 1, one, one, null) == -1 and "ld_reg" in err()
+    assert L.ssd3d_concat_rows(1, 9, one, one, 3, one, null) == -1
+
+
+def test_library_keeps_no_state(pkg):
+    """include/ssd3d.h promises a library that 'keeps no state between calls': no tuning setters in the ABI (round 1
+    had process-global ssd3d_tune_set_* knobs; every such choice is now an argument of an *_ex entry point) and no
+    developer hooks in the shipped build."""
+    import subprocess
+    out = subprocess.check_output(["nm", "-D", "--defined-only", pkg.LIB_PATH]).decode()
+    names = [ln.split()[-1] for ln in out.splitlines() if " T " in ln]
+    assert not [n for n in names if "tune" in n or "_dev_" in n or "_set_" in n], names
+    hdr = open(os.path.join(ROOT, "include", "ssd3d.h")).read()
+    assert "tune" not in hdr and "keeps no state" in hdr
+    bss = [ln for ln in subprocess.check_output(["nm", "--defined-only", pkg.LIB_PATH]).decode().splitlines()
+           if (" b " in ln or " d " in ln or " B " in ln or " D " in ln) and "g_" in ln and "ssd3d" in ln]
+    assert all("g_err" in ln for ln in bss), bss          # the only global: the thread-local last-error string
+
+
+def test_oracle_c_nms_twin_matches_python_restatement(oracle_ops):
+    from oracle import head as ohead
+    rng = np.random.default_rng(2)
+    for n, spread in ((256, 12.0), (64, 2.0), (5, 1.0)):
+        ctr = rng.uniform(-spread, spread, (2, n, 3)).astype(np.float32)
+        boxes = np.concatenate([ctr, rng.uniform(0.5, 4.5, (2, n, 3)).astype(np.float32),
+                                rng.uniform(-np.pi, np.pi, (2, n, 1)).astype(np.float32)], -1)
+        sc = rng.uniform(0, 1, (2, n)).astype(np.float32)
+        sc[:, 1:3] = sc[:, :1]
+        a, b = ohead.bev_nms(boxes, sc, 0.1, 50), oracle_ops.bev_nms(boxes, sc, 0.1, 50)
+        np.testing.assert_array_equal(a[0], b[0]); np.testing.assert_array_equal(a[1], b[1])
+
+
+def test_fps_part_bounds(pkg):
+    pb = pkg.layers_util._part_bounds
+    assert pb(4096, 4) == [(0, 1024), (1024, 2048), (2048, 3072), (3072, 4096)]
+    assert pb(4096, [0.34, 0.28, 0.22, 0.16]) == [(0, 1408), (1408, 2560), (2560, 3456), (3456, 4096)]
+    assert pb(512, 8)[-1][1] == 512 and all(a < b for a, b in pb(512, 8))
+    assert pb(100, 3) == [(0, 100)]                       # smaller than one 128-row tile: a single part
 
 
 def test_header_is_plain_c():

@@ -52,14 +52,64 @@ def test_fps_every_cluster_size(pkg, oracle_ops, cuda, cl, variant):
     pts = synth.kitti_like(3, 4096, seed=21)[..., :3].copy()
     pts[:, 2000:2100] = pts[:, 100:200]                              # extra duplicates
     exp = oracle_ops.farthest_point_sample(300, pts)
-    pkg.lib().ssd3d_tune_set_fps_cluster(cl)
-    pkg.lib().ssd3d_tune_set_fps_variant(variant)
-    try:
-        got = N(pkg.farthest_point_sample(300, T(pts, cuda)))
-    finally:
-        pkg.lib().ssd3d_tune_set_fps_cluster(0)
-        pkg.lib().ssd3d_tune_set_fps_variant(0)
+    got = N(pkg.farthest_point_sample(300, T(pts, cuda), cluster=cl, packet_kernel=bool(variant)))   # per-call, no library state
     np.testing.assert_array_equal(got, exp)
+
+
+@pytest.mark.parametrize("cluster", [0, -4, 8])
+@pytest.mark.parametrize("cuts", [(0, 700, 1024), (0, 1, 2, 513, 1024), (0, 1024)])
+def test_fps_resumable_rounds(pkg, oracle_ops, cuda, cuts, cluster):
+    """Rounds [j0, j1) in separate launches (running distances through `temp`) give the indices of one launch."""
+    pts = synth.kitti_like(3, 4096, seed=33)[..., :3].copy()
+    pts[:, 3000:3050] = pts[:, 10:60]
+    exp = oracle_ops.farthest_point_sample(1024, pts)
+    d = T(pts, cuda)
+    assert pkg.tf_ops.fps_supports_rounds(4096)
+    buf = torch.full((3, 1024), -7, dtype=torch.int32, device=cuda)
+    temp = torch.empty((3, 4096), dtype=torch.float32, device=cuda)
+    for j0, j1 in zip(cuts[:-1], cuts[1:]):
+        pkg.farthest_point_sample(1024, d, out=(buf, 0), rounds=(j0, j1), temp=temp, cluster=cluster)
+        assert (N(buf)[:, j1:] == -7).all()                       # later rounds untouched
+        np.testing.assert_array_equal(N(buf)[:, :j1], exp[:, :j1])   # a sample is final once its round is done
+
+
+def test_fps_strided_input_offset_output(pkg, oracle_ops, cuda):
+    """A [:, a:b] slice read in place; indices written, segment offset added, into a column block of a wider
+    buffer (what a fusion-sampling SA layer does, layers_util.py:84-111)."""
+    full = synth.kitti_like(3, 2048, seed=8)
+    xyz = T(full[..., :3].copy(), cuda)
+    feat = T(np.random.default_rng(1).standard_normal((3, 2048, 64)).astype(np.float32), cuda)
+    buf = torch.full((3, 600), -1, dtype=torch.int32, device=cuda)
+    seg = xyz[:, 1024:2048]
+    pkg.farthest_point_sample(200, seg, out=(buf, 100), idx_offset=1024)
+    exp = oracle_ops.farthest_point_sample(200, N(seg.contiguous())) + 1024
+    np.testing.assert_array_equal(N(buf)[:, 100:300], exp)
+    assert (N(buf)[:, :100] == -1).all() and (N(buf)[:, 300:] == -1).all()
+    # F-FPS (matrix-free and matrix route) on slices of xyz and features
+    segf = feat[:, 1024:2048]
+    ref = N(pkg.farthest_point_sample_with_distance(150, pkg.calc_square_dist(torch.cat([seg, segf], -1).contiguous()))) + 1024
+    pkg.tf_ops.farthest_point_sample_features(150, seg, segf, out=(buf, 300), idx_offset=1024)
+    np.testing.assert_array_equal(N(buf)[:, 300:450], ref)
+    pkg.farthest_point_sample_with_distance(150, pkg.calc_square_dist(pkg.tf_ops.concat_cols(seg, segf)), out=(buf, 450), idx_offset=1024)
+    np.testing.assert_array_equal(N(buf)[:, 450:600], ref)
+
+
+def test_fps_65536_vs_reference_kernel(pkg, ref_ops, cuda):
+    """BASELINE configs[2] top size: 65536 -> 1024 of 16384 rounds checked against the reference kernel (the 16-CTA
+    cluster path, P = 16), D-FPS on xyz and the generic-c kernel on xyz + 5 features."""
+    rng = np.random.default_rng(65536)
+    pts = np.concatenate([synth.kitti_like(2, 16384, seed=70 + i)[..., :3] for i in range(4)], axis=1).copy()
+    pts[:, 60000:60100] = pts[:, 5:105]                              # duplicates far apart in index
+    d = T(pts, cuda)
+    got = pkg.farthest_point_sample(1024, d)
+    assert torch.equal(got, ref_ops.farthest_point_sample(1024, d))
+    assert (got[:, 0] == 0).all() and int(got.max()) < 65536
+    f = T(np.concatenate([pts, rng.standard_normal((2, 65536, 5)).astype(np.float32)], -1), cuda)
+    assert torch.equal(pkg.farthest_point_sample(256, f), ref_ops.farthest_point_sample(256, f))
+    # F-FPS 'fused' route where no on-chip kernel holds the features (67 channels x 65536 points): the temp-based kernel
+    f67 = T(np.concatenate([pts[:1], rng.standard_normal((1, 65536, 64)).astype(np.float32)], -1), cuda)
+    assert pkg.lib().ssd3d_fps_needs_temp(65536, 67) == 1
+    assert torch.equal(pkg.farthest_point_sample(48, f67), ref_ops.farthest_point_sample(48, f67))
 
 
 def test_fps_full_size_vs_reference_kernel(pkg, ref_ops, cuda):
@@ -168,6 +218,40 @@ def test_query_ball_point_multi_equals_single_calls(pkg, cuda, dilated):
         assert torch.equal(idxs[i], a) and torch.equal(cnts[i], c)
 
 
+@pytest.mark.parametrize("dilated", [False, True])
+def test_ball_query_nan_inf_coordinates_vs_reference_kernel(pkg, ref_ops, oracle_ops, cuda, dilated):
+    """Non-finite coordinates follow the reference's arithmetic, not an input contract: in the plain query
+    max(sqrt(NaN), 1e-20) = 1e-20 < r, so a NaN distance HITS (tf_grouping_g.cu:237-241); in the dilated query every
+    comparison with NaN is false, so it never hits (:337-343).  +-Inf distances miss in both."""
+    rng = np.random.default_rng(77)
+    xyz1 = rng.uniform(0, 1, (2, 700, 3)).astype(np.float32)
+    xyz2 = np.array(xyz1[:, :96], copy=True)
+    xyz1[0, 5, 0] = np.nan; xyz1[0, 300, 2] = np.nan; xyz1[1, 17, 1] = np.inf; xyz1[1, 400] = -np.inf
+    xyz2[0, 3, 1] = np.nan; xyz2[1, 9, 0] = np.inf; xyz2[1, 10, 2] = -np.inf      # NaN / Inf queries too (inf - inf = NaN)
+    a, q = T(xyz1, cuda), T(xyz2, cuda)
+    for lo, hi, k in ((0.0, 0.3, 16), (0.3, 0.6, 32)):
+        if dilated:
+            idx, cnt = pkg.query_ball_point_dilated(lo, hi, k, a, q)
+            ridx, rcnt = ref_ops.query_ball_point_dilated(lo, hi, k, a, q)
+            eidx, ecnt = oracle_ops.query_ball_point_dilated(lo, hi, k, xyz1, xyz2)
+        else:
+            idx, cnt = pkg.query_ball_point(hi, k, a, q)
+            ridx, rcnt = ref_ops.query_ball_point(hi, k, a, q)
+            eidx, ecnt = oracle_ops.query_ball_point(hi, k, xyz1, xyz2)
+        assert torch.equal(cnt, rcnt)
+        np.testing.assert_array_equal(N(idx), _masked(N(ridx), N(rcnt)))
+        np.testing.assert_array_equal(N(cnt), ecnt)
+        np.testing.assert_array_equal(N(idx), eidx)
+    if not dilated:   # the NaN query hits everything in index order: its list is 0..k-1
+        idx, cnt = pkg.query_ball_point(0.3, 16, a, q)
+        assert N(cnt)[0, 3] == 16 and N(idx)[0, 3].tolist() == list(range(16))
+    # the one-pass multi-shell kernel agrees with the single calls on the same inputs
+    idxs, cnts = pkg.query_ball_point_multi([0.0, 0.3], [0.3, 0.6], [16, 32], a, q, dilated)
+    for i, (lo, hi, k) in enumerate(((0.0, 0.3, 16), (0.3, 0.6, 32))):
+        r = pkg.query_ball_point_dilated(lo, hi, k, a, q) if dilated else pkg.query_ball_point(hi, k, a, q)
+        assert torch.equal(idxs[i], r[0]) and torch.equal(cnts[i], r[1])
+
+
 def test_ball_query_full_size_vs_reference_kernel(pkg, ref_ops, cuda):
     """Layer-1 shape of BASELINE config 2: 4096 D-FPS queries over 16384 points, the three dilated shells."""
     pts = T(synth.kitti_like(1, 16384, seed=1003)[..., :3].copy(), cuda)
@@ -245,8 +329,17 @@ def test_three_interpolate_bit_exact(pkg, oracle_ops, ref_ops, cuda):
 # ---------------------------------------------------------------------------------------------------------
 # conv + BN + ReLU (+ max-pool): 1e-3 relative fp32 (BASELINE.json north star)
 # ---------------------------------------------------------------------------------------------------------
-def rel_err(got, exp):
-    return float(np.abs(got.astype(np.float64) - exp.astype(np.float64)).max() / max(1e-12, np.abs(exp).max()))
+def rel_err(got, exp, rtol=1e-3, atol_frac=2e-5):
+    """max|got-exp| / max|exp| (the global norm the tolerances are quoted in), after ALSO asserting the elementwise
+    bound |got - exp| <= rtol*|exp| + atol_frac*max|exp|: a small-magnitude feature may not hide behind a large one."""
+    g, e = got.astype(np.float64), exp.astype(np.float64)
+    scale = max(1e-12, np.abs(e).max())
+    excess = np.abs(g - e) - (rtol * np.abs(e) + atol_frac * scale)
+    if excess.size and excess.max() > 0:
+        k = np.unravel_index(np.argmax(excess), excess.shape)
+        raise AssertionError("elementwise bound exceeded at %s: got %r expected %r (max|exp| %g, %d of %d elements over)"
+                             % (k, g[k], e[k], scale, int((excess > 0).sum()), excess.size))
+    return float(np.abs(g - e).max() / scale)
 
 
 @pytest.mark.parametrize("rows,cin,cout", [(1000, 4, 16), (4096, 67, 64), (777, 131, 128), (512, 259, 256), (130, 512, 1024)])

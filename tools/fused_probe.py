@@ -25,8 +25,9 @@ def main():
     dev = torch.device("cuda:0")
     sel = [int(a) for a in sys.argv[1:] if "=" not in a] or range(len(CASES))
     kv = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
-    pkg.lib().ssd3d_tune_set_fused(int(kv.get("slots", 0)), int(kv.get("wg", 0)))
-    pkg.lib().ssd3d_tune_set_fused_mma_split(int(kv.get("nsplit", 0)))
+    if "slots" in kv or "wg" in kv:   # developer build only (nvcc -DSSD3D_DEV_HOOKS, loaded through SSD3D_LIB)
+        import ctypes
+        ctypes.CDLL(pkg.LIB_PATH).ssd3d_dev_set_fused(int(kv.get("slots", 0)), int(kv.get("wg", 0)))
     rng = np.random.default_rng(0)
     B = 8
     pts = torch.from_numpy(synth.kitti_like(B, 16384, seed=1000)).to(dev)

@@ -31,7 +31,6 @@ def main():
     dev = torch.device("cuda:0")
     sel = [int(a) for a in sys.argv[1:] if "=" not in a] or range(len(SHAPES))
     kv = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
-    pkg.lib().ssd3d_tune_set_mma_split(int(kv.get("nsplit", 0)))
     rng = np.random.default_rng(0)
     for i in sel:
         rows, cin, cout, pool, mode = SHAPES[i]

@@ -40,15 +40,12 @@ def main(out_path):
 
     # ---- D-FPS layer 1: 16384 -> 4096   (variant 0 = direct/scene-resident when it fits, 1 = xyz-in-packet)
     for variant in (0, 1):
-        pkg.lib().ssd3d_tune_set_fps_variant(variant)
         for cl in (0, 4, 8, 16):
-            pkg.lib().ssd3d_tune_set_fps_cluster(cl)
             try:
-                res["fps_L1_16384_4096_v%d_cl%d_ms" % (variant, cl)] = timeit(lambda: pkg.farthest_point_sample(4096, xyz))
+                res["fps_L1_16384_4096_v%d_cl%d_ms" % (variant, cl)] = timeit(
+                    lambda: pkg.farthest_point_sample(4096, xyz, cluster=cl, packet_kernel=bool(variant)))
             except Exception as e:  # noqa: BLE001
                 res["fps_L1_16384_4096_v%d_cl%d_ms" % (variant, cl)] = "ERR " + str(e)
-    pkg.lib().ssd3d_tune_set_fps_cluster(0)
-    pkg.lib().ssd3d_tune_set_fps_variant(0)
     if have_ref:
         res["ref_fps_L1_ms"] = timeit(lambda: ref_ops.farthest_point_sample(4096, xyz, sync=False), 1, 3)
     fidx = pkg.farthest_point_sample(4096, xyz)
@@ -57,32 +54,24 @@ def main(out_path):
     # ---- D-FPS layer 2/3 shapes
     x2 = new_xyz
     for cl in (0, 1, 2, 4, 8):
-        pkg.lib().ssd3d_tune_set_fps_cluster(cl)
-        res["fps_L2_4096_512_cl%d_ms" % cl] = timeit(lambda: pkg.farthest_point_sample(512, x2))
-    pkg.lib().ssd3d_tune_set_fps_cluster(0)
+        res["fps_L2_4096_512_cl%d_ms" % cl] = timeit(lambda: pkg.farthest_point_sample(512, x2, cluster=cl))
     if have_ref:
         res["ref_fps_L2_ms"] = timeit(lambda: ref_ops.farthest_point_sample(512, x2, sync=False), 1, 3)
     x3 = x2[:, :512].contiguous()
     for cl in (0, 1, 2):
-        pkg.lib().ssd3d_tune_set_fps_cluster(cl)
-        res["fps_L3_512_256_cl%d_ms" % cl] = timeit(lambda: pkg.farthest_point_sample(256, x3))
-    pkg.lib().ssd3d_tune_set_fps_cluster(0)
+        res["fps_L3_512_256_cl%d_ms" % cl] = timeit(lambda: pkg.farthest_point_sample(256, x3, cluster=cl))
 
     # ---- F-FPS layer 2: N=4096, 3+64 features -> 512: matrix route vs fused
     f2 = torch.randn((B, 4096, 67), device=dev)
     res["sqdist_L2_4096x67_ms"] = timeit(lambda: pkg.calc_square_dist(f2))
     d2 = pkg.calc_square_dist(f2)
     for cl in (0, 2, 4, 8, 16):
-        pkg.lib().ssd3d_tune_set_fps_cluster(cl)
-        res["fpsdist_L2_cl%d_ms" % cl] = timeit(lambda: pkg.farthest_point_sample_with_distance(512, d2))
-    pkg.lib().ssd3d_tune_set_fps_cluster(0)
+        res["fpsdist_L2_cl%d_ms" % cl] = timeit(lambda: pkg.farthest_point_sample_with_distance(512, d2, cluster=cl))
     for cl in (0, 8, 16):
-        pkg.lib().ssd3d_tune_set_fps_cluster(cl)
         try:
-            res["ffps_fused_L2_cl%d_ms" % cl] = timeit(lambda: pkg.farthest_point_sample(512, f2))
+            res["ffps_fused_L2_cl%d_ms" % cl] = timeit(lambda: pkg.farthest_point_sample(512, f2, cluster=cl))
         except Exception as e:  # noqa: BLE001
             res["ffps_fused_L2_cl%d_ms" % cl] = "ERR " + str(e)
-    pkg.lib().ssd3d_tune_set_fps_cluster(0)
     res["ffps_direct_L2_ms"] = timeit(lambda: pkg.farthest_point_sample_features(512, f2[..., :3].contiguous(), f2[..., 3:].contiguous()))
     x2c, p2c = f2[..., :3].contiguous(), f2[..., 3:].contiguous()
     res["ffps_direct_L2_ms"] = timeit(lambda: pkg.farthest_point_sample_features(512, x2c, p2c))
