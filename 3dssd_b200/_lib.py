@@ -21,6 +21,9 @@ _SIGNATURES = {
                                        c_void_p, c_void_p],
     "ssd3d_query_ball_point_multi": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p],
+    "ssd3d_query_ball_point_workspace": [c_int, c_int],
+    "ssd3d_query_ball_point_multi_ws": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_size_t, c_void_p],
     "ssd3d_group_point": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "ssd3d_three_nn": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ssd3d_three_interpolate": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
@@ -84,7 +87,7 @@ def lib():
         for name, argtypes in _SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = argtypes
-            fn.restype = ctypes.c_size_t if name == "ssd3d_sa_fused_smem" else c_int
+            fn.restype = ctypes.c_size_t if name in ("ssd3d_sa_fused_smem", "ssd3d_query_ball_point_workspace") else c_int
         l.ssd3d_last_error.restype = ctypes.c_char_p
         l.ssd3d_last_error.argtypes = []
         _lib = l

@@ -25,17 +25,26 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: developer variants, e.g. build(True, defines=("TC_PROFILE", "SF_PROFILE", "SSD3D_DEV_HOOKS"),
+    out="libssd3d_prof.so") -- loaded through the SSD3D_LIB environment variable by the probe tools; the product
+    library is always built without defines."""
+    if out is not None:
+        return _build_to(os.path.join(HERE, out), os.path.join(HERE, "build_" + os.path.splitext(out)[0]), defines, verbose)
     if not force and not needs_build():
         return LIB
+    return _build_to(LIB, os.path.join(HERE, "build"), (), verbose)
+
+
+def _build_to(lib_path, obj_dir, defines, verbose):
     nvcc = os.environ.get("NVCC", "nvcc")
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
     for src in sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -43,10 +52,14 @@ def build(force=False, verbose=False):
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out.decode()))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib_path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.check_call(cmd)
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "prof":
+        print(build(True, verbose=True, defines=("TC_PROFILE", "SF_PROFILE", "SSD3D_DEV_HOOKS"), out="libssd3d_prof.so"))
+    else:
+        print(build(force=True, verbose=True))

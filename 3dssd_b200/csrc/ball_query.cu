@@ -224,17 +224,21 @@ static float sq_threshold(float r)
     return t;
 }
 
+float bq_sq_threshold(float r) { return sq_threshold(r); }   // shared with ball_query_grid.cu
+
 template <int NS>
-static void launch_bq(bool dilated, dim3 grid, size_t smem, cudaStream_t st, const float *xyz1, const float *xyz2,
-                      const BqParams &p)
+static cudaError_t launch_bq(bool dilated, dim3 grid, size_t smem, cudaStream_t st, const float *xyz1, const float *xyz2,
+                             const BqParams &p)
 {
+    cudaError_t e;
     if (dilated) {
-        cudaFuncSetAttribute((const void *)ball_query_kernel<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ball_query_kernel<NS, true><<<grid, BQ_THREADS, smem, st>>>(xyz1, xyz2, p);
+        e = cudaFuncSetAttribute((const void *)ball_query_kernel<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) ball_query_kernel<NS, true><<<grid, BQ_THREADS, smem, st>>>(xyz1, xyz2, p);
     } else {
-        cudaFuncSetAttribute((const void *)ball_query_kernel<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ball_query_kernel<NS, false><<<grid, BQ_THREADS, smem, st>>>(xyz1, xyz2, p);
+        e = cudaFuncSetAttribute((const void *)ball_query_kernel<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) ball_query_kernel<NS, false><<<grid, BQ_THREADS, smem, st>>>(xyz1, xyz2, p);
     }
+    return e;
 }
 
 static int ball_query_multi(int b, int n, int m, int nq, int dilated, const float *min_r, const float *max_r,
@@ -271,12 +275,14 @@ static int ball_query_multi(int b, int n, int m, int nq, int dilated, const floa
     const size_t smem = (size_t)2 * BQ_TILE * 3 * sizeof(float) + (size_t)BQ_QPB * ktot * sizeof(int);
     SSD3D_REQUIRE(smem <= 200 * 1024, "query_ball_point: sum of nsample (%d) too large for the staging buffer", ktot);
     dim3 grid((unsigned)ceil_div(m, BQ_QPB), (unsigned)b);
+    cudaError_t e;
     switch (nq) {
-        case 1: launch_bq<1>(dilated != 0, grid, smem, st, xyz1, xyz2, p); break;
-        case 2: launch_bq<2>(dilated != 0, grid, smem, st, xyz1, xyz2, p); break;
-        case 3: launch_bq<3>(dilated != 0, grid, smem, st, xyz1, xyz2, p); break;
-        default: launch_bq<4>(dilated != 0, grid, smem, st, xyz1, xyz2, p); break;
+        case 1: e = launch_bq<1>(dilated != 0, grid, smem, st, xyz1, xyz2, p); break;
+        case 2: e = launch_bq<2>(dilated != 0, grid, smem, st, xyz1, xyz2, p); break;
+        case 3: e = launch_bq<3>(dilated != 0, grid, smem, st, xyz1, xyz2, p); break;
+        default: e = launch_bq<4>(dilated != 0, grid, smem, st, xyz1, xyz2, p); break;
     }
+    if (e != cudaSuccess) return cuda_status(e, "ball_query_kernel shared-memory opt-in");
     SSD3D_LAUNCH_CHECK("ball_query_kernel");
 }
 

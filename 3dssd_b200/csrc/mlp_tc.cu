@@ -23,6 +23,8 @@
 // resident across the n-tiles of its m-tile (TcParams::astat).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdio>
+#include <cstring>
 
 #include "common.cuh"
 #include "pool.cuh"
@@ -174,6 +176,18 @@ __device__ __forceinline__ void pooled_chunk(const TcParams &p, float (&v)[32], 
     }
 }
 
+// Developer instrumentation (nvcc -DTC_PROFILE): CTA 0 accumulates, per role, the cycles spent waiting on each barrier
+// and the cycles spent working; printed by the launcher.  Slots: 0 total | 1 tma wait-empty | 2 mma wait-afull |
+// 3 mma wait-full(B) | 4 mma wait-tempty | 5 mma issue | 6 prod wait-slot | 7 prod load+math | 8 epi wait-tfull | 9 epi work
+#ifdef TC_PROFILE
+__device__ long long tc_prof[16];
+#define TCP_DECL long long tcp_t = clock64(); const bool tcp_on = blockIdx.x == 0 && lane == 0
+#define TCP(i) do { if (tcp_on) { const long long t_ = clock64(); atomicAdd((unsigned long long *)&tc_prof[i], (unsigned long long)(t_ - tcp_t)); tcp_t = t_; } } while (0)
+#else
+#define TCP_DECL do { } while (0)
+#define TCP(i) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
@@ -250,11 +264,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bhi) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
             int it = 0, mt, nt;
+            TCP_DECL;
             for (int i = 0; tile_at(i, mt, nt); i++) {
                 for (int kb = 0; kb < nkb; kb++, it++) {
                     const int s = it % p.stages;
                     const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    TCP(15);
                     mbar_wait_cta(smem_u32(&empty_bar[s]), ph ^ 1u);
+                    TCP(1);
                     const uint32_t base = smem_u32(ring + (size_t)s * stage_bytes);
                     const uint32_t fb = smem_u32(&full_bar[s]);
                     mbar_arrive_expect_tx(fb, p.gather ? 2 * b_bytes : stage_bytes);
@@ -274,16 +291,22 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N = bn, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int it = 0, tcount = 0, mi = 0, mt, nt;
+            TCP_DECL;
             for (int i = 0; tile_at(i, mt, nt); i++, tcount++) {
                 const int acc = tcount & 1;
+                TCP(5);
                 mbar_wait_cta(smem_u32(&tempty_bar[acc]), (((uint32_t)(tcount >> 1)) & 1u) ^ 1u);
+                TCP(4);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
                 const bool last_nt = nt == p.n_tiles - 1;
                 for (int kb = 0; kb < nkb; kb++, it++) {
                     const int s = it % p.stages;
+                    TCP(5);
                     if (p.astat && nt == 0) mbar_wait_cta(smem_u32(&afull_bar[kb]), (uint32_t)mi & 1u);   // this m-tile's A k-block
+                    TCP(2);
                     mbar_wait_cta(smem_u32(&full_bar[s]), (uint32_t)(it / p.stages) & 1u);
+                    TCP(3);
                     tc_fence_after();
                     const uint32_t base = smem_u32(ring + (size_t)s * stage_bytes);
                     const uint32_t abase = p.astat ? smem_u32(smem) + (uint32_t)kb * 2u * TC_A_BYTES : base;
@@ -320,6 +343,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
             const bool vec4 = (p.g_c % 4 == 0) && (src_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.g_points) & 15u) == 0);
             const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
             int it = 0, mi = 0, mt, nt;
+            TCP_DECL;
             for (int i = 0; tile_at(i, mt, nt); i++) {
                 if (p.astat && nt != 0) continue;                 // A-stationary: the tile built for nt == 0 serves every n-tile
                 const uint32_t row = (uint32_t)mt * TC_BM + (uint32_t)r;
@@ -359,8 +383,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                         }
                     }
                     // (loads already in flight) wait for the slot: ring stage, or this k-block of the resident A tile
+                    if (warp == TC_PROD_WARP0) TCP(7);
                     if (p.astat) mbar_wait_cta(smem_u32(&aempty_bar[kb]), ((uint32_t)mi & 1u) ^ 1u);
                     else mbar_wait_cta(smem_u32(&empty_bar[s]), ((uint32_t)(it / p.stages) & 1u) ^ 1u);
+                    if (warp == TC_PROD_WARP0) TCP(6);
                     uint8_t *rowp = (p.astat ? smem + (size_t)kb * 2 * TC_A_BYTES : ring + (size_t)s * stage_bytes) + row_off;
 #pragma unroll
                     for (int c16 = 0; c16 < 8; c16++) {
@@ -398,9 +424,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
         const int h = (warp - TC_EPI_WARP0) >> 2;
         const int nchunks = (p.bn + 31) / 32;
         int tcount = 0, mt, nt;
+        TCP_DECL;
         for (int i = 0; tile_at(i, mt, nt); i++, tcount++) {
             const int acc = tcount & 1;
+            if (warp == TC_EPI_WARP0) TCP(9);
             mbar_wait_cta(smem_u32(&tfull_bar[acc]), ((uint32_t)(tcount >> 1)) & 1u);
+            if (warp == TC_EPI_WARP0) TCP(8);
             tc_fence_after();
             const long row = (long)mt * TC_BM + q * 32 + lane;
             const bool row_ok = row < p.rows;
@@ -768,7 +797,31 @@ static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const vo
     if (e != cudaSuccess) return cuda_status(e, "linear_tc attr");
     const int total = p.astat ? p.m_tiles : p.m_tiles * p.n_tiles;    // A-stationary CTAs own whole m-tiles
     const int grid = total < kNumSMs ? total : kNumSMs;
+#ifdef TC_PROFILE
+    const long long t_host0 = 0;
+    (void)t_host0;
+    cudaEvent_t pe0, pe1;
+    cudaEventCreate(&pe0); cudaEventCreate(&pe1);
+    cudaEventRecord(pe0, stream);
+#endif
     linear_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mah, mal, mbh, mbl, moh, mol, mof, p);
+#ifdef TC_PROFILE
+    {
+        cudaEventRecord(pe1, stream);
+        cudaDeviceSynchronize();
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, pe0, pe1);
+        long long h[16];
+        cudaMemcpyFromSymbol(h, tc_prof, sizeof(h));
+        fprintf(stderr, "tc_prof rows=%ld kp=%d n=%d bn=%d astat=%d stages=%d gather=%d pool=%d tiles/cta=%.1f  %.1f us |"
+                " tma_wait %lld | mma: afull %lld bfull %lld tempty %lld issue %lld | prod: wait %lld work %lld | epi: wait %lld work %lld\n",
+                rows, kp, n, p.bn, p.astat, p.stages, p.gather, pool, (double)total / grid, ms * 1e3, h[1], h[2], h[3], h[4], h[5], h[6], h[7],
+                h[8], h[9]);
+        memset(h, 0, sizeof(h));
+        cudaMemcpyToSymbol(tc_prof, h, sizeof(h));
+        cudaEventDestroy(pe0); cudaEventDestroy(pe1);
+    }
+#endif
     SSD3D_LAUNCH_CHECK("linear_tc_kernel");
 }
 

@@ -216,6 +216,9 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
         raise ValueError("QueryBallPoint expects positive nsample")     # tf_grouping.cpp:278
     b, n, _ = xyz1.shape
     m = xyz2.shape[1]
+    if n >= BQ_GRID_MIN_N and lib().ssd3d_query_ball_point_workspace(b, n):
+        i, c = query_ball_point_multi([0.0], [radius], [nsample], xyz1, xyz2, False)
+        return i[0], c[0]
     idx = torch.empty((b, m, int(nsample)), dtype=torch.int32, device=xyz1.device)
     cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
     check(lib().ssd3d_query_ball_point(b, n, m, float(radius), int(nsample), _p(xyz1), _p(xyz2), _p(idx), _p(cnt),
@@ -232,6 +235,9 @@ def query_ball_point_dilated(min_radius, max_radius, nsample, xyz1, xyz2):
         raise ValueError("QueryBallPointDilated expects positive nsample")
     b, n, _ = xyz1.shape
     m = xyz2.shape[1]
+    if n >= BQ_GRID_MIN_N and lib().ssd3d_query_ball_point_workspace(b, n):
+        i, c = query_ball_point_multi([min_radius], [max_radius], [nsample], xyz1, xyz2, True)
+        return i[0], c[0]
     idx = torch.empty((b, m, int(nsample)), dtype=torch.int32, device=xyz1.device)
     cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
     check(lib().ssd3d_query_ball_point_dilated(b, n, m, float(min_radius), float(max_radius), int(nsample), _p(xyz1),
@@ -239,9 +245,14 @@ def query_ball_point_dilated(min_radius, max_radius, nsample, xyz1, xyz2):
     return idx, cnt
 
 
-def query_ball_point_multi(min_radius_list, max_radius_list, nsample_list, xyz1, xyz2, dilated):
+BQ_GRID_MIN_N = 2048     # candidate sets at least this large take the spatially culled kernel (csrc/ball_query_grid.cu)
+
+
+def query_ball_point_multi(min_radius_list, max_radius_list, nsample_list, xyz1, xyz2, dilated, grid=None):
     """All radius shells of one SA layer in a single pass over the candidates (B200 fast path; same results
-    as calling query_ball_point[_dilated] once per shell).  Returns lists (idx_list, pts_cnt_list)."""
+    as calling query_ball_point[_dilated] once per shell).  Returns lists (idx_list, pts_cnt_list).
+    grid: None = automatic (the culled kernel for ndataset >= BQ_GRID_MIN_N), True / False = force / forbid it;
+    the outputs are identical either way."""
     xyz1, xyz2 = _bq_shapes(xyz1, xyz2)
     nq = len(max_radius_list)
     if not (len(nsample_list) == nq and len(min_radius_list) == nq and 1 <= nq <= 4):
@@ -260,10 +271,16 @@ def query_ball_point_multi(min_radius_list, max_radius_list, nsample_list, xyz1,
     ks = (ctypes.c_int * nq)(*[int(v) for v in nsample_list])
     pi = (ctypes.c_void_p * nq)(*[t.data_ptr() for t in idx])
     pc = (ctypes.c_void_p * nq)(*[t.data_ptr() for t in cnt])
-    check(lib().ssd3d_query_ball_point_multi(b, n, m, nq, 1 if dilated else 0, ctypes.cast(lo, ctypes.c_void_p),
-                                             ctypes.cast(hi, ctypes.c_void_p), ctypes.cast(ks, ctypes.c_void_p),
-                                             _p(xyz1), _p(xyz2), ctypes.cast(pi, ctypes.c_void_p),
-                                             ctypes.cast(pc, ctypes.c_void_p), _stream()), "query_ball_point_multi")
+    ws_bytes = int(lib().ssd3d_query_ball_point_workspace(b, n)) if (b and m) else 0
+    use_grid = ws_bytes > 0 and (n >= BQ_GRID_MIN_N if grid is None else bool(grid))
+    if grid and not use_grid and b and m:
+        raise ValueError("the culled ball query covers ndataset <= 16384, got %d" % n)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=xyz1.device) if use_grid else None
+    check(lib().ssd3d_query_ball_point_multi_ws(b, n, m, nq, 1 if dilated else 0, ctypes.cast(lo, ctypes.c_void_p),
+                                                ctypes.cast(hi, ctypes.c_void_p), ctypes.cast(ks, ctypes.c_void_p),
+                                                _p(xyz1), _p(xyz2), ctypes.cast(pi, ctypes.c_void_p),
+                                                ctypes.cast(pc, ctypes.c_void_p), _p(ws), ws_bytes if use_grid else 0,
+                                                _stream()), "query_ball_point_multi")
     return idx, cnt
 
 

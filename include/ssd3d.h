@@ -118,6 +118,17 @@ int ssd3d_query_ball_point_dilated(int b, int n, int m, float min_radius, float 
 int ssd3d_query_ball_point_multi(int b, int n, int m, int nqueries, int dilated, const float *min_radius,
                                  const float *max_radius, const int *nsample, const float *xyz1, const float *xyz2,
                                  int *const *idx, int *const *pts_cnt, ssd3d_stream_t stream);
+/* The same search with spatial culling (csrc/ball_query_grid.cu) for large candidate sets: `workspace` is caller-owned
+ * scratch of ssd3d_query_ball_point_workspace(b, n) bytes (16-byte aligned; 0 = this size has no culled kernel).  One
+ * small kernel bins the candidates of every scene into a uniform 2-D grid with cells >= r_max, the search then visits
+ * only the 3x3 cell neighbourhood of a query and restores "first nsample hits in ascending index" through a per-shell
+ * bitmap over candidate indices.  Same outputs, bit for bit, non-finite coordinates included.  workspace == NULL
+ * falls through to ssd3d_query_ball_point_multi. */
+size_t ssd3d_query_ball_point_workspace(int b, int n);
+int ssd3d_query_ball_point_multi_ws(int b, int n, int m, int nqueries, int dilated, const float *min_radius,
+                                    const float *max_radius, const int *nsample, const float *xyz1, const float *xyz2,
+                                    int *const *idx, int *const *pts_cnt, void *workspace, size_t workspace_bytes,
+                                    ssd3d_stream_t stream);
 
 /* replaces groupPointLauncher(b,n,c,m,nsample,points,idx,out)
  *   grouping/tf_grouping.cpp:446, grouping/tf_grouping_g.cu:476-479, kernel :362-379.

@@ -252,6 +252,49 @@ def test_ball_query_nan_inf_coordinates_vs_reference_kernel(pkg, ref_ops, oracle
         assert torch.equal(idxs[i], r[0]) and torch.equal(cnts[i], r[1])
 
 
+BQG_INPUTS = [
+    ("kitti8192", lambda: synth.kitti_like(2, 8192, seed=51)[..., :3].copy()),
+    ("cube3000", lambda: synth.uniform_cube(2, 3000, seed=4)),                       # n % 32 != 0
+    ("line2048", lambda: np.stack([np.linspace(0, 500, 2048, dtype=np.float32)] + [np.zeros(2048, np.float32)] * 2, -1)[None].repeat(2, 0)),
+    ("allsame2048", lambda: np.ones((1, 2048, 3), np.float32)),
+    ("nonfinite4096", None),
+]
+
+
+@pytest.mark.parametrize("name,gen", BQG_INPUTS, ids=[c[0] for c in BQG_INPUTS])
+@pytest.mark.parametrize("dilated", [False, True])
+def test_ball_query_culled_kernel_equals_exhaustive_and_oracle(pkg, oracle_ops, cuda, name, gen, dilated):
+    """The spatially culled kernel (uniform grid + index bitmap, csrc/ball_query_grid.cu) returns the bits of the
+    exhaustive kernel and of the oracle: clustered, uniform, collinear, coincident and non-finite inputs."""
+    if gen is None:
+        xyz1 = synth.kitti_like(2, 4096, seed=52)[..., :3].copy()
+        xyz1[0, 7, 1] = np.nan; xyz1[0, 3000] = np.inf          # scene 0: non-finite candidates -> one cell; scene 1 finite
+    else:
+        xyz1 = gen()
+    rng = np.random.default_rng(5)
+    m = 300
+    pick = rng.choice(xyz1.shape[1], m, replace=False)
+    xyz2 = np.ascontiguousarray(xyz1[:, pick] + rng.normal(0, 0.05, (xyz1.shape[0], m, 3)).astype(np.float32))
+    xyz2[:, 0] = xyz1[:, pick[0]]                                 # an exact self-hit (d == 0)
+    xyz2[:, 1] += 1.0e4                                           # far outside the bounding box: empty ball
+    if gen is None:
+        xyz2[1, 2, 0] = np.nan                                    # non-finite QUERY in a finite scene: scans every cell
+    a, q = T(xyz1, cuda), T(xyz2, cuda)
+    lows, highs, ks = [0.0, 0.3, 0.6], [0.3, 0.6, 1.7], [16, 32, 64]
+    gi, gc = pkg.query_ball_point_multi(lows, highs, ks, a, q, dilated, grid=True)
+    ei, ec = pkg.query_ball_point_multi(lows, highs, ks, a, q, dilated, grid=False)
+    for s in range(3):
+        assert torch.equal(gc[s], ec[s]), "cnt of shell %d" % s
+        assert torch.equal(gi[s], ei[s]), "idx of shell %d" % s
+        if dilated:
+            oi, oc = oracle_ops.query_ball_point_dilated(lows[s], highs[s], ks[s], xyz1, xyz2)
+        else:
+            oi, oc = oracle_ops.query_ball_point(highs[s], ks[s], xyz1, xyz2)
+        np.testing.assert_array_equal(N(gc[s]), oc)
+        np.testing.assert_array_equal(N(gi[s]), oi)
+    assert int(gc[2][:, 1].max()) == 0 or gen is None             # the far query found nothing
+
+
 def test_ball_query_full_size_vs_reference_kernel(pkg, ref_ops, cuda):
     """Layer-1 shape of BASELINE config 2: 4096 D-FPS queries over 16384 points, the three dilated shells."""
     pts = T(synth.kitti_like(1, 16384, seed=1003)[..., :3].copy(), cuda)
