@@ -65,6 +65,9 @@ _SIGNATURES = {
                                                 c_longlong, c_void_p, c_int, c_int, c_void_p],
     "ssd3d_gather_point_ex": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     "ssd3d_concat_rows": [c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "ssd3d_bn_train_workspace": [c_int],
+    "ssd3d_bn_train": [c_long, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p,
+                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p],
     "ssd3d_split_points": [c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "ssd3d_iota_idx": [c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "ssd3d_concat_cols": [c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p],
@@ -87,7 +90,7 @@ def lib():
         for name, argtypes in _SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = argtypes
-            fn.restype = ctypes.c_size_t if name in ("ssd3d_sa_fused_smem", "ssd3d_query_ball_point_workspace") else c_int
+            fn.restype = ctypes.c_size_t if name in ("ssd3d_sa_fused_smem", "ssd3d_query_ball_point_workspace", "ssd3d_bn_train_workspace") else c_int
         l.ssd3d_last_error.restype = ctypes.c_char_p
         l.ssd3d_last_error.argtypes = []
         _lib = l

@@ -3,8 +3,9 @@
 Mirrors /root/reference/lib/utils/layers_util.py: vote_layer :12-24, pointnet_sa_module :27-55,
 pointnet_sa_module_msg :59-189, pointnet_fp_module :192-225 -- same positional arguments and return values,
 torch CUDA tensors instead of TF tensors.  What TF resolved through variable scopes is passed explicitly as
-`params` (a dict keyed by the reference's variable names, or a params.PreparedParams).  Inference only:
-is_training must be False (training-mode BN / backward ops are SURVEY.md section 8f-3, not built yet).
+`params` (a dict keyed by the reference's variable names, or a params.PreparedParams).  is_training=True runs the
+convs with batch-statistics BatchNorm and updates the moving statistics in place (tf_util.py:424-444); the fused
+inference kernels fold BN and therefore serve is_training=False only.
 """
 import torch
 
@@ -16,6 +17,46 @@ from .params import prepare
 def _conv(pp, scope, x, bn=True, relu=True, pool=1, rowmask=None):
     f = pp.conv(scope, bn)
     return tf_ops.linear_bn_relu(x, f.w, f.scale, f.shift, relu=relu, pool=pool, rowmask=rowmask, cin=f.cin)
+
+
+def _conv_train(pp, scope, x, bn, bn_decay, relu=True):
+    """conv (+bias) -> training-mode BatchNorm -> ReLU, tf_util.conv2d / conv1d with is_training=True
+    (/root/reference/lib/utils/tf_util.py:51-124, :127-201, :424-444).  The contraction runs on the tensor-core path with
+    the BN-less fold (scale = 1, shift = bias); the batch statistics, the normalisation and the in-place update of the
+    moving statistics are one ssd3d_bn_train call."""
+    hi, lo = tf_ops.split_rows(x)
+    y, _ = tf_ops.linear_tc(hi, lo, pp.conv(scope, False), relu=bool(relu and not bn), want_f32=True, want_split=False)
+    if not bn:
+        return y
+    st = pp.bn_state(scope)
+    return tf_ops.bn_train(y, st["gamma"], st["beta"], st["moving_mean"], st["moving_variance"],
+                           decay=0.9 if bn_decay is None else float(bn_decay), relu=relu)[0]
+
+
+def _group_and_mlp_train(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, mlp_list, bn, bn_decay, dilated_group,
+                         use_agg, debug):
+    """Training-mode twin of _group_and_mlp: the literal op sequence of layers_util.py:137-185 (grouped tensor
+    materialised once, conv -> batch-norm -> relu per layer, reduce_max, mask, concat, aggregation)."""
+    nscale = len(radius_list)
+    min_r = [0.0 if (i == 0 or not dilated_group) else radius_list[i - 1] for i in range(nscale)]
+    idx_list, cnt_list = tf_ops.query_ball_point_multi(min_r, radius_list, nsample_list, xyz, new_xyz, dilated_group) \
+        if nscale <= 4 else ([], [])
+    if nscale > 4:
+        for i in range(nscale):
+            a, c = (tf_ops.query_ball_point_dilated(min_r[i], radius_list[i], nsample_list[i], xyz, new_xyz) if dilated_group
+                    else tf_ops.query_ball_point(radius_list[i], nsample_list[i], xyz, new_xyz))
+            idx_list.append(a); cnt_list.append(c)
+    debug["idx"].append(idx_list); debug["cnt"].append(cnt_list)
+    outs = []
+    for i in range(nscale):
+        g = tf_ops.group_concat(xyz, points, new_xyz, idx_list[i])                                  # :160-165
+        for j in range(len(mlp_list[i])):
+            g = _conv_train(pp, "%s/conv%d_%d" % (scope, i, j), g, bn, bn_decay)                    # :167-176
+        outs.append(tf_ops.rowgroup_max(g, nsample_list[i], cnt_list[i]))                           # :178-180
+    new_points = outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
+    if use_agg:
+        new_points = _conv_train(pp, scope + "/ensemble", new_points, bn, bn_decay)                 # :183-185
+    return new_points
 
 
 _CONSTS = {}
@@ -222,10 +263,10 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                    D-FPS halves separately; ball query + grouped MLP + aggregation of a part run on a side stream
                    while the sampling of the next part continues, and the per-part results are joined at the end.
                    Captured in a CUDA graph this is a plain dependency graph -- nothing polls."""
-    if is_training:
-        raise NotImplementedError("training-mode BatchNorm / backward ops are out of scope (inference only)")
     if use_attention:
         raise NotImplementedError("query_ball_point_withidx (use_attention) is unused by the shipped 3DSSD configs")
+    if is_training:
+        fps_parts = None                      # training takes the literal layer-by-layer schedule
     if mlp_mode not in ("tc", "fp32"):
         raise ValueError("mlp_mode must be 'tc' or 'fp32'")
     pp = prepare(params, xyz.device)
@@ -338,7 +379,11 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
         if former_fps_idx is not None:
             fps_idx = torch.cat([fps_idx, former_fps_idx], dim=-1).contiguous()    # :113-114
         new_xyz = tf_ops.gather_point(src_xyz, fps_idx)                            # :116-119
-        if nscale:
+        if nscale and is_training:
+            new_points = _group_and_mlp_train(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, mlp_list, bn,
+                                              bn_decay, dilated_group, use_agg, debug)
+            debug = {"idx": debug["idx"][0], "cnt": debug["cnt"][0]}
+        elif nscale:
             _compute_hoist(hoist, pp, scope, mlp_list, bn, points, stacks)
             new_points = _group_and_mlp(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, mlp_list, bn,
                                         dilated_group, use_agg, mlp_mode, stacks, hoist, gather_in_kernel, debug)
@@ -382,20 +427,16 @@ _KEEPALIVE = []   # latency mode: the last layers' cross-stream temporaries (fre
 
 def pointnet_sa_module(xyz, points, mlp, is_training, bn_decay, bn, scope, *, params):
     """Global SA layer (layer type SA_Layer_SSG_Last): concat[xyz, points] -> MLP -> max over all points."""
-    if is_training:
-        raise NotImplementedError("inference only")
     pp = prepare(params, xyz.device)
     g = torch.cat([xyz, points], dim=-1).contiguous()              # xyz FIRST here (:42)
     n = g.shape[1]
     for j in range(len(mlp)):
-        g = _conv(pp, "%s/conv%d" % (scope, j), g, bn=bn)
+        g = _conv_train(pp, "%s/conv%d" % (scope, j), g, bn, bn_decay) if is_training else _conv(pp, "%s/conv%d" % (scope, j), g, bn=bn)
     return g.max(dim=1).values if n else g
 
 
 def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay, scope, bn=True, *, params):
     """Feature propagation: inverse-distance interpolation from (xyz2, points2) onto xyz1, then an MLP."""
-    if is_training:
-        raise NotImplementedError("inference only")
     pp = prepare(params, xyz1.device)
     dist, idx = tf_ops.three_nn(xyz1, xyz2)
     dist = torch.clamp_min(dist, 1e-10)                            # :207
@@ -405,17 +446,19 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay,
     if points1 is not None:
         x = torch.cat([x, points1], dim=2).contiguous()            # :213-214
     for i in range(len(mlp)):
-        x = _conv(pp, "%s/conv_%d" % (scope, i), x, bn=bn)
+        x = _conv_train(pp, "%s/conv_%d" % (scope, i), x, bn, bn_decay) if is_training else _conv(pp, "%s/conv_%d" % (scope, i), x, bn=bn)
     return x
 
 
 def vote_layer(xyz, points, mlp_list, is_training, bn_decay, bn, scope, *, params,
                max_translate_range=_cfg.MAX_TRANSLATE_RANGE, mlp_mode="tc"):
     """Vote layer: per-point MLP -> 3 offsets, clamped to +-max_translate_range (layers_util.py:12-24)."""
-    if is_training:
-        raise NotImplementedError("inference only")
     pp = prepare(params, xyz.device)
-    if mlp_mode == "tc":
+    if is_training:
+        for i in range(len(mlp_list)):
+            points = _conv_train(pp, "%s/vote_layer_%d" % (scope, i), points, bn, bn_decay)
+        off = _conv_train(pp, scope + "/vote_offsets", points, False, bn_decay, relu=False)
+    elif mlp_mode == "tc":
         hi, lo = tf_ops.split_rows(points)
         for i in range(len(mlp_list)):
             points, (hi, lo) = tf_ops.linear_tc(hi, lo, pp.conv("%s/vote_layer_%d" % (scope, i), bn), want_split=True)

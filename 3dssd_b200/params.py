@@ -236,6 +236,30 @@ class PreparedParams:
             self._cache[key] = (zconv, wxs, [f.cout for f in convs])
         return self._cache[key]
 
+    # ---- training mode: BatchNorm state lives on the device and is updated in place by the forward -----------------
+    def bn_state(self, scope):
+        """{gamma, beta, moving_mean, moving_variance} of `scope` as device tensors; training-mode forwards update the
+        moving statistics in place.  commit_bn() writes them back to the parameter dict."""
+        key = ("bn_state", scope)
+        if key not in self._cache:
+            self._cache[key] = {k: torch.from_numpy(np.ascontiguousarray(self.raw[scope + "/bn/" + k], dtype=np.float32)).to(self.device)
+                                for k in ("gamma", "beta", "moving_mean", "moving_variance")}
+        return self._cache[key]
+
+    def commit_bn(self):
+        """Copy the moving statistics updated by training-mode forwards back into the raw parameter dict and drop every
+        folded form derived from the old ones (inference after training folds the new statistics)."""
+        touched = False
+        for key in [k for k in self._cache if isinstance(k, tuple) and k[0] == "bn_state"]:
+            st = self._cache[key]
+            for k in ("moving_mean", "moving_variance"):
+                self.raw[key[1] + "/bn/" + k] = st[k].detach().cpu().numpy()
+            touched = True
+        if touched:
+            for key in [k for k in self._cache if not (isinstance(k, tuple) and k[0] == "bn_state")]:
+                del self._cache[key]
+        return self
+
     def prepare_all(self):
         for k in self.raw:
             if k.endswith("/weights"):

@@ -779,3 +779,45 @@ def concat_rows(parts):
     check(lib().ssd3d_concat_rows(b, len(parts), ctypes.cast(src, ctypes.c_void_p), ctypes.cast(marr, ctypes.c_void_p), c,
                                   _p(out), _stream()), "concat_rows")
     return out
+
+
+# ---- training-mode BatchNorm -----------------------------------------------------------------
+
+BN_EPS = 1e-3   # tf.contrib.layers.batch_norm default epsilon
+
+
+def bn_train(x, gamma, beta, moving_mean=None, moving_var=None, decay=0.9, relu=True, eps=BN_EPS):
+    """Batch-statistics BatchNorm + activation over the last axis of x (tf_util.py:424-444, is_training=True);
+    moving_mean / moving_var (float32 CUDA tensors [c]) are updated IN PLACE like updates_collections=None does.
+    Returns (y, scale, shift, batch_mean, batch_var); (scale, shift) is the folded per-channel form."""
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise ValueError("x must be a float32 CUDA tensor")
+    x = x if x.is_contiguous() else x.contiguous()
+    c = x.shape[-1]
+    rows = x.numel() // c
+    for t, name in ((gamma, "gamma"), (beta, "beta"), (moving_mean, "moving_mean"), (moving_var, "moving_var")):
+        if t is not None and (t.dtype != torch.float32 or not t.is_cuda or tuple(t.shape) != (c,) or not t.is_contiguous()):
+            raise ValueError("%s must be a contiguous float32 CUDA tensor of shape (%d,)" % (name, c))
+    if (moving_mean is None) != (moving_var is None):
+        raise ValueError("moving_mean and moving_var go together")
+    dev = x.device
+    y = torch.empty_like(x)
+    scale, shift, bmean, bvar = (torch.empty((c,), dtype=torch.float32, device=dev) for _ in range(4))
+    ws = torch.empty((int(lib().ssd3d_bn_train_workspace(c)),), dtype=torch.uint8, device=dev)
+    check(lib().ssd3d_bn_train(rows, c, _p(x), c, _p(gamma), _p(beta), _p(moving_mean), _p(moving_var), float(decay), float(eps),
+                               _p(ws), _p(scale), _p(shift), _p(bmean), _p(bvar), 1 if relu else 0, _p(y), c, _stream()),
+          "bn_train")
+    return y, scale, shift, bmean, bvar
+
+
+def rowgroup_max(y, pool, rowmask=None):
+    """tf.reduce_max over runs of `pool` rows times (rowmask != 0) (layers_util.py:178-180): y (..., pool, c) -> (..., c)."""
+    if y.dtype != torch.float32 or not y.is_cuda:
+        raise ValueError("y must be a float32 CUDA tensor")
+    y = y if y.is_contiguous() else y.contiguous()
+    c, pool = y.shape[-1], int(pool)
+    if y.shape[-2] != pool:
+        raise ValueError("pool must equal the second-to-last dimension")
+    out = torch.empty(tuple(y.shape[:-2]) + (c,), dtype=torch.float32, device=y.device)
+    check(lib().ssd3d_rowgroup_max(y.numel() // (c * pool), pool, c, _p(y), c, _p(rowmask), _p(out), _stream()), "rowgroup_max")
+    return out

@@ -255,6 +255,18 @@ int ssd3d_bev_nms(int b, int n, const float *boxes, const float *scores, float i
 int ssd3d_rowgroup_max(long groups, int pool, int c, const float *y, int ldy, const int *rowmask, float *out,
                        ssd3d_stream_t stream);
 
+/* Training-mode BatchNorm + activation of one conv output (lib/utils/tf_util.py:424-444 with is_training=True:
+ * tf.contrib.layers.batch_norm(decay, updates_collections=None, fused=False), epsilon 0.001 passed as `eps`):
+ * batch mean / population variance of x[rows, c] over the rows, out = act(x * inv + (beta - mean * inv)) with
+ * inv = gamma * rsqrt(var + eps), and -- when moving_mean / moving_var are given -- their in-place update
+ * v -= (v - batch) * (1 - decay).  scale / shift [c] receive (inv, beta - mean*inv): the folded form the inference
+ * kernels take.  batch_mean / batch_var [c] are optional outputs.  workspace: ssd3d_bn_train_workspace(c) bytes.
+ * x and out may alias.  Statistics couple all rows: a batch sharded over GPUs needs its own reduction (not built). */
+size_t ssd3d_bn_train_workspace(int c);
+int ssd3d_bn_train(long rows, int c, const float *x, int ldx, const float *gamma, const float *beta, float *moving_mean,
+                   float *moving_var, float decay, float eps, void *workspace, float *scale, float *shift,
+                   float *batch_mean, float *batch_var, int relu, float *out, int ldo, ssd3d_stream_t stream);
+
 /* ---- the small elementwise stages of the path (csrc/misc.cu) --------------------------------- */
 
 /* points[rows, c] -> xyz[rows, 3], feat[rows, c-3]: the tf.slice pair of

@@ -13,9 +13,32 @@ import numpy as np
 from . import ops
 
 
-def _conv(params, scope, x, bn=True, relu=True):
+BN_EPS = 1e-3        # tf.contrib.layers.batch_norm default epsilon
+
+
+def _conv(params, scope, x, bn=True, relu=True, train=None):
+    """train = (decay, updates dict) selects training-mode BatchNorm (tf_util.py:424-444 with is_training=True:
+    tf.contrib.layers.batch_norm(fused=False, updates_collections=None)): batch moments over every axis but the channel
+    (population variance), y = x*inv + (beta - mean*inv) with inv = gamma*rsqrt(var + 0.001), and the moving statistics
+    after assign_moving_average (v -= (v - batch) * (1 - decay)) recorded in updates[scope]; all in float64."""
     w = params[scope + "/weights"]
     b = params.get(scope + "/biases")
+    if bn and train is not None:
+        decay, updates = train
+        y = ops.linear_bn_relu(x, w, b, None, False).astype(np.float64)
+        flat = y.reshape(-1, y.shape[-1])
+        mean = flat.mean(axis=0)
+        var = ((flat - mean) ** 2).mean(axis=0)
+        g, be = (params[scope + "/bn/" + k].astype(np.float64) for k in ("gamma", "beta"))
+        inv = g / np.sqrt(var + BN_EPS)
+        out = y * inv + (be - mean * inv)
+        if relu:
+            out = np.maximum(out, 0.0)
+        mm, mv = (params[scope + "/bn/" + k].astype(np.float64) for k in ("moving_mean", "moving_variance"))
+        updates[scope] = {"moving_mean": (mm - (mm - mean) * (1.0 - decay)).astype(np.float32),
+                          "moving_variance": (mv - (mv - var) * (1.0 - decay)).astype(np.float32),
+                          "batch_mean": mean.astype(np.float32), "batch_variance": var.astype(np.float32)}
+        return out.astype(np.float32)
     bnp = None
     if bn:
         bnp = tuple(params[scope + "/bn/" + k] for k in ("gamma", "beta", "moving_mean", "moving_variance"))
@@ -35,8 +58,12 @@ def ffps_indices(npoint, xyz, points, mode):
 def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_training, bn_decay, bn,
                            fps_sample_range_list, fps_method_list, npoint_list, former_fps_idx, use_attention,
                            scope, dilated_group, vote_ctr=None, aggregation_channel=None, *, params,
-                           ffps_mode="matrix", aggregation=True, return_debug=False):
-    assert not is_training and not use_attention
+                           ffps_mode="matrix", aggregation=True, return_debug=False, bn_updates=None):
+    """is_training=True: batch-statistics BatchNorm; the updated moving statistics land in bn_updates[scope]."""
+    assert not use_attention
+    train = None
+    if is_training:
+        train = (0.9 if bn_decay is None else float(bn_decay), {} if bn_updates is None else bn_updates)
     bs, n, _ = xyz.shape
     cur, last = [], 0
     for rng, method, npoint in zip(fps_sample_range_list, fps_method_list, npoint_list):
@@ -80,13 +107,13 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
         g_xyz = ops.group_point(xyz, idx) - new_xyz[:, :, None, :]                # :160-162
         g = np.concatenate([ops.group_point(points, idx), g_xyz], axis=-1)        # :163-165 features first
         for j in range(len(mlp_list[i])):
-            g = _conv(params, "%s/conv%d_%d" % (scope, i, j), g, bn=bn)           # :167-176
+            g = _conv(params, "%s/conv%d_%d" % (scope, i, j), g, bn=bn, train=train)   # :167-176
         new_points = g.max(axis=2) * mask[..., None].astype(np.float32)           # :178-180
         outs.append(new_points)
     if outs:
         new_points = np.concatenate(outs, axis=-1)
         if aggregation and aggregation_channel is not None and aggregation_channel != -1:   # cfg...AGGREGATION_SA_FEATURE :183-185
-            new_points = _conv(params, scope + "/ensemble", new_points, bn=bn)
+            new_points = _conv(params, scope + "/ensemble", new_points, bn=bn, train=train)
     else:
         new_points = ops.gather_point(points, fps_idx)             # :186-187
     if return_debug:

@@ -159,6 +159,45 @@ def test_sa_module_with_empty_balls_and_vote_ctr(pkg, oracle_ops, cuda):
     assert rel_err(got[1].cpu().numpy(), exp[1]) < TOL
 
 
+@pytest.mark.parametrize("decay", [None, 0.5])
+def test_sa_module_training_mode_batchnorm_vs_oracle(pkg, oracle_ops, cuda, decay):
+    """is_training=True: batch-statistics BatchNorm in every conv of the SA module, moving statistics
+    updated in place (tf_util.py:424-444), against the float64 restatement; then inference with the committed
+    statistics equals the oracle's inference on the updated parameters."""
+    from oracle import layers as olayers
+    rng = np.random.default_rng(11)
+    pts = compact_scene(2, 1024, seed=61)
+    xyz, feats = pts[..., :3].copy(), rng.standard_normal((2, 1024, 16)).astype(np.float32)
+    arch = [[[0], [0], [0.4, 0.8], [16, 32], [[16, 16, 32], [16, 32, 48]], True, [-1], ['D-FPS'], [128],
+             -1, False, 'SA_Layer', 'trn', True, -1, 64]]
+    params = dict(pkg.params.init_params(arch, 16, seed=8, random_bias=True))
+    args = (arch[0][2], arch[0][3], arch[0][4], True, decay, True, [-1], ['D-FPS'], [128], None, False, 'trn', True)
+    pp = pkg.params.prepare(params, cuda)
+    got = pkg.pointnet_sa_module_msg(torch.from_numpy(xyz).to(cuda), torch.from_numpy(feats).to(cuda), *args,
+                                     aggregation_channel=64, params=pp, return_debug=True)
+    upd = {}
+    exp = olayers.pointnet_sa_module_msg(xyz, feats, *args, aggregation_channel=64, params=params, return_debug=True,
+                                         bn_updates=upd)
+    np.testing.assert_array_equal(got[2].cpu().numpy(), exp[2])
+    for a, b in zip(got[3]["idx"], exp[3]["idx"]):
+        np.testing.assert_array_equal(a.cpu().numpy(), b)
+    assert rel_err(got[1].cpu().numpy(), exp[1]) < TOL
+    assert set(upd) == {"trn/conv%d_%d" % (i, j) for i in range(2) for j in range(3)} | {"trn/ensemble"}
+    for scope, u in upd.items():
+        st = pp.bn_state(scope)
+        assert rel_err(st["moving_mean"].cpu().numpy(), u["moving_mean"], atol_frac=1e-4) < 1e-4, scope
+        assert rel_err(st["moving_variance"].cpu().numpy(), u["moving_variance"], atol_frac=1e-4) < 1e-4, scope
+    # commit -> the parameter dict carries the new statistics and inference folds THEM
+    before = params["trn/conv0_0/bn/moving_mean"].copy()
+    pp.commit_bn()
+    assert not np.array_equal(params["trn/conv0_0/bn/moving_mean"], before)
+    args_inf = args[:3] + (False,) + args[4:]
+    got_i = pkg.pointnet_sa_module_msg(torch.from_numpy(xyz).to(cuda), torch.from_numpy(feats).to(cuda), *args_inf,
+                                       aggregation_channel=64, params=pp)
+    exp_i = olayers.pointnet_sa_module_msg(xyz, feats, *args_inf, aggregation_channel=64, params=params)
+    assert rel_err(got_i[1].cpu().numpy(), exp_i[1]) < TOL
+
+
 def test_fp_and_global_sa_modules_vs_oracle(pkg, oracle_ops, cuda):
     from oracle import layers as olayers
     rng = np.random.default_rng(6)

@@ -36,8 +36,10 @@ def test_no_cpu_fallback(pkg):
         pkg.farthest_point_sample(4, torch.zeros((1, 8, 3)))
     with pytest.raises(ValueError):
         pkg.query_ball_point(0.0, 4, torch.zeros((1, 8, 3)), torch.zeros((1, 2, 3)))
-    with pytest.raises(NotImplementedError):
-        pkg.pointnet_sa_module_msg(None, None, [], [], [], True, None, True, [], [], [], None, False, "s", False, params={})
+    with pytest.raises(NotImplementedError):     # use_attention (query_ball_point_withidx) is the one unbuilt branch
+        pkg.pointnet_sa_module_msg(None, None, [], [], [], False, None, True, [], [], [], None, True, "s", False, params={})
+    with pytest.raises(ValueError, match="CUDA"):   # training mode exists (row f3) but, like everything, only on the GPU
+        pkg.tf_ops.bn_train(torch.zeros((4, 3)), torch.ones(3), torch.zeros(3))
 
 
 def test_product_never_imports_oracle():

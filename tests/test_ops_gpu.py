@@ -812,3 +812,26 @@ def test_sa_mlp_fused_hoisted_vs_oracle(pkg, oracle_ops, cuda, b, n, c, m, k, ml
     y = pkg.sa_mlp_fused_hoisted(tx, z, 0, wxs[0], tn, ti, tc, stack)
     # absolute coordinates up to 70 m: |(x_j - c_i) . Wx| is compared on the scale of the layer's outputs
     assert y.shape == (b, m, mlp[-1]) and rel_err(N(y), exp) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------
+# training-mode BatchNorm (row f3)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,c", [(5000, 48), (131072, 256), (7, 3)])
+def test_bn_train_vs_float64(pkg, cuda, rows, c):
+    rng = np.random.default_rng(rows)
+    x = (rng.standard_normal((rows, c)) * rng.uniform(0.1, 5, c) + rng.uniform(-3, 3, c) + 100.0 * (np.arange(c) % 5 == 0)).astype(np.float32)
+    g, be = rng.uniform(0.5, 1.5, c).astype(np.float32), rng.normal(0, 0.2, c).astype(np.float32)
+    mm, mv = rng.normal(0, 1, c).astype(np.float32), rng.uniform(0.5, 2, c).astype(np.float32)
+    tmm, tmv = T(mm, cuda), T(mv, cuda)
+    y, scale, shift, bm, bv = pkg.tf_ops.bn_train(T(x, cuda), T(g, cuda), T(be, cuda), tmm, tmv, decay=0.9, relu=True)
+    xd = x.astype(np.float64)
+    mean, var = xd.mean(0), xd.var(0)
+    inv = g / np.sqrt(var + 1e-3)
+    exp = np.maximum(xd * inv + (be - mean * inv), 0)
+    assert rel_err(N(bm), mean.astype(np.float32), atol_frac=1e-6) < 1e-6
+    assert rel_err(N(bv), var.astype(np.float32), rtol=1e-4, atol_frac=1e-6) < 1e-4      # offset channels: E[x^2]-E[x]^2 in double
+    assert rel_err(N(y), exp.astype(np.float32)) < 1e-4
+    np.testing.assert_allclose(N(tmm), mm - (mm - mean) * 0.1, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(N(tmv), mv - (mv - var) * 0.1, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(N(scale), inv, rtol=1e-5)

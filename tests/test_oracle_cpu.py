@@ -274,3 +274,26 @@ def test_oracle_on_real_lidar_scene(oracle_ops):
         assert (np.diff(row[:c]) > 0).all() and (row[c:] == row[0]).all()
         ok = (d[i, :c] == 0) | ((d[i, :c] >= 0.4 - 1e-5) & (d[i, :c] < 0.8 + 1e-5))
         assert ok.all()
+
+
+def test_oracle_training_mode_batchnorm_properties(oracle_ops):
+    """The float64 restatement of training-mode BatchNorm (tf_util.py:424-444): with gamma = 1, beta = 0 every conv
+    output before the ReLU has zero batch mean / unit batch variance, decay = 0 makes the moving statistics equal the
+    batch statistics, and inference on the updated parameters reproduces the training output (same statistics)."""
+    from oracle import layers as olayers
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 50, 8, 6)).astype(np.float32)
+    prm = {"s/weights": rng.standard_normal((6, 5)).astype(np.float32), "s/biases": rng.standard_normal(5).astype(np.float32),
+           "s/bn/gamma": np.ones(5, np.float32), "s/bn/beta": np.zeros(5, np.float32),
+           "s/bn/moving_mean": rng.standard_normal(5).astype(np.float32), "s/bn/moving_variance": np.ones(5, np.float32)}
+    upd = {}
+    y = olayers._conv(prm, "s", x, bn=True, relu=False, train=(0.0, upd))
+    flat = y.reshape(-1, 5).astype(np.float64)
+    assert np.abs(flat.mean(0)).max() < 1e-5 and np.abs(flat.var(0) - upd["s"]["batch_variance"] / (upd["s"]["batch_variance"] + 1e-3)).max() < 1e-4
+    np.testing.assert_array_equal(upd["s"]["moving_mean"], upd["s"]["batch_mean"])
+    prm2 = dict(prm, **{"s/bn/moving_mean": upd["s"]["moving_mean"], "s/bn/moving_variance": upd["s"]["moving_variance"]})
+    y_inf = olayers._conv(prm2, "s", x, bn=True, relu=False)
+    assert np.abs(y_inf - y).max() < 1e-4
+    upd9 = {}
+    olayers._conv(prm, "s", x, bn=True, relu=True, train=(0.9, upd9))
+    np.testing.assert_allclose(upd9["s"]["moving_mean"], prm["s/bn/moving_mean"] * 0.9 + upd["s"]["batch_mean"] * 0.1, rtol=1e-5, atol=1e-6)
