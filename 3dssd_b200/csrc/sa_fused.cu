@@ -499,7 +499,7 @@ static int sf_slots(const SfPlan &pl)
     if (sf_total(pl, 1) <= SF_SMALL) return 1;
     int cols = 32;
     while (cols < pl.maxn) cols *= 2;
-    int s = g_sf_slots > 0 ? g_sf_slots : 3;
+    int s = g_sf_slots > 0 ? (g_sf_slots > 4 ? 4 : g_sf_slots) : 3;
     while (s > 1 && (sf_total(pl, s) > SF_SMEM_MAX || s * cols > 512)) s--;
     return s;
 }
@@ -598,7 +598,8 @@ static int sa_mlp_fused_impl(int b, int n, int c, int m, int nsample, const floa
     cudaError_t e = slots == 1 ? sf_launch<1, 1>(p, smem, per_sm, st)
                   : slots == 2 ? (wg == 4 ? sf_launch<2, 4>(p, smem, per_sm, st) : wg == 1 ? sf_launch<2, 1>(p, smem, per_sm, st)
                                                                                            : sf_launch<2, 2>(p, smem, per_sm, st))
-                               : (wg == 1 ? sf_launch<3, 1>(p, smem, per_sm, st) : sf_launch<3, 2>(p, smem, per_sm, st));
+                  : slots == 3 ? (wg == 1 ? sf_launch<3, 1>(p, smem, per_sm, st) : sf_launch<3, 2>(p, smem, per_sm, st))
+                               : sf_launch<4, 1>(p, smem, per_sm, st);
     if (e != cudaSuccess) return cuda_status(e, "sa_mlp_fused attr");
 #ifdef SF_PROFILE
     {
