@@ -639,6 +639,56 @@ group_concat_split_kernel(long rows, int n, int c, int m, int ns, const float *_
     }
 }
 
+// The operand of the conv that follows a HOISTED first conv (TcParams::gather == 2), materialised once in split bf16:
+//   row (i, j):  relu(z[idx[i,j], :] + (xyz[idx[i,j]] - new_xyz[i]) . wx)        zero-padded to kp columns.
+// For wide layers (K >= 256, 3DSSD layer 4) the A-stationary in-kernel producers starve the tensor pipe -- 128 KiB of
+// resident operand leave room for two narrow weight stages -- while this elementwise pass runs at memory speed on the whole
+// machine and the GEMM then takes the plain TMA-fed path.  One warp per row, one 8-column chunk per lane per step.
+__global__ void __launch_bounds__(256)
+hoist_expand_split_kernel(long rows, int n, int n1, int m, int ns, const float *__restrict__ xyz, const float *__restrict__ z,
+                          int ldz, const float *__restrict__ wx, const float *__restrict__ new_xyz,
+                          const int *__restrict__ idx, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int kp)
+{
+    extern __shared__ __align__(16) float hx_wx[];                      // [3][kp] zero padded
+    for (int i = threadIdx.x; i < 3 * kp; i += blockDim.x) {
+        const int a = i / kp, k = i - a * kp;
+        hx_wx[i] = k < n1 ? __ldg(wx + a * n1 + k) : 0.0f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const long rps = (long)m * ns;
+    const int nchunk = kp >> 3;
+    for (long row = warp0; row < rows; row += nwarps) {
+        const long scene = row / rps, q = row / ns;
+        const int a = __ldg(idx + row);
+        const float *px = xyz + ((size_t)scene * n + a) * 3, *pc = new_xyz + (size_t)q * 3;
+        const float dx = __ldg(px) - __ldg(pc), dy = __ldg(px + 1) - __ldg(pc + 1), dz = __ldg(px + 2) - __ldg(pc + 2);
+        const float *zr = z + ((size_t)scene * n + a) * ldz;
+        for (int ch = lane; ch < nchunk; ch += 32) {
+            const int k0 = ch * 8;
+            float f[8];
+            if (k0 + 8 <= n1) {
+                const float4 u0 = __ldg(reinterpret_cast<const float4 *>(zr + k0)), u1 = __ldg(reinterpret_cast<const float4 *>(zr + k0 + 4));
+                f[0] = u0.x; f[1] = u0.y; f[2] = u0.z; f[3] = u0.w; f[4] = u1.x; f[5] = u1.y; f[6] = u1.z; f[7] = u1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; e++) f[e] = k0 + e < n1 ? __ldg(zr + k0 + e) : 0.0f;
+            }
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const float v = fmaf(dz, hx_wx[2 * kp + k0 + e], fmaf(dy, hx_wx[kp + k0 + e], fmaf(dx, hx_wx[k0 + e], f[e])));
+                f[e] = k0 + e < n1 ? fmaxf(v, 0.0f) : 0.0f;
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++) split_pair(f[2 * t], f[2 * t + 1], hw[t], lw[t]);
+            *reinterpret_cast<uint4 *>(hi + (size_t)row * kp + k0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4 *>(lo + (size_t)row * kp + k0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -823,6 +873,24 @@ static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const vo
     }
 #endif
     SSD3D_LAUNCH_CHECK("linear_tc_kernel");
+}
+
+extern "C" int ssd3d_hoist_expand_split(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
+                                        const float *wx, const float *new_xyz, const int *idx, void *hi, void *lo, int kp,
+                                        ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0 && n1 > 0 && nsample > 0 && ldz >= n1, "hoist_expand_split: bad shape");
+    SSD3D_REQUIRE(kp % 16 == 0 && kp >= n1 && kp <= 4096, "hoist_expand_split: kp=%d must be a multiple of 16 in [n1, 4096]", kp);
+    SSD3D_REQUIRE(ldz % 4 == 0 && (reinterpret_cast<uintptr_t>(z) & 15u) == 0, "hoist_expand_split: z rows must be 16-byte aligned");
+    SSD3D_REQUIRE(xyz && z && wx && new_xyz && idx && hi && lo, "hoist_expand_split: null pointer");
+    SSD3D_REQUIRE(((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15u) == 0, "hoist_expand_split: outputs must be 16-byte aligned");
+    const long rows = (long)b * m * nsample;
+    if (rows == 0) return 0;
+    const long blocks_want = (rows + 7) / 8;
+    const int blocks = (int)(blocks_want < (long)kNumSMs * 32 ? blocks_want : (long)kNumSMs * 32);
+    hoist_expand_split_kernel<<<blocks, 256, (size_t)3 * kp * sizeof(float), (cudaStream_t)stream>>>(
+        rows, n, n1, m, nsample, xyz, z, ldz, wx, new_xyz, idx, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, kp);
+    SSD3D_LAUNCH_CHECK("hoist_expand_split_kernel");
 }
 
 extern "C" int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const void *a_lo, const void *b_hi,

@@ -120,6 +120,9 @@ def _part_bounds(npoint, fps_parts):
     return [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]]
 
 
+HOIST_EXPAND_MIN_K = 256   # hoisted second convs at least this wide materialise their operand (tf_ops.hoist_expand_split)
+
+
 class _Hoisted:
     """The per-point table of the hoisted first convs of a layer (see pointnet_sa_module_msg)."""
     __slots__ = ("scales", "z", "zoffs", "wxs", "stacks")
@@ -209,6 +212,14 @@ def _group_and_mlp(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, m
                         continue                  # folded into z and into the next conv's operand producer
                     if j == 1:
                         t = hscales.index(i)
+                        if f.kp >= HOIST_EXPAND_MIN_K and zoffs[t] % 4 == 0 and z.shape[2] % 4 == 0:
+                            # wide layer: materialise the operand once (elementwise, memory speed), plain TMA-fed GEMM
+                            hi, lo = tf_ops.hoist_expand_split(xyz, z, zoffs[t], wxs[t], new_xyz, idx)
+                            if nl == 2:
+                                tf_ops.linear_tc(hi, lo, f, **last_kw)
+                            else:
+                                _, (hi, lo) = tf_ops.linear_tc(hi, lo, f, want_f32=False, want_split=True)
+                            continue
                         if nl == 2:
                             tf_ops.linear_tc_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, f, want_split=False, **last_kw)
                         else:

@@ -604,6 +604,28 @@ def linear_tc_hoisted(xyz, z, zoff, wx, new_xyz, idx, f, relu=True, pool=1, rowm
     return y, sp
 
 
+def hoist_expand_split(xyz, z, zoff, wx, new_xyz, idx):
+    """The operand linear_tc_hoisted would build in its producer warps, materialised: (hi, lo) bf16 (b, m, nsample, kp) =
+    split(relu(z[idx] + (xyz[idx] - new_xyz) . wx)).  Followed by the plain linear_tc this is the faster route for wide
+    layers (K >= 256), where the resident operand of the in-kernel route leaves the weight ring two narrow stages."""
+    xyz = _req(xyz, "xyz", torch.float32, 3, 3)
+    new_xyz = _req(new_xyz, "new_xyz", torch.float32, 3, 3)
+    idx = _req(idx, "idx", torch.int32, 3)
+    z = _req(z, "z", torch.float32, 3)
+    wx = _req(wx, "wx", torch.float32, 2)
+    b, n, _ = xyz.shape
+    n1 = wx.shape[1]
+    if z.shape[:2] != (b, n) or wx.shape[0] != 3 or zoff < 0 or zoff + n1 > z.shape[2] or zoff % 4 or z.shape[2] % 4:
+        raise ValueError("z must be (b, n, ldz) with ldz, zoff multiples of 4, zoff + n1 <= ldz, and wx (3, n1)")
+    _, m, ns = idx.shape
+    kp = round16(n1)
+    hi = torch.empty((b, m, ns, kp), dtype=torch.bfloat16, device=xyz.device)
+    lo = torch.empty_like(hi)
+    check(lib().ssd3d_hoist_expand_split(b, n, n1, m, ns, _p(xyz), ctypes.c_void_p(z.data_ptr() + 4 * zoff), z.shape[2], _p(wx),
+                                         _p(new_xyz), _p(idx), _p(hi), _p(lo), kp, _stream()), "hoist_expand_split")
+    return hi, lo
+
+
 def sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=None, out_split=None):
     """One SA scale in one kernel: gather + concat + conv stack + max-pool + mask (layers_util.py:157-180).
     stack: params.FusedStack.  out_f32=(buffer, col_offset) / out_split=(hi, lo, col_offset) as linear_tc;

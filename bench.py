@@ -392,6 +392,7 @@ def main():
     groups = [dist.new_group(ranks=list(range(world))) if world > 1 else None for _ in range(P)]
     gathers = [pkg.dist.DetectionGather(total_scenes, dev, group=groups[k]) for k in range(P)]
     runners = []
+    gather_in_graph = True
     for k in range(P):
         if args.no_graph:
             static_in = pts.clone()
@@ -405,7 +406,28 @@ def main():
                 return o, r
             runners.append(replay)
         else:
-            runners.append(net.capture(pts, gather=gathers[k]))
+            try:
+                runners.append(net.capture(pts, gather=gathers[k]))
+            except RuntimeError as e:                      # NCCL refused capture: gather eagerly after the replay instead
+                if world == 1 or not gather_in_graph:
+                    raise
+                gather_in_graph = False
+                sys.stderr.write("bench.py: all-gather could not be captured (%s); running it eagerly per step\n" % str(e).splitlines()[0])
+                torch.cuda.synchronize()
+                break
+    if not gather_in_graph and not args.no_graph:
+        runners = []
+        for k in range(P):
+            inner = net.capture(pts, gather=None)
+            g = gathers[k]
+
+            def replay(points=None, inner=inner, g=g):
+                o, (blk, cnt) = inner(points)
+                ob, oc = g.out()
+                ob.copy_(blk, non_blocking=True); oc.copy_(cnt, non_blocking=True)
+                g.gather()
+                return o, (blk, cnt)
+            runners.append(replay)
     main_s = torch.cuda.current_stream()
 
     def barrier():
@@ -464,7 +486,9 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     # ---- single-step latency: one step at a time, sync after each, latency-mode network --------------------
-    lat_runner = net_lat.capture(pts, gather=pkg.dist.DetectionGather(total_scenes, dev, group=groups[0])) if not args.no_graph else None
+    lat_runner = None
+    if not args.no_graph:
+        lat_runner = net_lat.capture(pts, gather=pkg.dist.DetectionGather(total_scenes, dev, group=groups[0]) if gather_in_graph else None)
     thr_runner = runners[0]
 
     def serial_latency(run, nrep):
@@ -522,7 +546,7 @@ def main():
                        "global_batch": SCENES_PER_GPU * world, "points": NPOINTS, "parallelism": "scene-sharded dp%d" % world,
                        "ffps": args.ffps_mode, "mlp": args.mlp_mode, "cuda_graph": not args.no_graph,
                        "l2": "flushed (256 MiB write) before every timed step",
-                       "steps_in_flight": P, "fps_cluster": args.fps_cluster,
+                       "steps_in_flight": P, "fps_cluster": args.fps_cluster, "allgather_in_graph": bool(gather_in_graph and not args.no_graph),
                        "latency_ms_single_step": latency_ms,
                        "latency_ms_single_step_throughput_graph": latency_thr_ms,
                        "latency_note": "one step at a time with a sync after each (as the reference arm runs): latency-mode "

@@ -199,6 +199,12 @@ int ssd3d_linear_tc_hoisted(int b, int n, int n1, int m, int nsample, const floa
                             const void *b_lo, const float *scale, const float *shift, int relu, int pool,
                             const int *rowmask, float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split,
                             ssd3d_stream_t stream);
+/* The operand of ssd3d_linear_tc_hoisted materialised instead of built inside the GEMM: hi/lo[b*m*nsample, kp] bf16 =
+ * split(relu(z[idx] + (xyz[idx] - new_xyz) . wx)), zero padded to kp.  For wide layers (K >= 256) an elementwise pass at
+ * memory speed + the plain TMA-fed ssd3d_linear_tc beats in-kernel production (lib/utils/layers_util.py:160-176). */
+int ssd3d_hoist_expand_split(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
+                             const float *wx, const float *new_xyz, const int *idx, void *hi, void *lo, int kp,
+                             ssd3d_stream_t stream);
 /* Same idea for a scale that fits the fused kernel (ssd3d_sa_mlp_fused): the stack passed here starts at the scale's
  * SECOND conv, the first operand row is relu(z[idx] + (xyz[idx] - new_xyz) . wx), built during the gather. */
 int ssd3d_sa_mlp_fused_hoisted(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,

@@ -774,6 +774,14 @@ def test_hoisted_first_conv_matches_oracle_and_gather_path(pkg, oracle_ops, cuda
         _, (hi, lo) = pkg.linear_tc_hoisted(tx, z, 0, wxs[0], tn, ti, f1)
         y, _ = pkg.linear_tc(hi, lo, pp.conv(scopes[2], True), pool=k, rowmask=tc, want_f32=True, want_split=False)
     assert y.shape == (b, m, mlp[-1]) and rel_err(N(y), exp) < 1e-4
+    # the materialised form of the same operand (wide layers take it): identical split operand -> identical GEMM result
+    ehi, elo = pkg.tf_ops.hoist_expand_split(tx, z, 0, wxs[0], tn, ti)
+    if len(mlp) == 2:
+        y2, _ = pkg.linear_tc(ehi, elo, f1, pool=k, rowmask=tc, want_f32=True, want_split=False)
+    else:
+        _, (hi2, lo2) = pkg.linear_tc(ehi, elo, f1, want_f32=False, want_split=True)
+        y2, _ = pkg.linear_tc(hi2, lo2, pp.conv(scopes[2], True), pool=k, rowmask=tc, want_f32=True, want_split=False)
+    assert rel_err(N(y2), N(y)) < 1e-6
 
 
 @pytest.mark.parametrize("b,n,c,m,k,mlp", [
