@@ -534,6 +534,11 @@ ffps_cluster_kernel(int n, int ca, int cb, int m, const float *__restrict__ fa, 
         fence_mbar_init_cluster();
     }
     __syncthreads();
+    // Resumable like fps3_direct_kernel: rounds [jbeg, jend); the running distances travel through io.temp, the last
+    // winner is re-read from the index output and its feature row from global memory.
+    const int jbeg = io.j0 > 1 ? io.j0 : 1, jend = io.j1 < m ? io.j1 : m;
+    const bool resume = io.j0 > 0, save = io.j1 < m;
+    float *tsave = io.temp + (size_t)scene * n;
     float f[P][CP], td[P], sq[P];
     uint32_t key[P];
 #pragma unroll
@@ -550,15 +555,16 @@ ffps_cluster_kernel(int n, int ca, int cb, int m, const float *__restrict__ fa, 
         for (int l = 0; l < CP; l++) s2 = __fmaf_rn(f[i][l], f[i][l], s2);     // sqdist's squared-norm chain
         sq[i] = s2;
         sqS[i * FPS_T + tid] = s2;
-        td[i] = k < n ? 1e38f : -1.0f;
+        td[i] = k < n ? (resume ? tsave[k] : 1e38f) : -1.0f;
         key[i] = fps_key(k);
     }
-    // round 0 picks point 0: its row (owned by CTA 0, local point 0) is read from global memory by every CTA
+    // the point picked last (point 0 at the start of the sampling): its row is read from global memory by every CTA
     {
+        const int old0 = resume ? idxs[jbeg - 1] - io.ioff : 0;
         Packet &p0 = cl_pk[0];
         for (int l = tid; l < CP; l += FPS_T) {
             float v = 0.0f;
-            if (l < c) v = l < ca ? __ldg(A + l) : __ldg(B + (l - ca));
+            if (l < c) v = l < ca ? __ldg(A + (size_t)old0 * ca + l) : __ldg(B + (size_t)old0 * cb + (l - ca));
             p0.feat[l] = v;
         }
         __syncthreads();
@@ -570,11 +576,12 @@ ffps_cluster_kernel(int n, int ca, int cb, int m, const float *__restrict__ fa, 
     }
     __syncthreads();
     if (CL > 1) cluster_sync_all();       // every CTA's barriers exist before any peer st.async targets them
-    if (g == 0) idxs[0] = io.ioff;
+    if (g == 0 && !resume) idxs[0] = io.ioff;
 
     const Packet *oldp = &cl_pk[0];
-    for (int j = 1; j < m; j++) {
-        const int par = j & 1;
+    for (int j = jbeg; j < jend; j++) {
+        const int r = j - jbeg + 1;       // 1-based round of THIS launch: buffer parity / barrier phase
+        const int par = r & 1;
         // ---- row `old` of the distance matrix for this thread's points
         float dot[P];
 #pragma unroll
@@ -646,7 +653,7 @@ ffps_cluster_kernel(int n, int ca, int cb, int m, const float *__restrict__ fa, 
             oldp = &cl_pk[par];
             win_key = oldp->key;
         } else {
-            mbar_wait_cta(smem_u32(&mbar[par]), ((j - 1) >> 1) & 1);
+            mbar_wait_cta(smem_u32(&mbar[par]), ((r - 1) >> 1) & 1);
             const uint32_t v = lane < CL ? cl_pk[par * CL + lane].val : 0u;
             const uint32_t kk = lane < CL ? cl_pk[par * CL + lane].key : KEY_INVALID;
             uint32_t m3, k3;
@@ -656,6 +663,13 @@ ffps_cluster_kernel(int n, int ca, int cb, int m, const float *__restrict__ fa, 
             win_key = k3;
         }
         if (g == 0) idxs[j] = (win_key != KEY_INVALID ? fps_key_to_k(win_key) : 0) + io.ioff;
+    }
+    if (save) {
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+            const int k = g + i * TT;
+            if (k < n) tsave[k] = td[i];
+        }
     }
     if (CL > 1) cluster_sync_all();
 }
@@ -980,8 +994,12 @@ extern "C" int ssd3d_ffps_supported(int n, int c) { return n > 0 && c > 0 && ffp
 // farthest_point_sample_with_distance(m, calc_square_dist(concat[fa, fb])) without the [b,n,n] matrix; same indices.
 extern "C" int ssd3d_farthest_point_sample_features_ex(int b, int n, int ca, int cb, int m, const float *fa,
                                                        long long fa_stride, const float *fb, long long fb_stride,
-                                                       int *out, int ldo, int idx_offset, ssd3d_stream_t stream)
+                                                       float *temp, int *out, int ldo, int idx_offset, int j0, int j1,
+                                                       ssd3d_stream_t stream)
 {
+    SSD3D_REQUIRE(0 <= j0 && j0 <= j1 && j1 <= m, "farthest_point_sample_features: rounds [%d,%d) outside [0,%d]", j0, j1, m);
+    SSD3D_REQUIRE((j0 == 0 && j1 == m) || temp != nullptr, "farthest_point_sample_features: a partial range of rounds carries its state in temp[b,n]");
+    if (j0 == j1) return 0;
     SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0 && ca > 0 && cb >= 0, "farthest_point_sample_features: bad shape b=%d n=%d m=%d c=%d+%d", b, n, m, ca, cb);
     SSD3D_REQUIRE(ldo >= m && fa_stride >= (long long)n * ca && fb_stride >= (long long)n * cb,
                   "farthest_point_sample_features: strides smaller than a row");
@@ -994,7 +1012,7 @@ extern "C" int ssd3d_farthest_point_sample_features_ex(int b, int n, int ca, int
         return SSD3D_ERR_UNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const FpsIO io = {fa_stride, fb_stride, ldo, idx_offset, 0, m, nullptr};
+    const FpsIO io = {fa_stride, fb_stride, ldo, idx_offset, j0, j1, temp};
     int rc;
     if (c <= 68) {
         rc = cl == 1 ? launch_ffps_t<1, 2, 68>(b, n, ca, cb, m, fa, fb, out, io, st)
@@ -1013,6 +1031,6 @@ extern "C" int ssd3d_farthest_point_sample_features_ex(int b, int n, int ca, int
 extern "C" int ssd3d_farthest_point_sample_features(int b, int n, int ca, int cb, int m, const float *fa, const float *fb,
                                                     int *out, ssd3d_stream_t stream)
 {
-    return ssd3d_farthest_point_sample_features_ex(b, n, ca, cb, m, fa, (long long)n * ca, fb, (long long)n * cb, out, m, 0,
-                                                   stream);
+    return ssd3d_farthest_point_sample_features_ex(b, n, ca, cb, m, fa, (long long)n * ca, fb, (long long)n * cb, nullptr, out,
+                                                   m, 0, 0, m, stream);
 }

@@ -345,6 +345,21 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
         ev.record(main)
         return ev
 
+    def ffps_segment(npoint, tmp_xyz, tmp_points, lo, col):
+        """F-FPS of one segment; in latency mode the matrix-free kernel runs as two resumable launches, so the first
+        half of its samples is handed to the consumers while the second half is still being picked."""
+        c = tmp_xyz.shape[2] + tmp_points.shape[2]
+        if in_parts and ffps_mode == "direct" and c <= 68 and npoint >= 256 and tf_ops.ffps_supported(tmp_xyz.shape[1], c):
+            temp = torch.empty((bs, tmp_xyz.shape[1]), dtype=torch.float32, device=dev)
+            keep.append(temp)
+            for j0, j1 in _part_bounds(npoint, 2):
+                tf_ops.farthest_point_sample_features(npoint, tmp_xyz, tmp_points, out=(fps_idx, col), idx_offset=lo,
+                                                      rounds=(j0, j1), temp=temp)
+                parts.append((col + j0, col + j1, ev_main()))
+            return
+        ffps_indices(npoint, tmp_xyz, tmp_points, ffps_mode, out=(fps_idx, col), idx_offset=lo)
+        parts.append((col, col + npoint, ev_main() if in_parts else None))
+
     lone = len(segs) == 1
     for kind, lo, hi, npoint, width in segs:
         tmp_xyz, tmp_points = xyz[:, lo:hi], points[:, lo:hi]     # read in place (scene-strided)
@@ -356,12 +371,10 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
             c0 = col
             ev_d = on_side(lambda: tf_ops.farthest_point_sample(npoint, tmp_xyz, out=(fps_idx, c0 + npoint), idx_offset=lo,
                                                                 cluster=fps_cluster))
-            ffps_indices(npoint, tmp_xyz, tmp_points, ffps_mode, out=(fps_idx, col), idx_offset=lo)
-            parts.append((col, col + npoint, ev_main() if in_parts else None))
+            ffps_segment(npoint, tmp_xyz, tmp_points, lo, col)
             parts.append((col + npoint, col + 2 * npoint, ev_d))
         elif kind == "F":
-            ffps_indices(npoint, tmp_xyz, tmp_points, ffps_mode, out=(fps_idx, col), idx_offset=lo)
-            parts.append((col, col + npoint, ev_main() if in_parts else None))
+            ffps_segment(npoint, tmp_xyz, tmp_points, lo, col)
         elif not lone:                                            # D-FPS segment next to other segments: side stream
             c0 = col
             ev_d = on_side(lambda: tf_ops.farthest_point_sample(npoint, tmp_xyz, out=(fps_idx, c0), idx_offset=lo,

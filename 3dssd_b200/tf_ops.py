@@ -129,10 +129,10 @@ def ffps_supported(n, c):
     return bool(lib().ssd3d_ffps_supported(int(n), int(c)))
 
 
-def farthest_point_sample_features(npoint, xyz, points=None, *, out=None, idx_offset=0):
+def farthest_point_sample_features(npoint, xyz, points=None, *, out=None, idx_offset=0, rounds=None, temp=None):
     """F-FPS on concat[xyz, points] without the distance matrix: the same indices as
     farthest_point_sample_with_distance(npoint, calc_square_dist(concat[xyz, points])) (layers_util.py:94-96).
-    Keyword extensions as farthest_point_sample."""
+    Keyword extensions as farthest_point_sample (out, idx_offset, rounds + temp)."""
     xyz, sa = _scene_strided(xyz, "xyz")
     b, n, ca = xyz.shape
     cb, sb = 0, 0
@@ -145,8 +145,11 @@ def farthest_point_sample_features(npoint, xyz, points=None, *, out=None, idx_of
         points = None
     npoint = int(npoint)
     o, optr, ldo = _idx_out(out, b, npoint, xyz.device)
-    check(lib().ssd3d_farthest_point_sample_features_ex(b, n, ca, cb, npoint, _p(xyz), sa, _p(points), sb,
-                                                        ctypes.c_void_p(optr), ldo, int(idx_offset), _stream()),
+    j0, j1 = (0, npoint) if rounds is None else (int(rounds[0]), int(rounds[1]))
+    if (j0, j1) != (0, npoint) and (temp is None or temp.dtype != torch.float32 or not temp.is_contiguous() or temp.numel() < b * n):
+        raise ValueError("a partial range of rounds needs a contiguous float32 temp buffer of batch * n elements")
+    check(lib().ssd3d_farthest_point_sample_features_ex(b, n, ca, cb, npoint, _p(xyz), sa, _p(points), sb, _p(temp),
+                                                        ctypes.c_void_p(optr), ldo, int(idx_offset), j0, j1, _stream()),
           "farthest_point_sample_features")
     return o
 

@@ -81,10 +81,11 @@ int ssd3d_farthest_point_sample_with_distance_ex(int b, int n, int m, const floa
  * SSD3D_ERR_UNSUPPORTED and the caller takes the two-call route. */
 int ssd3d_farthest_point_sample_features(int b, int n, int ca, int cb, int m, const float *fa, const float *fb,
                                          int *out, ssd3d_stream_t stream);
-/* ... with scene strides of fa / fb in floats and explicit output placement (see ssd3d_farthest_point_sample_ex). */
+/* ... with scene strides of fa / fb in floats, explicit output placement and a range of rounds [j0, j1) with the
+ * running distances in temp[b,n] (see ssd3d_farthest_point_sample_ex; temp may be NULL for the full range). */
 int ssd3d_farthest_point_sample_features_ex(int b, int n, int ca, int cb, int m, const float *fa, long long fa_stride,
-                                            const float *fb, long long fb_stride, int *out, int ldo, int idx_offset,
-                                            ssd3d_stream_t stream);
+                                            const float *fb, long long fb_stride, float *temp, int *out, int ldo,
+                                            int idx_offset, int j0, int j1, ssd3d_stream_t stream);
 int ssd3d_ffps_supported(int n, int c);
 
 /* replaces gatherpointLauncher(b,n,m,c,inp,idx,out)

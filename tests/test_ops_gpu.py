@@ -73,6 +73,20 @@ def test_fps_resumable_rounds(pkg, oracle_ops, cuda, cuts, cluster):
         np.testing.assert_array_equal(N(buf)[:, :j1], exp[:, :j1])   # a sample is final once its round is done
 
 
+def test_ffps_resumable_rounds(pkg, cuda):
+    """The matrix-free F-FPS in separate launches of rounds equals one launch (and therefore the matrix route)."""
+    rng = np.random.default_rng(21)
+    xyz = T(synth.kitti_like(2, 4096, seed=12)[..., :3].copy(), cuda)
+    feat = T(np.maximum(rng.standard_normal((2, 4096, 64)), 0).astype(np.float32), cuda)
+    feat[:, 2000:2040] = feat[:, :40]; xyz[:, 2000:2040] = xyz[:, :40]        # duplicates
+    one = pkg.tf_ops.farthest_point_sample_features(512, xyz, feat)
+    buf = torch.full((2, 512), -3, dtype=torch.int32, device=cuda)
+    temp = torch.empty((2, 4096), dtype=torch.float32, device=cuda)
+    for j0, j1 in ((0, 256), (256, 300), (300, 512)):
+        pkg.tf_ops.farthest_point_sample_features(512, xyz, feat, out=(buf, 0), rounds=(j0, j1), temp=temp)
+        assert torch.equal(buf[:, :j1], one[:, :j1]) and bool((buf[:, j1:] == -3).all())
+
+
 def test_fps_strided_input_offset_output(pkg, oracle_ops, cuda):
     """A [:, a:b] slice read in place; indices written, segment offset added, into a column block of a wider
     buffer (what a fusion-sampling SA layer does, layers_util.py:84-111)."""
