@@ -24,5 +24,5 @@ int cuda_status(cudaError_t e, const char *what)
 
 }  // namespace ssd3d
 
-extern "C" int ssd3d_version(void) { return 1; }
+extern "C" int ssd3d_version(void) { return 2; }
 extern "C" const char *ssd3d_last_error(void) { return ssd3d::g_err; }

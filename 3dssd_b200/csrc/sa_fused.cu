@@ -61,6 +61,7 @@ struct SfParams {
     uint32_t tmem_alloc;             // power of two >= slots * tmem_cols
     float *out_f32; int ld_f32;
     __nv_bfloat16 *out_hi, *out_lo; int ld_split;
+    int pool_first;                  // caller guarantees scale >= 0 in the LAST layer: pool raw accumulators, affine after
 };
 
 __device__ __forceinline__ void sf_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -144,6 +145,72 @@ __device__ __forceinline__ uint32_t sf_f2ord(float x)
 }
 __device__ __forceinline__ float sf_ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 
+// ---- shape policies -------------------------------------------------------------------------------------------------
+// The kernel body is written once against a policy C that answers every shape question (layer count, padded K / N of a
+// layer, block layout, blob offsets, neighbours per group).  SfDyn reads the answers from the parameter block at run
+// time (any stack the planner accepts); SfStat<...> answers at COMPILE time for the stacks of the shipped 3DSSD
+// configuration, so that after unrolling the layer loop every address computation, chunk bound and pooling width is a
+// literal: profiling the dynamic kernel showed ~50% of its issued instructions to be integer / branch / uniform-register
+// bookkeeping of exactly these questions (profiles/r02_fused_instruction_mix.txt).
+__host__ __device__ constexpr int sf_r16(int x) { return (x + 15) / 16 * 16; }
+__host__ __device__ constexpr int sf_rbt_of(int kp) { return kp % 64 == 0 ? 0 : (kp % 64 <= 16 ? 32 : (kp % 64 <= 32 ? 64 : 128)); }
+__host__ __device__ constexpr uint32_t sf_abuf_of(int kp)
+{
+    return (uint32_t)(((kp / 64) * 2 * 128 * 128 + 2 * 128 * sf_rbt_of(kp) + 1023) / 1024 * 1024);
+}
+
+struct SfDyn {
+    static constexpr bool kStatic = false;
+    const SfParams &p;
+    __device__ __forceinline__ explicit SfDyn(const SfParams &p_) : p(p_) {}
+    __device__ __forceinline__ int nl() const { return p.nl; }
+    __device__ __forceinline__ int ns() const { return p.ns; }
+    __device__ __forceinline__ int c() const { return p.c; }
+    __device__ __forceinline__ bool hoist() const { return p.hoist != 0; }
+    __device__ __forceinline__ int kp(int l) const { return p.kp[l]; }
+    __device__ __forceinline__ int npad(int l) const { return p.npad[l]; }
+    __device__ __forceinline__ int nout(int l) const { return p.nout[l]; }
+    __device__ __forceinline__ int nfull(int l) const { return p.nfull[l]; }
+    __device__ __forceinline__ int rbt(int l) const { return p.rbt[l]; }
+    __device__ __forceinline__ uint32_t w_off(int l) const { return p.w_off[l]; }
+    __device__ __forceinline__ uint32_t w_half(int l) const { return p.w_half[l]; }
+    __device__ __forceinline__ uint32_t ss_off(int l) const { return p.ss_off[l]; }
+    __device__ __forceinline__ int sspad(int l) const { return p.sspad[l]; }
+    __device__ __forceinline__ uint32_t w_total() const { return p.w_total; }
+    __device__ __forceinline__ uint32_t ss_total() const { return p.ss_total; }
+    __device__ __forceinline__ uint32_t abuf_bytes() const { return p.abuf_bytes; }
+    __device__ __forceinline__ uint32_t tmem_cols() const { return p.tmem_cols; }
+};
+
+// Hoisted stacks of two convs (the shipped configuration): operand width K0 = n1 of the hoisted first conv, then
+// K0 -> N0 -> N1, NS neighbours per group.
+template <int K0, int N0, int N1, int NS>
+struct SfStat {
+    static constexpr bool kStatic = true;
+    __device__ __forceinline__ explicit SfStat(const SfParams &) {}
+    static constexpr int KP0 = sf_r16(K0), NP0 = sf_r16(N0), NP1 = sf_r16(N1);
+    __device__ __forceinline__ constexpr int nl() const { return 2; }
+    __device__ __forceinline__ constexpr int ns() const { return NS; }
+    __device__ __forceinline__ constexpr int c() const { return K0; }
+    __device__ __forceinline__ constexpr bool hoist() const { return true; }
+    __device__ __forceinline__ constexpr int kp(int l) const { return l == 0 ? KP0 : NP0; }
+    __device__ __forceinline__ constexpr int npad(int l) const { return l == 0 ? NP0 : NP1; }
+    __device__ __forceinline__ constexpr int nout(int l) const { return l == 0 ? N0 : N1; }
+    __device__ __forceinline__ constexpr int nfull(int l) const { return kp(l) / 64; }
+    __device__ __forceinline__ constexpr int rbt(int l) const { return sf_rbt_of(kp(l)); }
+    __device__ __forceinline__ constexpr uint32_t w_half(int l) const { return (uint32_t)(npad(l) * (nfull(l) * 128 + rbt(l))); }
+    __device__ __forceinline__ constexpr uint32_t w_off(int l) const { return l == 0 ? 0u : 2u * w_half(0); }
+    __device__ __forceinline__ constexpr int sspad(int l) const { return (npad(l) + 31) / 32 * 32; }
+    __device__ __forceinline__ constexpr uint32_t ss_off(int l) const { return l == 0 ? 0u : 2u * (uint32_t)sspad(0); }
+    __device__ __forceinline__ constexpr uint32_t w_total() const { return 2u * w_half(0) + 2u * w_half(1); }
+    __device__ __forceinline__ constexpr uint32_t ss_total() const { return 2u * (uint32_t)sspad(0) + 2u * (uint32_t)sspad(1); }
+    __device__ __forceinline__ constexpr uint32_t abuf_bytes() const { return sf_abuf_of(KP0) > sf_abuf_of(NP0) ? sf_abuf_of(KP0) : sf_abuf_of(NP0); }
+    __device__ __forceinline__ constexpr uint32_t tmem_cols() const
+    {
+        return (NP0 > NP1 ? NP0 : NP1) <= 32 ? 32u : ((NP0 > NP1 ? NP0 : NP1) <= 64 ? 64u : ((NP0 > NP1 ? NP0 : NP1) <= 128 ? 128u : 256u));
+    }
+};
+
 #ifdef SF_PROFILE
 __device__ long long sf_prof[16];
 #define SF_T(i) do { if (prof_on) { const long long t_ = clock64(); sf_prof[i] += t_ - t_prev; t_prev = t_; } } while (0)
@@ -151,9 +218,12 @@ __device__ long long sf_prof[16];
 #define SF_T(i) do { } while (0)
 #endif
 
-template <int POOL>
+// Max-pool of one 32-column chunk over runs of POOL rows + mask + store.  AFTER: v holds RAW accumulators and the folded
+// affine + ReLU is applied to the pooled values only (valid when the layer's scale is >= 0: fma(x, s, t) is then monotone
+// non-decreasing in x, so max_i relu(fma(x_i, s, t)) == relu(fma(max_i x_i, s, t)) exactly) -- 1/POOL of the epilogue math.
+template <int POOL, bool AFTER>
 __device__ __forceinline__ void sf_pool_store(const SfParams &p, float (&v)[32], int lane, int q, int tile,
-                                              int col0, int nout, float *xs, int wg_bar)
+                                              int col0, int nout, float *xs, int wg_bar, const float *sc, const float *sh)
 {
     constexpr int GP = POOL >= 32 ? 32 : POOL;
     constexpr int KEEP = 32 / GP;
@@ -174,9 +244,12 @@ __device__ __forceinline__ void sf_pool_store(const SfParams &p, float (&v)[32],
     const bool masked = p.cnt && p.cnt[gg] == 0;
 #pragma unroll
     for (int k = 0; k < KEEP; k++) {
-        const int col = col0 + (lane % GP) * KEEP + k;
+        const int cc = (lane % GP) * KEEP + k;
+        const int col = col0 + cc;
         if (col >= nout) continue;
-        const float mx = masked ? 0.0f : v[k];
+        float mx = v[k];
+        if (AFTER) mx = fmaxf(fmaf(mx, sc[col0 + cc], sh[col0 + cc]), 0.0f);
+        mx = masked ? 0.0f : mx;
         if (p.out_f32) asm volatile("st.global.f32 [%0], %1;" ::"l"(p.out_f32 + (size_t)gg * p.ld_f32 + col), "f"(mx) : "memory");
         if (p.out_hi) {
             const __nv_bfloat16 hb = __float2bfloat16_rn(mx);
@@ -188,11 +261,12 @@ __device__ __forceinline__ void sf_pool_store(const SfParams &p, float (&v)[32],
 }
 
 // SLOTS tiles in flight per CTA, WG warpgroups (128 threads) working on each: the warpgroups of a slot split the
-// 16-byte chunks of the gather and the 32-column chunks of every epilogue between them.
-template <int SLOTS, int WG>
+// 16-byte chunks of the gather and the 32-column chunks of every epilogue between them.  C: shape policy (above).
+template <class C, int SLOTS, int WG>
 __global__ void __launch_bounds__(SF_THREADS * SLOTS * WG, SLOTS * WG == 1 ? 6 : 1)
 sa_fused_kernel(const SfParams p)
 {
+    const C cfg(p);
     // pointers inside the by-value parameter struct carry no address space: tell the compiler they are global
     __builtin_assume(__isGlobal(p.xyz)); __builtin_assume(__isGlobal(p.new_xyz)); __builtin_assume(__isGlobal(p.idx));
     __builtin_assume(p.points == nullptr || __isGlobal(p.points)); __builtin_assume(p.cnt == nullptr || __isGlobal(p.cnt));
@@ -201,9 +275,9 @@ sa_fused_kernel(const SfParams p)
     // 1 KiB alignment by pointer arithmetic on the __shared__ array (an integer round-trip would demote every access
     // through these pointers to generic LD/ST with 64-bit address math)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t *wsm = smem + (size_t)SLOTS * p.abuf_bytes;  // weight images (1024-aligned: buffers are multiples of 1 KiB)
-    float *ss = reinterpret_cast<float *>(wsm + p.w_total);
-    float *wxs = ss + p.ss_total;                        // [3][kp0] hoisted mode: Wx * s1, zero beyond c
+    uint8_t *wsm = smem + (size_t)SLOTS * cfg.abuf_bytes();  // weight images (1024-aligned: buffers are multiples of 1 KiB)
+    float *ss = reinterpret_cast<float *>(wsm + cfg.w_total());
+    float *wxs = ss + cfg.ss_total();                    // [3][kp0] hoisted mode: Wx * s1, zero beyond c
 
     __shared__ unsigned long long w_bar, mma_bar[SLOTS];
     __shared__ uint32_t tmem_base_smem;
@@ -219,31 +293,32 @@ sa_fused_kernel(const SfParams p)
     const int slot_u = __shfl_sync(0xffffffffu, slot, 0);
     const bool issuer_warp = __shfl_sync(0xffffffffu, (tid % ST) >> 5, 0) == 0;
     const int slot_bar = 1 + slot, wg_bar = 1 + SLOTS + slot * WG + wg;
-    uint8_t *buf = smem + (size_t)slot * p.abuf_bytes;   // the slot's operand buffer (every layer, in place)
+    uint8_t *buf = smem + (size_t)slot * cfg.abuf_bytes();   // the slot's operand buffer (every layer, in place)
     float *xs = xs_all[slot * WG + wg];
+    const int kp0 = cfg.kp(0);
 
     if (tid == 0) {
         mbar_init(smem_u32(&w_bar), 1);
 #pragma unroll
         for (int i = 0; i < SLOTS; i++) mbar_init(smem_u32(&mma_bar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_arrive_expect_tx(smem_u32(&w_bar), p.w_total);
-        bulk_g2s(smem_u32(wsm), p.w_blob, p.w_total, smem_u32(&w_bar));
+        mbar_arrive_expect_tx(smem_u32(&w_bar), cfg.w_total());
+        bulk_g2s(smem_u32(wsm), p.w_blob, cfg.w_total(), smem_u32(&w_bar));
     }
     if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(p.tmem_alloc) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (uint32_t i = tid; i < p.ss_total; i += NT) ss[i] = __ldg(p.ss_blob + i);
-    if (p.hoist)
-        for (int i = tid; i < 3 * p.kp[0]; i += NT) {
-            const int a3 = i / p.kp[0], k = i - a3 * p.kp[0];
-            wxs[i] = k < p.c ? __ldg(p.wx + a3 * p.c + k) : 0.0f;
+    for (uint32_t i = tid; i < cfg.ss_total(); i += NT) ss[i] = __ldg(p.ss_blob + i);
+    if (cfg.hoist())
+        for (int i = tid; i < 3 * kp0; i += NT) {
+            const int a3 = i / kp0, k = i - a3 * kp0;
+            wxs[i] = k < cfg.c() ? __ldg(p.wx + a3 * cfg.c() + k) : 0.0f;
         }
     sf_fence_before();
     __syncthreads();
     sf_fence_after();
-    const uint32_t tmem = tmem_base_smem + (uint32_t)slot * p.tmem_cols;
+    const uint32_t tmem = tmem_base_smem + (uint32_t)slot * cfg.tmem_cols();
     const uint32_t bar = smem_u32(&mma_bar[slot]);
     mbar_wait_cta(smem_u32(&w_bar), 0);                  // weights landed (async proxy writes, read by UMMA only)
 
@@ -252,9 +327,9 @@ sa_fused_kernel(const SfParams p)
     long long t_prev = clock64();
 #endif
     uint32_t mma_phase = 0;
-    const int k0 = p.hoist ? p.c : p.c + 3;              // valid operand columns
-    const int pitch = p.hoist ? p.ldz : p.c;
-    const bool vec = (p.c & 3) == 0 && (pitch & 3) == 0; // source rows are 16-byte aligned: float4 gathers
+    const int k0 = cfg.hoist() ? cfg.c() : cfg.c() + 3;  // valid operand columns
+    const int pitch = cfg.hoist() ? p.ldz : cfg.c();
+    const bool vec = (cfg.c() & 3) == 0 && (pitch & 3) == 0; // source rows are 16-byte aligned: float4 gathers
 
     const int tile0 = blockIdx.x * SLOTS + slot, tstep = gridDim.x * SLOTS;
     // neighbour index of this thread's row, fetched one tile ahead (rows < 2^31: checked by the launcher)
@@ -264,7 +339,7 @@ sa_fused_kernel(const SfParams p)
         {
             const uint32_t row = (uint32_t)tile * 128u + (uint32_t)r;
             const bool ok = (long)row < p.rows;
-            const uint32_t qi = ok ? row / (uint32_t)p.ns : 0u;        // == scene*m + query
+            const uint32_t qi = ok ? row / (uint32_t)cfg.ns() : 0u;    // == scene*m + query
             const uint32_t scene = qi / (uint32_t)p.m;
             const int a = a_next;
             {
@@ -274,18 +349,19 @@ sa_fused_kernel(const SfParams p)
             const float *src_f = p.points + ((size_t)scene * p.n + a) * pitch;
             const float *src_x = p.xyz + ((size_t)scene * p.n + a) * 3;
             const float *ctr = p.new_xyz + (size_t)qi * 3;
-            const int nchunk = p.kp[0] >> 3;
-            const SfRowMap map0(r, p.nfull[0], p.rbt[0]);
+            const int nchunk = kp0 >> 3;
+            const SfRowMap map0(r, cfg.nfull(0), cfg.rbt(0));
             float dx = 0.0f, dy = 0.0f, dz = 0.0f;
-            if (p.hoist && ok) {
+            if (cfg.hoist() && ok) {
                 dx = __ldg(src_x) - __ldg(ctr); dy = __ldg(src_x + 1) - __ldg(ctr + 1); dz = __ldg(src_x + 2) - __ldg(ctr + 2);
             }
+#pragma unroll (C::kStatic ? 4 : 1)
             for (int cg0 = wg * U; cg0 < nchunk; cg0 += WG * U) {     // U chunks of 8 columns in flight per thread
                 float f[U][8];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     const int kb = (cg0 + u) * 8;
-                    if (vec && ok && kb + 8 <= p.c) {
+                    if (vec && ok && kb + 8 <= cfg.c()) {
                         const float4 lo4 = __ldg(reinterpret_cast<const float4 *>(src_f + kb));
                         const float4 hi4 = __ldg(reinterpret_cast<const float4 *>(src_f + kb + 4));
                         f[u][0] = lo4.x; f[u][1] = lo4.y; f[u][2] = lo4.z; f[u][3] = lo4.w;
@@ -296,8 +372,8 @@ sa_fused_kernel(const SfParams p)
                             const int k = kb + e;
                             float val = 0.0f;
                             if (ok) {
-                                if (k < p.c) val = __ldg(src_f + k);
-                                else if (k < k0) val = __ldg(src_x + (k - p.c)) - __ldg(ctr + (k - p.c));   // never in hoisted mode
+                                if (k < cfg.c()) val = __ldg(src_f + k);
+                                else if (k < k0) val = __ldg(src_x + (k - cfg.c())) - __ldg(ctr + (k - cfg.c()));   // never in hoisted mode
                             }
                             f[u][e] = val;
                         }
@@ -306,13 +382,13 @@ sa_fused_kernel(const SfParams p)
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     if (cg0 + u >= nchunk) break;
-                    if (p.hoist) {                                     // relu(z + d . Wx'); padded columns and rows stay 0
+                    if (cfg.hoist()) {                                 // relu(z + d . Wx'); padded columns and rows stay 0
                         const float *w = wxs + (cg0 + u) * 8;
 #pragma unroll
                         for (int e4 = 0; e4 < 8; e4 += 4) {
                             const float4 w0 = *reinterpret_cast<const float4 *>(w + e4);
-                            const float4 w1 = *reinterpret_cast<const float4 *>(w + p.kp[0] + e4);
-                            const float4 w2 = *reinterpret_cast<const float4 *>(w + 2 * p.kp[0] + e4);
+                            const float4 w1 = *reinterpret_cast<const float4 *>(w + kp0 + e4);
+                            const float4 w2 = *reinterpret_cast<const float4 *>(w + 2 * kp0 + e4);
                             f[u][e4 + 0] = fmaxf(fmaf(dz, w2.x, fmaf(dy, w1.x, fmaf(dx, w0.x, f[u][e4 + 0]))), 0.0f);
                             f[u][e4 + 1] = fmaxf(fmaf(dz, w2.y, fmaf(dy, w1.y, fmaf(dx, w0.y, f[u][e4 + 1]))), 0.0f);
                             f[u][e4 + 2] = fmaxf(fmaf(dz, w2.z, fmaf(dy, w1.z, fmaf(dx, w0.z, f[u][e4 + 2]))), 0.0f);
@@ -329,7 +405,8 @@ sa_fused_kernel(const SfParams p)
             }
         }
         SF_T(0);                                                       // gather
-        for (int l = 0; l < p.nl; l++) {
+#pragma unroll (C::kStatic ? SF_MAX_LAYERS : 1)
+        for (int l = 0; l < cfg.nl(); l++) {
             // operand written with ordinary stores -> make it visible to the tensor-core (async) proxy
             sf_fence_async_smem();
             sf_fence_before();
@@ -339,17 +416,18 @@ sa_fused_kernel(const SfParams p)
                 sf_fence_after();
                 // one MMA per k-step covers the whole layer width: a tcgen05.mma costs ~N/2 cycles plus a fixed
                 // per-instruction part, so narrower MMAs only add overhead (measured in round 1)
-                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.npad[l] >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-                const uint32_t tmem_u = tmem_base_smem + (uint32_t)slot_u * p.tmem_cols;
-                const uint32_t abase = smem_u32(smem) + (uint32_t)slot_u * p.abuf_bytes;
-                const uint32_t wbase = smem_u32(wsm) + p.w_off[l];
-                const int nfull = p.nfull[l], rbt = p.rbt[l];
+                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(cfg.npad(l) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                const uint32_t tmem_u = tmem_base_smem + (uint32_t)slot_u * cfg.tmem_cols();
+                const uint32_t abase = smem_u32(smem) + (uint32_t)slot_u * cfg.abuf_bytes();
+                const uint32_t wbase = smem_u32(wsm) + cfg.w_off(l);
+                const int nfull = cfg.nfull(l), rbt = cfg.rbt(l);
                 uint32_t acc = 0u;
                 // descriptors advance by (bytes >> 4) in their address field; shared memory < 256 KiB: no carry out of it
+#pragma unroll (C::kStatic ? 4 : 1)
                 for (int kb = 0; kb < nfull; kb++) {
                     const uint64_t a_hi = sf_desc(abase + (uint32_t)kb * (2u * 128u * 128u), 128);
-                    const uint64_t b_hi = sf_desc(wbase + (uint32_t)kb * ((uint32_t)p.npad[l] * 128u), 128);
-                    const uint64_t a_lo = a_hi + ((128u * 128u) >> 4), b_lo = b_hi + (p.w_half[l] >> 4);
+                    const uint64_t b_hi = sf_desc(wbase + (uint32_t)kb * ((uint32_t)cfg.npad(l) * 128u), 128);
+                    const uint64_t a_lo = a_hi + ((128u * 128u) >> 4), b_lo = b_hi + (cfg.w_half(l) >> 4);
 #pragma unroll
                     for (int kin = 0; kin < 4; kin++) {
                         if (elect_one()) {
@@ -362,9 +440,10 @@ sa_fused_kernel(const SfParams p)
                 }
                 if (rbt) {
                     const uint64_t a_hi = sf_desc(abase + (uint32_t)nfull * (2u * 128u * 128u), rbt);
-                    const uint64_t b_hi = sf_desc(wbase + (uint32_t)nfull * ((uint32_t)p.npad[l] * 128u), rbt);
-                    const uint64_t a_lo = a_hi + ((128u * (uint32_t)rbt) >> 4), b_lo = b_hi + (p.w_half[l] >> 4);
+                    const uint64_t b_hi = sf_desc(wbase + (uint32_t)nfull * ((uint32_t)cfg.npad(l) * 128u), rbt);
+                    const uint64_t a_lo = a_hi + ((128u * (uint32_t)rbt) >> 4), b_lo = b_hi + (cfg.w_half(l) >> 4);
                     const int nt = rbt == 128 ? 3 : (rbt >> 5);              // 16-wide k-steps of the tail block
+#pragma unroll (C::kStatic ? 3 : 1)
                     for (int kin = 0; kin < nt; kin++) {
                         if (elect_one()) {
                             sf_mma(tmem_u, a_hi + 2 * kin, b_hi + 2 * kin, idesc, acc);
@@ -376,36 +455,47 @@ sa_fused_kernel(const SfParams p)
                 }
                 if (elect_one()) sf_commit(smem_u32(&mma_bar[slot_u]));
                 __syncwarp();
+                SF_T(2 + 4 * l);                                       // MMA issue
+                // ONE warp of the slot polls the mbarrier; the others sleep at the slot's named barrier (a hardware
+                // barrier costs no issue slots -- the all-warps poll loop was a quarter of the kernel's instructions)
+                mbar_wait_cta(bar, mma_phase);                       // MMAs done: accumulator ready, operand buffer free
+                sf_fence_before();
             }
-            SF_T(2 + 4 * l);                                           // MMA issue
-            mbar_wait_cta(bar, mma_phase);                           // MMAs done: accumulator ready, operand buffer free
+            sf_bar_sync(slot_bar, ST);
             mma_phase ^= 1u;
             SF_T(3 + 4 * l);                                           // MMA wait
             sf_fence_after();
             // ---- epilogue of layer l
-            const float *sc = ss + p.ss_off[l];
-            const float *sh = sc + p.sspad[l];
-            const bool last = l == p.nl - 1;
-            const SfRowMap mapn(r, last ? 0 : p.nfull[l + 1], last ? 32 : p.rbt[l + 1]);
-            const int nchunks = (p.npad[l] + 31) / 32;
+            const float *sc = ss + cfg.ss_off(l);
+            const float *sh = sc + cfg.sspad(l);
+            const bool last = l == cfg.nl() - 1;
+            const bool pool_first = last && p.pool_first;              // last layer with scale >= 0: pool raw accumulators
+            const SfRowMap mapn(r, last ? 0 : cfg.nfull(l + 1), last ? 32 : cfg.rbt(l + 1));
+            const int nchunks = (cfg.npad(l) + 31) / 32;
+#pragma unroll (C::kStatic ? 4 : 1)
             for (int ci = wg; ci < nchunks; ci += WG) {
                 const int c0 = ci * 32;
                 uint32_t rr[32];
                 sf_tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
                 float v[32];
+                if (pool_first) {
 #pragma unroll
-                for (int j4 = 0; j4 < 32; j4 += 4) {                  // scale/shift are zero-padded to 32-column chunks
-                    const float4 s4 = *reinterpret_cast<const float4 *>(sc + c0 + j4);
-                    const float4 h4 = *reinterpret_cast<const float4 *>(sh + c0 + j4);
-                    v[j4 + 0] = fmaxf(fmaf(__uint_as_float(rr[j4 + 0]), s4.x, h4.x), 0.0f);   // every conv has a ReLU
-                    v[j4 + 1] = fmaxf(fmaf(__uint_as_float(rr[j4 + 1]), s4.y, h4.y), 0.0f);
-                    v[j4 + 2] = fmaxf(fmaf(__uint_as_float(rr[j4 + 2]), s4.z, h4.z), 0.0f);
-                    v[j4 + 3] = fmaxf(fmaf(__uint_as_float(rr[j4 + 3]), s4.w, h4.w), 0.0f);
+                    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(rr[j]);
+                } else {
+#pragma unroll
+                    for (int j4 = 0; j4 < 32; j4 += 4) {              // scale/shift are zero-padded to 32-column chunks
+                        const float4 s4 = *reinterpret_cast<const float4 *>(sc + c0 + j4);
+                        const float4 h4 = *reinterpret_cast<const float4 *>(sh + c0 + j4);
+                        v[j4 + 0] = fmaxf(fmaf(__uint_as_float(rr[j4 + 0]), s4.x, h4.x), 0.0f);   // every conv has a ReLU
+                        v[j4 + 1] = fmaxf(fmaf(__uint_as_float(rr[j4 + 1]), s4.y, h4.y), 0.0f);
+                        v[j4 + 2] = fmaxf(fmaf(__uint_as_float(rr[j4 + 2]), s4.z, h4.z), 0.0f);
+                        v[j4 + 3] = fmaxf(fmaf(__uint_as_float(rr[j4 + 3]), s4.w, h4.w), 0.0f);
+                    }
                 }
                 if (!last) {
 #pragma unroll
                     for (int j8 = 0; j8 < 32; j8 += 8) {
-                        if (c0 + j8 >= p.kp[l + 1]) break;
+                        if (c0 + j8 >= cfg.kp(l + 1)) break;
                         uint32_t hw[4], lw[4], lo_off;
 #pragma unroll
                         for (int t = 0; t < 4; t++) sf_split_pair(v[j8 + 2 * t], v[j8 + 2 * t + 1], hw[t], lw[t]);
@@ -413,13 +503,21 @@ sa_fused_kernel(const SfParams p)
                         *reinterpret_cast<uint4 *>(buf + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                         *reinterpret_cast<uint4 *>(buf + off + lo_off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     }
+                } else if (pool_first) {
+                    switch (cfg.ns()) {
+                        case 8: sf_pool_store<8, true>(p, v, lane, q, tile, c0, cfg.nout(l), xs, wg_bar, sc, sh); break;
+                        case 16: sf_pool_store<16, true>(p, v, lane, q, tile, c0, cfg.nout(l), xs, wg_bar, sc, sh); break;
+                        case 32: sf_pool_store<32, true>(p, v, lane, q, tile, c0, cfg.nout(l), xs, wg_bar, sc, sh); break;
+                        case 64: sf_pool_store<64, true>(p, v, lane, q, tile, c0, cfg.nout(l), xs, wg_bar, sc, sh); break;
+                        default: sf_pool_store<128, true>(p, v, lane, q, tile, c0, cfg.nout(l), xs, wg_bar, sc, sh); break;
+                    }
                 } else {
-                    switch (p.ns) {
-                        case 8: sf_pool_store<8>(p, v, lane, q, tile, c0, p.nout[l], xs, wg_bar); break;
-                        case 16: sf_pool_store<16>(p, v, lane, q, tile, c0, p.nout[l], xs, wg_bar); break;
-                        case 32: sf_pool_store<32>(p, v, lane, q, tile, c0, p.nout[l], xs, wg_bar); break;
-                        case 64: sf_pool_store<64>(p, v, lane, q, tile, c0, p.nout[l], xs, wg_bar); break;
-                        default: sf_pool_store<128>(p, v, lane, q, tile, c0, p.nout[l], xs, wg_bar); break;
+                    switch (cfg.ns()) {
+                        case 8: sf_pool_store<8, false>(p, v, lane, q, tile, c0, cfg.nout(l), xs, wg_bar, sc, sh); break;
+                        case 16: sf_pool_store<16, false>(p, v, lane, q, tile, c0, cfg.nout(l), xs, wg_bar, sc, sh); break;
+                        case 32: sf_pool_store<32, false>(p, v, lane, q, tile, c0, cfg.nout(l), xs, wg_bar, sc, sh); break;
+                        case 64: sf_pool_store<64, false>(p, v, lane, q, tile, c0, cfg.nout(l), xs, wg_bar, sc, sh); break;
+                        default: sf_pool_store<128, false>(p, v, lane, q, tile, c0, cfg.nout(l), xs, wg_bar, sc, sh); break;
                     }
                 }
             }
@@ -487,10 +585,11 @@ constexpr size_t SF_SMALL = 36 * 1024;                     // <= this: single-sl
 // Developer build only (-DSSD3D_DEV_HOOKS, csrc/ssd3d_dev.h): override the slot / warpgroup shape from a probe script.
 // The shipped library has no such state.
 #ifdef SSD3D_DEV_HOOKS
-static int g_sf_slots = 0, g_sf_wg = 0;
+static int g_sf_slots = 0, g_sf_wg = 0, g_sf_dynamic = 0;
 extern "C" void ssd3d_dev_set_fused(int slots, int wg) { g_sf_slots = slots; g_sf_wg = wg; }
+extern "C" void ssd3d_dev_set_fused_dynamic(int on) { g_sf_dynamic = on; }   // force the run-time-shape kernel (A/B timing)
 #else
-constexpr int g_sf_slots = 0, g_sf_wg = 0;
+constexpr int g_sf_slots = 0, g_sf_wg = 0, g_sf_dynamic = 0;
 #endif
 
 // Slots per CTA for a stack: 1 for small stacks (several CTAs per SM), else as many as fit one SM (<= 3).
@@ -513,16 +612,34 @@ extern "C" size_t ssd3d_sa_fused_smem(int c, int nl, const int *nout)
     return total <= SF_SMEM_MAX ? total : 0;
 }
 
-template <int SLOTS, int WG>
+template <class C, int SLOTS, int WG>
 static cudaError_t sf_launch(const SfParams &p, size_t smem, int per_sm, cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute((const void *)sa_fused_kernel<SLOTS, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute((const void *)sa_fused_kernel<C, SLOTS, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int ctas = (p.tiles + SLOTS - 1) / SLOTS;
     int grid = kNumSMs * per_sm;
     if (grid > ctas) grid = ctas;
-    sa_fused_kernel<SLOTS, WG><<<grid, SF_THREADS * SLOTS * WG, smem, stream>>>(p);
+    sa_fused_kernel<C, SLOTS, WG><<<grid, SF_THREADS * SLOTS * WG, smem, stream>>>(p);
     return cudaSuccess;
+}
+
+// The hoisted two-conv stacks of the shipped 3DSSD configuration (configs/kitti/3dssd/3dssd.yaml:47-52) have compile-time
+// twins of the kernel: layer 1 [16 -> 16 -> 32] x32 and [32 -> 32 -> 64] x64 neighbours, layer 2 [64 -> 64 -> 128] x32 and
+// [64 -> 96 -> 128] x64.  Returns false when (shape, slots, warpgroups) has no twin: the caller takes the dynamic kernel.
+static bool sf_launch_static(const SfParams &p, int slots, int wg, size_t smem, int per_sm, cudaStream_t st, cudaError_t *e)
+{
+    if (!p.hoist || p.nl != 2) return false;
+    const int k0 = p.c, n0 = p.nout[0], n1 = p.nout[1], ns = p.ns;
+    if (slots == 1 && wg == 1) {
+        if (k0 == 16 && n0 == 16 && n1 == 32 && ns == 32) { *e = sf_launch<SfStat<16, 16, 32, 32>, 1, 1>(p, smem, per_sm, st); return true; }
+        if (k0 == 32 && n0 == 32 && n1 == 64 && ns == 64) { *e = sf_launch<SfStat<32, 32, 64, 64>, 1, 1>(p, smem, per_sm, st); return true; }
+    }
+    if (slots == 3 && wg == 2) {
+        if (k0 == 64 && n0 == 64 && n1 == 128 && ns == 32) { *e = sf_launch<SfStat<64, 64, 128, 32>, 3, 2>(p, smem, per_sm, st); return true; }
+        if (k0 == 64 && n0 == 96 && n1 == 128 && ns == 64) { *e = sf_launch<SfStat<64, 96, 128, 64>, 3, 2>(p, smem, per_sm, st); return true; }
+    }
+    return false;
 }
 
 // w_blob: per layer { hi image | lo image }, each image = k-blocks of [npad x (64 | tail)] bf16 in the canonical
@@ -530,8 +647,8 @@ static cudaError_t sf_launch(const SfParams &p, size_t smem, int per_sm, cudaStr
 // wx != NULL selects the hoisted mode: `points` is the per-point table z (pitch ldz), c its width.
 static int sa_mlp_fused_impl(int b, int n, int c, int m, int nsample, const float *xyz, const float *points, int ldz,
                              const float *wx, const float *new_xyz, const int *idx, const int *pts_cnt, int nl,
-                             const int *nout, const void *w_blob, const float *ss_blob, float *out_f32, int ld_f32,
-                             void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream)
+                             const int *nout, const void *w_blob, const float *ss_blob, int last_scale_nonneg,
+                             float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream)
 {
     const bool hoist = wx != nullptr;
     SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0 && c >= 0, "sa_mlp_fused: bad shape");
@@ -557,6 +674,7 @@ static int sa_mlp_fused_impl(int b, int n, int c, int m, int nsample, const floa
     p.tiles = (int)((p.rows + 127) / 128);
     p.xyz = xyz; p.points = points; p.new_xyz = new_xyz; p.idx = idx; p.cnt = pts_cnt;
     p.hoist = hoist ? 1 : 0; p.ldz = ldz; p.wx = wx;
+    p.pool_first = last_scale_nonneg ? 1 : 0;
     p.nl = nl;
     int kprev = (k_in + 15) / 16 * 16;
     uint32_t woff = 0, ssoff = 0;
@@ -595,11 +713,13 @@ static int sa_mlp_fused_impl(int b, int n, int c, int m, int nsample, const floa
     }
     const int wg = slots == 1 ? 1 : (g_sf_wg > 0 ? g_sf_wg : 2);
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = slots == 1 ? sf_launch<1, 1>(p, smem, per_sm, st)
-                  : slots == 2 ? (wg == 4 ? sf_launch<2, 4>(p, smem, per_sm, st) : wg == 1 ? sf_launch<2, 1>(p, smem, per_sm, st)
-                                                                                           : sf_launch<2, 2>(p, smem, per_sm, st))
-                  : slots == 3 ? (wg == 1 ? sf_launch<3, 1>(p, smem, per_sm, st) : sf_launch<3, 2>(p, smem, per_sm, st))
-                               : sf_launch<4, 1>(p, smem, per_sm, st);
+    cudaError_t e = cudaSuccess;
+    if (g_sf_dynamic || !sf_launch_static(p, slots, wg, smem, per_sm, st, &e))
+        e = slots == 1 ? sf_launch<SfDyn, 1, 1>(p, smem, per_sm, st)
+          : slots == 2 ? (wg == 4 ? sf_launch<SfDyn, 2, 4>(p, smem, per_sm, st) : wg == 1 ? sf_launch<SfDyn, 2, 1>(p, smem, per_sm, st)
+                                                                                           : sf_launch<SfDyn, 2, 2>(p, smem, per_sm, st))
+          : slots == 3 ? (wg == 1 ? sf_launch<SfDyn, 3, 1>(p, smem, per_sm, st) : sf_launch<SfDyn, 3, 2>(p, smem, per_sm, st))
+                       : sf_launch<SfDyn, 4, 1>(p, smem, per_sm, st);
     if (e != cudaSuccess) return cuda_status(e, "sa_mlp_fused attr");
 #ifdef SF_PROFILE
     {
@@ -618,21 +738,22 @@ static int sa_mlp_fused_impl(int b, int n, int c, int m, int nsample, const floa
 
 extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
                                   const float *new_xyz, const int *idx, const int *pts_cnt, int nl, const int *nout,
-                                  const void *w_blob, const float *ss_blob, float *out_f32, int ld_f32, void *out_hi,
-                                  void *out_lo, int ld_split, ssd3d_stream_t stream)
+                                  const void *w_blob, const float *ss_blob, int last_scale_nonneg, float *out_f32, int ld_f32,
+                                  void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream)
 {
     return sa_mlp_fused_impl(b, n, c, m, nsample, xyz, points, c, nullptr, new_xyz, idx, pts_cnt, nl, nout, w_blob, ss_blob,
-                             out_f32, ld_f32, out_hi, out_lo, ld_split, stream);
+                             last_scale_nonneg, out_f32, ld_f32, out_hi, out_lo, ld_split, stream);
 }
 
 // The fused SA scale with its first conv hoisted (see ssd3d_linear_tc_hoisted): z[b,n,ldz] per-point table (this scale's
 // n1 columns start at z), wx = Wx*s1 as [3][n1]; the stack (w_blob / ss_blob / nout) starts at the scale's SECOND conv.
 extern "C" int ssd3d_sa_mlp_fused_hoisted(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
                                           const float *wx, const float *new_xyz, const int *idx, const int *pts_cnt, int nl,
-                                          const int *nout, const void *w_blob, const float *ss_blob, float *out_f32,
-                                          int ld_f32, void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream)
+                                          const int *nout, const void *w_blob, const float *ss_blob, int last_scale_nonneg,
+                                          float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split,
+                                          ssd3d_stream_t stream)
 {
     SSD3D_REQUIRE(z && wx, "sa_mlp_fused_hoisted: null table pointer");
     return sa_mlp_fused_impl(b, n, n1, m, nsample, xyz, z, ldz, wx, new_xyz, idx, pts_cnt, nl, nout, w_blob, ss_blob,
-                             out_f32, ld_f32, out_hi, out_lo, ld_split, stream);
+                             last_scale_nonneg, out_f32, ld_f32, out_hi, out_lo, ld_split, stream);
 }

@@ -168,20 +168,30 @@ class FusedStack:
         dev = convs[0].w.device
         self.nout = [f.cout for f in convs]
         self.cin = cin
+        # The LAST layer is stored with non-negative scales: (x.w) * s + t == (x.(w * sgn s)) * |s| + t, exactly (a sign
+        # flip is exact in bf16).  fma(acc, |s|, t) is then monotone in acc, so the kernel may max-pool the raw
+        # accumulators and apply scale / shift / ReLU to the pooled values only (ssd3d.h: last_scale_nonneg).
+        self.last_scale_nonneg = True
         wparts, sparts = [], []
         kp = round16(cin)
-        for f in convs:
+        for li, f in enumerate(convs):
             npad = round16(f.cout)
             assert f.kp == kp, (f.kp, kp)
+            b_hi, b_lo, scale = f.b_hi, f.b_lo, f.scale
+            if li == len(convs) - 1:
+                sgn = torch.where(scale < 0, -torch.ones_like(scale), torch.ones_like(scale))
+                b_hi = (b_hi.float() * sgn.unsqueeze(1)).to(torch.bfloat16)
+                b_lo = (b_lo.float() * sgn.unsqueeze(1)).to(torch.bfloat16)
+                scale = scale.abs()
             hi = torch.zeros((npad, kp), dtype=torch.bfloat16, device=dev)
             lo = torch.zeros_like(hi)
-            hi[: f.cout] = f.b_hi
-            lo[: f.cout] = f.b_lo
+            hi[: f.cout] = b_hi
+            lo[: f.cout] = b_lo
             wparts += [_swizzled_image(hi), _swizzled_image(lo)]
             sspad = (npad + 31) // 32 * 32                 # the kernel reads scale/shift in 32-column chunks
             sc = torch.zeros(sspad, dtype=torch.float32, device=dev)
             sh = torch.zeros(sspad, dtype=torch.float32, device=dev)
-            sc[: f.cout] = f.scale
+            sc[: f.cout] = scale
             sh[: f.cout] = f.shift
             sparts += [sc, sh]
             kp = npad

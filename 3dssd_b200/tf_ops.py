@@ -660,8 +660,8 @@ def sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=None, out_split=
     nout = (ctypes.c_int * len(stack.nout))(*stack.nout)
     vp = ctypes.c_void_p
     check(lib().ssd3d_sa_mlp_fused(b, n, c, m, ns, _p(xyz), _p(points), _p(new_xyz), _p(idx), _p(cnt), len(stack.nout),
-                                   ctypes.cast(nout, vp), _p(stack.w_blob), _p(stack.ss_blob), vp(pf), ldf, vp(ph),
-                                   vp(pl), lds, _stream()), "sa_mlp_fused")
+                                   ctypes.cast(nout, vp), _p(stack.w_blob), _p(stack.ss_blob), 1 if stack.last_scale_nonneg else 0,
+                                   vp(pf), ldf, vp(ph), vp(pl), lds, _stream()), "sa_mlp_fused")
     return y
 
 
@@ -697,7 +697,8 @@ def sa_mlp_fused_hoisted(xyz, z, zoff, wx, new_xyz, idx, cnt, stack, out_f32=Non
     vp = ctypes.c_void_p
     check(lib().ssd3d_sa_mlp_fused_hoisted(b, n, n1, m, ns, _p(xyz), vp(z.data_ptr() + 4 * zoff), z.shape[2], _p(wx), _p(new_xyz),
                                            _p(idx), _p(cnt), len(stack.nout), ctypes.cast(nout, vp), _p(stack.w_blob),
-                                           _p(stack.ss_blob), vp(pf), ldf, vp(ph), vp(pl), lds, _stream()), "sa_mlp_fused_hoisted")
+                                           _p(stack.ss_blob), 1 if stack.last_scale_nonneg else 0, vp(pf), ldf, vp(ph), vp(pl),
+                                           lds, _stream()), "sa_mlp_fused_hoisted")
     return y
 
 

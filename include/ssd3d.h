@@ -29,7 +29,7 @@ extern "C" {
 typedef void *ssd3d_stream_t;
 
 /* ABI version of this header (bumped on any signature change). */
-int ssd3d_version(void);
+int ssd3d_version(void);   /* 2 since round 2 (explicit-placement *_ex entry points, last_scale_nonneg) */
 /* Human-readable description of the last non-zero status returned on this thread. */
 const char *ssd3d_last_error(void);
 
@@ -210,8 +210,8 @@ int ssd3d_hoist_expand_split(int b, int n, int n1, int m, int nsample, const flo
  * SECOND conv, the first operand row is relu(z[idx] + (xyz[idx] - new_xyz) . wx), built during the gather. */
 int ssd3d_sa_mlp_fused_hoisted(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
                                const float *wx, const float *new_xyz, const int *idx, const int *pts_cnt, int nl,
-                               const int *nout, const void *w_blob, const float *ss_blob, float *out_f32, int ld_f32,
-                               void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream);
+                               const int *nout, const void *w_blob, const float *ss_blob, int last_scale_nonneg,
+                               float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream);
 /* hi/lo[row, 0:kp] = split(x[row, 0:c]), zero padded (kp % 8 == 0). */
 int ssd3d_split_rows(long rows, int c, const float *x, int ldx, void *hi, void *lo, int kp, ssd3d_stream_t stream);
 /* ssd3d_group_concat fused with the split: hi/lo [b*m*nsample, kp] bf16. */
@@ -222,12 +222,15 @@ int ssd3d_group_concat_split(int b, int n, int c, int m, int nsample, const floa
  * lib/utils/layers_util.py:157-180) for layer stacks whose weights fit in shared memory.
  * ssd3d_sa_fused_smem returns the shared-memory bytes needed, or 0 if the stack does not fit (use the per-layer
  * path then).  w_blob / ss_blob are the pre-swizzled split weights and folded scale/shift built by the host
- * (3dssd_b200/params.py: FusedStack).  Outputs as ssd3d_linear_tc with pool = nsample. */
+ * (3dssd_b200/params.py: FusedStack).  Outputs as ssd3d_linear_tc with pool = nsample.
+ * last_scale_nonneg != 0: the caller guarantees scale >= 0 in the LAST layer (fold the sign of a negative BatchNorm
+ * gamma into that layer's weight column -- FusedStack does); the kernel then max-pools the raw accumulators and applies
+ * scale / shift / ReLU to the pooled values only (exactly the same result: the affine map is monotone). */
 size_t ssd3d_sa_fused_smem(int c, int nl, const int *nout);
 int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
                        const float *new_xyz, const int *idx, const int *pts_cnt, int nl, const int *nout,
-                       const void *w_blob, const float *ss_blob, float *out_f32, int ld_f32, void *out_hi, void *out_lo,
-                       int ld_split, ssd3d_stream_t stream);
+                       const void *w_blob, const float *ss_blob, int last_scale_nonneg, float *out_f32, int ld_f32,
+                       void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream);
 
 /* ---- backward operators (training graphs) ---------------------------------------------------
  * Each zero-fills its output first, as the reference's TF ops do with cudaMemset before the launcher. */

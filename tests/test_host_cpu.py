@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(pkg):
         assert hasattr(lib, name), "libssd3d.so does not export %s" % name
     assert declared == set(pkg.EXPORTS), declared ^ set(pkg.EXPORTS)
     lib.ssd3d_version.restype = ctypes.c_int
-    assert lib.ssd3d_version() == 1
+    assert lib.ssd3d_version() == 2
 
 
 def test_no_cpu_fallback(pkg):
@@ -194,9 +194,9 @@ def test_c_abi_argument_validation_needs_no_gpu(pkg):
                                           ctypes.cast(k, ctypes.c_void_p), one, one, ctypes.cast(ptrs, ctypes.c_void_p),
                                           ctypes.cast(ptrs, ctypes.c_void_p), null) == -1 and "positive radius" in err()
     nout = (ctypes.c_int * 3)(128, 128, 256)
-    assert L.ssd3d_sa_mlp_fused(1, 64, 128, 8, 32, one, one, one, one, null, 3, ctypes.cast(nout, ctypes.c_void_p), one, one,
+    assert L.ssd3d_sa_mlp_fused(1, 64, 128, 8, 32, one, one, one, one, null, 3, ctypes.cast(nout, ctypes.c_void_p), one, one, 1,
                                 one, 256, null, null, 0, null) == -2 and "does not fit" in err()
-    assert L.ssd3d_sa_mlp_fused(1, 64, 1, 8, 7, one, one, one, one, null, 3, ctypes.cast(nout, ctypes.c_void_p), one, one,
+    assert L.ssd3d_sa_mlp_fused(1, 64, 1, 8, 7, one, one, one, one, null, 3, ctypes.cast(nout, ctypes.c_void_p), one, one, 0,
                                 one, 256, null, null, 0, null) == -1 and "nsample" in err()
     assert L.ssd3d_linear_tc(128, 20, 16, one, one, one, one, one, one, 1, 1, null, one, 16, null, null, 0, null) == -1 and "multiple of 16" in err()
     assert L.ssd3d_version() > 0

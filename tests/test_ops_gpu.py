@@ -817,7 +817,8 @@ def test_sa_mlp_fused_hoisted_vs_oracle(pkg, oracle_ops, cuda, b, n, c, m, k, ml
     for j, cout in enumerate(mlp):
         P._conv_init(rng, prm, "s/conv0_%d" % j, cin, cout, True)
         prm["s/conv0_%d/biases" % j] = rng.standard_normal(cout).astype(np.float32)
-        scopes.append("s/conv0_%d" % j)
+        prm["s/conv0_%d/bn/gamma" % j][1::3] *= -1.0                  # negative BatchNorm scales: the last layer's are
+        scopes.append("s/conv0_%d" % j)                               # folded into its weights (pool-before-affine)
         cin = cout
     pp = P.prepare(prm, cuda)
     g = np.concatenate([oracle_ops.group_point(feats, idx), oracle_ops.group_point(xyz, idx) - new_xyz[:, :, None]], -1)
