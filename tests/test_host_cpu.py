@@ -253,6 +253,61 @@ def test_fps_part_bounds(pkg):
     assert pb(100, 3) == [(0, 100)]                       # smaller than one 128-row tile: a single part
 
 
+def _bq_grid_cells(xyz, r_max):
+    """float32 restatement of the cell arithmetic of csrc/ball_query_grid.cu (bq_grid_build_kernel / bqg_cell_coord)."""
+    f = np.float32
+    lo, hi = xyz.min(0), xyz.max(0)
+    ext = (hi - lo).astype(np.float32)
+    order = np.argsort(-ext, kind="stable")
+    a0, a1 = int(order[0]), int(order[1])
+    c = f(r_max) * f(1.01)
+    while True:
+        fa, fb = np.floor(ext[a0] / c) + f(1), np.floor(ext[a1] / c) + f(1)
+        if fa * fb <= 8192:
+            break
+        c = f(c * f(1.25))
+    inv_c = f(1) / c
+
+    def cell(v, mn, nc):
+        u = ((v.astype(np.float32) - f(mn)) * inv_c).astype(np.float32)
+        return np.clip(np.floor(u).astype(np.int64), 0, int(nc) - 1)
+    return (a0, a1), (lo[a0], lo[a1]), (int(fa), int(fb)), cell, float(c)
+
+
+@pytest.mark.parametrize("name", ["kitti", "cube", "line", "huge-extent", "boundary"])
+def test_ball_query_grid_culling_rule_never_drops_a_hit(pkg, name):
+    """The culled ball query (csrc/ball_query_grid.cu) visits the 3x3 cell neighbourhood of a query.  Property behind its
+    bit-exactness: for EVERY (query, candidate) pair the reference would accept for the largest radius, the cells differ
+    by at most one on both grid axes -- checked here on the float32 cell arithmetic, incl. points placed exactly on cell
+    boundaries and extents that push the cell count to its cap."""
+    import importlib
+    synth = importlib.import_module("3dssd_b200.synth")
+    rng = np.random.default_rng(3)
+    r_max = 0.8
+    if name == "kitti":
+        xyz = synth.kitti_like(1, 16384, seed=9)[0, :, :3]
+    elif name == "cube":
+        xyz = rng.uniform(0, 1, (4096, 3)).astype(np.float32); r_max = 0.2
+    elif name == "line":
+        xyz = np.stack([np.linspace(0, 5000, 8192, dtype=np.float32), np.zeros(8192, np.float32), np.zeros(8192, np.float32)], -1)
+    elif name == "huge-extent":
+        xyz = (rng.uniform(-1, 1, (4096, 3)) * np.array([3.0e4, 2.0e4, 5.0])).astype(np.float32); r_max = 0.3
+    else:
+        base = synth.kitti_like(1, 2048, seed=2)[0, :, :3]
+        (a0, a1), (m0, m1), _, _, c = _bq_grid_cells(base, r_max)
+        xyz = base.copy()
+        xyz[::2, a0] = np.float32(m0) + np.round((xyz[::2, a0] - m0) / c).astype(np.float32) * np.float32(c)   # on cell boundaries
+    (a0, a1), (m0, m1), (na, nb), cell, c = _bq_grid_cells(xyz, r_max)
+    assert na * nb <= 8192 and c >= r_max * 1.0099
+    q = xyz[rng.choice(len(xyz), 256, replace=False)] + rng.normal(0, r_max / 3, (256, 3)).astype(np.float32)
+    d = np.sqrt(((q[:, None, :].astype(np.float64) - xyz[None].astype(np.float64)) ** 2).sum(-1))
+    qi, ki = np.nonzero(d <= r_max * (1 + 1e-6))                  # everything the fp32 test could accept, with slack
+    assert len(qi) > 0
+    da = np.abs(cell(q[:, a0], m0, na)[qi] - cell(xyz[:, a0], m0, na)[ki])
+    db = np.abs(cell(q[:, a1], m1, nb)[qi] - cell(xyz[:, a1], m1, nb)[ki])
+    assert da.max() <= 1 and db.max() <= 1
+
+
 def test_header_is_plain_c():
     """include/ssd3d.h is the drop-in boundary: it must compile as C99 and as C++ with nothing but the standard
     headers (no torch / CUDA types in any signature)."""
