@@ -59,7 +59,9 @@ def _build_to(lib_path, obj_dir, defines, verbose):
 
 if __name__ == "__main__":
     import sys
-    if len(sys.argv) > 1 and sys.argv[1] == "prof":
+    if len(sys.argv) > 1 and sys.argv[1] == "dev":
+        print(build(True, verbose=False, defines=("SSD3D_DEV_HOOKS",), out="libssd3d_dev.so"))
+    elif len(sys.argv) > 1 and sys.argv[1] == "prof":
         print(build(True, verbose=True, defines=("TC_PROFILE", "SF_PROFILE", "SSD3D_DEV_HOOKS"), out="libssd3d_prof.so"))
     else:
         print(build(force=True, verbose=True))

@@ -1,5 +1,8 @@
 """Runs the fused SA-scale kernel on layer-1 / layer-2 shaped inputs (for timing and ncu captures).
-usage: python tools/fused_probe.py [case-index]"""
+usage: python tools/fused_probe.py [case-index ...] [hoist=1] [dyn=1] [slots=S wg=W]
+  hoist=1 (default)  the hoisted form the model runs (first conv in the per-point table); hoist=0 the literal 3-conv stack
+  dyn=1 / slots / wg developer build only (SSD3D_LIB=3dssd_b200/libssd3d_dev.so): force the run-time-shape kernel /
+                     the slot x warpgroup shape, for A/B timing against the compile-time-shape kernels"""
 import importlib
 import os
 import sys
@@ -25,9 +28,12 @@ def main():
     dev = torch.device("cuda:0")
     sel = [int(a) for a in sys.argv[1:] if "=" not in a] or range(len(CASES))
     kv = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
-    if "slots" in kv or "wg" in kv:   # developer build only (nvcc -DSSD3D_DEV_HOOKS, loaded through SSD3D_LIB)
+    if "slots" in kv or "wg" in kv or "dyn" in kv:   # developer build only (nvcc -DSSD3D_DEV_HOOKS, loaded through SSD3D_LIB)
         import ctypes
-        ctypes.CDLL(pkg.LIB_PATH).ssd3d_dev_set_fused(int(kv.get("slots", 0)), int(kv.get("wg", 0)))
+        dl = ctypes.CDLL(pkg.LIB_PATH)
+        dl.ssd3d_dev_set_fused(int(kv.get("slots", 0)), int(kv.get("wg", 0)))
+        dl.ssd3d_dev_set_fused_dynamic(int(kv.get("dyn", 0)))
+    hoist = int(kv.get("hoist", 1))
     rng = np.random.default_rng(0)
     B = 8
     pts = torch.from_numpy(synth.kitti_like(B, 16384, seed=1000)).to(dev)
@@ -44,8 +50,15 @@ def main():
             scopes.append("s/conv0_%d" % j)
             cin = cout
         pp = P.prepare(prm, dev)
-        stack = pp.fused_stack(scopes, True, c + 3, limit=0)
-        run = lambda: pkg.sa_mlp_fused(xyz, feats, new_xyz, idx, cnt, stack)
+        if hoist:
+            zconv, wxs, n1s = pp.hoisted([scopes[0]], True, c)
+            hst = pp.fused_stack(scopes[1:], True, n1s[0], limit=0)
+            p_hi, p_lo = pkg.split_rows(feats)
+            z, _ = pkg.linear_tc(p_hi, p_lo, zconv, relu=False, want_f32=True, want_split=False)
+            run = lambda: pkg.sa_mlp_fused_hoisted(xyz, z, 0, wxs[0], new_xyz, idx, cnt, hst)
+        else:
+            stack = pp.fused_stack(scopes, True, c + 3, limit=0)
+            run = lambda: pkg.sa_mlp_fused(xyz, feats, new_xyz, idx, cnt, stack)
         for _ in range(3):
             run()
         torch.cuda.synchronize()
@@ -55,7 +68,8 @@ def main():
             e0.record(); run(); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         rows = B * m * k
-        print("case %d n=%d c=%d m=%d k=%d mlp=%s rows=%d: %.1f us" % (i, n, c, m, k, mlp, rows, 1e3 * float(np.median(ts))), flush=True)
+        print("case %d n=%d c=%d m=%d k=%d mlp=%s rows=%d hoist=%d %s: %.1f us" % (i, n, c, m, k, mlp, rows, hoist, " ".join(sys.argv[1:]),
+                                                                              1e3 * float(np.median(ts))), flush=True)
 
 
 if __name__ == "__main__":
