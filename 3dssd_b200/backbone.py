@@ -41,7 +41,7 @@ class SABackbone:
         self.fuse_scale = fuse_scale
         self.fps_cluster = fps_cluster
         self.latency_mode = latency_mode
-        self.fps_parts = list(fps_parts)
+        self.fps_parts = fps_parts if isinstance(fps_parts, int) else list(fps_parts)
         self.head = head                      # optional head.DetectionHead: real detections instead of the stand-in block
         self._graph = None
 

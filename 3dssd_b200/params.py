@@ -168,6 +168,7 @@ class FusedStack:
         dev = convs[0].w.device
         self.nout = [f.cout for f in convs]
         self.cin = cin
+        self.convs = list(convs)            # the folded layers the blobs were built from (introspection / CPU dry runs)
         # The LAST layer is stored with non-negative scales: (x.w) * s + t == (x.(w * sgn s)) * |s| + t, exactly (a sign
         # flip is exact in bf16).  fma(acc, |s|, t) is then monotone in acc, so the kernel may max-pool the raw
         # accumulators and apply scale / shift / ReLU to the pooled values only (ssd3d.h: last_scale_nonneg).
