@@ -288,8 +288,10 @@ fps3_direct_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
         const int r = j - jbeg + 1;                      // 1-based round of THIS launch: slot parity / barrier phase
         const int par = r & 1;
         if (tid == 0) mbar_arrive_expect_tx(smem_u32(&mbar[par]), NSLOT * 8);
-        float best = -1.0f;
-        int bi = 0;
+        // ---- distance update of the thread's P points, then their arg-max as a TREE (depth log2 P) instead of a serial
+        // "first strictly greater" scan (depth P): the scan's compare + select chain was ~150 of the ~830 cycles of a
+        // round.  Ties keep the lower slot (a higher slot wins only when STRICTLY greater), i.e. the scan's answer.
+        float tv[P];
         {
             // packed fp32 pairs (FADD2 / FMUL2 / FFMA2): same IEEE operations as d = fma(dz,dz, fma(dy,dy, dx*dx))
             const float2 nox = make_float2(-ox, -ox), noy = make_float2(-oy, -oy), noz = make_float2(-oz, -oz);
@@ -301,10 +303,8 @@ fps3_direct_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
                 float2 d = __fmul2_rn(dx, dx);
                 d = __ffma2_rn(dy, dy, d);
                 d = __ffma2_rn(dz, dz, d);
-                const float t0 = fminf(d.x, td[i]), t1 = fminf(d.y, td[i + 1]);
-                td[i] = t0; td[i + 1] = t1;
-                if (t0 > best) { best = t0; bi = i; }
-                if (t1 > best) { best = t1; bi = i + 1; }
+                td[i] = fminf(d.x, td[i]); td[i + 1] = fminf(d.y, td[i + 1]);
+                tv[i] = td[i]; tv[i + 1] = td[i + 1];
             }
             if (P & 1) {
                 constexpr int i = P - 1;
@@ -312,14 +312,26 @@ fps3_direct_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
                 float d = __fmul_rn(dx, dx);
                 d = __fmaf_rn(dy, dy, d);
                 d = __fmaf_rn(dz, dz, d);
-                const float t = fminf(d, td[i]);
-                td[i] = t;
-                if (t > best) { best = t; bi = i; }
+                td[i] = fminf(d, td[i]);
+                tv[i] = td[i];
             }
         }
+        int tk[P];                                       // k of slot i (compile-time offsets from the thread's base)
+#pragma unroll
+        for (int i = 0; i < P; i++) tk[i] = Map::k_of(g, i);
+#pragma unroll
+        for (int sdist = 1; sdist < P; sdist *= 2) {
+#pragma unroll
+            for (int i = 0; i + sdist < P; i += 2 * sdist) {
+                const bool up = tv[i + sdist] > tv[i];
+                tv[i] = up ? tv[i + sdist] : tv[i];
+                tk[i] = up ? tk[i + sdist] : tk[i];
+            }
+        }
+        const float best = tv[0];
         const uint32_t u = __float_as_uint(fmaxf(best, 0.0f));
         uint32_t mx, kmin;
-        warp_argmax(u, best >= 0.0f ? fps_key(Map::k_of(g, bi)) : KEY_INVALID, mx, kmin);
+        warp_argmax(u, best >= 0.0f ? fps_key(tk[0]) : KEY_INVALID, mx, kmin);
         if (lane < CL) {
             const unsigned long long pk = ((unsigned long long)mx << 32) | (unsigned long long)kmin;
             st_async_b64(mapa(smem_u32(&slots[par][rank * FPS_NW + warp]), (uint32_t)lane),

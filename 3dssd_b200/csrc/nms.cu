@@ -77,6 +77,8 @@ bev_nms_kernel(int n, int npow2, const float *__restrict__ boxes, const float *_
                 const float area_b = (b.z - b.x) * (b.w - b.y);
                 if (area_a <= 0.0f || area_b <= 0.0f) continue;
                 const float iw = fminf(a.z, b.z) - fmaxf(a.x, b.x), ih = fminf(a.w, b.w) - fmaxf(a.y, b.y);
+                // disjoint rectangles (the common case): inter == 0, IoU == 0 (or NaN), never > threshold -- skip the divide
+                if (iou_thr >= 0.0f && (!(iw > 0.0f) || !(ih > 0.0f))) continue;
                 const float inter = fmaxf(iw, 0.0f) * fmaxf(ih, 0.0f);
                 if (inter / (area_a + area_b - inter) > iou_thr) bits |= 1u << t;
             }
