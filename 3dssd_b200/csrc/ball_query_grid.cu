@@ -14,6 +14,8 @@
 //      coalesced 16-byte records), evaluates the reference's distance recipe, and marks every hit in a per-shell BITMAP
 //      over candidate indices in shared memory (n <= 16384 bits).  Scanning the bitmap in word order then yields the hits
 //      in ascending index, whatever order the cells delivered them in -- first-K semantics without any sort.
+//      A query whose neighbourhood holds more than n/8 candidates takes the index-order scan with early exit instead: a
+//      dense ball is full after a few hundred candidates, where culling would still visit (and mark) thousands.
 // Non-finite coordinates keep the reference's behaviour (NaN distances hit in the plain query, never in the dilated one):
 // a scene containing any collapses to a single cell, i.e. the exhaustive scan.
 #include <math.h>
@@ -182,12 +184,18 @@ struct BqgParams {
     int *cnt[BQG_MAX_SHELLS];
 };
 
+// Bitmap word wi of a shell lives at wi + (wi >> lg): one pad word per lane chunk of 2^lg words, so that the chunks of
+// consecutive lanes start an ODD number of words apart and the per-lane sequential reads of the read-back are free of
+// bank conflicts (unpadded, 16-word chunks collide 16 ways: that alone was ~90% of the first version's run time).
+constexpr int BQG_WORDS_P = BQG_WORDS + 32;
+
 template <int NS, bool DILATED>
 __global__ void __launch_bounds__(BQG_THREADS)
-ball_query_grid_kernel(const float *__restrict__ xyz2, const uint8_t *__restrict__ ws, const BqgParams p)
+ball_query_grid_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, const uint8_t *__restrict__ ws,
+                       const BqgParams p)
 {
     extern __shared__ uint4 dyn_smem4[];
-    uint32_t *bitmaps = reinterpret_cast<uint32_t *>(dyn_smem4);       // [BQG_WARPS][NS][BQG_WORDS]
+    uint32_t *bitmaps = reinterpret_cast<uint32_t *>(dyn_smem4);       // [BQG_WARPS][NS][BQG_WORDS_P]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int scene = blockIdx.y;
     const int n = p.n, m = p.m;
@@ -195,32 +203,85 @@ ball_query_grid_kernel(const float *__restrict__ xyz2, const uint8_t *__restrict
     const BqgHeader h = *reinterpret_cast<const BqgHeader *>(base);
     const int *cell_start = reinterpret_cast<const int *>(base + sizeof(BqgHeader));
     const float4 *rec = reinterpret_cast<const float4 *>(base + sizeof(BqgHeader) + ((size_t)(BQG_MAX_CELLS + 1) * 4 + 15) / 16 * 16);
-    uint32_t *bm = bitmaps + (size_t)warp * NS * BQG_WORDS;
+    const float *cand = xyz1 + (size_t)scene * n * 3;
+    uint32_t *bm = bitmaps + (size_t)warp * NS * BQG_WORDS_P;
     const int words = (n + 31) >> 5;                                   // bitmap words in use
-    const int wpl = (words + 31) >> 5;                                 // words per lane (contiguous chunk, <= 16)
+    int lg = 1;                                                        // words per lane chunk = 2^lg >= ceil(words / 32), >= 2
+    while ((32 << lg) < words) lg++;
+    const int wpl = 1 << lg;
+    const int words_p = 32 * (wpl + 1);                                // padded words in use (<= BQG_WORDS_P)
 
     for (int qq = 0; qq < BQG_QPW; qq++) {
         const int qi = (blockIdx.x * BQG_WARPS + warp) * BQG_QPW + qq;
         if (qi >= m) break;                                            // warp-uniform
         const float *qsrc = xyz2 + ((size_t)scene * m + qi) * 3;
         const float qx = qsrc[0], qy = qsrc[1], qz = qsrc[2];
-        // ---- clear this warp's bitmaps
-        for (int w = lane; w < NS * BQG_WORDS / 4; w += 32) {
-            const int s = w / (BQG_WORDS / 4), j = w - s * (BQG_WORDS / 4);
-            if (j * 4 < words) reinterpret_cast<uint4 *>(bm + s * BQG_WORDS)[j] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        __syncwarp();
-        // ---- the 3x3 cell neighbourhood = three contiguous record ranges
         const float q3[3] = {qx, qy, qz};
+        const bool qfin = fabsf(qx) <= 3.0e38f && fabsf(qy) <= 3.0e38f && fabsf(qz) <= 3.0e38f;
         const int ca = bqg_cell_coord(q3[h.axis_a], h.min_a, h.inv_c, h.na);
         const int cb = bqg_cell_coord(q3[h.axis_b], h.min_b, h.inv_c, h.nb);
-        // a query with a non-finite coordinate has no cell: it scans everything (its NaN distances hit in the plain query)
-        const bool qfin = fabsf(qx) <= 3.0e38f && fabsf(qy) <= 3.0e38f && fabsf(qz) <= 3.0e38f;
-        const int a_lo = !qfin ? 0 : (ca > 0 ? ca - 1 : 0), a_hi = !qfin ? h.na - 1 : (ca + 1 < h.na ? ca + 1 : h.na - 1);
-        const int b_lo = !qfin ? 0 : (cb > 0 ? cb - 1 : 0), b_hi = !qfin ? h.nb - 1 : (cb + 1 < h.nb ? cb + 1 : h.nb - 1);
-        for (int rb = b_lo; rb <= b_hi; rb++) {
-            const int j0 = cell_start[rb * h.na + a_lo], j1 = cell_start[rb * h.na + a_hi + 1];
-            for (int j = j0 + lane; j < j1; j += 32) {
+        const int a_lo = ca > 0 ? ca - 1 : 0, a_hi = ca + 1 < h.na ? ca + 1 : h.na - 1;
+        const int b_lo = cb > 0 ? cb - 1 : 0, b_hi = cb + 1 < h.nb ? cb + 1 : h.nb - 1;
+        // population of the 3x3 cell neighbourhood (three contiguous record ranges)
+        int j0r[3], j1r[3], ncand = 0;
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++) {
+            const int rb = b_lo + rr;
+            j0r[rr] = rb <= b_hi ? cell_start[rb * h.na + a_lo] : 0;
+            j1r[rr] = rb <= b_hi ? cell_start[rb * h.na + a_hi + 1] : 0;
+            ncand += j1r[rr] - j0r[rr];
+        }
+        if (!qfin || ncand * 8 > n) {
+            // ---- DENSE neighbourhood (or a query with a non-finite coordinate, whose NaN distances hit everywhere in the
+            // plain query): culling buys nothing, and a dense ball fills its nsample slots within the first few hundred
+            // candidates -- scan in index order and stop as soon as every shell is full, like the reference does.
+            int cnt[NS], first[NS];
+#pragma unroll
+            for (int s = 0; s < NS; s++) { cnt[s] = 0; first[s] = 0; }
+            for (int k0 = 0; k0 < n; k0 += 32) {
+                bool all_full = true;
+#pragma unroll
+                for (int s = 0; s < NS; s++) all_full = all_full && cnt[s] >= p.nsample[s];
+                if (all_full) break;
+                const int k = k0 + lane;
+                const bool in = k < n;
+                const float cx = in ? __ldg(cand + 3 * k) : 0.0f, cy = in ? __ldg(cand + 3 * k + 1) : 0.0f, cz = in ? __ldg(cand + 3 * k + 2) : 0.0f;
+                const float dx = qx - cx, dy = qy - cy, dz = qz - cz;
+                float t = __fmul_rn(dy, dy);
+                t = __fmaf_rn(dx, dx, t);
+                t = __fmaf_rn(dz, dz, t);
+#pragma unroll
+                for (int s = 0; s < NS; s++) {
+                    const bool hit = in && (DILATED ? (t == 0.0f || (t >= p.t_lo[s] && t < p.t_hi[s])) : !(t >= p.t_hi[s]));
+                    const uint32_t hs = __ballot_sync(0xffffffffu, hit);
+                    const int ns = p.nsample[s], c0 = cnt[s];
+                    if (hs != 0u && c0 < ns) {
+                        int *dst = p.idx[s] + ((size_t)scene * m + qi) * ns;
+                        const int pos = c0 + __popc(hs & ((1u << lane) - 1u));
+                        if (hit && pos < ns) dst[pos] = k;
+                        if (c0 == 0) first[s] = k0 + __ffs(hs) - 1;
+                        cnt[s] = min(ns, c0 + __popc(hs));
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                const int ns = p.nsample[s], c = cnt[s];
+                int *dst = p.idx[s] + ((size_t)scene * m + qi) * ns;
+                for (int l = c + lane; l < ns; l += 32) dst[l] = first[s];   // back-fill (zeros for an empty ball)
+                if (lane == 0) p.cnt[s][(size_t)scene * m + qi] = c;
+            }
+            continue;
+        }
+        // ---- SPARSE neighbourhood: mark the hits of the three record ranges in the per-shell index bitmaps
+        for (int w = lane; w * 4 < NS * BQG_WORDS_P; w += 32) {
+            const int s = (w * 4) / BQG_WORDS_P, j = w * 4 - s * BQG_WORDS_P;
+            if (j < words_p) reinterpret_cast<uint4 *>(bm)[w] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++) {
+            for (int j = j0r[rr] + lane; j < j1r[rr]; j += 32) {
                 const float4 c = __ldg(rec + j);
                 // the reference's contracted recipe: t = dy*dy ; t = fma(dx,dx,t) ; t = fma(dz,dz,t)   (query - candidate)
                 const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
@@ -230,25 +291,23 @@ ball_query_grid_kernel(const float *__restrict__ xyz2, const uint8_t *__restrict
                 const bool near = DILATED ? (t < p.t_max) : !(t >= p.t_max);
                 if (near) {
                     const int k = __float_as_int(c.w);
+                    const int wi = k >> 5;
 #pragma unroll
                     for (int s = 0; s < NS; s++) {
                         const bool hit = DILATED ? (t == 0.0f || (t >= p.t_lo[s] && t < p.t_hi[s])) : !(t >= p.t_hi[s]);
-                        if (hit) atomicOr(bm + s * BQG_WORDS + (k >> 5), 1u << (k & 31));
+                        if (hit) atomicOr(bm + s * BQG_WORDS_P + wi + (wi >> lg), 1u << (k & 31));
                     }
                 }
             }
         }
         __syncwarp();
-        // ---- read the bitmaps back in index order: lane L owns words [L*wpl, (L+1)*wpl)
+        // ---- read the bitmaps back in index order: lane L owns words [L*wpl, (L+1)*wpl), stored from L*(wpl+1)
 #pragma unroll
         for (int s = 0; s < NS; s++) {
-            const uint32_t *b = bm + s * BQG_WORDS;
+            const uint32_t *b = bm + s * BQG_WORDS_P + lane * (wpl + 1);
             const int ns = p.nsample[s];
             int mine = 0;
-            for (int w = 0; w < wpl; w++) {
-                const int wi = lane * wpl + w;
-                mine += wi < words ? __popc(b[wi]) : 0;
-            }
+            for (int w = 0; w < wpl; w++) mine += __popc(b[w]);            // words beyond `words` were cleared and never set
             int incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -259,16 +318,14 @@ ball_query_grid_kernel(const float *__restrict__ xyz2, const uint8_t *__restrict
             const int c = total < ns ? total : ns;
             int pos = incl - mine;                                         // hits before this lane's words
             int *dst = p.idx[s] + ((size_t)scene * m + qi) * ns;
-            // first hit (for the back-fill): the lowest set bit of the whole bitmap
-            int first = 0x7fffffff;
+            int first = 0x7fffffff;                                        // lowest set bit of the whole bitmap (back-fill)
             if (mine > 0 && pos < ns) {
                 for (int w = 0; w < wpl && pos < ns; w++) {
-                    const int wi = lane * wpl + w;
-                    uint32_t bits = wi < words ? b[wi] : 0u;
+                    uint32_t bits = b[w];
                     while (bits != 0u && pos < ns) {
                         const int bit = __ffs(bits) - 1;
                         bits &= bits - 1u;
-                        const int k = wi * 32 + bit;
+                        const int k = (lane * wpl + w) * 32 + bit;
                         if (pos == 0) first = k;
                         dst[pos++] = k;
                     }
@@ -286,15 +343,18 @@ ball_query_grid_kernel(const float *__restrict__ xyz2, const uint8_t *__restrict
 float bq_sq_threshold(float r);   // ball_query.cu
 
 template <int NS>
-static void launch_bqg(bool dilated, dim3 grid, size_t smem, cudaStream_t st, const float *xyz2, const uint8_t *ws, const BqgParams &p)
+static cudaError_t launch_bqg(bool dilated, dim3 grid, size_t smem, cudaStream_t st, const float *xyz1, const float *xyz2,
+                              const uint8_t *ws, const BqgParams &p)
 {
+    cudaError_t e;
     if (dilated) {
-        cudaFuncSetAttribute((const void *)ball_query_grid_kernel<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ball_query_grid_kernel<NS, true><<<grid, BQG_THREADS, smem, st>>>(xyz2, ws, p);
+        e = cudaFuncSetAttribute((const void *)ball_query_grid_kernel<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) ball_query_grid_kernel<NS, true><<<grid, BQG_THREADS, smem, st>>>(xyz1, xyz2, ws, p);
     } else {
-        cudaFuncSetAttribute((const void *)ball_query_grid_kernel<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ball_query_grid_kernel<NS, false><<<grid, BQG_THREADS, smem, st>>>(xyz2, ws, p);
+        e = cudaFuncSetAttribute((const void *)ball_query_grid_kernel<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) ball_query_grid_kernel<NS, false><<<grid, BQG_THREADS, smem, st>>>(xyz1, xyz2, ws, p);
     }
+    return e;
 }
 
 }  // namespace ssd3d
@@ -344,13 +404,15 @@ extern "C" int ssd3d_query_ball_point_multi_ws(int b, int n, int m, int nqueries
     bq_grid_build_kernel<<<b, BQG_BUILD_T, 0, st>>>(n, rmax, xyz1, (uint8_t *)workspace);
     int rc = cuda_status(cudaGetLastError(), "bq_grid_build_kernel");
     if (rc) return rc;
-    const size_t smem = (size_t)BQG_WARPS * nqueries * BQG_WORDS * 4;
+    const size_t smem = (size_t)BQG_WARPS * nqueries * BQG_WORDS_P * 4;
     dim3 grid((unsigned)ceil_div(m, BQG_WARPS * BQG_QPW), (unsigned)b);
+    cudaError_t e;
     switch (nqueries) {
-        case 1: launch_bqg<1>(dilated != 0, grid, smem, st, xyz2, (const uint8_t *)workspace, p); break;
-        case 2: launch_bqg<2>(dilated != 0, grid, smem, st, xyz2, (const uint8_t *)workspace, p); break;
-        case 3: launch_bqg<3>(dilated != 0, grid, smem, st, xyz2, (const uint8_t *)workspace, p); break;
-        default: launch_bqg<4>(dilated != 0, grid, smem, st, xyz2, (const uint8_t *)workspace, p); break;
+        case 1: e = launch_bqg<1>(dilated != 0, grid, smem, st, xyz1, xyz2, (const uint8_t *)workspace, p); break;
+        case 2: e = launch_bqg<2>(dilated != 0, grid, smem, st, xyz1, xyz2, (const uint8_t *)workspace, p); break;
+        case 3: e = launch_bqg<3>(dilated != 0, grid, smem, st, xyz1, xyz2, (const uint8_t *)workspace, p); break;
+        default: e = launch_bqg<4>(dilated != 0, grid, smem, st, xyz1, xyz2, (const uint8_t *)workspace, p); break;
     }
+    if (e != cudaSuccess) return cuda_status(e, "ball_query_grid_kernel shared-memory opt-in");
     SSD3D_LAUNCH_CHECK("ball_query_grid_kernel");
 }
