@@ -33,8 +33,9 @@ namespace ssd3d {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int TC_PROD_WARP0 = 2;          // warps 2..5: A-operand producers of the gather mode (one tile row per thread)
-constexpr int TC_PROD_WARPS = 4;
+constexpr int TC_PROD_WARP0 = 2;          // warps 2..9: A-operand producers of the gather modes: two threads per tile row, each
+constexpr int TC_PROD_WARPS = 8;          // builds 4 of the 8 16-byte chunks of a k-block (round 2: with 4 warps the producers
+                                          // were busy 50% of the kernel while the MMA warp waited for them 35% of it)
 constexpr int TC_EPI_WARP0 = TC_PROD_WARP0 + TC_PROD_WARPS;   // warps 6..13: epilogue (warp%4 selects the TMEM lane quarter)
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARP0 + TC_EPI_WARPS) * 32;
@@ -336,7 +337,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
         // values are split into bf16 hi/lo and stored as 16-byte chunks in the K-major SWIZZLE_128B layout the UMMA
         // descriptor expects.
         if (p.gather) {
-            const int r = threadIdx.x - TC_PROD_WARP0 * 32;
+            const int pt = threadIdx.x - TC_PROD_WARP0 * 32;
+            const int r = pt & (TC_BM - 1);                      // tile row
+            const int c16_0 = (pt >> 7) * 4;                     // this thread's 4 chunks of every k-block
             const uint32_t rps = (uint32_t)p.g_m * (uint32_t)p.g_ns;
             const bool hoisted = p.gather == 2;
             const int src_pitch = hoisted ? p.g_ldz : p.g_c;
@@ -360,15 +363,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                 }
                 for (int kb = 0; kb < nkb; kb++, it++) {
                     const int s = it % p.stages;
-                    float f[8][8];
+                    float f[4][8];
 #pragma unroll
-                    for (int c16 = 0; c16 < 8; c16++) {
-                        const int k0 = kb * TC_BK + c16 * 8;
+                    for (int cc = 0; cc < 4; cc++) {
+                        const int k0 = kb * TC_BK + (c16_0 + cc) * 8;
                         if (vec4 && ok && k0 + 8 <= p.g_c) {
                             const float4 u0 = __ldg(reinterpret_cast<const float4 *>(src_f + k0));
                             const float4 u1 = __ldg(reinterpret_cast<const float4 *>(src_f + k0 + 4));
-                            f[c16][0] = u0.x; f[c16][1] = u0.y; f[c16][2] = u0.z; f[c16][3] = u0.w;
-                            f[c16][4] = u1.x; f[c16][5] = u1.y; f[c16][6] = u1.z; f[c16][7] = u1.w;
+                            f[cc][0] = u0.x; f[cc][1] = u0.y; f[cc][2] = u0.z; f[cc][3] = u0.w;
+                            f[cc][4] = u1.x; f[cc][5] = u1.y; f[cc][6] = u1.z; f[cc][7] = u1.w;
                         } else {
 #pragma unroll
                             for (int e = 0; e < 8; e++) {
@@ -378,7 +381,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                                     if (k < p.g_c) val = __ldg(src_f + k);
                                     else if (!hoisted && k < p.g_c + 3) val = __ldg(src_x + (k - p.g_c)) - __ldg(ctr + (k - p.g_c));
                                 }
-                                f[c16][e] = val;
+                                f[cc][e] = val;
                             }
                         }
                     }
@@ -389,7 +392,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                     if (warp == TC_PROD_WARP0) TCP(6);
                     uint8_t *rowp = (p.astat ? smem + (size_t)kb * 2 * TC_A_BYTES : ring + (size_t)s * stage_bytes) + row_off;
 #pragma unroll
-                    for (int c16 = 0; c16 < 8; c16++) {
+                    for (int cc = 0; cc < 4; cc++) {
+                        const int c16 = c16_0 + cc;
                         const int k0 = kb * TC_BK + c16 * 8;
                         if (k0 >= p.kp) break;
                         if (hoisted) {                                   // relu(z + d . Wx'); rows beyond the tensor stay 0
@@ -398,15 +402,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                                 const float4 w0 = *reinterpret_cast<const float4 *>(s_wx + k0 + e4);
                                 const float4 w1 = *reinterpret_cast<const float4 *>(s_wx + p.kp + k0 + e4);
                                 const float4 w2 = *reinterpret_cast<const float4 *>(s_wx + 2 * p.kp + k0 + e4);
-                                f[c16][e4 + 0] = fmaxf(fmaf(dz, w2.x, fmaf(dy, w1.x, fmaf(dx, w0.x, f[c16][e4 + 0]))), 0.0f);
-                                f[c16][e4 + 1] = fmaxf(fmaf(dz, w2.y, fmaf(dy, w1.y, fmaf(dx, w0.y, f[c16][e4 + 1]))), 0.0f);
-                                f[c16][e4 + 2] = fmaxf(fmaf(dz, w2.z, fmaf(dy, w1.z, fmaf(dx, w0.z, f[c16][e4 + 2]))), 0.0f);
-                                f[c16][e4 + 3] = fmaxf(fmaf(dz, w2.w, fmaf(dy, w1.w, fmaf(dx, w0.w, f[c16][e4 + 3]))), 0.0f);
+                                f[cc][e4 + 0] = fmaxf(fmaf(dz, w2.x, fmaf(dy, w1.x, fmaf(dx, w0.x, f[cc][e4 + 0]))), 0.0f);
+                                f[cc][e4 + 1] = fmaxf(fmaf(dz, w2.y, fmaf(dy, w1.y, fmaf(dx, w0.y, f[cc][e4 + 1]))), 0.0f);
+                                f[cc][e4 + 2] = fmaxf(fmaf(dz, w2.z, fmaf(dy, w1.z, fmaf(dx, w0.z, f[cc][e4 + 2]))), 0.0f);
+                                f[cc][e4 + 3] = fmaxf(fmaf(dz, w2.w, fmaf(dy, w1.w, fmaf(dx, w0.w, f[cc][e4 + 3]))), 0.0f);
                             }
                         }
                         uint32_t hw[4], lw[4];
 #pragma unroll
-                        for (int t = 0; t < 4; t++) split_pair(f[c16][2 * t], f[c16][2 * t + 1], hw[t], lw[t]);
+                        for (int t = 0; t < 4; t++) split_pair(f[cc][2 * t], f[cc][2 * t + 1], hw[t], lw[t]);
                         const uint32_t off = (uint32_t)((c16 ^ (r & 7)) << 4);
                         *reinterpret_cast<uint4 *>(rowp + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                         *reinterpret_cast<uint4 *>(rowp + TC_A_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);

@@ -5,7 +5,8 @@ import re
 import sys
 
 
-def main(path, marker="fps3_cluster_kernel<8, 8>", which=-2):
+def main(path, marker="split_points_kernel", which=-3):
+    """One step = the launches from one `marker` kernel (the first kernel of a step) to the next."""
     rows = []
     lines = [l for l in open(path) if l.startswith('"')]
     rd = csv.reader(lines)
@@ -33,4 +34,4 @@ def main(path, marker="fps3_cluster_kernel<8, 8>", which=-2):
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:2])
+    main(sys.argv[1], *(sys.argv[2:3] or ["split_points_kernel"]), *([int(sys.argv[3])] if len(sys.argv) > 3 else []))
