@@ -23,7 +23,7 @@ class SABackbone:
 
     def __init__(self, arch=None, params=None, in_channels=_cfg.INPUT_CHANNELS - 3, device="cuda", ffps_mode="direct",
                  seed=0, mlp_mode="tc", fuse_scale=True, head=None, gather_in_kernel=True, hoist_first=2, fps_cluster=0,
-                 latency_mode=False, fps_parts=(0.34, 0.28, 0.22, 0.16)):
+                 latency_mode=False, fps_parts=(0.34, 0.28, 0.22, 0.16), fps_packet=False):
         """fps_cluster: CTAs per scene of the D-FPS kernels (0 heuristic, < 0 cap; see tf_ops.farthest_point_sample).
         latency_mode: minimise the time of ONE step instead of the throughput of many in flight -- every SA layer
         consumes its sampling in parts (pointnet_sa_module_msg `fps_parts`): a lone D-FPS (layer 1) is cut into
@@ -40,6 +40,7 @@ class SABackbone:
         self.hoist_first = hoist_first
         self.fuse_scale = fuse_scale
         self.fps_cluster = fps_cluster
+        self.fps_packet = fps_packet
         self.latency_mode = latency_mode
         self.fps_parts = fps_parts if isinstance(fps_parts, int) else list(fps_parts)
         self.head = head                      # optional head.DetectionHead: real detections instead of the stand-in block
@@ -66,7 +67,7 @@ class SABackbone:
                                              agg, params=self.params, ffps_mode=self.ffps_mode, return_debug=True,
                                              mlp_mode=self.mlp_mode, fuse_scale=self.fuse_scale,
                                              gather_in_kernel=self.gather_in_kernel, hoist_first=self.hoist_first,
-                                             fps_cluster=self.fps_cluster, fps_parts=parts)
+                                             fps_cluster=self.fps_cluster, fps_parts=parts, fps_packet=self.fps_packet)
                 xyz_list.append(r[0]); feat_list.append(r[1]); fps_list.append(r[2]); dbg.append(r[3])
             elif ltype == "Vote_Layer":
                 nx, nf, off = L.vote_layer(xyz_list[xyz_i[0]], feat_list[feat_i[0]], mlps, False, None, bn, scope,

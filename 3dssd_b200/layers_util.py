@@ -263,11 +263,14 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                            fps_sample_range_list, fps_method_list, npoint_list, former_fps_idx, use_attention, scope,
                            dilated_group, vote_ctr=None, aggregation_channel=None, debugging=False, epsilon=1e-5, *,
                            params, ffps_mode="direct", aggregation=None, return_debug=False, mlp_mode="tc",
-                           fuse_scale=True, gather_in_kernel=True, hoist_first=2, fps_cluster=0, fps_parts=None):
+                           fuse_scale=True, gather_in_kernel=True, hoist_first=2, fps_cluster=0, fps_parts=None,
+                           fps_packet=False):
     """PointNet++ SA module with multi-scale grouping; returns (new_xyz, new_points, fps_idx).
 
     Keyword extensions (none changes a result):
       fps_cluster  CTAs per scene of the D-FPS kernels (tf_ops.farthest_point_sample `cluster`);
+      fps_packet   D-FPS with the coordinates-in-packet kernel (64 KiB of shared memory per CTA instead of the whole
+                   scene: other kernels can share its SMs);
       fps_parts    latency mode.  FPS emits its samples in order, and a sample is final once its round is done, so the
                    layer consumes the sampling IN PARTS: a lone D-FPS runs as resumable launches of rounds (an int =
                    that many equal parts, or a list of fractions), a fusion-sampling layer hands over its F-FPS and
@@ -388,7 +391,8 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                                              cluster=fps_cluster)
                 parts.append((col + j0, col + j1, ev_main()))
         else:
-            tf_ops.farthest_point_sample(npoint, tmp_xyz, out=(fps_idx, col), idx_offset=lo, cluster=fps_cluster)
+            tf_ops.farthest_point_sample(npoint, tmp_xyz, out=(fps_idx, col), idx_offset=lo, cluster=fps_cluster,
+                                         packet_kernel=fps_packet)
             parts.append((col, col + npoint, ev_main() if in_parts else None))
         col += width
 

@@ -314,6 +314,7 @@ def main():
     ap.add_argument("--pipeline", type=int, default=8, help="steps in flight (independent CUDA graphs on separate streams)")
     ap.add_argument("--fps-cluster", type=int, default=None,
                     help="CTAs per scene of the D-FPS kernels: 0 heuristic, >0 exact, <0 cap; default -4 when steps are pipelined (frees SMs), else 0")
+    ap.add_argument("--fps-packet", action="store_true", help="experiment: lone D-FPS with the coordinates-in-packet kernel (small shared-memory footprint)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-scenes", type=int, default=2)
     args = ap.parse_args()
@@ -350,7 +351,8 @@ def main():
     head = pkg.DetectionHead(params=head_params, device=dev)
     mk = dict(in_channels=1, device=dev, ffps_mode=args.ffps_mode, mlp_mode=args.mlp_mode, head=head,
               gather_in_kernel=bool(args.gather_in_kernel), hoist_first=args.hoist_first)
-    net = pkg.SABackbone(arch, params, fps_cluster=args.fps_cluster, latency_mode=bool(args.no_graph and args.latency_mode), **mk)
+    net = pkg.SABackbone(arch, params, fps_cluster=args.fps_cluster, latency_mode=bool(args.no_graph and args.latency_mode),
+                         fps_packet=args.fps_packet, **mk)
     net_lat = pkg.SABackbone(arch, params, fps_cluster=0, latency_mode=True, **mk)
     pts = torch.from_numpy(pts_np).to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
