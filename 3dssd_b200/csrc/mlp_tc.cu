@@ -64,7 +64,8 @@ struct TcParams {
     // astat ("A-stationary", gather modes): the produced A tile of an m-tile (all its k-blocks) stays in shared memory
     // while the CTA sweeps that m-tile's n-tiles, so the producers build it once instead of once per n-tile; only the
     // weights travel through the ring.  Tiles are then enumerated m-major per CTA.
-    int astat;
+    int astat;       // 0: A through the ring; 1: one resident A tile; 2: TWO resident A tiles (the producers build m-tile
+                     // i+1 while the MMAs of m-tile i run -- with one buffer the two strictly alternate)
     int gather, g_n, g_c, g_m, g_ns, g_ldz;
     const float *g_xyz, *g_points, *g_new_xyz, *g_wx;
     const int *g_idx;
@@ -200,7 +201,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     // carve: [stages] x { A_hi | A_lo | B_hi | B_lo }, per-warp output blocks (4 KiB each), then scale/shift
     const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 2;
     const int nkb = (p.kp + TC_BK - 1) / TC_BK;
-    const uint32_t a_region = p.astat ? (uint32_t)nkb * 2u * TC_A_BYTES : 0u;       // [nkb] x { A_hi | A_lo }
+    const uint32_t a_tile = (uint32_t)nkb * 2u * TC_A_BYTES;                        // one resident A tile: [nkb] x { A_hi | A_lo }
+    const uint32_t a_region = (uint32_t)p.astat * a_tile;
     const uint32_t stage_bytes = (p.astat ? 0u : 2 * TC_A_BYTES) + 2 * b_bytes;     // ring stage
     const uint32_t b_off = p.astat ? 0u : 2 * TC_A_BYTES;                           // B_hi inside a stage
     // 1 KiB alignment by pointer arithmetic on the __shared__ array (an integer round-trip would demote every access
@@ -214,7 +216,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     float *s_wx = s_shift + ncov;                                        // [3][kp] (hoisted mode only)
 
     __shared__ unsigned long long full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tfull_bar[2], tempty_bar[2];
-    __shared__ unsigned long long afull_bar[TC_MAX_AKB], aempty_bar[TC_MAX_AKB];
+    __shared__ unsigned long long afull_bar[2 * TC_MAX_AKB], aempty_bar[2 * TC_MAX_AKB];   // [A buffer][k-block]
     __shared__ uint32_t tmem_base_smem;
     __shared__ float pool_xs[2 * 4 * 32];
 
@@ -235,7 +237,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     if (threadIdx.x == 0) {
         // full barrier: the TMA thread's expect_tx arrival (+ one arrival per producer warp in gather mode)
         for (int s = 0; s < p.stages; s++) { mbar_init(smem_u32(&full_bar[s]), (p.gather && !p.astat) ? 1 + TC_PROD_WARPS : 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-        for (int k = 0; k < TC_MAX_AKB; k++) { mbar_init(smem_u32(&afull_bar[k]), TC_PROD_WARPS); mbar_init(smem_u32(&aempty_bar[k]), 1); }
+        for (int k = 0; k < 2 * TC_MAX_AKB; k++) { mbar_init(smem_u32(&afull_bar[k]), TC_PROD_WARPS); mbar_init(smem_u32(&aempty_bar[k]), 1); }
         for (int a = 0; a < 2; a++) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -304,13 +306,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                 for (int kb = 0; kb < nkb; kb++, it++) {
                     const int s = it % p.stages;
                     TCP(5);
-                    if (p.astat && nt == 0) mbar_wait_cta(smem_u32(&afull_bar[kb]), (uint32_t)mi & 1u);   // this m-tile's A k-block
+                    const int ab = p.astat == 2 ? (mi & 1) : 0;                 // resident A buffer of this m-tile
+                    const uint32_t aph = (uint32_t)(p.astat == 2 ? (mi >> 1) : mi) & 1u;   // how often it has been used before
+                    if (p.astat && nt == 0) mbar_wait_cta(smem_u32(&afull_bar[ab * TC_MAX_AKB + kb]), aph);   // this m-tile's A k-block
                     TCP(2);
                     mbar_wait_cta(smem_u32(&full_bar[s]), (uint32_t)(it / p.stages) & 1u);
                     TCP(3);
                     tc_fence_after();
                     const uint32_t base = smem_u32(ring + (size_t)s * stage_bytes);
-                    const uint32_t abase = p.astat ? smem_u32(smem) + (uint32_t)kb * 2u * TC_A_BYTES : base;
+                    const uint32_t abase = p.astat ? smem_u32(smem) + (uint32_t)ab * a_tile + (uint32_t)kb * 2u * TC_A_BYTES : base;
                     const int ksteps = min(TC_BK, p.kp - kb * TC_BK) / 16;
                     const uint64_t a_hi = umma_desc(abase), a_lo = umma_desc(abase + TC_A_BYTES);
                     const uint64_t b_hi = umma_desc(base + b_off), b_lo = umma_desc(base + b_off + b_bytes);
@@ -322,7 +326,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                             umma_bf16(d_tmem, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
                         }
                         umma_commit(smem_u32(&empty_bar[s]));   // ring stage free once these MMAs retire
-                        if (p.astat && last_nt) umma_commit(smem_u32(&aempty_bar[kb]));   // A k-block free for the next m-tile
+                        if (p.astat && last_nt) umma_commit(smem_u32(&aempty_bar[ab * TC_MAX_AKB + kb]));   // A k-block free again
                     }
                     __syncwarp();
                 }
@@ -387,10 +391,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                     }
                     // (loads already in flight) wait for the slot: ring stage, or this k-block of the resident A tile
                     if (warp == TC_PROD_WARP0) TCP(7);
-                    if (p.astat) mbar_wait_cta(smem_u32(&aempty_bar[kb]), ((uint32_t)mi & 1u) ^ 1u);
+                    const int ab = p.astat == 2 ? (mi & 1) : 0;
+                    const uint32_t aph = (uint32_t)(p.astat == 2 ? (mi >> 1) : mi) & 1u;
+                    if (p.astat) mbar_wait_cta(smem_u32(&aempty_bar[ab * TC_MAX_AKB + kb]), aph ^ 1u);
                     else mbar_wait_cta(smem_u32(&empty_bar[s]), ((uint32_t)(it / p.stages) & 1u) ^ 1u);
                     if (warp == TC_PROD_WARP0) TCP(6);
-                    uint8_t *rowp = (p.astat ? smem + (size_t)kb * 2 * TC_A_BYTES : ring + (size_t)s * stage_bytes) + row_off;
+                    uint8_t *rowp = (p.astat ? smem + (size_t)ab * a_tile + (size_t)kb * 2 * TC_A_BYTES : ring + (size_t)s * stage_bytes) + row_off;
 #pragma unroll
                     for (int cc = 0; cc < 4; cc++) {
                         const int c16 = c16_0 + cc;
@@ -417,7 +423,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                     }
                     fence_async_smem();                                   // generic-proxy stores -> visible to the tensor core
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(p.astat ? &afull_bar[kb] : &full_bar[s]));
+                    if (lane == 0) mbar_arrive(smem_u32(p.astat ? &afull_bar[ab * TC_MAX_AKB + kb] : &full_bar[s]));
                 }
                 mi++;
             }
@@ -799,12 +805,28 @@ static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const vo
     int bn = 0, stages = 0;
     p.astat = 0;
     if (g && nkb <= TC_MAX_AKB) {
-        const size_t a_region = (size_t)nkb * 2 * TC_A_BYTES;
+        const size_t a_tile = (size_t)nkb * 2 * TC_A_BYTES;
+        // First choice: TWO resident A tiles, so that producing m-tile i+1 overlaps the MMAs of m-tile i (with one tile the
+        // two alternate: measured 50% producer-busy / 20% tensor-busy on the layer-3 shapes).  The second tile is paid for
+        // with the per-warp TMA store blocks: split outputs then leave as direct 16-byte stores.
+        if (pool <= 1 && want_split && !want_f32) {
+            const bool saved = tma_store;
+            tma_store = false;
+            const int b = ncover < 128 ? ncover : 128;
+            const size_t need = 2 * a_tile + misc_bytes(b);
+            if (need + 2 * (size_t)(2 * b * TC_BK * 2) <= budget) {
+                bn = b;
+                stages = (int)((budget - need) / (size_t)(2 * b * TC_BK * 2));
+                p.astat = 2;
+            } else {
+                tma_store = saved;
+            }
+        }
         const int cands[4] = {256, 128, 96, 64};            // widest tile first: a tcgen05.mma has a fixed cost per instruction
         for (int ci = tma_store ? 1 : 0; ci < 4 && !bn; ci++) {
             const int cand = cands[ci];
             const int b = ncover < cand ? ncover : cand;
-            const size_t need = a_region + misc_bytes(b);
+            const size_t need = a_tile + misc_bytes(b);
             if (need + 2 * (size_t)(2 * b * TC_BK * 2) <= budget) {
                 bn = b;
                 stages = (int)((budget - need) / (size_t)(2 * b * TC_BK * 2));
@@ -812,6 +834,7 @@ static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const vo
             }
         }
     }
+    p.tma_store = tma_store ? 1 : 0;
     if (!bn) {
         const int bn_cap = tma_store ? 128 : 256;
         bn = ncover < bn_cap ? ncover : bn_cap;
@@ -821,7 +844,7 @@ static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const vo
     p.n_tiles = (ncover + p.bn - 1) / p.bn;
     p.m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
     const size_t stage_bytes = (p.astat ? 0 : 2 * (size_t)TC_A_BYTES) + 2 * (size_t)p.bn * TC_BK * 2;
-    const size_t pool_bytes = misc_bytes(p.bn) + (p.astat ? (size_t)nkb * 2 * TC_A_BYTES : 0);
+    const size_t pool_bytes = misc_bytes(p.bn) + (size_t)p.astat * nkb * 2 * TC_A_BYTES;
     SSD3D_REQUIRE((size_t)p.n_tiles * p.bn <= 4096, "linear_tc: n=%d too wide for the staged scale/shift", n);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     SSD3D_REQUIRE(stages >= 2, "linear_tc: tile does not fit shared memory");
