@@ -307,7 +307,12 @@ ball_query_grid_kernel(const float *__restrict__ xyz1, const float *__restrict__
             const uint32_t *b = bm + s * BQG_WORDS_P + lane * (wpl + 1);
             const int ns = p.nsample[s];
             int mine = 0;
-            for (int w = 0; w < wpl; w++) mine += __popc(b[w]);            // words beyond `words` were cleared and never set
+            uint32_t nz = 0u;                                              // which of this lane's words hold hits
+            for (int w = 0; w < wpl; w++) {
+                const uint32_t bits = b[w];                                // words beyond `words` were cleared and never set
+                mine += __popc(bits);
+                nz |= (bits != 0u ? 1u : 0u) << w;
+            }
             int incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -319,16 +324,18 @@ ball_query_grid_kernel(const float *__restrict__ xyz1, const float *__restrict__
             int pos = incl - mine;                                         // hits before this lane's words
             int *dst = p.idx[s] + ((size_t)scene * m + qi) * ns;
             int first = 0x7fffffff;                                        // lowest set bit of the whole bitmap (back-fill)
-            if (mine > 0 && pos < ns) {
-                for (int w = 0; w < wpl && pos < ns; w++) {
-                    uint32_t bits = b[w];
-                    while (bits != 0u && pos < ns) {
-                        const int bit = __ffs(bits) - 1;
-                        bits &= bits - 1u;
-                        const int k = (lane * wpl + w) * 32 + bit;
-                        if (pos == 0) first = k;
-                        dst[pos++] = k;
-                    }
+            // only the lanes that hold hits walk, and only over their non-empty words (the first version walked all 16
+            // words of a lane: 70% of the kernel's instructions)
+            while (nz != 0u && pos < ns) {
+                const int w = __ffs(nz) - 1;
+                nz &= nz - 1u;
+                uint32_t bits = b[w];
+                while (bits != 0u && pos < ns) {
+                    const int bit = __ffs(bits) - 1;
+                    bits &= bits - 1u;
+                    const int k = (lane * wpl + w) * 32 + bit;
+                    if (pos == 0) first = k;
+                    dst[pos++] = k;
                 }
             }
             first = __reduce_min_sync(0xffffffffu, first);
