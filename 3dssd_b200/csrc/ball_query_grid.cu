@@ -39,6 +39,7 @@ struct BqgHeader {
     int na, nb, axis_a, axis_b, pad;
 };
 static_assert(sizeof(BqgHeader) == 32, "header is two 16-byte pieces");
+struct BqgCounters { int *ptr[BQG_MAX_SHELLS]; };   // unit-list counters the build kernel resets (see BqgParams::units)
 
 __host__ __device__ inline size_t bqg_scene_bytes(int n)
 {
@@ -55,8 +56,9 @@ __device__ __forceinline__ int bqg_cell_coord(float v, float mn, float inv_c, in
 }
 
 __global__ void __launch_bounds__(BQG_BUILD_T, 1)
-bq_grid_build_kernel(int n, float r_max, const float *__restrict__ xyz, uint8_t *__restrict__ ws)
+bq_grid_build_kernel(int n, float r_max, const float *__restrict__ xyz, uint8_t *__restrict__ ws, const BqgCounters zero)
 {
+    if (blockIdx.x == 0 && threadIdx.x < BQG_MAX_SHELLS && zero.ptr[threadIdx.x] != nullptr) *zero.ptr[threadIdx.x] = 0;
     __shared__ int counts[BQG_MAX_CELLS + 1];
     __shared__ float red[6][32];
     __shared__ int s_bad, s_scan[32];
@@ -182,12 +184,24 @@ struct BqgParams {
     float t_max;
     int *idx[BQG_MAX_SHELLS];
     int *cnt[BQG_MAX_SHELLS];
+    // optional per-shell UNIT LISTS for the grouped MLP (include/ssd3d.h, ssd3d_query_ball_point_multi_ws): units[s][0] counts
+    // the units, units[s][1 + u] = (group << 4) | j names rows 8j .. 8j+7 of that group's neighbour list.  A group with cnt
+    // hits gets ceil(cnt / 8) units: the slots beyond cnt repeat the first hit and cannot change a max-pool.
+    int *units[BQG_MAX_SHELLS];
 };
 
 // Bitmap word wi of a shell lives at wi + (wi >> lg): one pad word per lane chunk of 2^lg words, so that the chunks of
 // consecutive lanes start an ODD number of words apart and the per-lane sequential reads of the read-back are free of
 // bank conflicts (unpadded, 16-word chunks collide 16 ways: that alone was ~90% of the first version's run time).
 constexpr int BQG_WORDS_P = BQG_WORDS + 32;
+
+__device__ __forceinline__ void bqg_emit_units(int *units, int group, int cnt)
+{
+    if (units == nullptr || cnt <= 0) return;
+    const int nu = (cnt + 7) >> 3;
+    const int base = atomicAdd(units, nu);                 // order of the list is irrelevant: the consumer max-pools
+    for (int j = 0; j < nu; j++) units[1 + base + j] = (group << 4) | j;
+}
 
 template <int NS, bool DILATED>
 __global__ void __launch_bounds__(BQG_THREADS)
@@ -269,7 +283,10 @@ ball_query_grid_kernel(const float *__restrict__ xyz1, const float *__restrict__
                 const int ns = p.nsample[s], c = cnt[s];
                 int *dst = p.idx[s] + ((size_t)scene * m + qi) * ns;
                 for (int l = c + lane; l < ns; l += 32) dst[l] = first[s];   // back-fill (zeros for an empty ball)
-                if (lane == 0) p.cnt[s][(size_t)scene * m + qi] = c;
+                if (lane == 0) {
+                    p.cnt[s][(size_t)scene * m + qi] = c;
+                    bqg_emit_units(p.units[s], scene * m + qi, c);
+                }
             }
             continue;
         }
@@ -341,7 +358,10 @@ ball_query_grid_kernel(const float *__restrict__ xyz1, const float *__restrict__
             first = __reduce_min_sync(0xffffffffu, first);
             if (c > 0) for (int l = c + lane; l < ns; l += 32) dst[l] = first;      // tf_grouping_g.cu:245-248 back-fill
             else for (int l = lane; l < ns; l += 32) dst[l] = 0;                     // empty ball: the caller's idx * (cnt > 0)
-            if (lane == 0) p.cnt[s][(size_t)scene * m + qi] = c;
+            if (lane == 0) {
+                p.cnt[s][(size_t)scene * m + qi] = c;
+                bqg_emit_units(p.units[s], scene * m + qi, c);
+            }
         }
         __syncwarp();
     }
@@ -376,12 +396,14 @@ extern "C" size_t ssd3d_query_ball_point_workspace(int b, int n)
 
 extern "C" int ssd3d_query_ball_point_multi_ws(int b, int n, int m, int nqueries, int dilated, const float *min_radius,
                                                const float *max_radius, const int *nsample, const float *xyz1,
-                                               const float *xyz2, int *const *idx, int *const *pts_cnt, void *workspace,
-                                               size_t workspace_bytes, ssd3d_stream_t stream)
+                                               const float *xyz2, int *const *idx, int *const *pts_cnt, int *const *units,
+                                               void *workspace, size_t workspace_bytes, ssd3d_stream_t stream)
 {
-    if (workspace == nullptr || workspace_bytes == 0)
+    if (workspace == nullptr || workspace_bytes == 0) {
+        SSD3D_REQUIRE(units == nullptr, "query_ball_point: unit lists are produced by the culled kernel only (pass a workspace)");
         return ssd3d_query_ball_point_multi(b, n, m, nqueries, dilated, min_radius, max_radius, nsample, xyz1, xyz2, idx,
                                             pts_cnt, stream);
+    }
     SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0, "query_ball_point: bad shape b=%d n=%d m=%d", b, n, m);
     SSD3D_REQUIRE(n <= BQG_MAX_N, "query_ball_point (grid): n=%d exceeds %d; pass no workspace", n, BQG_MAX_N);
     SSD3D_REQUIRE(nqueries >= 1 && nqueries <= BQG_MAX_SHELLS, "query_ball_point: 1..%d radius shells per call, got %d", BQG_MAX_SHELLS, nqueries);
@@ -404,11 +426,16 @@ extern "C" int ssd3d_query_ball_point_multi_ws(int b, int n, int m, int nqueries
         rmax = fmaxf(rmax, max_radius[s]);
         p.idx[s] = idx[s];
         p.cnt[s] = pts_cnt[s];
+        p.units[s] = units ? units[s] : nullptr;
+        SSD3D_REQUIRE(!p.units[s] || nsample[s] <= 128, "query_ball_point: unit lists cover nsample <= 128");
+        SSD3D_REQUIRE(!p.units[s] || (long)b * m < (1L << 27), "query_ball_point: too many groups for a unit list");
     }
     p.t_max = tmax;
     if (b == 0 || m == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    bq_grid_build_kernel<<<b, BQG_BUILD_T, 0, st>>>(n, rmax, xyz1, (uint8_t *)workspace);
+    BqgCounters zero = {};
+    for (int s = 0; s < nqueries; s++) zero.ptr[s] = p.units[s];
+    bq_grid_build_kernel<<<b, BQG_BUILD_T, 0, st>>>(n, rmax, xyz1, (uint8_t *)workspace, zero);
     int rc = cuda_status(cudaGetLastError(), "bq_grid_build_kernel");
     if (rc) return rc;
     const size_t smem = (size_t)BQG_WARPS * nqueries * BQG_WORDS_P * 4;

@@ -26,6 +26,13 @@ __global__ void split_points_kernel(long rows, int c, const float *__restrict__ 
     }
 }
 
+__global__ void fill_zero_kernel(float4 *__restrict__ x4, long n4, float *__restrict__ tail, int ntail)
+{
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n4; e += (long)gridDim.x * blockDim.x)
+        x4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0.0f;
+}
+
 __global__ void iota_idx_kernel(int b, int m, int start, int *__restrict__ out, int ldo)
 {
     const int total = b * m;
@@ -190,4 +197,15 @@ extern "C" int ssd3d_concat_rows(int b, int parts, const float *const *src, cons
     if (b == 0 || tot == 0) return 0;
     concat_rows_kernel<<<grid_for((long)b * tot * c, 256), 256, 0, (cudaStream_t)stream>>>(b, a, out);
     SSD3D_LAUNCH_CHECK("concat_rows_kernel");
+}
+
+extern "C" int ssd3d_fill_zero(float *x, long count, ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(count >= 0, "fill_zero: negative count");
+    if (count == 0) return 0;
+    SSD3D_REQUIRE(x != nullptr && (reinterpret_cast<uintptr_t>(x) & 15u) == 0, "fill_zero: pointer must be non-null and 16-byte aligned");
+    const long n4 = count / 4;
+    fill_zero_kernel<<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4 *>(x), n4, x + n4 * 4,
+                                                                                       (int)(count - n4 * 4));
+    SSD3D_LAUNCH_CHECK("fill_zero_kernel");
 }

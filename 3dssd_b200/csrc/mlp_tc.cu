@@ -806,10 +806,13 @@ static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const vo
     p.astat = 0;
     if (g && nkb <= TC_MAX_AKB) {
         const size_t a_tile = (size_t)nkb * 2 * TC_A_BYTES;
-        // First choice: TWO resident A tiles, so that producing m-tile i+1 overlaps the MMAs of m-tile i (with one tile the
-        // two alternate: measured 50% producer-busy / 20% tensor-busy on the layer-3 shapes).  The second tile is paid for
-        // with the per-warp TMA store blocks: split outputs then leave as direct 16-byte stores.
-        if (pool <= 1 && want_split && !want_f32) {
+        // TWO resident A tiles would let the producers build m-tile i+1 while the MMAs of m-tile i run (with one tile the two
+        // alternate).  The second tile has to be paid for with the per-warp TMA store blocks -- split outputs then leave as
+        // direct 16-byte stores -- and that trade LOSES on the layer-3 shapes: 33 / 43 / 47 us with one tile + TMA stores vs
+        // 57 / 71 / 80 us with two tiles + direct stores (round 2, profiles/r02_bench_1gpu_run4_two_a_tiles.json).  The kernel
+        // keeps the capability (TcParams::astat == 2); the planner does not choose it.
+        constexpr bool kTwoATiles = false;
+        if (kTwoATiles && pool <= 1 && want_split && !want_f32) {
             const bool saved = tma_store;
             tma_store = false;
             const int b = ncover < 128 ? ncover : 128;

@@ -38,6 +38,10 @@ struct SfParams {
     int tiles;
     const float *xyz, *points, *new_xyz;
     const int *idx, *cnt;
+    // unit list (ssd3d_query_ball_point_multi_ws): when set, a tile is 16 UNITS of 8 rows -- units[1 + u] = (group << 4) | j
+    // names rows 8j..8j+7 of neighbour list `group` -- instead of 128 consecutive rows, units[0] is their number, and the
+    // pooled result is combined across the units of a group with atomicMax on the (non-negative) fp32 output
+    const int *units;
     // hoisted first conv (see ssd3d_linear_tc_hoisted in include/ssd3d.h): `points` is the per-point table z (row pitch
     // ldz, c = its width n1), the operand row is relu(z[idx] + (xyz[idx] - new_xyz) . wx) with wx = [3][c], and the
     // stack starts at the scale's SECOND conv (K = c, no xyz columns appended)
@@ -260,6 +264,26 @@ __device__ __forceinline__ void sf_pool_store(const SfParams &p, float (&v)[32],
     }
 }
 
+// Unit-list mode: a unit is 8 rows = 8 consecutive lanes.  Max over the unit, then atomicMax into out[group]: post-ReLU
+// values are >= 0, where the unsigned order of the bit patterns is the float order (a -0.0 is folded to +0.0), and the
+// caller zero-fills the output, which is also the result of a group without hits (the mask of layers_util.py:180).
+template <bool AFTER>
+__device__ __forceinline__ void sf_pool_atomic8(const SfParams &p, float (&v)[32], int lane, int col0, int nout, const float *sc,
+                                                const float *sh, int group, bool ok)
+{
+    warp_colmax_transpose<8>(v, lane);                    // lane owns columns (lane % 8) * 4 + k of its unit in v[k]
+    if (!ok) return;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int cc = (lane & 7) * 4 + k;
+        const int col = col0 + cc;
+        if (col >= nout) continue;
+        float mx = v[k];
+        if (AFTER) mx = fmaxf(fmaf(mx, sc[col0 + cc], sh[col0 + cc]), 0.0f);
+        atomicMax(reinterpret_cast<unsigned int *>(p.out_f32 + (size_t)group * p.ld_f32 + col), __float_as_uint(mx) & 0x7fffffffu);
+    }
+}
+
 // SLOTS tiles in flight per CTA, WG warpgroups (128 threads) working on each: the warpgroups of a slot split the
 // 16-byte chunks of the gather and the 32-column chunks of every epilogue between them.  C: shape policy (above).
 template <class C, int SLOTS, int WG>
@@ -332,20 +356,41 @@ sa_fused_kernel(const SfParams p)
     const bool vec = (cfg.c() & 3) == 0 && (pitch & 3) == 0; // source rows are 16-byte aligned: float4 gathers
 
     const int tile0 = blockIdx.x * SLOTS + slot, tstep = gridDim.x * SLOTS;
-    // neighbour index of this thread's row, fetched one tile ahead (rows < 2^31: checked by the launcher)
-    int a_next = (tile0 < p.tiles && (long)tile0 * 128 + r < p.rows) ? __ldg(p.idx + (size_t)tile0 * 128u + r) : 0;
-    for (int tile = tile0; tile < p.tiles; tile += tstep) {
+    const int *units = p.units;
+    __builtin_assume(units == nullptr || __isGlobal(units));
+    const bool compact = units != nullptr;
+    const int nunits = compact ? __ldg(units) : 0;
+    const int tiles = compact ? (nunits + 15) >> 4 : p.tiles;
+    // neighbour index (and, in unit-list mode, unit descriptor) of this thread's row, fetched one tile ahead
+    // (rows < 2^31: checked by the launcher)
+    auto fetch = [&](int t, int &desc, int &a) {
+        desc = -1; a = 0;
+        if (t >= tiles) return;
+        if (compact) {
+            const int ui = t * 16 + (r >> 3);
+            if (ui < nunits) {
+                desc = __ldg(units + 1 + ui);
+                a = __ldg(p.idx + (size_t)(desc >> 4) * (uint32_t)cfg.ns() + (uint32_t)(((desc & 15) << 3) + (r & 7)));
+            }
+        } else if ((long)t * 128 + r < p.rows) {
+            desc = 0;
+            a = __ldg(p.idx + (size_t)t * 128u + r);
+        }
+    };
+    int d_next, a_next;
+    fetch(tile0, d_next, a_next);
+    int my_group = 0;                                                  // unit-list mode: the group this thread's row belongs to
+    bool my_ok = false;
+    for (int tile = tile0; tile < tiles; tile += tstep) {
         // ---- gather + centre-subtract + concat + split -> buf (layers_util.py:157-165)
         {
             const uint32_t row = (uint32_t)tile * 128u + (uint32_t)r;
-            const bool ok = (long)row < p.rows;
-            const uint32_t qi = ok ? row / (uint32_t)cfg.ns() : 0u;    // == scene*m + query
+            const bool ok = d_next >= 0;
+            const uint32_t qi = !ok ? 0u : (compact ? (uint32_t)(d_next >> 4) : row / (uint32_t)cfg.ns());    // == scene*m + query
             const uint32_t scene = qi / (uint32_t)p.m;
             const int a = a_next;
-            {
-                const long nrow = (long)(tile + tstep) * 128 + r;
-                a_next = (tile + tstep < p.tiles && nrow < p.rows) ? __ldg(p.idx + nrow) : 0;
-            }
+            my_group = (int)qi; my_ok = ok;
+            fetch(tile + tstep, d_next, a_next);
             const float *src_f = p.points + ((size_t)scene * p.n + a) * pitch;
             const float *src_x = p.xyz + ((size_t)scene * p.n + a) * 3;
             const float *ctr = p.new_xyz + (size_t)qi * 3;
@@ -503,6 +548,9 @@ sa_fused_kernel(const SfParams p)
                         *reinterpret_cast<uint4 *>(buf + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                         *reinterpret_cast<uint4 *>(buf + off + lo_off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     }
+                } else if (compact) {
+                    if (pool_first) sf_pool_atomic8<true>(p, v, lane, c0, cfg.nout(l), sc, sh, my_group, my_ok);
+                    else sf_pool_atomic8<false>(p, v, lane, c0, cfg.nout(l), sc, sh, my_group, my_ok);
                 } else if (pool_first) {
                     switch (cfg.ns()) {
                         case 8: sf_pool_store<8, true>(p, v, lane, q, tile, c0, cfg.nout(l), xs, wg_bar, sc, sh); break;
@@ -646,7 +694,7 @@ static bool sf_launch_static(const SfParams &p, int slots, int wg, size_t smem, 
 // K-major swizzled layout (built by params.FusedStack); ss_blob: per layer { scale[sspad] | shift[sspad] }.
 // wx != NULL selects the hoisted mode: `points` is the per-point table z (pitch ldz), c its width.
 static int sa_mlp_fused_impl(int b, int n, int c, int m, int nsample, const float *xyz, const float *points, int ldz,
-                             const float *wx, const float *new_xyz, const int *idx, const int *pts_cnt, int nl,
+                             const float *wx, const float *new_xyz, const int *idx, const int *pts_cnt, const int *units, int nl,
                              const int *nout, const void *w_blob, const float *ss_blob, int last_scale_nonneg,
                              float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream)
 {
@@ -657,6 +705,7 @@ static int sa_mlp_fused_impl(int b, int n, int c, int m, int nsample, const floa
     SSD3D_REQUIRE(xyz && new_xyz && idx && w_blob && ss_blob && (points || c == 0), "sa_mlp_fused: null pointer");
     SSD3D_REQUIRE(!hoist || (c > 0 && ldz >= c), "sa_mlp_fused_hoisted: bad table shape n1=%d ldz=%d", c, ldz);
     SSD3D_REQUIRE(out_f32 || (out_hi && out_lo), "sa_mlp_fused: no output requested");
+    SSD3D_REQUIRE(!units || (out_f32 && !out_hi && !out_lo), "sa_mlp_fused: a unit list combines through atomicMax on the (zero-filled) fp32 output only");
     SSD3D_REQUIRE((reinterpret_cast<uintptr_t>(w_blob) & 15u) == 0, "sa_mlp_fused: weight blob must be 16-byte aligned");
     SSD3D_REQUIRE(!points || (c & 3) || (hoist && (ldz & 3)) || (reinterpret_cast<uintptr_t>(points) & 15u) == 0,
                   "sa_mlp_fused: points must be 16-byte aligned when c is a multiple of 4");
@@ -672,7 +721,7 @@ static int sa_mlp_fused_impl(int b, int n, int c, int m, int nsample, const floa
     if (p.rows == 0) return 0;
     SSD3D_REQUIRE(p.rows < (1L << 31) - 128, "sa_mlp_fused: too many grouped rows (%ld)", p.rows);
     p.tiles = (int)((p.rows + 127) / 128);
-    p.xyz = xyz; p.points = points; p.new_xyz = new_xyz; p.idx = idx; p.cnt = pts_cnt;
+    p.xyz = xyz; p.points = points; p.new_xyz = new_xyz; p.idx = idx; p.cnt = pts_cnt; p.units = units;
     p.hoist = hoist ? 1 : 0; p.ldz = ldz; p.wx = wx;
     p.pool_first = last_scale_nonneg ? 1 : 0;
     p.nl = nl;
@@ -737,23 +786,23 @@ static int sa_mlp_fused_impl(int b, int n, int c, int m, int nsample, const floa
 }
 
 extern "C" int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
-                                  const float *new_xyz, const int *idx, const int *pts_cnt, int nl, const int *nout,
-                                  const void *w_blob, const float *ss_blob, int last_scale_nonneg, float *out_f32, int ld_f32,
-                                  void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream)
+                                  const float *new_xyz, const int *idx, const int *pts_cnt, const int *units, int nl,
+                                  const int *nout, const void *w_blob, const float *ss_blob, int last_scale_nonneg,
+                                  float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream)
 {
-    return sa_mlp_fused_impl(b, n, c, m, nsample, xyz, points, c, nullptr, new_xyz, idx, pts_cnt, nl, nout, w_blob, ss_blob,
+    return sa_mlp_fused_impl(b, n, c, m, nsample, xyz, points, c, nullptr, new_xyz, idx, pts_cnt, units, nl, nout, w_blob, ss_blob,
                              last_scale_nonneg, out_f32, ld_f32, out_hi, out_lo, ld_split, stream);
 }
 
 // The fused SA scale with its first conv hoisted (see ssd3d_linear_tc_hoisted): z[b,n,ldz] per-point table (this scale's
 // n1 columns start at z), wx = Wx*s1 as [3][n1]; the stack (w_blob / ss_blob / nout) starts at the scale's SECOND conv.
 extern "C" int ssd3d_sa_mlp_fused_hoisted(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
-                                          const float *wx, const float *new_xyz, const int *idx, const int *pts_cnt, int nl,
-                                          const int *nout, const void *w_blob, const float *ss_blob, int last_scale_nonneg,
-                                          float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split,
-                                          ssd3d_stream_t stream)
+                                          const float *wx, const float *new_xyz, const int *idx, const int *pts_cnt,
+                                          const int *units, int nl, const int *nout, const void *w_blob, const float *ss_blob,
+                                          int last_scale_nonneg, float *out_f32, int ld_f32, void *out_hi, void *out_lo,
+                                          int ld_split, ssd3d_stream_t stream)
 {
     SSD3D_REQUIRE(z && wx, "sa_mlp_fused_hoisted: null table pointer");
-    return sa_mlp_fused_impl(b, n, n1, m, nsample, xyz, z, ldz, wx, new_xyz, idx, pts_cnt, nl, nout, w_blob, ss_blob,
+    return sa_mlp_fused_impl(b, n, n1, m, nsample, xyz, z, ldz, wx, new_xyz, idx, pts_cnt, units, nl, nout, w_blob, ss_blob,
                              last_scale_nonneg, out_f32, ld_f32, out_hi, out_lo, ld_split, stream);
 }

@@ -120,6 +120,7 @@ def _part_bounds(npoint, fps_parts):
     return [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]]
 
 
+COMPACT_GROUPS = True      # fused SA scales convolve only the 8-row units that hold distinct neighbours (tf_ops.sa_mlp_fused `units`)
 HOIST_EXPAND_MIN_K = 256   # hoisted second convs at least this wide materialise their operand (tf_ops.hoist_expand_split)
 
 
@@ -160,8 +161,14 @@ def _group_and_mlp(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, m
     bs = xyz.shape[0]
     nscale = len(radius_list)
     min_r = [0.0 if (i == 0 or not dilated_group) else radius_list[i - 1] for i in range(nscale)]   # :137-141
+    units_list = [None] * nscale
+    tc_path = (mlp_mode == "tc" and all(k in (8, 16, 32, 64, 128) for k in nsample_list) and all(m[-1] % 8 == 0 for m in mlp_list))
     if nscale <= 4:   # one pass over the candidates for all shells
-        idx_list, cnt_list = tf_ops.query_ball_point_multi(min_r, radius_list, nsample_list, xyz, new_xyz, dilated_group)
+        want_units = COMPACT_GROUPS and tc_path and any(st is not None for st in stacks)
+        res = tf_ops.query_ball_point_multi(min_r, radius_list, nsample_list, xyz, new_xyz, dilated_group, return_units=want_units)
+        idx_list, cnt_list = res[0], res[1]
+        if want_units:
+            units_list = res[2]
     else:
         idx_list, cnt_list = [], []
         for i in range(nscale):
@@ -172,16 +179,21 @@ def _group_and_mlp(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, m
             idx_list.append(a); cnt_list.append(c)
     debug["idx"].append(idx_list); debug["cnt"].append(cnt_list)
     # tensor-core path needs pooling widths the epilogue covers and 16-byte aligned column slices of the concat buffers
-    tc = (mlp_mode == "tc" and all(k in (8, 16, 32, 64, 128) for k in nsample_list)
-          and all(m[-1] % 8 == 0 for m in mlp_list))
+    tc = tc_path
     if tc:
         # tensor-core path: every scale pools straight into its slice of the concat buffer (fp32 for the
         # caller, split bf16 for the aggregation conv), activations stay split between layers
         m_q = new_xyz.shape[1]
         ctot = sum(m[-1] for m in mlp_list)
         concat = torch.empty((bs, m_q, ctot), dtype=torch.float32, device=xyz.device)
+        # unit-list mode: the fused scales combine their 8-row units with atomicMax on the ZERO-FILLED fp32 concat buffer; the
+        # split copy the aggregation conv reads is then made once, from the finished buffer
+        compact = any(units_list[i] is not None and stacks[i] is not None for i in range(nscale))
+        if compact:
+            tf_ops.fill_zero(concat)
         cat_hi = cat_lo = None
-        if use_agg:
+        split_in_epilogue = use_agg and not compact
+        if split_in_epilogue:
             ldc = tf_ops.round16(ctot)
             mk = torch.zeros if ldc != ctot else torch.empty
             cat_hi = mk((bs, m_q, ldc), dtype=torch.bfloat16, device=xyz.device)
@@ -193,20 +205,20 @@ def _group_and_mlp(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, m
             nl = len(mlp_list[i])
             stack = stacks[i]
             if stack is not None:                                              # whole scale in one kernel
+                fkw = dict(out_f32=(concat, off), out_split=(cat_hi, cat_lo, off) if split_in_epilogue else None,
+                           units=units_list[i] if compact else None)
                 if hstacks.get(i) is not None:
                     t = hscales.index(i)
-                    tf_ops.sa_mlp_fused_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, cnt, hstacks[i], out_f32=(concat, off),
-                                                out_split=(cat_hi, cat_lo, off) if use_agg else None)
+                    tf_ops.sa_mlp_fused_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, cnt, hstacks[i], **fkw)
                 else:
-                    tf_ops.sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=(concat, off),
-                                        out_split=(cat_hi, cat_lo, off) if use_agg else None)
+                    tf_ops.sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, **fkw)
                 off += mlp_list[i][-1]
                 continue
             hi = lo = None
             for j in range(nl):
                 f = pp.conv("%s/conv%d_%d" % (scope, i, j), bn)
                 last_kw = dict(pool=nsample_list[i], rowmask=cnt, out_f32=(concat, off),
-                               out_split=(cat_hi, cat_lo, off) if use_agg else None)   # :167-180 conv+BN+ReLU+max+mask
+                               out_split=(cat_hi, cat_lo, off) if split_in_epilogue else None)   # :167-180 conv+BN+ReLU+max+mask
                 if i in hscales:
                     if j == 0:
                         continue                  # folded into z and into the next conv's operand producer
@@ -240,6 +252,8 @@ def _group_and_mlp(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, m
             off += mlp_list[i][-1]
         new_points = concat
         if use_agg:                                                            # :183-185
+            if not split_in_epilogue:
+                cat_hi, cat_lo = tf_ops.split_rows(concat)
             new_points, _ = tf_ops.linear_tc(cat_hi, cat_lo, pp.conv(scope + "/ensemble", bn))
         return new_points
     outs = []

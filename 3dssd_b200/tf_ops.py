@@ -251,11 +251,13 @@ def query_ball_point_dilated(min_radius, max_radius, nsample, xyz1, xyz2):
 BQ_GRID_MIN_N = 2048     # candidate sets at least this large take the spatially culled kernel (csrc/ball_query_grid.cu)
 
 
-def query_ball_point_multi(min_radius_list, max_radius_list, nsample_list, xyz1, xyz2, dilated, grid=None):
+def query_ball_point_multi(min_radius_list, max_radius_list, nsample_list, xyz1, xyz2, dilated, grid=None, return_units=False):
     """All radius shells of one SA layer in a single pass over the candidates (B200 fast path; same results
     as calling query_ball_point[_dilated] once per shell).  Returns lists (idx_list, pts_cnt_list).
     grid: None = automatic (the culled kernel for ndataset >= BQ_GRID_MIN_N), True / False = force / forbid it;
-    the outputs are identical either way."""
+    the outputs are identical either way.
+    return_units: also return, per shell, the UNIT LIST of the grouped MLP (int32 tensor, include/ssd3d.h
+    ssd3d_query_ball_point_multi_ws) or None where the culled kernel was not used: (idx_list, pts_cnt_list, units_list)."""
     xyz1, xyz2 = _bq_shapes(xyz1, xyz2)
     nq = len(max_radius_list)
     if not (len(nsample_list) == nq and len(min_radius_list) == nq and 1 <= nq <= 4):
@@ -279,11 +281,19 @@ def query_ball_point_multi(min_radius_list, max_radius_list, nsample_list, xyz1,
     if grid and not use_grid and b and m:
         raise ValueError("the culled ball query covers ndataset <= 16384, got %d" % n)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=xyz1.device) if use_grid else None
+    units = [None] * nq
+    pu = ctypes.c_void_p(0)
+    if return_units and use_grid and all(int(k) <= 128 for k in nsample_list):
+        units = [torch.empty((1 + b * m * ((int(k) + 7) // 8),), dtype=torch.int32, device=xyz1.device) for k in nsample_list]
+        parr = (ctypes.c_void_p * nq)(*[t.data_ptr() for t in units])
+        pu = ctypes.cast(parr, ctypes.c_void_p)
     check(lib().ssd3d_query_ball_point_multi_ws(b, n, m, nq, 1 if dilated else 0, ctypes.cast(lo, ctypes.c_void_p),
                                                 ctypes.cast(hi, ctypes.c_void_p), ctypes.cast(ks, ctypes.c_void_p),
                                                 _p(xyz1), _p(xyz2), ctypes.cast(pi, ctypes.c_void_p),
-                                                ctypes.cast(pc, ctypes.c_void_p), _p(ws), ws_bytes if use_grid else 0,
+                                                ctypes.cast(pc, ctypes.c_void_p), pu, _p(ws), ws_bytes if use_grid else 0,
                                                 _stream()), "query_ball_point_multi")
+    if return_units:
+        return idx, cnt, units
     return idx, cnt
 
 
@@ -629,10 +639,23 @@ def hoist_expand_split(xyz, z, zoff, wx, new_xyz, idx):
     return hi, lo
 
 
-def sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=None, out_split=None):
+def _units_check(units, out_f32, out_split):
+    if units is None:
+        return
+    if units.dtype != torch.int32 or not units.is_cuda or not units.is_contiguous():
+        raise ValueError("units must be the int32 CUDA unit list returned by query_ball_point_multi(return_units=True)")
+    if out_f32 is None or out_split is not None:
+        raise ValueError("a unit list needs out_f32=(zero-filled buffer, col_offset) and no out_split (results combine through atomicMax)")
+
+
+def sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=None, out_split=None, units=None):
     """One SA scale in one kernel: gather + concat + conv stack + max-pool + mask (layers_util.py:157-180).
     stack: params.FusedStack.  out_f32=(buffer, col_offset) / out_split=(hi, lo, col_offset) as linear_tc;
-    without them a fresh (b, m, C3) fp32 tensor is returned."""
+    without them a fresh (b, m, C3) fp32 tensor is returned.
+    units: the scale's unit list (query_ball_point_multi(return_units=True)): only the listed 8-row units are convolved
+    -- the skipped rows repeat a group's first neighbour and cannot change the max-pool -- and results are combined with
+    atomicMax into out_f32, which must be zero-filled (fill_zero)."""
+    _units_check(units, out_f32, out_split)
     xyz = _req(xyz, "xyz", torch.float32, 3, 3)
     new_xyz = _req(new_xyz, "new_xyz", torch.float32, 3, 3)
     idx = _req(idx, "idx", torch.int32, 3)
@@ -659,15 +682,16 @@ def sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=None, out_split=
         lds, ph, pl = hb.shape[-1], hb.data_ptr() + 2 * off, lb.data_ptr() + 2 * off
     nout = (ctypes.c_int * len(stack.nout))(*stack.nout)
     vp = ctypes.c_void_p
-    check(lib().ssd3d_sa_mlp_fused(b, n, c, m, ns, _p(xyz), _p(points), _p(new_xyz), _p(idx), _p(cnt), len(stack.nout),
+    check(lib().ssd3d_sa_mlp_fused(b, n, c, m, ns, _p(xyz), _p(points), _p(new_xyz), _p(idx), _p(cnt), _p(units), len(stack.nout),
                                    ctypes.cast(nout, vp), _p(stack.w_blob), _p(stack.ss_blob), 1 if stack.last_scale_nonneg else 0,
                                    vp(pf), ldf, vp(ph), vp(pl), lds, _stream()), "sa_mlp_fused")
     return y
 
 
-def sa_mlp_fused_hoisted(xyz, z, zoff, wx, new_xyz, idx, cnt, stack, out_f32=None, out_split=None):
+def sa_mlp_fused_hoisted(xyz, z, zoff, wx, new_xyz, idx, cnt, stack, out_f32=None, out_split=None, units=None):
     """sa_mlp_fused with the scale's first conv hoisted into the per-point table z (see linear_tc_hoisted): `stack` is the
-    params.FusedStack of the REMAINING convs (its input width == wx.shape[1])."""
+    params.FusedStack of the REMAINING convs (its input width == wx.shape[1]).  units: as sa_mlp_fused."""
+    _units_check(units, out_f32, out_split)
     xyz = _req(xyz, "xyz", torch.float32, 3, 3)
     new_xyz = _req(new_xyz, "new_xyz", torch.float32, 3, 3)
     idx = _req(idx, "idx", torch.int32, 3)
@@ -696,7 +720,7 @@ def sa_mlp_fused_hoisted(xyz, z, zoff, wx, new_xyz, idx, cnt, stack, out_f32=Non
     nout = (ctypes.c_int * len(stack.nout))(*stack.nout)
     vp = ctypes.c_void_p
     check(lib().ssd3d_sa_mlp_fused_hoisted(b, n, n1, m, ns, _p(xyz), vp(z.data_ptr() + 4 * zoff), z.shape[2], _p(wx), _p(new_xyz),
-                                           _p(idx), _p(cnt), len(stack.nout), ctypes.cast(nout, vp), _p(stack.w_blob),
+                                           _p(idx), _p(cnt), _p(units), len(stack.nout), ctypes.cast(nout, vp), _p(stack.w_blob),
                                            _p(stack.ss_blob), 1 if stack.last_scale_nonneg else 0, vp(pf), ldf, vp(ph), vp(pl),
                                            lds, _stream()), "sa_mlp_fused_hoisted")
     return y
@@ -725,6 +749,14 @@ def bev_nms(boxes, scores, iou_threshold, max_output, cls_id=0, out=None):
 
 
 # ---- the small elementwise stages (csrc/misc.cu): one kernel each, so a captured step holds no framework kernels ----
+
+def fill_zero(t):
+    """t[...] = 0 for a contiguous float32 CUDA tensor, as a kernel of this library."""
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError("fill_zero takes a contiguous float32 CUDA tensor")
+    check(lib().ssd3d_fill_zero(_p(t), t.numel(), _stream()), "fill_zero")
+    return t
+
 
 def split_points(points):
     """(b, n, 3 + c) -> xyz (b, n, 3), features (b, n, c): single_stage_detector.py:116-117."""

@@ -258,9 +258,12 @@ class MlpTimer:
             return 2.0 * idx.numel() * f.kp * r16(f.cout)
         stack = a[5] if name == "sa_mlp_fused" else a[7]
         idx = a[3] if name == "sa_mlp_fused" else a[5]
+        rows = idx.numel()
+        if kw.get("units") is not None:                 # unit-list route: 128-row tiles of 16 listed 8-row units
+            rows = (int(kw["units"][0].item()) + 15) // 16 * 128
         k, tot = r16(stack.cin), 0.0
         for n in stack.nout:
-            tot += 2.0 * idx.numel() * k * r16(n)
+            tot += 2.0 * rows * k * r16(n)
             k = r16(n)
         return tot
 
@@ -274,7 +277,7 @@ class MlpTimer:
                 e0.record()
                 r = _fn(*a, **kw)
                 e1.record()
-                self.rec.append((_n, e0, e1, 3.0 * self._flops(_n, a, kw)))
+                self.rec.append((_n, e0, e1, 3.0 * self._flops(_n, a, kw)))      # (may read a unit count: after the events)
                 return r
             setattr(self.tf_ops, n, wrap)
         return self
@@ -373,7 +376,7 @@ def main():
 
         def __call__(self, *a):
             n = 1
-            if self.name == "ssd3d_query_ball_point_multi_ws" and getattr(a[12], "value", None):
+            if self.name == "ssd3d_query_ball_point_multi_ws" and getattr(a[13], "value", None):
                 n = 2                                   # culled ball query: grid build + search
             elif self.name == "ssd3d_bn_train":
                 n = 3

@@ -124,12 +124,17 @@ int ssd3d_query_ball_point_multi(int b, int n, int m, int nqueries, int dilated,
  * small kernel bins the candidates of every scene into a uniform 2-D grid with cells >= r_max, the search then visits
  * only the 3x3 cell neighbourhood of a query and restores "first nsample hits in ascending index" through a per-shell
  * bitmap over candidate indices.  Same outputs, bit for bit, non-finite coordinates included.  workspace == NULL
- * falls through to ssd3d_query_ball_point_multi. */
+ * falls through to ssd3d_query_ball_point_multi.
+ * units (optional, host array of nqueries device pointers, entries may be NULL): per-shell UNIT LISTS for the grouped MLP.
+ * units[s] holds 1 + b*m*ceil(nsample[s]/8) ints: [0] = number of units, [1 + u] = (group << 4) | j naming rows 8j..8j+7
+ * of neighbour list `group` (= scene*m + query).  A group with cnt hits gets ceil(cnt/8) units -- slots beyond cnt repeat
+ * the first hit (tf_grouping_g.cu:245-248) and cannot change the max-pool that follows (layers_util.py:178), so the
+ * grouped MLP needs only these rows (ssd3d_sa_mlp_fused*, `units`).  The list order is unspecified. */
 size_t ssd3d_query_ball_point_workspace(int b, int n);
 int ssd3d_query_ball_point_multi_ws(int b, int n, int m, int nqueries, int dilated, const float *min_radius,
                                     const float *max_radius, const int *nsample, const float *xyz1, const float *xyz2,
-                                    int *const *idx, int *const *pts_cnt, void *workspace, size_t workspace_bytes,
-                                    ssd3d_stream_t stream);
+                                    int *const *idx, int *const *pts_cnt, int *const *units, void *workspace,
+                                    size_t workspace_bytes, ssd3d_stream_t stream);
 
 /* replaces groupPointLauncher(b,n,c,m,nsample,points,idx,out)
  *   grouping/tf_grouping.cpp:446, grouping/tf_grouping_g.cu:476-479, kernel :362-379.
@@ -209,8 +214,8 @@ int ssd3d_hoist_expand_split(int b, int n, int n1, int m, int nsample, const flo
 /* Same idea for a scale that fits the fused kernel (ssd3d_sa_mlp_fused): the stack passed here starts at the scale's
  * SECOND conv, the first operand row is relu(z[idx] + (xyz[idx] - new_xyz) . wx), built during the gather. */
 int ssd3d_sa_mlp_fused_hoisted(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
-                               const float *wx, const float *new_xyz, const int *idx, const int *pts_cnt, int nl,
-                               const int *nout, const void *w_blob, const float *ss_blob, int last_scale_nonneg,
+                               const float *wx, const float *new_xyz, const int *idx, const int *pts_cnt, const int *units,
+                               int nl, const int *nout, const void *w_blob, const float *ss_blob, int last_scale_nonneg,
                                float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream);
 /* hi/lo[row, 0:kp] = split(x[row, 0:c]), zero padded (kp % 8 == 0). */
 int ssd3d_split_rows(long rows, int c, const float *x, int ldx, void *hi, void *lo, int kp, ssd3d_stream_t stream);
@@ -225,12 +230,17 @@ int ssd3d_group_concat_split(int b, int n, int c, int m, int nsample, const floa
  * (3dssd_b200/params.py: FusedStack).  Outputs as ssd3d_linear_tc with pool = nsample.
  * last_scale_nonneg != 0: the caller guarantees scale >= 0 in the LAST layer (fold the sign of a negative BatchNorm
  * gamma into that layer's weight column -- FusedStack does); the kernel then max-pools the raw accumulators and applies
- * scale / shift / ReLU to the pooled values only (exactly the same result: the affine map is monotone). */
+ * scale / shift / ReLU to the pooled values only (exactly the same result: the affine map is monotone).
+ * units != NULL: the unit list of this scale from ssd3d_query_ball_point_multi_ws.  The kernel then convolves only the
+ * listed 8-row units instead of all nsample rows of every group -- the rows it skips repeat a group's first neighbour and
+ * cannot change the max-pool -- and combines the units of a group with atomicMax on out_f32, which the caller must have
+ * ZERO-FILLED (zero is also the masked result of a group without neighbours); out_hi / out_lo must be NULL.  Identical
+ * results; the work shrinks from b*m*nsample rows to 8 * sum(ceil(cnt / 8)). */
 size_t ssd3d_sa_fused_smem(int c, int nl, const int *nout);
 int ssd3d_sa_mlp_fused(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
-                       const float *new_xyz, const int *idx, const int *pts_cnt, int nl, const int *nout,
-                       const void *w_blob, const float *ss_blob, int last_scale_nonneg, float *out_f32, int ld_f32,
-                       void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream);
+                       const float *new_xyz, const int *idx, const int *pts_cnt, const int *units, int nl,
+                       const int *nout, const void *w_blob, const float *ss_blob, int last_scale_nonneg, float *out_f32,
+                       int ld_f32, void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream);
 
 /* ---- backward operators (training graphs) ---------------------------------------------------
  * Each zero-fills its output first, as the reference's TF ops do with cudaMemset before the launcher. */
@@ -282,6 +292,8 @@ int ssd3d_bn_train(long rows, int c, const float *x, int ldx, const float *gamma
 /* points[rows, c] -> xyz[rows, 3], feat[rows, c-3]: the tf.slice pair of
  * lib/modeling/single_stage_detector.py:116-117.  feat may be NULL when c == 3. */
 int ssd3d_split_points(long rows, int c, const float *points, float *xyz, float *feat, ssd3d_stream_t stream);
+/* x[0:count] = 0 (fp32): the zero fill the unit-list mode of ssd3d_sa_mlp_fused needs, as a kernel of this library. */
+int ssd3d_fill_zero(float *x, long count, ssd3d_stream_t stream);
 /* out[s*ldo + j] = start + j, s < b, j < m: tf.tile(tf.range(npoint)) of lib/utils/layers_util.py:91-92, :100-101. */
 int ssd3d_iota_idx(int b, int m, int start, int *out, int ldo, ssd3d_stream_t stream);
 /* out[b,n,ca+cb] = concat(a[b,n,ca], bsrc[b,n,cb]) with scene strides in floats: tf.concat([xyz, points], -1) in

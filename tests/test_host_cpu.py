@@ -194,10 +194,12 @@ def test_c_abi_argument_validation_needs_no_gpu(pkg):
                                           ctypes.cast(k, ctypes.c_void_p), one, one, ctypes.cast(ptrs, ctypes.c_void_p),
                                           ctypes.cast(ptrs, ctypes.c_void_p), null) == -1 and "positive radius" in err()
     nout = (ctypes.c_int * 3)(128, 128, 256)
-    assert L.ssd3d_sa_mlp_fused(1, 64, 128, 8, 32, one, one, one, one, null, 3, ctypes.cast(nout, ctypes.c_void_p), one, one, 1,
+    assert L.ssd3d_sa_mlp_fused(1, 64, 128, 8, 32, one, one, one, one, null, null, 3, ctypes.cast(nout, ctypes.c_void_p), one, one, 1,
                                 one, 256, null, null, 0, null) == -2 and "does not fit" in err()
-    assert L.ssd3d_sa_mlp_fused(1, 64, 1, 8, 7, one, one, one, one, null, 3, ctypes.cast(nout, ctypes.c_void_p), one, one, 0,
+    assert L.ssd3d_sa_mlp_fused(1, 64, 1, 8, 7, one, one, one, one, null, null, 3, ctypes.cast(nout, ctypes.c_void_p), one, one, 0,
                                 one, 256, null, null, 0, null) == -1 and "nsample" in err()
+    assert L.ssd3d_sa_mlp_fused(1, 64, 1, 8, 32, one, one, one, one, null, one, 3, ctypes.cast(nout, ctypes.c_void_p), one, one, 0,
+                                null, 256, one, one, 256, null) == -1 and "unit list" in err()       # units need the fp32 output only
     assert L.ssd3d_linear_tc(128, 20, 16, one, one, one, one, one, one, 1, 1, null, one, 16, null, null, 0, null) == -1 and "multiple of 16" in err()
     assert L.ssd3d_version() > 0
     # the explicit-placement entry points (round 2): strides, round ranges and the cluster request are validated up front

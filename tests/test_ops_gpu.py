@@ -837,6 +837,69 @@ def test_sa_mlp_fused_hoisted_vs_oracle(pkg, oracle_ops, cuda, b, n, c, m, k, ml
     assert y.shape == (b, m, mlp[-1]) and rel_err(N(y), exp) < 1e-4
 
 
+@pytest.mark.parametrize("c,ks,mlps,hoist", [
+    (1, [32, 32, 64], [[16, 16, 32], [16, 16, 32], [32, 32, 64]], False),      # layer 1
+    (64, [32, 32, 64], [[64, 64, 128], [64, 64, 128], [64, 96, 128]], True),   # layer 2 (first conv hoisted)
+    (7, [16, 8, 128], [[48, 32], [16], [32, 32, 64]], False),                  # other group sizes
+])
+def test_sa_mlp_fused_unit_list_equals_dense(pkg, cuda, c, ks, mlps, hoist):
+    """The unit-list route (only the 8-row units holding distinct neighbours are convolved, combined by atomicMax) gives
+    the SAME BITS as the dense route: a group's skipped rows repeat its first neighbour (grouping/tf_grouping_g.cu:99-109),
+    whose activation is already inside unit 0.  Dense clusters (cnt > nsample), isolated centres (cnt = 1) and empty
+    dilated shells (cnt = 0) are all present; every third BatchNorm scale is negative."""
+    rng = np.random.default_rng(c + sum(ks))
+    b, n, m = 3, 4096, 600
+    centres = rng.uniform(0, 40, (b, 40, 3))
+    clustered = centres[np.arange(b)[:, None], rng.integers(0, 40, (b, 1500))] + rng.normal(0, 0.15, (b, 1500, 3))
+    xyz = np.concatenate([clustered, rng.uniform(0, 40, (b, n - 1500, 3))], 1).astype(np.float32)
+    perm = rng.permutation(n)
+    xyz = np.ascontiguousarray(xyz[:, perm])
+    feats = np.maximum(rng.standard_normal((b, n, c)), 0).astype(np.float32)
+    tx, tf = T(xyz, cuda), T(feats, cuda)
+    tn = tx[:, :m].contiguous()
+    lows, highs = [0.0, 0.2, 0.4], [0.2, 0.4, 0.8]
+    idxs, cnts, units = pkg.query_ball_point_multi(lows, highs, ks, tx, tn, True, grid=True, return_units=True)
+    i0, c0 = pkg.query_ball_point_multi(lows, highs, ks, tx, tn, True, grid=False)
+    P = importlib.import_module("3dssd_b200.params")
+    for s in range(3):
+        assert units[s] is not None and torch.equal(idxs[s], i0[s]) and torch.equal(cnts[s], c0[s])
+        cnt = N(cnts[s]); k = ks[s]
+        u = N(units[s]); nu = int(u[0])
+        assert nu == int(np.minimum((np.minimum(cnt, k) + 7) // 8, (k + 7) // 8)[cnt > 0].sum())   # ceil(min(cnt, K) / 8) per non-empty group
+        grp, j = u[1:1 + nu] >> 4, u[1:1 + nu] & 15
+        want = sorted((int(g), int(jj)) for g in np.flatnonzero(cnt.reshape(-1) > 0)
+                      for jj in range((min(int(cnt.reshape(-1)[g]), k) + 7) // 8))
+        assert sorted(zip(grp.tolist(), j.tolist())) == want
+        assert (cnt == 0).any() or s == 0
+        prm, scopes, cin = {}, [], c + 3
+        for jn, cout in enumerate(mlps[s]):
+            P._conv_init(rng, prm, "s/conv%d_%d" % (s, jn), cin, cout, True)
+            prm["s/conv%d_%d/bn/gamma" % (s, jn)][1::3] *= -1.0
+            scopes.append("s/conv%d_%d" % (s, jn)); cin = cout
+        pp = P.prepare(prm, cuda)
+        ld = mlps[s][-1] + 32
+        dense = torch.full((b, m, ld), -1.0, device=cuda)
+        comp = torch.full((b, m, ld), -1.0, device=cuda)
+        comp[..., 16:16 + mlps[s][-1]] = 0.0
+        if hoist:
+            zconv, wxs, n1s = pp.hoisted([scopes[0]], True, c)
+            p_hi, p_lo = pkg.split_rows(tf)
+            z, _ = pkg.linear_tc(p_hi, p_lo, zconv, relu=False, want_f32=True, want_split=False)
+            stack = pp.fused_stack(scopes[1:], True, n1s[0], limit=0)
+            assert stack is not None
+            pkg.sa_mlp_fused_hoisted(tx, z, 0, wxs[0], tn, idxs[s], cnts[s], stack, out_f32=(dense, 16))
+            pkg.sa_mlp_fused_hoisted(tx, z, 0, wxs[0], tn, idxs[s], cnts[s], stack, out_f32=(comp, 16), units=units[s])
+        else:
+            stack = pp.fused_stack(scopes, True, c + 3, limit=0)
+            assert stack is not None
+            pkg.sa_mlp_fused(tx, tf, tn, idxs[s], cnts[s], stack, out_f32=(dense, 16))
+            pkg.sa_mlp_fused(tx, tf, tn, idxs[s], cnts[s], stack, out_f32=(comp, 16), units=units[s])
+        assert torch.equal(dense, comp)
+        assert float(dense[..., 16:16 + mlps[s][-1]].abs().max()) > 0
+    with pytest.raises(ValueError):
+        pkg.sa_mlp_fused(tx, tf, tn, idxs[0], cnts[0], stack, units=units[0])          # needs the zero-filled out_f32
+
+
 # ---------------------------------------------------------------------------------------------------------
 # training-mode BatchNorm (row f3)
 # ---------------------------------------------------------------------------------------------------------

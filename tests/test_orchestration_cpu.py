@@ -63,10 +63,11 @@ def dry(monkeypatch, oracle_ops):
     def iota(b, npoint, device, *, out=None, start=0):
         return place(np.tile(np.arange(npoint, dtype=np.int32)[None], (b, 1)), out, start, b, npoint)
 
-    def bq_multi(lows, highs, ks, xyz1, xyz2, dilated, grid=None):
+    def bq_multi(lows, highs, ks, xyz1, xyz2, dilated, grid=None, return_units=False):
         res = [(o.query_ball_point_dilated(lo, hi, k, n(xyz1), n(xyz2)) if dilated else o.query_ball_point(hi, k, n(xyz1), n(xyz2)))
                for lo, hi, k in zip(lows, highs, ks)]
-        return [t(r[0]) for r in res], [t(r[1]) for r in res]
+        out = [t(r[0]) for r in res], [t(r[1]) for r in res]
+        return out + ([None] * len(ks),) if return_units else out      # no unit lists on the CPU: the dense route
 
     def group_concat(xyz, points, new_xyz, idx, ldx=None):
         g = np.concatenate([o.group_point(n(points), n(idx)), o.group_point(n(xyz), n(idx)) - n(new_xyz)[:, :, None]], -1)
@@ -143,11 +144,11 @@ def dry(monkeypatch, oracle_ops):
         y, _ = emit(x, ns, cnt if cnt is not None else None, out_f32 is None and out_split is None, False, out_f32, out_split)
         return y
 
-    def sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=None, out_split=None):
+    def sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=None, out_split=None, units=None):
         assert points.shape[-1] + 3 == stack.cin
         return fused(grouped(xyz, points, new_xyz, idx), cnt, stack, out_f32, out_split, idx.shape[-1])
 
-    def sa_mlp_fused_hoisted(xyz, z, zoff, wx, new_xyz, idx, cnt, stack, out_f32=None, out_split=None):
+    def sa_mlp_fused_hoisted(xyz, z, zoff, wx, new_xyz, idx, cnt, stack, out_f32=None, out_split=None, units=None):
         assert wx.shape[1] == stack.cin
         return fused(hoisted_operand(xyz, z, zoff, wx, new_xyz, idx), cnt, stack, out_f32, out_split, idx.shape[-1])
 
