@@ -44,6 +44,13 @@ _SIGNATURES = {
                                c_int, c_void_p],
     "ssd3d_hoist_expand_split": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_int, c_void_p],
+    "ssd3d_hoist_expand_split_units": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "ssd3d_linear_tc_units": [c_long, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                              c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    "ssd3d_linear_tc_hoisted_units": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                                      c_void_p, c_void_p, c_int, c_void_p],
     "ssd3d_split_rows": [c_long, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "ssd3d_group_concat_split": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_int, c_void_p],

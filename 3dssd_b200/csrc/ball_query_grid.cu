@@ -369,6 +369,52 @@ ball_query_grid_kernel(const float *__restrict__ xyz1, const float *__restrict__
 
 float bq_sq_threshold(float r);   // ball_query.cu
 
+// Unit lists from finished neighbour counts (the exhaustive kernel's route: small candidate sets): one CTA per shell scans
+// the groups in order -- a group with cnt hits owns ceil(cnt / 8) units -- so this list is in group order.
+constexpr int GU_THREADS = 1024;
+struct GuParams { const int *cnt[BQG_MAX_SHELLS]; int *units[BQG_MAX_SHELLS]; int nsample[BQG_MAX_SHELLS]; };
+
+__global__ void __launch_bounds__(GU_THREADS)
+group_units_kernel(int groups, const GuParams p)
+{
+    const int s = blockIdx.x;
+    int *units = p.units[s];
+    if (units == nullptr) return;
+    const int *cnt = p.cnt[s];
+    const int ns = p.nsample[s];
+    __shared__ int warp_tot[GU_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (groups + GU_THREADS - 1) / GU_THREADS;
+    const int g0 = min(groups, tid * per), g1 = min(groups, g0 + per);
+    int mine = 0;
+    for (int g = g0; g < g1; g++) mine += (min(__ldg(cnt + g), ns) + 7) >> 3;
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int t = warp_tot[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, t, d);
+            if (lane >= d) t += o;
+        }
+        warp_tot[lane] = t;                                   // inclusive totals of the warps
+    }
+    __syncthreads();
+    int pos = incl - mine + (warp > 0 ? warp_tot[warp - 1] : 0);
+    if (tid == GU_THREADS - 1) units[0] = pos + mine;
+    for (int g = g0; g < g1; g++) {
+        const int nu = (min(__ldg(cnt + g), ns) + 7) >> 3;
+        for (int j = 0; j < nu; j++) units[1 + pos + j] = (g << 4) | j;
+        pos += nu;
+    }
+}
+
 template <int NS>
 static cudaError_t launch_bqg(bool dilated, dim3 grid, size_t smem, cudaStream_t st, const float *xyz1, const float *xyz2,
                               const uint8_t *ws, const BqgParams &p)
@@ -400,9 +446,17 @@ extern "C" int ssd3d_query_ball_point_multi_ws(int b, int n, int m, int nqueries
                                                void *workspace, size_t workspace_bytes, ssd3d_stream_t stream)
 {
     if (workspace == nullptr || workspace_bytes == 0) {
-        SSD3D_REQUIRE(units == nullptr, "query_ball_point: unit lists are produced by the culled kernel only (pass a workspace)");
-        return ssd3d_query_ball_point_multi(b, n, m, nqueries, dilated, min_radius, max_radius, nsample, xyz1, xyz2, idx,
-                                            pts_cnt, stream);
+        const int rc = ssd3d_query_ball_point_multi(b, n, m, nqueries, dilated, min_radius, max_radius, nsample, xyz1, xyz2, idx,
+                                                    pts_cnt, stream);
+        if (rc || units == nullptr || b == 0 || m == 0) return rc;
+        GuParams gp = {};
+        for (int s = 0; s < nqueries; s++) {
+            gp.cnt[s] = pts_cnt[s]; gp.units[s] = units[s]; gp.nsample[s] = nsample[s];
+            SSD3D_REQUIRE(!units[s] || nsample[s] <= 128, "query_ball_point: unit lists cover nsample <= 128");
+            SSD3D_REQUIRE(!units[s] || (long)b * m < (1L << 27), "query_ball_point: too many groups for a unit list");
+        }
+        group_units_kernel<<<nqueries, GU_THREADS, 0, (cudaStream_t)stream>>>(b * m, gp);
+        SSD3D_LAUNCH_CHECK("group_units_kernel");
     }
     SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0, "query_ball_point: bad shape b=%d n=%d m=%d", b, n, m);
     SSD3D_REQUIRE(n <= BQG_MAX_N, "query_ball_point (grid): n=%d exceeds %d; pass no workspace", n, BQG_MAX_N);

@@ -69,6 +69,13 @@ struct TcParams {
     int gather, g_n, g_c, g_m, g_ns, g_ldz;
     const float *g_xyz, *g_points, *g_new_xyz, *g_wx;
     const int *g_idx;
+    // UNIT-LIST mode (include/ssd3d.h, ssd3d_query_ball_point_multi_ws): units[0] = U, units[1 + u] = (group << 4) | j names
+    // rows 8j .. 8j+7 of a group's neighbour list.  The matrix this launch works on then has U * 8 rows -- compact row
+    // 8u + e is neighbour slot 8j + e of that group -- instead of `rows` (which stays the capacity of the buffers): the
+    // gather producers look their source up through the list, and unit_pool max-pools each 8-row unit and combines the
+    // units of a group with atomicMax on out_f32[group] (zero-filled by the caller; values are post-ReLU, >= 0).
+    const int *units;
+    int unit_pool;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -178,6 +185,21 @@ __device__ __forceinline__ void pooled_chunk(const TcParams &p, float (&v)[32], 
     }
 }
 
+// Unit-list twin of pooled_chunk<8>: lanes 8u' .. 8u'+7 of a warp hold one unit; its column maxima go to the unit's GROUP row.
+__device__ __forceinline__ void pooled_units_chunk(const TcParams &p, float (&v)[32], int lane, int q, int mt, int col0, int nunits)
+{
+    warp_colmax_transpose<8>(v, lane);               // lane owns columns (lane % 8) * 4 + k of its unit in v[k]
+    const int ui = mt * (TC_BM / 8) + ((q * 32 + lane) >> 3);
+    if (ui >= nunits) return;
+    const int group = __ldg(p.units + 1 + ui) >> 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int col = col0 + (lane & 7) * 4 + k;
+        if (col >= p.n) continue;
+        atomicMax(reinterpret_cast<unsigned int *>(p.out_f32 + (size_t)group * p.ld_f32 + col), __float_as_uint(v[k]) & 0x7fffffffu);
+    }
+}
+
 // Developer instrumentation (nvcc -DTC_PROFILE): CTA 0 accumulates, per role, the cycles spent waiting on each barrier
 // and the cycles spent working; printed by the launcher.  Slots: 0 total | 1 tma wait-empty | 2 mma wait-afull |
 // 3 mma wait-full(B) | 4 mma wait-tempty | 5 mma issue | 6 prod wait-slot | 7 prod load+math | 8 epi wait-tfull | 9 epi work
@@ -221,17 +243,21 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
     __shared__ float pool_xs[2 * 4 * 32];
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
+    // unit-list mode: the row count comes from the list (written earlier on this stream), p.rows is the buffers' capacity
+    const int nunits = p.units ? __ldg(p.units) : 0;
+    const long rows = p.units ? (long)nunits * 8 : p.rows;
+    const int m_tiles = p.units ? (nunits + TC_BM / 8 - 1) / (TC_BM / 8) : p.m_tiles;
     // local tile i of this CTA -> (mt, nt): n-major round robin over all tiles, or (astat) every n-tile of an m-tile
     auto tile_at = [&](int i, int &mt, int &nt) -> bool {
         if (p.astat) {
             mt = (int)blockIdx.x + (i / p.n_tiles) * (int)gridDim.x;
             nt = i % p.n_tiles;
-            return mt < p.m_tiles;
+            return mt < m_tiles;
         }
         const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         mt = tile / p.n_tiles;
         nt = tile - mt * p.n_tiles;
-        return tile < p.m_tiles * p.n_tiles;
+        return tile < m_tiles * p.n_tiles;
     };
 
     if (threadIdx.x == 0) {
@@ -354,8 +380,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
             for (int i = 0; tile_at(i, mt, nt); i++) {
                 if (p.astat && nt != 0) continue;                 // A-stationary: the tile built for nt == 0 serves every n-tile
                 const uint32_t row = (uint32_t)mt * TC_BM + (uint32_t)r;
-                const bool ok = (long)row < p.rows;
-                const uint32_t rr = ok ? row : 0u;
+                const bool ok = (long)row < rows;
+                uint32_t rr = ok ? row : 0u;                      // position of this row's neighbour in idx[]
+                if (p.units && ok) {
+                    const uint32_t desc = (uint32_t)__ldg(p.units + 1 + (row >> 3));
+                    rr = (desc >> 4) * (uint32_t)p.g_ns + ((desc & 15u) << 3) + (row & 7u);
+                }
                 const uint32_t scene = rr / rps, q = rr / (uint32_t)p.g_ns;
                 const int a = __ldg(p.g_idx + rr);
                 const float *src_f = p.g_points + ((size_t)scene * p.g_n + a) * src_pitch;
@@ -442,7 +472,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
             if (warp == TC_EPI_WARP0) TCP(8);
             tc_fence_after();
             const long row = (long)mt * TC_BM + q * 32 + lane;
-            const bool row_ok = row < p.rows;
+            const bool row_ok = row < rows;
             for (int ci = h; ci < nchunks; ci += 2) {
                 const int c0 = ci * 32;
                 uint32_t r[32];
@@ -525,6 +555,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_const
                             }
                         }
                     }
+                } else if (p.unit_pool) {
+                    pooled_units_chunk(p, v, lane, q, mt, col0, nunits);
                 } else {
                     switch (p.pool) {
                         case 8: pooled_chunk<8>(p, v, lane, q, h, mt, col0, pool_xs); break;
@@ -657,9 +689,11 @@ group_concat_split_kernel(long rows, int n, int c, int m, int ns, const float *_
 __global__ void __launch_bounds__(256)
 hoist_expand_split_kernel(long rows, int n, int n1, int m, int ns, const float *__restrict__ xyz, const float *__restrict__ z,
                           int ldz, const float *__restrict__ wx, const float *__restrict__ new_xyz,
-                          const int *__restrict__ idx, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int kp)
+                          const int *__restrict__ idx, const int *__restrict__ units, __nv_bfloat16 *__restrict__ hi,
+                          __nv_bfloat16 *__restrict__ lo, int kp)
 {
     extern __shared__ __align__(16) float hx_wx[];                      // [3][kp] zero padded
+    if (units) rows = (long)__ldg(units) * 8;                           // unit-list mode (TcParams::units): compact rows
     for (int i = threadIdx.x; i < 3 * kp; i += blockDim.x) {
         const int a = i / kp, k = i - a * kp;
         hx_wx[i] = k < n1 ? __ldg(wx + a * n1 + k) : 0.0f;
@@ -670,8 +704,13 @@ hoist_expand_split_kernel(long rows, int n, int n1, int m, int ns, const float *
     const long rps = (long)m * ns;
     const int nchunk = kp >> 3;
     for (long row = warp0; row < rows; row += nwarps) {
-        const long scene = row / rps, q = row / ns;
-        const int a = __ldg(idx + row);
+        long src = row;                                                  // position of this row's neighbour in idx[]
+        if (units) {
+            const unsigned desc = (unsigned)__ldg(units + 1 + (row >> 3));
+            src = (long)(desc >> 4) * ns + ((desc & 15u) << 3) + (row & 7);
+        }
+        const long scene = src / rps, q = src / ns;
+        const int a = __ldg(idx + src);
         const float *px = xyz + ((size_t)scene * n + a) * 3, *pc = new_xyz + (size_t)q * 3;
         const float dx = __ldg(px) - __ldg(pc), dy = __ldg(px + 1) - __ldg(pc + 1), dz = __ldg(px + 2) - __ldg(pc + 2);
         const float *zr = z + ((size_t)scene * n + a) * ldz;
@@ -761,9 +800,18 @@ struct TcGather { int b, n, c, m, ns; const float *xyz, *points, *new_xyz; const
 static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const void *a_lo, const TcGather *g,
                             const void *b_hi, const void *b_lo, const float *scale, const float *shift, int relu, int pool,
                             const int *rowmask, float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split,
-                            cudaStream_t stream)
+                            cudaStream_t stream, const int *units = nullptr, int unit_pool = 0)
 {
     SSD3D_REQUIRE(rows >= 0 && kp > 0 && n > 0, "linear_tc: bad shape rows=%ld kp=%d n=%d", rows, kp, n);
+    if (units) {
+        SSD3D_REQUIRE(rows % 8 == 0 && pool == 1 && rowmask == nullptr, "linear_tc (unit list): rows=%ld must be a multiple of 8, no pool / rowmask", rows);
+        if (unit_pool) {
+            SSD3D_REQUIRE(relu && out_f32 && !out_hi, "linear_tc (unit list): pooling combines post-ReLU values by atomicMax into out_f32 only");
+            pool = 8;
+        }
+    } else {
+        SSD3D_REQUIRE(!unit_pool, "linear_tc: unit_pool needs a unit list");
+    }
     SSD3D_REQUIRE(kp % 16 == 0, "linear_tc: kp=%d must be a multiple of 16", kp);
     SSD3D_REQUIRE((g || (a_hi && a_lo)) && b_hi && b_lo && scale && shift, "linear_tc: null operand pointer");
     SSD3D_REQUIRE(out_f32 || (out_hi && out_lo), "linear_tc: no output requested");
@@ -853,6 +901,7 @@ static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const vo
     SSD3D_REQUIRE(stages >= 2, "linear_tc: tile does not fit shared memory");
     p.stages = stages;
     p.scale = scale; p.shift = shift; p.relu = relu; p.pool = pool; p.rowmask = rowmask;
+    p.units = units; p.unit_pool = unit_pool;
     p.out_f32 = out_f32; p.ld_f32 = ld_f32;
     p.out_hi = (__nv_bfloat16 *)out_hi; p.out_lo = (__nv_bfloat16 *)out_lo; p.ld_split = ld_split;
 
@@ -905,9 +954,9 @@ static int linear_tc_launch(long rows, int kp, int n, const void *a_hi, const vo
     SSD3D_LAUNCH_CHECK("linear_tc_kernel");
 }
 
-extern "C" int ssd3d_hoist_expand_split(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
-                                        const float *wx, const float *new_xyz, const int *idx, void *hi, void *lo, int kp,
-                                        ssd3d_stream_t stream)
+static int hoist_expand_split_launch(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
+                                     const float *wx, const float *new_xyz, const int *idx, const int *units, void *hi,
+                                     void *lo, int kp, ssd3d_stream_t stream)
 {
     SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0 && n1 > 0 && nsample > 0 && ldz >= n1, "hoist_expand_split: bad shape");
     SSD3D_REQUIRE(kp % 16 == 0 && kp >= n1 && kp <= 4096, "hoist_expand_split: kp=%d must be a multiple of 16 in [n1, 4096]", kp);
@@ -919,8 +968,51 @@ extern "C" int ssd3d_hoist_expand_split(int b, int n, int n1, int m, int nsample
     const long blocks_want = (rows + 7) / 8;
     const int blocks = (int)(blocks_want < (long)kNumSMs * 32 ? blocks_want : (long)kNumSMs * 32);
     hoist_expand_split_kernel<<<blocks, 256, (size_t)3 * kp * sizeof(float), (cudaStream_t)stream>>>(
-        rows, n, n1, m, nsample, xyz, z, ldz, wx, new_xyz, idx, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, kp);
+        rows, n, n1, m, nsample, xyz, z, ldz, wx, new_xyz, idx, units, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, kp);
     SSD3D_LAUNCH_CHECK("hoist_expand_split_kernel");
+}
+
+extern "C" int ssd3d_hoist_expand_split(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
+                                        const float *wx, const float *new_xyz, const int *idx, void *hi, void *lo, int kp,
+                                        ssd3d_stream_t stream)
+{
+    return hoist_expand_split_launch(b, n, n1, m, nsample, xyz, z, ldz, wx, new_xyz, idx, nullptr, hi, lo, kp, stream);
+}
+
+extern "C" int ssd3d_hoist_expand_split_units(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z,
+                                              int ldz, const float *wx, const float *new_xyz, const int *idx,
+                                              const int *units, void *hi, void *lo, int kp, ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(units && nsample % 8 == 0 && nsample <= 128, "hoist_expand_split_units: needs a unit list and nsample a multiple of 8, <= 128");
+    return hoist_expand_split_launch(b, n, n1, m, nsample, xyz, z, ldz, wx, new_xyz, idx, units, hi, lo, kp, stream);
+}
+
+// Unit-list forms of ssd3d_linear_tc / ssd3d_linear_tc_hoisted (TcParams::units): the matrix has units[0] * 8 rows (`rows` /
+// b*m*nsample is the capacity of the buffers).  unit_pool != 0: each 8-row unit is max-pooled and combined into
+// out_f32[group] by atomicMax (ReLU required, out_f32 zero-filled by the caller, no split output).
+extern "C" int ssd3d_linear_tc_units(long rows, int kp, int n, const void *a_hi, const void *a_lo, const void *b_hi,
+                                     const void *b_lo, const float *scale, const float *shift, int relu, const int *units,
+                                     int unit_pool, float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split,
+                                     ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(units, "linear_tc_units: null unit list");
+    return linear_tc_launch(rows, kp, n, a_hi, a_lo, nullptr, b_hi, b_lo, scale, shift, relu, 1, nullptr, out_f32, ld_f32,
+                            out_hi, out_lo, ld_split, (cudaStream_t)stream, units, unit_pool);
+}
+
+extern "C" int ssd3d_linear_tc_hoisted_units(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z,
+                                             int ldz, const float *wx, const float *new_xyz, const int *idx,
+                                             const int *units, int nout, const void *b_hi, const void *b_lo,
+                                             const float *scale, const float *shift, int relu, int unit_pool, float *out_f32,
+                                             int ld_f32, void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream)
+{
+    SSD3D_REQUIRE(b >= 0 && n > 0 && m >= 0 && n1 > 0 && nsample > 0 && ldz >= n1, "linear_tc_hoisted_units: bad shape");
+    SSD3D_REQUIRE(xyz && new_xyz && idx && z && wx && units, "linear_tc_hoisted_units: null pointer");
+    SSD3D_REQUIRE(nsample % 8 == 0 && nsample <= 128, "linear_tc_hoisted_units: nsample=%d must be a multiple of 8, <= 128", nsample);
+    TcGather g = {b, n, n1, m, nsample, xyz, z, new_xyz, idx, ldz, wx};
+    const int kp = (n1 + 15) / 16 * 16;
+    return linear_tc_launch((long)b * m * nsample, kp, nout, nullptr, nullptr, &g, b_hi, b_lo, scale, shift, relu, 1, nullptr,
+                            out_f32, ld_f32, out_hi, out_lo, ld_split, (cudaStream_t)stream, units, unit_pool);
 }
 
 extern "C" int ssd3d_linear_tc(long rows, int kp, int n, const void *a_hi, const void *a_lo, const void *b_hi,

@@ -164,7 +164,7 @@ def _group_and_mlp(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, m
     units_list = [None] * nscale
     tc_path = (mlp_mode == "tc" and all(k in (8, 16, 32, 64, 128) for k in nsample_list) and all(m[-1] % 8 == 0 for m in mlp_list))
     if nscale <= 4:   # one pass over the candidates for all shells
-        want_units = COMPACT_GROUPS and tc_path and any(st is not None for st in stacks)
+        want_units = COMPACT_GROUPS and tc_path and (any(st is not None for st in stacks) or bool(hoist.scales))
         res = tf_ops.query_ball_point_multi(min_r, radius_list, nsample_list, xyz, new_xyz, dilated_group, return_units=want_units)
         idx_list, cnt_list = res[0], res[1]
         if want_units:
@@ -188,7 +188,9 @@ def _group_and_mlp(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, m
         concat = torch.empty((bs, m_q, ctot), dtype=torch.float32, device=xyz.device)
         # unit-list mode: the fused scales combine their 8-row units with atomicMax on the ZERO-FILLED fp32 concat buffer; the
         # split copy the aggregation conv reads is then made once, from the finished buffer
-        compact = any(units_list[i] is not None and stacks[i] is not None for i in range(nscale))
+        # (layer-by-layer scales with a hoisted first conv take the same route through the *_units forms of their kernels)
+        use_units = [units_list[i] is not None and (stacks[i] is not None or i in hoist.scales) for i in range(nscale)]
+        compact = any(use_units)
         if compact:
             tf_ops.fill_zero(concat)
         cat_hi = cat_lo = None
@@ -206,7 +208,7 @@ def _group_and_mlp(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, m
             stack = stacks[i]
             if stack is not None:                                              # whole scale in one kernel
                 fkw = dict(out_f32=(concat, off), out_split=(cat_hi, cat_lo, off) if split_in_epilogue else None,
-                           units=units_list[i] if compact else None)
+                           units=units_list[i] if use_units[i] else None)
                 if hstacks.get(i) is not None:
                     t = hscales.index(i)
                     tf_ops.sa_mlp_fused_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, cnt, hstacks[i], **fkw)
@@ -219,6 +221,10 @@ def _group_and_mlp(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, m
                 f = pp.conv("%s/conv%d_%d" % (scope, i, j), bn)
                 last_kw = dict(pool=nsample_list[i], rowmask=cnt, out_f32=(concat, off),
                                out_split=(cat_hi, cat_lo, off) if split_in_epilogue else None)   # :167-180 conv+BN+ReLU+max+mask
+                ukw = {}
+                if use_units[i]:                  # compact rows; the last conv pools 8-row units into the zero-filled concat
+                    ukw = dict(units=units_list[i])
+                    last_kw = dict(out_f32=(concat, off), units=units_list[i], unit_pool=True)
                 if i in hscales:
                     if j == 0:
                         continue                  # folded into z and into the next conv's operand producer
@@ -226,16 +232,16 @@ def _group_and_mlp(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, m
                         t = hscales.index(i)
                         if f.kp >= HOIST_EXPAND_MIN_K and zoffs[t] % 4 == 0 and z.shape[2] % 4 == 0:
                             # wide layer: materialise the operand once (elementwise, memory speed), plain TMA-fed GEMM
-                            hi, lo = tf_ops.hoist_expand_split(xyz, z, zoffs[t], wxs[t], new_xyz, idx)
+                            hi, lo = tf_ops.hoist_expand_split(xyz, z, zoffs[t], wxs[t], new_xyz, idx, **ukw)
                             if nl == 2:
                                 tf_ops.linear_tc(hi, lo, f, **last_kw)
                             else:
-                                _, (hi, lo) = tf_ops.linear_tc(hi, lo, f, want_f32=False, want_split=True)
+                                _, (hi, lo) = tf_ops.linear_tc(hi, lo, f, want_f32=False, want_split=True, **ukw)
                             continue
                         if nl == 2:
                             tf_ops.linear_tc_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, f, want_split=False, **last_kw)
                         else:
-                            _, (hi, lo) = tf_ops.linear_tc_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, f)
+                            _, (hi, lo) = tf_ops.linear_tc_hoisted(xyz, z, zoffs[t], wxs[t], new_xyz, idx, f, **ukw)
                         continue
                 if j == 0 and gather_in_kernel:   # :160-165 inside the kernel's operand load (no [B,M,K,C] tensor)
                     if nl == 1:
@@ -246,7 +252,7 @@ def _group_and_mlp(pp, scope, xyz, points, new_xyz, radius_list, nsample_list, m
                 if j == 0:                        # :160-165 fused with the split, materialised once in bf16 hi/lo
                     hi, lo = tf_ops.group_concat_split(xyz, points, new_xyz, idx)
                 if j < nl - 1:
-                    _, (hi, lo) = tf_ops.linear_tc(hi, lo, f, want_f32=False, want_split=True)
+                    _, (hi, lo) = tf_ops.linear_tc(hi, lo, f, want_f32=False, want_split=True, **ukw)
                 else:
                     tf_ops.linear_tc(hi, lo, f, **last_kw)
             off += mlp_list[i][-1]

@@ -257,7 +257,7 @@ def query_ball_point_multi(min_radius_list, max_radius_list, nsample_list, xyz1,
     grid: None = automatic (the culled kernel for ndataset >= BQ_GRID_MIN_N), True / False = force / forbid it;
     the outputs are identical either way.
     return_units: also return, per shell, the UNIT LIST of the grouped MLP (int32 tensor, include/ssd3d.h
-    ssd3d_query_ball_point_multi_ws) or None where the culled kernel was not used: (idx_list, pts_cnt_list, units_list)."""
+    ssd3d_query_ball_point_multi_ws), or None for nsample > 128: (idx_list, pts_cnt_list, units_list)."""
     xyz1, xyz2 = _bq_shapes(xyz1, xyz2)
     nq = len(max_radius_list)
     if not (len(nsample_list) == nq and len(min_radius_list) == nq and 1 <= nq <= 4):
@@ -283,7 +283,7 @@ def query_ball_point_multi(min_radius_list, max_radius_list, nsample_list, xyz1,
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=xyz1.device) if use_grid else None
     units = [None] * nq
     pu = ctypes.c_void_p(0)
-    if return_units and use_grid and all(int(k) <= 128 for k in nsample_list):
+    if return_units and all(int(k) <= 128 for k in nsample_list):
         units = [torch.empty((1 + b * m * ((int(k) + 7) // 8),), dtype=torch.int32, device=xyz1.device) for k in nsample_list]
         parr = (ctypes.c_void_p * nq)(*[t.data_ptr() for t in units])
         pu = ctypes.cast(parr, ctypes.c_void_p)
@@ -534,11 +534,28 @@ def _tc_outputs(lead, n, pool, dev, want_f32, want_split, out_f32, out_split):
     return y, pf, ldf, sp, ph, pl, lds
 
 
+def _tc_units_check(units, unit_pool, pool, rowmask, relu, out_f32, out_split, want_split):
+    if units is None:
+        if unit_pool:
+            raise ValueError("unit_pool needs a unit list")
+        return
+    if units.dtype != torch.int32 or not units.is_cuda or not units.is_contiguous():
+        raise ValueError("units must be the int32 CUDA unit list returned by query_ball_point_multi(return_units=True)")
+    if int(pool) != 1 or rowmask is not None:
+        raise ValueError("a unit list replaces pool / rowmask (unit_pool=True pools the listed 8-row units)")
+    if unit_pool and (not relu or out_f32 is None or out_split is not None or want_split):
+        raise ValueError("unit_pool needs relu, out_f32=(zero-filled buffer, col_offset) and no split output")
+
+
 def linear_tc(a_hi, a_lo, f, relu=True, pool=1, rowmask=None, want_f32=True, want_split=False, out_f32=None,
-              out_split=None):
+              out_split=None, units=None, unit_pool=False):
     """One folded conv layer on the tensor cores.  a_hi/a_lo (..., kp) bf16; f: params.FoldedConv.
     Returns (y_f32 or None, (hi, lo) or None).  out_f32=(buffer, col_offset) / out_split=(hi_buf, lo_buf, col_offset)
-    write into slices of preallocated (..., ld) buffers (the concat of the SA scales) instead of allocating."""
+    write into slices of preallocated (..., ld) buffers (the concat of the SA scales) instead of allocating.
+    units: the operand holds COMPACT rows (8 per listed unit, include/ssd3d.h ssd3d_linear_tc_units) in its first
+    units[0] * 8 rows; outputs are compact likewise, or -- unit_pool=True, the last conv of a scale -- every unit is
+    max-pooled and combined into out_f32[group] by atomicMax (buffer zero-filled by the caller)."""
+    _tc_units_check(units, unit_pool, pool, rowmask, relu, out_f32, out_split, want_split)
     if a_hi.dtype != torch.bfloat16 or a_lo.dtype != torch.bfloat16 or a_hi.shape != a_lo.shape:
         raise ValueError("a_hi / a_lo must be bfloat16 tensors of the same shape")
     kp = a_hi.shape[-1]
@@ -554,6 +571,11 @@ def linear_tc(a_hi, a_lo, f, relu=True, pool=1, rowmask=None, want_f32=True, wan
     n = f.cout
     y, pf, ldf, sp, ph, pl, lds = _tc_outputs(lead, n, pool, a_hi.device, want_f32, want_split, out_f32, out_split)
     vp = ctypes.c_void_p
+    if units is not None:
+        check(lib().ssd3d_linear_tc_units(rows, kp, n, _p(a_hi), _p(a_lo), _p(f.b_hi), _p(f.b_lo), _p(f.scale), _p(f.shift),
+                                          1 if relu else 0, _p(units), 1 if unit_pool else 0, vp(pf), ldf, vp(ph), vp(pl), lds,
+                                          _stream()), "linear_tc_units")
+        return y, sp
     check(lib().ssd3d_linear_tc(rows, kp, n, _p(a_hi), _p(a_lo), _p(f.b_hi), _p(f.b_lo), _p(f.scale), _p(f.shift),
                                 1 if relu else 0, pool, _p(rowmask), vp(pf), ldf, vp(ph), vp(pl), lds, _stream()),
           "linear_tc")
@@ -589,10 +611,12 @@ def linear_tc_gather(xyz, points, new_xyz, idx, f, relu=True, pool=1, rowmask=No
 
 
 def linear_tc_hoisted(xyz, z, zoff, wx, new_xyz, idx, f, relu=True, pool=1, rowmask=None, want_f32=False, want_split=True,
-                      out_f32=None, out_split=None):
+                      out_f32=None, out_split=None, units=None, unit_pool=False):
     """Second conv of an SA scale fed by the hoisted first conv (include/ssd3d.h, ssd3d_linear_tc_hoisted).
     z: (b, n, ldz) fp32 per-point table = (features . Wf) * s1 + t1 for all scales of the layer, this scale's
-    columns start at zoff; wx: (3, n1) fp32 = Wx * s1; f: params.FoldedConv of the second conv (cin == n1)."""
+    columns start at zoff; wx: (3, n1) fp32 = Wx * s1; f: params.FoldedConv of the second conv (cin == n1).
+    units / unit_pool: as linear_tc (the source rows are looked up through the list, outputs are compact)."""
+    _tc_units_check(units, unit_pool, pool, rowmask, relu, out_f32, out_split, want_split)
     xyz = _req(xyz, "xyz", torch.float32, 3, 3)
     new_xyz = _req(new_xyz, "new_xyz", torch.float32, 3, 3)
     idx = _req(idx, "idx", torch.int32, 3)
@@ -611,16 +635,23 @@ def linear_tc_hoisted(xyz, z, zoff, wx, new_xyz, idx, f, relu=True, pool=1, rowm
     lead = (b, m) if pool > 1 else (b, m, ns)
     y, pf, ldf, sp, ph, pl, lds = _tc_outputs(lead, f.cout, pool, xyz.device, want_f32, want_split, out_f32, out_split)
     vp = ctypes.c_void_p
+    if units is not None:
+        check(lib().ssd3d_linear_tc_hoisted_units(b, n, n1, m, ns, _p(xyz), vp(z.data_ptr() + 4 * zoff), z.shape[2], _p(wx),
+                                                  _p(new_xyz), _p(idx), _p(units), f.cout, _p(f.b_hi), _p(f.b_lo), _p(f.scale),
+                                                  _p(f.shift), 1 if relu else 0, 1 if unit_pool else 0, vp(pf), ldf, vp(ph),
+                                                  vp(pl), lds, _stream()), "linear_tc_hoisted_units")
+        return y, sp
     check(lib().ssd3d_linear_tc_hoisted(b, n, n1, m, ns, _p(xyz), vp(z.data_ptr() + 4 * zoff), z.shape[2], _p(wx), _p(new_xyz),
                                         _p(idx), f.cout, _p(f.b_hi), _p(f.b_lo), _p(f.scale), _p(f.shift), 1 if relu else 0,
                                         pool, _p(rowmask), vp(pf), ldf, vp(ph), vp(pl), lds, _stream()), "linear_tc_hoisted")
     return y, sp
 
 
-def hoist_expand_split(xyz, z, zoff, wx, new_xyz, idx):
+def hoist_expand_split(xyz, z, zoff, wx, new_xyz, idx, units=None):
     """The operand linear_tc_hoisted would build in its producer warps, materialised: (hi, lo) bf16 (b, m, nsample, kp) =
     split(relu(z[idx] + (xyz[idx] - new_xyz) . wx)).  Followed by the plain linear_tc this is the faster route for wide
-    layers (K >= 256), where the resident operand of the in-kernel route leaves the weight ring two narrow stages."""
+    layers (K >= 256), where the resident operand of the in-kernel route leaves the weight ring two narrow stages.
+    units: only the listed 8-row units are built, as compact rows at the start of the buffers."""
     xyz = _req(xyz, "xyz", torch.float32, 3, 3)
     new_xyz = _req(new_xyz, "new_xyz", torch.float32, 3, 3)
     idx = _req(idx, "idx", torch.int32, 3)
@@ -634,6 +665,12 @@ def hoist_expand_split(xyz, z, zoff, wx, new_xyz, idx):
     kp = round16(n1)
     hi = torch.empty((b, m, ns, kp), dtype=torch.bfloat16, device=xyz.device)
     lo = torch.empty_like(hi)
+    if units is not None:
+        _tc_units_check(units, False, 1, None, True, None, None, False)
+        check(lib().ssd3d_hoist_expand_split_units(b, n, n1, m, ns, _p(xyz), ctypes.c_void_p(z.data_ptr() + 4 * zoff), z.shape[2],
+                                                   _p(wx), _p(new_xyz), _p(idx), _p(units), _p(hi), _p(lo), kp, _stream()),
+              "hoist_expand_split_units")
+        return hi, lo
     check(lib().ssd3d_hoist_expand_split(b, n, n1, m, ns, _p(xyz), ctypes.c_void_p(z.data_ptr() + 4 * zoff), z.shape[2], _p(wx),
                                          _p(new_xyz), _p(idx), _p(hi), _p(lo), kp, _stream()), "hoist_expand_split")
     return hi, lo

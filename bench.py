@@ -247,20 +247,21 @@ class MlpTimer:
 
     def _flops(self, name, a, kw):
         r16 = self._r16
+        urows = None
+        if kw.get("units") is not None:                 # unit-list route: 128-row tiles of 16 listed 8-row units
+            urows = (int(kw["units"][0].item()) + 15) // 16 * 128
         if name == "linear_tc":
             hi, f = a[0], a[2]
-            return 2.0 * (hi.numel() // hi.shape[-1]) * f.kp * r16(f.cout)
+            return 2.0 * (urows if urows is not None else hi.numel() // hi.shape[-1]) * f.kp * r16(f.cout)
         if name == "linear_tc_hoisted":
             idx, f = a[5], a[6]
-            return 2.0 * idx.numel() * f.kp * r16(f.cout)
+            return 2.0 * (urows if urows is not None else idx.numel()) * f.kp * r16(f.cout)
         if name == "linear_tc_gather":
             idx, f = a[3], a[4]
             return 2.0 * idx.numel() * f.kp * r16(f.cout)
         stack = a[5] if name == "sa_mlp_fused" else a[7]
         idx = a[3] if name == "sa_mlp_fused" else a[5]
-        rows = idx.numel()
-        if kw.get("units") is not None:                 # unit-list route: 128-row tiles of 16 listed 8-row units
-            rows = (int(kw["units"][0].item()) + 15) // 16 * 128
+        rows = urows if urows is not None else idx.numel()
         k, tot = r16(stack.cin), 0.0
         for n in stack.nout:
             tot += 2.0 * rows * k * r16(n)
@@ -376,8 +377,8 @@ def main():
 
         def __call__(self, *a):
             n = 1
-            if self.name == "ssd3d_query_ball_point_multi_ws" and getattr(a[13], "value", None):
-                n = 2                                   # culled ball query: grid build + search
+            if self.name == "ssd3d_query_ball_point_multi_ws" and (getattr(a[13], "value", None) or getattr(a[12], "value", None)):
+                n = 2                                   # culled ball query: grid build + search; exhaustive + unit lists: search + list
             elif self.name == "ssd3d_bn_train":
                 n = 3
             counter["n"] += n

@@ -129,7 +129,8 @@ int ssd3d_query_ball_point_multi(int b, int n, int m, int nqueries, int dilated,
  * units[s] holds 1 + b*m*ceil(nsample[s]/8) ints: [0] = number of units, [1 + u] = (group << 4) | j naming rows 8j..8j+7
  * of neighbour list `group` (= scene*m + query).  A group with cnt hits gets ceil(cnt/8) units -- slots beyond cnt repeat
  * the first hit (tf_grouping_g.cu:245-248) and cannot change the max-pool that follows (layers_util.py:178), so the
- * grouped MLP needs only these rows (ssd3d_sa_mlp_fused*, `units`).  The list order is unspecified. */
+ * grouped MLP needs only these rows (ssd3d_sa_mlp_fused*, ssd3d_linear_tc*_units).  The list order is unspecified.
+ * Without a workspace the list is built from the finished counts by one more small kernel. */
 size_t ssd3d_query_ball_point_workspace(int b, int n);
 int ssd3d_query_ball_point_multi_ws(int b, int n, int m, int nqueries, int dilated, const float *min_radius,
                                     const float *max_radius, const int *nsample, const float *xyz1, const float *xyz2,
@@ -211,6 +212,23 @@ int ssd3d_linear_tc_hoisted(int b, int n, int n1, int m, int nsample, const floa
 int ssd3d_hoist_expand_split(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
                              const float *wx, const float *new_xyz, const int *idx, void *hi, void *lo, int kp,
                              ssd3d_stream_t stream);
+/* UNIT-LIST forms of the three calls above (units: ssd3d_query_ball_point_multi_ws).  The grouped matrix then has
+ * units[0] * 8 rows: compact row 8u + e is neighbour slot 8j + e of the group unit u names, and the buffers keep their
+ * full capacity (rows / b*m*nsample rows).  ssd3d_hoist_expand_split_units and ssd3d_linear_tc_hoisted_units look their
+ * source rows up through the list; ssd3d_linear_tc_units consumes compact rows.  unit_pool != 0 (last conv of a scale,
+ * layers_util.py:176-180): every 8-row unit is max-pooled and combined into out_f32[group, :] with atomicMax -- requires
+ * relu != 0 (values >= 0), no split output, and out_f32 ZERO-FILLED by the caller (which also is the cnt == 0 mask). */
+int ssd3d_hoist_expand_split_units(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
+                                   const float *wx, const float *new_xyz, const int *idx, const int *units, void *hi,
+                                   void *lo, int kp, ssd3d_stream_t stream);
+int ssd3d_linear_tc_units(long rows, int kp, int n, const void *a_hi, const void *a_lo, const void *b_hi, const void *b_lo,
+                          const float *scale, const float *shift, int relu, const int *units, int unit_pool,
+                          float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split, ssd3d_stream_t stream);
+int ssd3d_linear_tc_hoisted_units(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,
+                                  const float *wx, const float *new_xyz, const int *idx, const int *units, int nout,
+                                  const void *b_hi, const void *b_lo, const float *scale, const float *shift, int relu,
+                                  int unit_pool, float *out_f32, int ld_f32, void *out_hi, void *out_lo, int ld_split,
+                                  ssd3d_stream_t stream);
 /* Same idea for a scale that fits the fused kernel (ssd3d_sa_mlp_fused): the stack passed here starts at the scale's
  * SECOND conv, the first operand row is relu(z[idx] + (xyz[idx] - new_xyz) . wx), built during the gather. */
 int ssd3d_sa_mlp_fused_hoisted(int b, int n, int n1, int m, int nsample, const float *xyz, const float *z, int ldz,

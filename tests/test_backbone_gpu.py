@@ -266,6 +266,28 @@ def test_backbone_latency_mode_small_equals_default(pkg, cuda, parts):
             assert torch.equal(x, y)
 
 
+def test_backbone_unit_lists_do_not_change_a_bit(pkg, cuda):
+    """layers_util.COMPACT_GROUPS (grouped MLPs convolve only the 8-row units that hold distinct neighbours) is an
+    execution detail: every layer's features are bit-identical with it on and off -- full-size layer table, real
+    neighbour statistics of the synthetic KITTI-like clouds, and a dense cloud where most groups are full."""
+    lu = pkg.layers_util
+    arch = pkg.config.ARCH_3DSSD
+    params = pkg.params.init_params(arch, 1, seed=3, random_bias=True)
+    dense_cloud = compact_scene(2, 16384, seed=5)
+    for pts_np in (synth.kitti_like(2, 16384, seed=1234), dense_cloud):
+        pts = torch.from_numpy(pts_np).to(cuda)
+        net = pkg.SABackbone(arch, params, in_channels=1, device=cuda)
+        assert lu.COMPACT_GROUPS
+        a = net.forward(pts)
+        try:
+            lu.COMPACT_GROUPS = False
+            b = net.forward(pts)
+        finally:
+            lu.COMPACT_GROUPS = True
+        for li in range(1, len(arch) + 1):
+            assert torch.equal(a[1][li], b[1][li]), "features of layer %d" % li
+
+
 def test_backbone_full_size_properties_and_graph_replay(pkg, cuda):
     """Full configs[1] batch: shapes, invariants the domain offers, and CUDA-graph replay == eager."""
     net = pkg.SABackbone(device=cuda)

@@ -857,6 +857,7 @@ def test_sa_mlp_fused_unit_list_equals_dense(pkg, cuda, c, ks, mlps, hoist):
     feats = np.maximum(rng.standard_normal((b, n, c)), 0).astype(np.float32)
     tx, tf = T(xyz, cuda), T(feats, cuda)
     tn = tx[:, :m].contiguous()
+    tn[:, -20:] += 500.0                                       # centres with no neighbour in any shell: cnt = 0
     lows, highs = [0.0, 0.2, 0.4], [0.2, 0.4, 0.8]
     idxs, cnts, units = pkg.query_ball_point_multi(lows, highs, ks, tx, tn, True, grid=True, return_units=True)
     i0, c0 = pkg.query_ball_point_multi(lows, highs, ks, tx, tn, True, grid=False)
@@ -870,7 +871,7 @@ def test_sa_mlp_fused_unit_list_equals_dense(pkg, cuda, c, ks, mlps, hoist):
         want = sorted((int(g), int(jj)) for g in np.flatnonzero(cnt.reshape(-1) > 0)
                       for jj in range((min(int(cnt.reshape(-1)[g]), k) + 7) // 8))
         assert sorted(zip(grp.tolist(), j.tolist())) == want
-        assert (cnt == 0).any() or s == 0
+        assert (cnt == 0).any() and (cnt == 1).any() and (cnt > 8).any()
         prm, scopes, cin = {}, [], c + 3
         for jn, cout in enumerate(mlps[s]):
             P._conv_init(rng, prm, "s/conv%d_%d" % (s, jn), cin, cout, True)
@@ -898,6 +899,68 @@ def test_sa_mlp_fused_unit_list_equals_dense(pkg, cuda, c, ks, mlps, hoist):
         assert float(dense[..., 16:16 + mlps[s][-1]].abs().max()) > 0
     with pytest.raises(ValueError):
         pkg.sa_mlp_fused(tx, tf, tn, idxs[0], cnts[0], stack, units=units[0])          # needs the zero-filled out_f32
+
+
+@pytest.mark.parametrize("c,k,mlp,expand", [
+    (64, 32, [64, 96, 128], False),      # hoisted second conv built inside the GEMM (layer-3 route), three convs
+    (64, 64, [64, 128], False),          # two convs: the hoisted conv is the pooled one
+    (256, 32, [256, 256, 320], True),    # operand materialised by hoist_expand_split (layer-4 route)
+    (32, 16, [32, 40], True),
+])
+def test_linear_tc_unit_list_equals_dense(pkg, cuda, c, k, mlp, expand):
+    """Layer-by-layer scales through the *_units kernels (compact rows, 8-row units pooled by atomicMax) give the same bits
+    as the dense kernels.  Small candidate set: the unit list comes from group_units_kernel, in group order."""
+    rng = np.random.default_rng(c + k)
+    b, n, m = 3, 512, 200
+    xyz = np.concatenate([rng.normal(0, 0.4, (b, 200, 3)) + 5.0, rng.uniform(0, 30, (b, n - 200, 3))], 1).astype(np.float32)
+    xyz = np.ascontiguousarray(xyz[:, rng.permutation(n)])
+    feats = np.maximum(rng.standard_normal((b, n, c)), 0).astype(np.float32)
+    tx, tf = T(xyz, cuda), T(feats, cuda)
+    tn = tx[:, :m].contiguous()
+    tn[:, -10:] += 500.0
+    (idx,), (cnt,), (units,) = pkg.query_ball_point_multi([0.0], [1.2], [k], tx, tn, False, return_units=True)
+    cn = N(cnt).reshape(-1)
+    assert (cn == 0).any() and (cn == 1).any() and (cn > 8).any()
+    want = [(g << 4) | j for g in range(cn.size) for j in range((min(int(cn[g]), k) + 7) // 8)]
+    u = N(units)
+    assert int(u[0]) == len(want) and u[1:1 + len(want)].tolist() == want
+    P = importlib.import_module("3dssd_b200.params")
+    prm, scopes, cin = {}, [], c + 3
+    for jn, cout in enumerate(mlp):
+        P._conv_init(rng, prm, "s/conv0_%d" % jn, cin, cout, True)
+        prm["s/conv0_%d/bn/gamma" % jn][1::3] *= -1.0
+        scopes.append("s/conv0_%d" % jn); cin = cout
+    pp = P.prepare(prm, cuda)
+    zconv, wxs, n1s = pp.hoisted([scopes[0]], True, c)
+    p_hi, p_lo = pkg.split_rows(tf)
+    z, _ = pkg.linear_tc(p_hi, p_lo, zconv, relu=False, want_f32=True, want_split=False)
+    ld = mlp[-1] + 32
+    dense = torch.full((b, m, ld), -1.0, device=cuda)
+    comp = torch.full((b, m, ld), -1.0, device=cuda)
+    comp[..., 16:16 + mlp[-1]] = 0.0
+
+    def run(out, ukw, last_kw):
+        f1 = pp.conv(scopes[1], True)
+        if len(mlp) == 2:
+            if expand:
+                hi, lo = pkg.tf_ops.hoist_expand_split(tx, z, 0, wxs[0], tn, idx, **ukw)
+                pkg.linear_tc(hi, lo, f1, out_f32=(out, 16), **last_kw)
+            else:
+                pkg.linear_tc_hoisted(tx, z, 0, wxs[0], tn, idx, f1, want_split=False, out_f32=(out, 16), **last_kw)
+            return
+        if expand:
+            hi, lo = pkg.tf_ops.hoist_expand_split(tx, z, 0, wxs[0], tn, idx, **ukw)
+            _, (hi, lo) = pkg.linear_tc(hi, lo, f1, want_f32=False, want_split=True, **ukw)
+        else:
+            _, (hi, lo) = pkg.linear_tc_hoisted(tx, z, 0, wxs[0], tn, idx, f1, **ukw)
+        pkg.linear_tc(hi, lo, pp.conv(scopes[2], True), out_f32=(out, 16), **last_kw)
+
+    run(dense, {}, dict(pool=k, rowmask=cnt))
+    run(comp, dict(units=units), dict(units=units, unit_pool=True))
+    assert torch.equal(dense, comp)
+    assert float(dense[..., 16:16 + mlp[-1]].max()) > 0
+    with pytest.raises(ValueError):
+        pkg.linear_tc(p_hi, p_lo, zconv, units=units, pool=8)
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -67,7 +67,16 @@ def dry(monkeypatch, oracle_ops):
         res = [(o.query_ball_point_dilated(lo, hi, k, n(xyz1), n(xyz2)) if dilated else o.query_ball_point(hi, k, n(xyz1), n(xyz2)))
                for lo, hi, k in zip(lows, highs, ks)]
         out = [t(r[0]) for r in res], [t(r[1]) for r in res]
-        return out + ([None] * len(ks),) if return_units else out      # no unit lists on the CPU: the dense route
+        if not return_units:
+            return out
+        units = []                                                   # the unit lists of include/ssd3d.h, in REVERSED group order
+        for r, k in zip(res, ks):                                    # (the order is unspecified: consumers may not rely on it)
+            cnt = r[1].reshape(-1)
+            lst = [(g << 4) | j for g in range(cnt.size - 1, -1, -1) for j in range((min(int(cnt[g]), k) + 7) // 8)]
+            u = np.full(1 + cnt.size * ((k + 7) // 8), -1, np.int32)
+            u[0] = len(lst); u[1:1 + len(lst)] = lst
+            units.append(t(u))
+        return out + (units,)
 
     def group_concat(xyz, points, new_xyz, idx, ldx=None):
         g = np.concatenate([o.group_point(n(points), n(idx)), o.group_point(n(xyz), n(idx)) - n(new_xyz)[:, :, None]], -1)
@@ -114,13 +123,44 @@ def dry(monkeypatch, oracle_ops):
             sp = split_rows(y)
         return ret, sp
 
+    def compact(x, units):
+        """Dense grouped rows (b, m, ns, C) -> the compact layout of the *_units kernels: 8 rows per listed unit at the start
+        of the buffer, NaN beyond (so that anything consuming rows it should not shows up)."""
+        b, m, ns, c = x.shape
+        u = n(units); nu = int(u[0])
+        flat = x.reshape(b * m, ns, c)
+        out = torch.full((b * m * ns, c), float("nan"), dtype=x.dtype)
+        for i in range(nu):
+            g, j = int(u[1 + i]) >> 4, int(u[1 + i]) & 15
+            out[8 * i: 8 * i + 8] = flat[g, 8 * j: 8 * j + 8]
+        return out.reshape(b, m, ns, c)
+
+    def unit_pool_into(y, units, out_f32):
+        """atomicMax of every unit's column maxima into its group's row of the caller's buffer (no fill of other groups)."""
+        buf, off = out_f32
+        u = n(units); nu = int(u[0])
+        rows = y.reshape(-1, y.shape[-1])
+        flat = buf.view(-1, buf.shape[-1])
+        assert not torch.isnan(flat[:, off: off + rows.shape[1]]).any()
+        for i in range(nu):
+            g = int(u[1 + i]) >> 4
+            mx = rows[8 * i: 8 * i + 8].max(dim=0).values
+            assert not torch.isnan(mx).any() and (mx >= 0).all()
+            flat[g, off: off + rows.shape[1]] = torch.maximum(flat[g, off: off + rows.shape[1]], mx)
+        return buf, None
+
     def conv(x, f, relu=True):
         y = (x[..., : f.cin].double() @ f.w.double()) * f.scale.double() + f.shift.double()
         return (torch.relu(y) if relu else y).float()
 
-    def linear_tc(a_hi, a_lo, f, relu=True, pool=1, rowmask=None, want_f32=True, want_split=False, out_f32=None, out_split=None):
+    def linear_tc(a_hi, a_lo, f, relu=True, pool=1, rowmask=None, want_f32=True, want_split=False, out_f32=None, out_split=None,
+                  units=None, unit_pool=False):
         assert a_hi.shape[-1] == f.kp and a_hi.dtype == torch.bfloat16
-        return emit(conv(unsplit(a_hi, a_lo), f, relu), pool, rowmask, want_f32, want_split, out_f32, out_split)
+        y = conv(unsplit(a_hi, a_lo), f, relu)
+        if unit_pool:
+            assert units is not None and relu and pool == 1 and rowmask is None and out_split is None and not want_split
+            return unit_pool_into(y, units, out_f32)
+        return emit(y, pool, rowmask, want_f32, want_split, out_f32, out_split)
 
     def grouped(xyz, points, new_xyz, idx):
         return group_concat(xyz, points, new_xyz, idx)
@@ -134,28 +174,42 @@ def dry(monkeypatch, oracle_ops):
     def linear_tc_gather(xyz, points, new_xyz, idx, f, relu=True, pool=1, rowmask=None, want_f32=False, want_split=True, out_f32=None, out_split=None):
         return emit(conv(grouped(xyz, points, new_xyz, idx), f, relu), pool, rowmask, want_f32, want_split, out_f32, out_split)
 
-    def linear_tc_hoisted(xyz, z, zoff, wx, new_xyz, idx, f, relu=True, pool=1, rowmask=None, want_f32=False, want_split=True, out_f32=None, out_split=None):
+    def linear_tc_hoisted(xyz, z, zoff, wx, new_xyz, idx, f, relu=True, pool=1, rowmask=None, want_f32=False, want_split=True, out_f32=None, out_split=None,
+                          units=None, unit_pool=False):
         assert f.cin == wx.shape[1]
-        return emit(conv(hoisted_operand(xyz, z, zoff, wx, new_xyz, idx), f, relu), pool, rowmask, want_f32, want_split, out_f32, out_split)
+        x = hoisted_operand(xyz, z, zoff, wx, new_xyz, idx)
+        if units is not None:
+            y = conv(compact(x, units), f, relu)
+            if unit_pool:
+                return unit_pool_into(y, units, out_f32)
+            return emit(y, 1, None, want_f32, want_split, out_f32, out_split)
+        return emit(conv(x, f, relu), pool, rowmask, want_f32, want_split, out_f32, out_split)
 
-    def fused(x, cnt, stack, out_f32, out_split, ns):
+    def fused(x, cnt, stack, out_f32, out_split, ns, units=None):
+        if units is not None:
+            assert out_split is None
+            x = compact(x, units)
         for f in stack.convs:
             x = conv(x, f)
+        if units is not None:
+            return unit_pool_into(x, units, out_f32)[0]
         y, _ = emit(x, ns, cnt if cnt is not None else None, out_f32 is None and out_split is None, False, out_f32, out_split)
         return y
 
     def sa_mlp_fused(xyz, points, new_xyz, idx, cnt, stack, out_f32=None, out_split=None, units=None):
         assert points.shape[-1] + 3 == stack.cin
-        return fused(grouped(xyz, points, new_xyz, idx), cnt, stack, out_f32, out_split, idx.shape[-1])
+        return fused(grouped(xyz, points, new_xyz, idx), cnt, stack, out_f32, out_split, idx.shape[-1], units)
 
     def sa_mlp_fused_hoisted(xyz, z, zoff, wx, new_xyz, idx, cnt, stack, out_f32=None, out_split=None, units=None):
         assert wx.shape[1] == stack.cin
-        return fused(hoisted_operand(xyz, z, zoff, wx, new_xyz, idx), cnt, stack, out_f32, out_split, idx.shape[-1])
+        return fused(hoisted_operand(xyz, z, zoff, wx, new_xyz, idx), cnt, stack, out_f32, out_split, idx.shape[-1], units)
 
     fakes = dict(
+        fill_zero=lambda x: x.zero_(),
         split_rows=split_rows, linear_tc=linear_tc, linear_tc_gather=linear_tc_gather, linear_tc_hoisted=linear_tc_hoisted,
         sa_mlp_fused=sa_mlp_fused, sa_mlp_fused_hoisted=sa_mlp_fused_hoisted,
-        hoist_expand_split=lambda xyz, z, zoff, wx, new_xyz, idx: split_rows(hoisted_operand(xyz, z, zoff, wx, new_xyz, idx)),
+        hoist_expand_split=lambda xyz, z, zoff, wx, new_xyz, idx, units=None: split_rows(
+            hoisted_operand(xyz, z, zoff, wx, new_xyz, idx) if units is None else compact(hoisted_operand(xyz, z, zoff, wx, new_xyz, idx), units)),
         group_concat_split=lambda xyz, points, new_xyz, idx, kp=None: split_rows(grouped(xyz, points, new_xyz, idx), kp),
         split_points=lambda p: (p[..., :3].contiguous(), p[..., 3:].contiguous()),
         farthest_point_sample=fps, farthest_point_sample_features=ffps, farthest_point_sample_with_distance=fpsd,
