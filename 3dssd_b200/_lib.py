@@ -69,6 +69,7 @@ _SIGNATURES = {
     "ssd3d_farthest_point_sample_ex": [c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_void_p],
     "ssd3d_fps_supports_rounds": [c_int, c_int],
+    "ssd3d_fps_temp_elems": [c_int, c_int, c_int, c_int],
     "ssd3d_farthest_point_sample_with_distance_ex": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                                      c_void_p],
     "ssd3d_farthest_point_sample_features_ex": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p,
@@ -101,6 +102,8 @@ def lib():
             fn = getattr(l, name)
             fn.argtypes = argtypes
             fn.restype = ctypes.c_size_t if name in ("ssd3d_sa_fused_smem", "ssd3d_query_ball_point_workspace", "ssd3d_bn_train_workspace") else c_int
+            if name == "ssd3d_fps_temp_elems":
+                fn.restype = c_long
         l.ssd3d_last_error.restype = ctypes.c_char_p
         l.ssd3d_last_error.argtypes = []
         _lib = l

@@ -19,28 +19,12 @@
 // which is reproduced by reducing the pair (value bits, key) with key = (k mod 1024, k div 1024).
 // Distances use the reference's contracted arithmetic: d = fma(dz,dz, fma(dy,dy, dx*dx)).
 #include "common.cuh"
+#include "fps.cuh"
 
 namespace ssd3d {
 
 constexpr int FPS_T = 256;  // threads per CTA
 constexpr int FPS_NW = FPS_T / 32;
-constexpr uint32_t KEY_INVALID = 0x7FFFFFFFu;
-
-// Where a launch reads and writes (the *_ex entry points of include/ssd3d.h): scene strides of the inputs in
-// elements (so a [:, a:b] slice of a dense [b,N,c] tensor needs no copy), row stride + value offset of the index
-// output (so the segments of a fusion-sampling layer land directly in the concatenated fps_idx tensor with the
-// segment offset already added, layers_util.py:109-111), and -- fps3_direct_kernel only -- the range of rounds
-// [j0, j1) this launch runs, the running distances travelling through `temp` between launches.
-struct FpsIO {
-    long long sa, sb;   // scene stride of inp / fa (sa) and fb (sb), in floats
-    int ldo, ioff;      // out row stride (ints), offset added to every stored index
-    int j0, j1;         // rounds [j0, j1) of 0..m (round 0 = "sample point 0")
-    float *temp;        // [b, n] running distances (resume state; NULL when j0 == 0 && j1 == m)
-};
-
-__device__ __forceinline__ uint32_t fps_key(int k) { return ((uint32_t)(k & 1023) << 21) | (uint32_t)(k >> 10); }
-__device__ __forceinline__ int fps_key_to_k(uint32_t key) { return (int)(((key & 0x1FFFFFu) << 10) | (key >> 21)); }
-
 // Ownership map: slot i of global thread g (g = cta_rank*256 + tid, TT = CL*256 threads per scene).
 // Each thread owns points of one residue class mod 1024 (or 1024/TT classes when TT < 1024), visited
 // in ascending key order, so "first strictly greater" inside a thread == smallest key among its maxima.
@@ -71,13 +55,6 @@ struct __align__(16) FpsPacket {
     uint32_t pad[3];
 };
 static_assert(sizeof(FpsPacket) == 32, "packet must be two 16-byte pieces");
-
-// (value,key) arg-max across a warp: max value, then min key among the lanes holding it.
-__device__ __forceinline__ void warp_argmax(uint32_t u, uint32_t key_if_valid, uint32_t &mx, uint32_t &kmin)
-{
-    mx = __reduce_max_sync(0xffffffffu, u);
-    kmin = __reduce_min_sync(0xffffffffu, (u == mx) ? key_if_valid : KEY_INVALID);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // Shared per-round machinery: given this thread's candidate (best value, slot, key), produce the
@@ -902,6 +879,14 @@ static bool fps3_direct_fits(int n, int cl, const float *inp, long long sa)
            (reinterpret_cast<uintptr_t>(inp) & 15u) == 0 && (sa % 4) == 0 && pick_p(n, cl) <= 16;
 }
 
+// floats of `temp` per scene a partial range of rounds needs: the running distances, plus (bucket kernel) the permutation
+extern "C" long ssd3d_fps_temp_elems(int n, int c, int m, int flags)
+{
+    if (n <= 0) return 0;
+    if (c == 3 && fps3_bucket_applies(n, m, nullptr, 0, flags)) return 2L * n;
+    return n;
+}
+
 extern "C" int ssd3d_fps_supports_rounds(int n, int c)
 {
     if (c != 3) return 0;
@@ -926,7 +911,12 @@ extern "C" int ssd3d_farthest_point_sample_ex(int b, int n, int c, int m, const 
     const bool partial = j0 > 0 || j1 < m;
     FpsIO io = {in_stride, 0, ldo, idx_offset, j0, j1, temp};
     int rc = -100;
-    if (c == 3) {
+    if (c == 3 && fps3_bucket_applies(n, m, inp, in_stride, flags)) {
+        // large scenes: one CTA per scene with spatial pruning (fps_bucket.cu); `cluster` does not apply
+        SSD3D_REQUIRE(!partial || temp != nullptr, "farthest_point_sample: a partial range of rounds carries its state in temp[b, 2n] "
+                      "(ssd3d_fps_temp_elems)");
+        rc = launch_fps3_bucket(b, n, m, inp, out, io, st);
+    } else if (c == 3) {
         int cl = pick_cl_xyz(n, cluster);
         while (cl < 16 && pick_p(n, cl) > 16) cl *= 2;
         // direct variant: whole scene resident in every CTA (bulk copy needs 16-byte aligned source and size)

@@ -404,7 +404,7 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                                                                 cluster=fps_cluster))
             parts.append((col, col + npoint, ev_d))
         elif in_parts and not isinstance(fps_parts, bool) and tf_ops.fps_supports_rounds(hi - lo, 3):
-            temp = torch.empty((bs, hi - lo), dtype=torch.float32, device=dev)
+            temp = torch.empty((bs, tf_ops.fps_temp_elems(hi - lo, 3, npoint)), dtype=torch.float32, device=dev)
             keep.append(temp)
             for j0, j1 in _part_bounds(npoint, fps_parts):
                 tf_ops.farthest_point_sample(npoint, tmp_xyz, out=(fps_idx, col), idx_offset=lo, rounds=(j0, j1), temp=temp,

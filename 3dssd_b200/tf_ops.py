@@ -70,17 +70,30 @@ def _idx_out(out, b, npoint, device):
     return buf[:, col:col + npoint], buf.data_ptr() + 4 * col, buf.shape[1]
 
 
-def farthest_point_sample(npoint, inp, *, out=None, idx_offset=0, rounds=None, temp=None, cluster=0, packet_kernel=False):
+def _fps_flags(packet_kernel, bucket_kernel):
+    return (1 if packet_kernel else 0) | (0 if bucket_kernel is None else (4 if bucket_kernel else 2))
+
+
+def fps_temp_elems(n, c=3, npoint=0, packet_kernel=False, bucket_kernel=None):
+    """float32 elements per scene of the `temp` buffer farthest_point_sample(..., rounds=...) carries its state in."""
+    return int(lib().ssd3d_fps_temp_elems(int(n), int(c), int(npoint), _fps_flags(packet_kernel, bucket_kernel)))
+
+
+def farthest_point_sample(npoint, inp, *, out=None, idx_offset=0, rounds=None, temp=None, cluster=0, packet_kernel=False,
+                          bucket_kernel=None):
     """inp: (batch, ndataset, c) float32 -> (batch, npoint) int32.  tf_sampling.py:43-51; shape check
     tf_sampling.cpp:142 (rank 3).
 
     Keyword extensions (include/ssd3d.h, ssd3d_farthest_point_sample_ex; none changes the sampled indices):
       out=(buffer, col)   write into columns [col, col+npoint) of an int32 (batch, L) buffer and return that view;
       idx_offset          added to every index (segment offset of a fusion-sampling layer, layers_util.py:109);
-      rounds=(j0, j1), temp   run only rounds [j0, j1); `temp` (batch, n) float32 carries the running distances
-                          between the calls (j0 == 0 starts fresh); the output must be the same buffer in every call;
+      rounds=(j0, j1), temp   run only rounds [j0, j1); `temp` (batch, fps_temp_elems(n, c, npoint)) float32 carries the
+                          running state between the calls (j0 == 0 starts fresh); the output must be the same buffer in
+                          every call;
       cluster             CTAs per scene: 0 heuristic, >0 exact, <0 heuristic capped at -cluster;
-      packet_kernel       use the general cluster kernel even where the resident-scene one applies (tests)."""
+      packet_kernel       use the general cluster kernel even where the resident-scene one applies (tests);
+      bucket_kernel       None: automatic (xyz scenes of 8192 < n <= 16384 points take the single-CTA kernel with spatial
+                          pruning, csrc/fps_bucket.cu), True / False: force (64 <= n <= 16384) / forbid it."""
     inp, stride = _scene_strided(inp, "inp")
     npoint = int(npoint)
     if npoint < 0:
@@ -88,14 +101,16 @@ def farthest_point_sample(npoint, inp, *, out=None, idx_offset=0, rounds=None, t
     b, n, c = inp.shape
     o, optr, ldo = _idx_out(out, b, npoint, inp.device)
     j0, j1 = (0, npoint) if rounds is None else (int(rounds[0]), int(rounds[1]))
+    flags = _fps_flags(packet_kernel, bucket_kernel)
+    elems = int(lib().ssd3d_fps_temp_elems(n, c, npoint, flags))
     if temp is None and (lib().ssd3d_fps_needs_temp(n, c) or (j0, j1) != (0, npoint)):
         if (j0, j1) != (0, npoint):
-            raise ValueError("a partial range of rounds needs the caller's temp (batch, n) float32 buffer")
-        temp = torch.empty((b, n), dtype=torch.float32, device=inp.device)
-    if temp is not None and (temp.dtype != torch.float32 or not temp.is_contiguous() or temp.numel() < b * n):
-        raise ValueError("temp must be a contiguous float32 buffer of at least batch * n elements")
+            raise ValueError("a partial range of rounds needs the caller's temp (batch, fps_temp_elems(...)) float32 buffer")
+        temp = torch.empty((b, elems), dtype=torch.float32, device=inp.device)
+    if temp is not None and (temp.dtype != torch.float32 or not temp.is_contiguous() or temp.numel() < b * elems):
+        raise ValueError("temp must be a contiguous float32 buffer of at least batch * fps_temp_elems(n, c, npoint) elements")
     check(lib().ssd3d_farthest_point_sample_ex(b, n, c, npoint, _p(inp), stride, _p(temp), ctypes.c_void_p(optr), ldo,
-                                               int(idx_offset), j0, j1, int(cluster), 1 if packet_kernel else 0, _stream()),
+                                               int(idx_offset), j0, j1, int(cluster), flags, _stream()),
           "farthest_point_sample")
     return o
 

@@ -50,18 +50,24 @@ int ssd3d_fps_needs_temp(int n, int c);
  *   in_stride   floats between consecutive scenes of inp (>= n*c): a [:, a:b] slice of a dense [b,N,c] tensor;
  *   ldo         ints between consecutive rows of out (>= m): a column block of the concatenated fps_idx tensor;
  *   idx_offset  added to every stored index (the `+ last_fps_end_index` of :109);
- *   j0, j1      run only rounds [j0, j1) of 0..m; the running distances travel through temp[b,n] between the launches
- *               (required when the range is partial).  A sample is final as soon as its round is done, so work on the
- *               first samples can overlap the remaining rounds.  Partial ranges need ssd3d_fps_supports_rounds(n, c);
+ *   j0, j1      run only rounds [j0, j1) of 0..m; the running state travels through temp[b, E] between the launches
+ *               (required when the range is partial), E = ssd3d_fps_temp_elems(n, c, m, flags) floats per scene.  A
+ *               sample is final as soon as its round is done, so work on the first samples can overlap the remaining
+ *               rounds.  Partial ranges need ssd3d_fps_supports_rounds(n, c);
  *   cluster     CTAs per scene: 0 = heuristic, 1/2/4/8/16 = exactly that, negative = heuristic capped at -cluster
  *               (FPS is latency-bound: fewer CTAs cost little time and leave SMs to concurrent work);
  *   flags       bit 0: use the general cluster kernel (coordinates travel in the packets) even where the
- *               resident-scene kernel applies.
+ *               resident-scene kernel applies; bit 1: never / bit 2: always (64 <= n <= 16384) take the single-CTA
+ *               kernel with spatial pruning (csrc/fps_bucket.cu) that c == 3 scenes of 8192 < n <= 16384 points and
+ *               m >= 256 get by default -- points grouped into spatially compact buckets of 32, a round updates only
+ *               the buckets whose bounding box lies closer to the new sample than their largest running distance
+ *               (the others provably keep every distance), so one SM per scene suffices; `cluster` is ignored there.
  * No state is kept in the library: every choice is an argument. */
 int ssd3d_farthest_point_sample_ex(int b, int n, int c, int m, const float *inp, long long in_stride, float *temp,
                                    int *out, int ldo, int idx_offset, int j0, int j1, int cluster, int flags,
                                    ssd3d_stream_t stream);
 int ssd3d_fps_supports_rounds(int n, int c);
+long ssd3d_fps_temp_elems(int n, int c, int m, int flags);
 
 /* replaces farthestpointsamplingwithdistLauncher(b,n,m,inp,temp,out)
  *   sampling/tf_sampling.cpp:164, sampling/tf_sampling_g.cu:396-398, kernel :181-230.

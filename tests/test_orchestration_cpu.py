@@ -48,9 +48,9 @@ def dry(monkeypatch, oracle_ops):
         buf[:, col + j0: col + j1] = t(res[:, j0:j1])
         return buf[:, col: col + npoint]
 
-    def fps(npoint, inp, *, out=None, idx_offset=0, rounds=None, temp=None, cluster=0, packet_kernel=False):
+    def fps(npoint, inp, *, out=None, idx_offset=0, rounds=None, temp=None, cluster=0, packet_kernel=False, bucket_kernel=None):
         if rounds is not None and tuple(rounds) != (0, npoint):
-            assert temp is not None and temp.shape == (inp.shape[0], inp.shape[1])
+            assert temp is not None and temp.shape == (inp.shape[0], 2 * inp.shape[1])      # fps_temp_elems of the fake
         return place(o.farthest_point_sample(npoint, n(inp)), out, idx_offset, inp.shape[0], npoint, rounds)
 
     def ffps(npoint, xyz, points=None, *, out=None, idx_offset=0, rounds=None, temp=None):
@@ -218,6 +218,7 @@ def dry(monkeypatch, oracle_ops):
         query_ball_point_multi=bq_multi, group_concat=group_concat, linear_bn_relu=linear_bn_relu,
         concat_rows=lambda parts: torch.cat(list(parts), dim=1).contiguous(),
         fps_supports_rounds=lambda nn, c=3: True, ffps_supported=lambda nn, c: c <= 68,
+        fps_temp_elems=lambda nn, c=3, npoint=0, **kw: 2 * nn,
         vote_translate=lambda xyz, off, rng: xyz + torch.minimum(torch.maximum(off[..., :3], torch.tensor(rng)), -torch.tensor(rng)),
     )
     for k, v in fakes.items():
