@@ -23,11 +23,14 @@ class SABackbone:
 
     def __init__(self, arch=None, params=None, in_channels=_cfg.INPUT_CHANNELS - 3, device="cuda", ffps_mode="direct",
                  seed=0, mlp_mode="tc", fuse_scale=True, head=None, gather_in_kernel=True, hoist_first=2, fps_cluster=0,
-                 latency_mode=False, fps_parts=(0.34, 0.28, 0.22, 0.16), fps_packet=False):
+                 latency_mode=False, fps_parts=(0.34, 0.28, 0.22, 0.16), fps_packet=False, fps_bucket=None):
         """fps_cluster: CTAs per scene of the D-FPS kernels (0 heuristic, < 0 cap; see tf_ops.farthest_point_sample).
         latency_mode: minimise the time of ONE step instead of the throughput of many in flight -- every SA layer
         consumes its sampling in parts (pointnet_sa_module_msg `fps_parts`): a lone D-FPS (layer 1) is cut into
-        resumable launches with the given round fractions, fusion-sampling layers hand over their halves separately."""
+        resumable launches with the given round fractions, fusion-sampling layers hand over their halves separately.
+        fps_bucket: layer-1 D-FPS kernel (tf_ops.farthest_point_sample `bucket_kernel`): the single-CTA kernel with spatial
+        pruning occupies one SM per scene but its round is longer than the 8-CTA cluster kernel's, so the default takes it
+        for throughput (many steps in flight share the SMs) and the cluster kernel in latency mode.  Same indices."""
         self.arch = _cfg.ARCH_3DSSD if arch is None else arch
         self.in_channels = in_channels
         self.device = torch.device(device)
@@ -41,6 +44,7 @@ class SABackbone:
         self.fuse_scale = fuse_scale
         self.fps_cluster = fps_cluster
         self.fps_packet = fps_packet
+        self.fps_bucket = (False if latency_mode else None) if fps_bucket is None else bool(fps_bucket)
         self.latency_mode = latency_mode
         self.fps_parts = fps_parts if isinstance(fps_parts, int) else list(fps_parts)
         self.head = head                      # optional head.DetectionHead: real detections instead of the stand-in block
@@ -67,7 +71,8 @@ class SABackbone:
                                              agg, params=self.params, ffps_mode=self.ffps_mode, return_debug=True,
                                              mlp_mode=self.mlp_mode, fuse_scale=self.fuse_scale,
                                              gather_in_kernel=self.gather_in_kernel, hoist_first=self.hoist_first,
-                                             fps_cluster=self.fps_cluster, fps_parts=parts, fps_packet=self.fps_packet)
+                                             fps_cluster=self.fps_cluster, fps_parts=parts, fps_packet=self.fps_packet,
+                                             fps_bucket=self.fps_bucket)
                 xyz_list.append(r[0]); feat_list.append(r[1]); fps_list.append(r[2]); dbg.append(r[3])
             elif ltype == "Vote_Layer":
                 nx, nf, off = L.vote_layer(xyz_list[xyz_i[0]], feat_list[feat_i[0]], mlps, False, None, bn, scope,

@@ -284,11 +284,12 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                            dilated_group, vote_ctr=None, aggregation_channel=None, debugging=False, epsilon=1e-5, *,
                            params, ffps_mode="direct", aggregation=None, return_debug=False, mlp_mode="tc",
                            fuse_scale=True, gather_in_kernel=True, hoist_first=2, fps_cluster=0, fps_parts=None,
-                           fps_packet=False):
+                           fps_packet=False, fps_bucket=None):
     """PointNet++ SA module with multi-scale grouping; returns (new_xyz, new_points, fps_idx).
 
     Keyword extensions (none changes a result):
       fps_cluster  CTAs per scene of the D-FPS kernels (tf_ops.farthest_point_sample `cluster`);
+      fps_bucket   lone D-FPS kernel choice (tf_ops.farthest_point_sample `bucket_kernel`: None automatic, False = cluster kernel);
       fps_packet   D-FPS with the coordinates-in-packet kernel (64 KiB of shared memory per CTA instead of the whole
                    scene: other kernels can share its SMs);
       fps_parts    latency mode.  FPS emits its samples in order, and a sample is final once its round is done, so the
@@ -404,15 +405,15 @@ def pointnet_sa_module_msg(xyz, points, radius_list, nsample_list, mlp_list, is_
                                                                 cluster=fps_cluster))
             parts.append((col, col + npoint, ev_d))
         elif in_parts and not isinstance(fps_parts, bool) and tf_ops.fps_supports_rounds(hi - lo, 3):
-            temp = torch.empty((bs, tf_ops.fps_temp_elems(hi - lo, 3, npoint)), dtype=torch.float32, device=dev)
+            temp = torch.empty((bs, tf_ops.fps_temp_elems(hi - lo, 3, npoint, bucket_kernel=fps_bucket)), dtype=torch.float32, device=dev)
             keep.append(temp)
             for j0, j1 in _part_bounds(npoint, fps_parts):
                 tf_ops.farthest_point_sample(npoint, tmp_xyz, out=(fps_idx, col), idx_offset=lo, rounds=(j0, j1), temp=temp,
-                                             cluster=fps_cluster)
+                                             cluster=fps_cluster, bucket_kernel=fps_bucket)
                 parts.append((col + j0, col + j1, ev_main()))
         else:
             tf_ops.farthest_point_sample(npoint, tmp_xyz, out=(fps_idx, col), idx_offset=lo, cluster=fps_cluster,
-                                         packet_kernel=fps_packet)
+                                         packet_kernel=fps_packet, bucket_kernel=fps_bucket)
             parts.append((col, col + npoint, ev_main() if in_parts else None))
         col += width
 

@@ -319,6 +319,8 @@ def main():
     ap.add_argument("--fps-cluster", type=int, default=None,
                     help="CTAs per scene of the D-FPS kernels: 0 heuristic, >0 exact, <0 cap; default -4 when steps are pipelined (frees SMs), else 0")
     ap.add_argument("--fps-packet", action="store_true", help="experiment: lone D-FPS with the coordinates-in-packet kernel (small shared-memory footprint)")
+    ap.add_argument("--fps-bucket", default="auto", choices=["auto", "on", "off"],
+                    help="layer-1 D-FPS of the throughput step: auto/on = single-CTA kernel with spatial pruning, off = cluster kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-scenes", type=int, default=2)
     args = ap.parse_args()
@@ -356,7 +358,7 @@ def main():
     mk = dict(in_channels=1, device=dev, ffps_mode=args.ffps_mode, mlp_mode=args.mlp_mode, head=head,
               gather_in_kernel=bool(args.gather_in_kernel), hoist_first=args.hoist_first)
     net = pkg.SABackbone(arch, params, fps_cluster=args.fps_cluster, latency_mode=bool(args.no_graph and args.latency_mode),
-                         fps_packet=args.fps_packet, **mk)
+                         fps_packet=args.fps_packet, fps_bucket={"auto": None, "on": True, "off": False}[args.fps_bucket], **mk)
     net_lat = pkg.SABackbone(arch, params, fps_cluster=0, latency_mode=True, **mk)
     pts = torch.from_numpy(pts_np).to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
@@ -391,6 +393,9 @@ def main():
     torch.cuda.synchronize()
     for n in counted:
         setattr(L, n, Counting(n, originals[n]))
+    # the GPU is held busy while the host enqueues the whole step, so that each event pair brackets kernel time only (an
+    # idle GPU would add the host's launch preparation -- tensor-map encoding, ctypes -- to every short kernel)
+    torch.cuda._sleep(int(0.08 * 1.9e9))
     with MlpTimer(torch, pkg.tf_ops) as mt:
         out = net.forward(pts)
         net.detections(out[0], out[1], out=gather0.out())
@@ -520,24 +525,28 @@ def main():
 
     # ---- the layer-1 D-FPS chain timed alone with events on its stream -------------------------------------
     xyz = pts[..., :3].contiguous()
-    for _ in range(3):
-        pkg.farthest_point_sample(4096, xyz)
-    torch.cuda.synchronize()
-    kev = []
-    for _ in range(max(5, min(args.steps, 20))):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        pkg.farthest_point_sample(4096, xyz)
-        e1.record()
-        kev.append((e0, e1))
-    torch.cuda.synchronize()
-    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+
+    def time_fps(bucket):
+        for _ in range(3):
+            pkg.farthest_point_sample(4096, xyz, bucket_kernel=bucket)
+        torch.cuda.synchronize()
+        kev = []
+        for _ in range(max(5, min(args.steps, 20))):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pkg.farthest_point_sample(4096, xyz, bucket_kernel=bucket)
+            e1.record()
+            kev.append((e0, e1))
+        torch.cuda.synchronize()
+        return float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    k_ms = time_fps(False)            # 8-CTA cluster kernel: the latency-mode step
+    kb_ms = time_fps(True)            # single-CTA kernel with spatial pruning: the throughput step
 
     if world > 1:
-        t = torch.tensor([k_ms, mlp_ms, latency_ms, latency_thr_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([k_ms, mlp_ms, latency_ms, latency_thr_ms, kb_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        k_ms, mlp_ms, latency_ms, latency_thr_ms = (float(v) for v in t.tolist())
+        k_ms, mlp_ms, latency_ms, latency_thr_ms, kb_ms = (float(v) for v in t.tolist())
 
     if rank == 0:
         peaks = {}
@@ -558,7 +567,7 @@ def main():
                        "global_batch": SCENES_PER_GPU * world, "points": NPOINTS, "parallelism": "scene-sharded dp%d" % world,
                        "ffps": args.ffps_mode, "mlp": args.mlp_mode, "cuda_graph": not args.no_graph,
                        "l2": "flushed (256 MiB write) before every timed step",
-                       "steps_in_flight": P, "fps_cluster": args.fps_cluster, "allgather_in_graph": bool(gather_in_graph and not args.no_graph),
+                       "steps_in_flight": P, "fps_cluster": args.fps_cluster, "fps_l1_kernel": "cluster" if net.fps_bucket is False else "bucket (1 CTA per scene)", "allgather_in_graph": bool(gather_in_graph and not args.no_graph),
                        "latency_ms_single_step": latency_ms,
                        "latency_ms_single_step_throughput_graph": latency_thr_ms,
                        "latency_note": "one step at a time with a sync after each (as the reference arm runs): latency-mode "
@@ -586,7 +595,10 @@ def main():
                                  "peak = MEASURED_PEAKS.json bf16_tflops (burst: kernels timed one at a time)"
                                  + ("" if peaks else " [fallback 1700: file absent]")
                                  + "; algorithmic = 2*B*M*K*sum(Cin*Cout) unpadded incl. the hoisted first convs (SURVEY 8d), fp32-grade"},
-            "roofline_fps": {"bound": "latency", "kernel": "fps3_direct_kernel (D-FPS layer 1, 16384->4096, B=8, 8 CTAs per scene), timed alone",
+            "roofline_fps": {"bound": "latency", "kernel": "fps3_direct_kernel (D-FPS layer 1, 16384->4096, B=8, 8 CTAs per scene: the latency-mode step), timed alone",
+                             "throughput_kernel": {"kernel": "fps3_bucket_kernel (same sampling, ONE CTA per scene, spatial pruning: the throughput step)",
+                                                   "kernel_ms": kb_ms, "ns_per_round": kb_ms * 1e6 / 4095, "sm_ms_per_batch": 8 * kb_ms,
+                                                   "cluster_kernel_sm_ms_per_batch": 64 * k_ms},
                              "kernel_ms": k_ms, "rounds": 4095, "ns_per_round": k_ms * 1e6 / 4095,
                              "floor_ns_per_round": 271.0,
                              "floor_note": "critical path of one round at 1.965 GHz: 4 packed distance updates + compare chain (~60 cyc) "
