@@ -614,8 +614,15 @@ def main():
             line["cpu_baseline"] = cpu_baseline(arch, params, head_params, pts_np, args.cpu_scenes)
         print(json.dumps(line))
     if world > 1:
+        # Every number is out.  The captured step graphs hold NCCL kernels of their pipelines' communicators and NCCL's
+        # communicator teardown waits for the graphs that captured it (destroy_process_group() hung here for the full time limit
+        # of a 2-GPU run, after the JSON line was printed): meet at a barrier, then leave without the teardown.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_reference(args, torch, pkg, arch, params, head_params, pts_np, rank, world, dev, sampler):
