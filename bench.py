@@ -246,6 +246,7 @@ class MlpTimer:
         return (int(x) + 15) // 16 * 16
 
     def _flops(self, name, a, kw):
+        """Called from summary(), after the step has drained (a unit count is read back from the device)."""
         r16 = self._r16
         urows = None
         if kw.get("units") is not None:                 # unit-list route: 128-row tiles of 16 listed 8-row units
@@ -278,7 +279,7 @@ class MlpTimer:
                 e0.record()
                 r = _fn(*a, **kw)
                 e1.record()
-                self.rec.append((_n, e0, e1, 3.0 * self._flops(_n, a, kw)))      # (may read a unit count: after the events)
+                self.rec.append((_n, e0, e1, a, kw))
                 return r
             setattr(self.tf_ops, n, wrap)
         return self
@@ -291,7 +292,8 @@ class MlpTimer:
         self.torch.cuda.synchronize()
         per = {}
         tot_ms = tot_fl = 0.0
-        for n, e0, e1, fl in self.rec:
+        for n, e0, e1, a, kw in self.rec:
+            fl = 3.0 * self._flops(n, a, kw)
             ms = e0.elapsed_time(e1)
             tot_ms += ms; tot_fl += fl
             d = per.setdefault(n, [0, 0.0, 0.0])
@@ -315,7 +317,7 @@ def main():
     ap.add_argument("--hoist-first", type=int, default=2, help="first conv of an SA scale evaluated per point (hoisted), not per grouped row: 0 off, 1 layer-by-layer scales, 2 all")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu captures)")
     ap.add_argument("--latency-mode", action="store_true", help="with --no-graph: run the latency-mode network (for ncu captures)")
-    ap.add_argument("--pipeline", type=int, default=8, help="steps in flight (independent CUDA graphs on separate streams)")
+    ap.add_argument("--pipeline", type=int, default=24, help="steps in flight (independent CUDA graphs on separate streams)")
     ap.add_argument("--fps-cluster", type=int, default=None,
                     help="CTAs per scene of the D-FPS kernels: 0 heuristic, >0 exact, <0 cap; default -4 when steps are pipelined (frees SMs), else 0")
     ap.add_argument("--fps-packet", action="store_true", help="experiment: lone D-FPS with the coordinates-in-packet kernel (small shared-memory footprint)")
