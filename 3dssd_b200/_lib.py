@@ -68,6 +68,8 @@ _SIGNATURES = {
     "ssd3d_ffps_supported": [c_int, c_int],
     "ssd3d_farthest_point_sample_ex": [c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_void_p],
+    "ssd3d_peer_allgather": [c_void_p, ctypes.c_size_t, c_void_p, c_int, c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t,
+                             ctypes.c_size_t, c_void_p, c_void_p, c_void_p],
     "ssd3d_fps_supports_rounds": [c_int, c_int],
     "ssd3d_fps_temp_elems": [c_int, c_int, c_int, c_int],
     "ssd3d_farthest_point_sample_with_distance_ex": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -73,14 +73,17 @@ class DetectionGather:
         self.b_local = hi - lo
         self.b_max = (self.total + self.world - 1) // self.world
         self.block_bytes = self.b_max * self.max_output * BLOCK_COLS * 4
-        self.slice_bytes = self.block_bytes + self.b_max * 4
+        self.slice_bytes = (self.block_bytes + self.b_max * 4 + 15) // 16 * 16      # 16-byte multiple (vector copies)
+        self._alloc(device)
+
+    def _alloc(self, device):
         self.send = torch.zeros((self.slice_bytes,), dtype=torch.uint8, device=device)
         self.raw = self.send if self.world == 1 else torch.zeros((self.world * self.slice_bytes,), dtype=torch.uint8,
                                                                  device=device)
 
     def _views(self, buf):
         blk = buf[: self.block_bytes].view(torch.float32).view(self.b_max, self.max_output, BLOCK_COLS)
-        cnt = buf[self.block_bytes: self.slice_bytes].view(torch.int32)
+        cnt = buf[self.block_bytes: self.block_bytes + self.b_max * 4].view(torch.int32)
         return blk, cnt
 
     def out(self):
@@ -100,6 +103,71 @@ class DetectionGather:
         if self.world == 1:
             return blocks[0], counts[0]
         return torch.cat(blocks, dim=0), torch.cat(counts, dim=0)
+
+
+def peer_layout(world, slice_bytes):
+    """Byte offsets inside one pipeline's share of the symmetric allocation (csrc/peer_gather.cu):
+    ((recv_off parity 0, parity 1), (flag_off parity 0, parity 1), total bytes)."""
+    recv = world * slice_bytes
+    flags = (world * 4 + 15) // 16 * 16
+    return (0, recv), (2 * recv, 2 * recv + flags), 2 * recv + 2 * flags
+
+
+class PeerArena:
+    """ONE symmetric allocation (mapped into every rank of `group`) shared by all step pipelines of a process: a single
+    rendezvous instead of one per pipeline.  take(nbytes) hands out 256-byte aligned shares, in the same order on every rank."""
+
+    def __init__(self, nbytes, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = dist.group.WORLD if group is None else group
+        self.buf = symm.empty((int(nbytes),), dtype=torch.uint8, device=device)
+        self.handle = symm.rendezvous(self.buf, self.group)
+        self.buf.zero_()                                  # flags start at 0, before any peer can write
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+        self.peer_bases = [int(p) for p in self.handle.buffer_ptrs]
+        self.used = 0
+
+    @staticmethod
+    def share_bytes(world, slice_bytes):
+        return (peer_layout(world, slice_bytes)[2] + 255) // 256 * 256
+
+    def take(self, nbytes):
+        off = self.used
+        self.used += (int(nbytes) + 255) // 256 * 256
+        if self.used > self.buf.numel():
+            raise ValueError("PeerArena exhausted")
+        return off
+
+
+class PeerGather(DetectionGather):
+    """DetectionGather with the exchange done by ONE kernel of this library over NVLink peer memory
+    (tf_ops.peer_allgather, csrc/peer_gather.cu) instead of ncclAllGather: every rank stores its slice straight into
+    the peers' symmetric buffers, publishes a flag and waits for theirs.  Same interface and the same `raw` layout;
+    capturable; pipelines need no process group of their own (nothing here is a communicator).  Every rank must call
+    gather() the same number of times."""
+
+    def __init__(self, total_scenes, device, arena, max_output=MAX_OUTPUT_NUM):
+        self.arena = arena
+        super().__init__(total_scenes, device, group=arena.group, max_output=max_output)
+
+    def _alloc(self, device):
+        from . import tf_ops                                   # (tf_ops does not import this module)
+        self._tf_ops = tf_ops
+        super()._alloc(device)
+        self.raw = torch.zeros((self.world * self.slice_bytes,), dtype=torch.uint8, device=device)
+        self.recv_off, self.flag_off, total = peer_layout(self.world, self.slice_bytes)
+        base = self.arena.take(total)
+        self.peers = torch.tensor([b + base for b in self.arena.peer_bases], dtype=torch.int64, device=device)
+        self.state = torch.zeros((4,), dtype=torch.int32, device=device)   # replay count, CTA count, time-outs
+
+    def timeouts(self):
+        """Waits that gave up (a peer that never delivered): 0 in a healthy run.  Synchronises."""
+        return int(self.state[2].item())
+
+    def gather(self):
+        self._tf_ops.peer_allgather(self.send, self.peers, self.world, self.rank, self.slice_bytes, self.recv_off, self.flag_off,
+                                    self.state, self.raw)
 
 
 def gather_detections(block, count, total_scenes, group=None):

@@ -810,6 +810,21 @@ def fill_zero(t):
     return t
 
 
+def peer_allgather(send, peers, world, rank, slice_bytes, recv_off, flag_off, state, out):
+    """All-gather of one slice per rank over NVLink peer memory (include/ssd3d.h, ssd3d_peer_allgather).
+    send: uint8 [slice_bytes]; peers: int64 CUDA tensor [world] of the ranks' symmetric-buffer bases as mapped in THIS
+    process; state: int32 [>= 3] zero-initialised, owned by this exchange (state[2] counts waits that timed out); out: uint8
+    [world * slice_bytes]."""
+    for name, t, dt in (("send", send, torch.uint8), ("peers", peers, torch.int64), ("state", state, torch.int32), ("out", out, torch.uint8)):
+        if t.dtype != dt or not t.is_cuda or not t.is_contiguous():
+            raise ValueError("%s must be a contiguous CUDA tensor of %s" % (name, dt))
+    if send.numel() < slice_bytes or out.numel() < world * slice_bytes or peers.numel() < world or state.numel() < 3:
+        raise ValueError("peer_allgather: buffers smaller than world=%d slices of %d bytes" % (world, slice_bytes))
+    check(lib().ssd3d_peer_allgather(_p(send), int(slice_bytes), _p(peers), int(world), int(rank), int(recv_off[0]), int(recv_off[1]),
+                                     int(flag_off[0]), int(flag_off[1]), _p(state), _p(out), _stream()), "peer_allgather")
+    return out
+
+
 def split_points(points):
     """(b, n, 3 + c) -> xyz (b, n, 3), features (b, n, c): single_stage_detector.py:116-117."""
     points = _req(points, "points", torch.float32, 3)

@@ -323,6 +323,8 @@ def main():
     ap.add_argument("--fps-packet", action="store_true", help="experiment: lone D-FPS with the coordinates-in-packet kernel (small shared-memory footprint)")
     ap.add_argument("--fps-bucket", default="auto", choices=["auto", "on", "off"],
                     help="layer-1 D-FPS of the throughput step: auto/on = single-CTA kernel with spatial pruning, off = cluster kernel")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: the per-step all-gather as this library's peer-memory kernel (default) or as ncclAllGather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-scenes", type=int, default=2)
     args = ap.parse_args()
@@ -402,14 +404,37 @@ def main():
         out = net.forward(pts)
         net.detections(out[0], out[1], out=gather0.out())
     mlp_ms, mlp_flops, mlp_per = mt.summary()
-    launches_per_step = counter["n"] + (1 if world > 1 else 0)                 # + ncclAllGather
+    launches_per_step = counter["n"] + (1 if world > 1 else 0)                 # + the exchange (peer_allgather_kernel / ncclAllGather)
     for n in counted:
         setattr(L, n, originals[n])
 
     # ---- steps in flight: P independent step pipelines (own CUDA graph + static buffers + stream + communicator).
     streams = [torch.cuda.Stream(device=dev) for _ in range(P)]
-    groups = [dist.new_group(ranks=list(range(world))) if world > 1 else None for _ in range(P)]
-    gathers = [pkg.dist.DetectionGather(total_scenes, dev, group=groups[k]) for k in range(P)]
+    exchange = "none" if world == 1 else args.exchange
+    gathers = None
+    if exchange == "peer":
+        # one symmetric allocation for all pipelines (+ the latency-mode graph), the exchange itself is a kernel of libssd3d
+        try:
+            probe = pkg.dist.DetectionGather(total_scenes, dev)
+            arena = pkg.dist.PeerArena((P + 2) * pkg.dist.PeerArena.share_bytes(world, probe.slice_bytes), dev)
+            gathers = [pkg.dist.PeerGather(total_scenes, dev, arena) for _ in range(P)]
+            # cross-check against ncclAllGather once, eagerly: same bytes on every rank
+            chk_p, chk_n = pkg.dist.PeerGather(total_scenes, dev, arena), pkg.dist.DetectionGather(total_scenes, dev)
+            o = net.forward(pts)
+            for g in (chk_p, chk_n):
+                net.detections(o[0], o[1], out=g.out())
+                g.gather()
+            torch.cuda.synchronize()
+            same = torch.tensor([int(torch.equal(chk_p.raw, chk_n.raw) and chk_p.timeouts() == 0)], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            if int(same.item()) != 1:
+                raise RuntimeError("peer exchange disagrees with ncclAllGather")
+        except Exception as e:  # noqa: BLE001 -- no symmetric memory on this box: fall back to NCCL, and say so
+            sys.stderr.write("bench.py: peer-memory exchange unavailable (%s); using ncclAllGather\n" % str(e).splitlines()[0])
+            exchange, gathers = "nccl", None
+    groups = [dist.new_group(ranks=list(range(world))) if exchange == "nccl" else None for _ in range(P)]
+    if gathers is None:
+        gathers = [pkg.dist.DetectionGather(total_scenes, dev, group=groups[k]) for k in range(P)]
     runners = []
     gather_in_graph = True
     for k in range(P):
@@ -507,7 +532,10 @@ def main():
     # ---- single-step latency: one step at a time, sync after each, latency-mode network --------------------
     lat_runner = None
     if not args.no_graph:
-        lat_runner = net_lat.capture(pts, gather=pkg.dist.DetectionGather(total_scenes, dev, group=groups[0]) if gather_in_graph else None)
+        lat_gather = None
+        if gather_in_graph:
+            lat_gather = pkg.dist.PeerGather(total_scenes, dev, arena) if exchange == "peer" else pkg.dist.DetectionGather(total_scenes, dev, group=groups[0])
+        lat_runner = net_lat.capture(pts, gather=lat_gather)
     thr_runner = runners[0]
 
     def serial_latency(run, nrep):
@@ -570,6 +598,9 @@ def main():
                        "ffps": args.ffps_mode, "mlp": args.mlp_mode, "cuda_graph": not args.no_graph,
                        "l2": "flushed (256 MiB write) before every timed step",
                        "steps_in_flight": P, "fps_cluster": args.fps_cluster, "fps_l1_kernel": "cluster" if net.fps_bucket is False else "bucket (1 CTA per scene)", "allgather_in_graph": bool(gather_in_graph and not args.no_graph),
+                       "exchange": {"peer": "libssd3d peer_allgather_kernel over NVLink peer memory (symmetric buffers), inside the step graph",
+                                    "nccl": "ncclAllGather, one communicator per pipeline", "none": "single GPU"}[exchange],
+                       "exchange_timeouts": sum(g.timeouts() for g in gathers) if exchange == "peer" else 0,
                        "latency_ms_single_step": latency_ms,
                        "latency_ms_single_step_throughput_graph": latency_thr_ms,
                        "latency_note": "one step at a time with a sync after each (as the reference arm runs): latency-mode "

@@ -338,6 +338,22 @@ int ssd3d_vote_translate(long rows, const float *xyz, const float *offsets, int 
 int ssd3d_decode_dist_anchor_free(long rows, int angle_bins, const float *center_xyz, const float *pred_reg, int ld_reg,
                                   const float *pred_cls, int ld_cls, float *boxes, float *scores, ssd3d_stream_t stream);
 
+/* ---- sharded step: exchange over NVLink peer memory ---------------------------------------- */
+
+/* All-gather of one slice per rank as ONE kernel (csrc/peer_gather.cu): no reference counterpart (the reference's
+ * inference is single-GPU, lib/core/evaluator.py:145-147); replaces the ncclAllGather of the per-scene detection blocks at
+ * the end of a sharded step.  peer_base: DEVICE array [world] with the base address of every rank's symmetric buffer as
+ * mapped in this process (e.g. torch.distributed._symmetric_memory buffer_ptrs); inside it, for parity q in {0,1}:
+ * recv_off<q> = world slices of slice_bytes, flag_off<q> = world int32 flags, all zero before the first call.  The call
+ * stores src into slot `rank` of every peer's receive area, publishes replay number s (kept in state[0], so a captured
+ * launch needs no changing argument; state = 3 zero-initialised ints owned by this exchange) with release semantics at
+ * system scope, waits for the peers' flags and copies the received slices to out[world][slice_bytes].  Every rank must
+ * make the same sequence of calls; two parities make reuse safe without acknowledgements.  A wait of ~4 s gives up and
+ * increments state[2] instead of hanging the GPU. */
+int ssd3d_peer_allgather(const void *src, size_t slice_bytes, void *const *peer_base, int world, int rank,
+                         size_t recv_off0, size_t recv_off1, size_t flag_off0, size_t flag_off1, int *state, void *out,
+                         ssd3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1011,6 +1011,36 @@ def test_linear_tc_unit_list_equals_dense(pkg, cuda, c, k, mlp, expand):
         pkg.linear_tc(p_hi, p_lo, zconv, units=units, pool=8)
 
 
+def test_peer_allgather_protocol_three_simulated_ranks(pkg, cuda):
+    """csrc/peer_gather.cu on ONE device: three "ranks" are three streams, each with its own symmetric buffer (here plain
+    allocations of the same process -- the kernel only sees addresses).  Several replays: parity reuse, the device-side
+    replay counter and the flag protocol; every rank ends with everybody's slice of that replay."""
+    dist_mod = pkg.dist
+    world, slice_bytes = 3, 28832
+    recv_off, flag_off, total = dist_mod.peer_layout(world, slice_bytes)
+    assert recv_off[1] == world * slice_bytes and flag_off[0] == 2 * world * slice_bytes and total >= flag_off[1] + world * 4
+    sym = [torch.zeros((total,), dtype=torch.uint8, device=cuda) for _ in range(world)]
+    peers = torch.tensor([t.data_ptr() for t in sym], dtype=torch.int64, device=cuda)
+    send = [torch.zeros((slice_bytes,), dtype=torch.uint8, device=cuda) for _ in range(world)]
+    out = [torch.zeros((world * slice_bytes,), dtype=torch.uint8, device=cuda) for _ in range(world)]
+    state = [torch.zeros((4,), dtype=torch.int32, device=cuda) for _ in range(world)]
+    streams = [torch.cuda.Stream(device=cuda) for _ in range(world)]
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    for replay in range(1, 6):
+        payload = [torch.randint(0, 256, (slice_bytes,), dtype=torch.uint8, generator=gen) for _ in range(world)]
+        for r in range(world):
+            send[r].copy_(payload[r])
+        torch.cuda.synchronize()
+        for r in (2, 0, 1):                                      # launch order != rank order: early ranks wait for late ones
+            with torch.cuda.stream(streams[r]):
+                pkg.tf_ops.peer_allgather(send[r], peers, world, r, slice_bytes, recv_off, flag_off, state[r], out[r])
+        torch.cuda.synchronize()
+        want = torch.cat(payload)
+        for r in range(world):
+            assert torch.equal(out[r].cpu(), want), "rank %d replay %d" % (r, replay)
+            assert state[r].cpu().tolist()[:3] == [replay, 0, 0]
+
+
 # ---------------------------------------------------------------------------------------------------------
 # training-mode BatchNorm (row f3)
 # ---------------------------------------------------------------------------------------------------------
