@@ -602,6 +602,33 @@ __global__ void split_rows_kernel(long rows, int c, const float *__restrict__ x,
     }
 }
 
+// the same, one 8-column chunk per thread and step: two 16-byte loads (when the source rows allow), two 16-byte stores
+__global__ void __launch_bounds__(256)
+split_rows_v8_kernel(unsigned nchunks, int c, const float *__restrict__ x, int ldx, __nv_bfloat16 *__restrict__ hi,
+                     __nv_bfloat16 *__restrict__ lo, int kp, int vec)
+{
+    const unsigned cpr = (unsigned)kp >> 3;                            // chunks per row
+    for (unsigned ch = blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += gridDim.x * blockDim.x) {
+        const unsigned row = ch / cpr;
+        const int k0 = (int)(ch - row * cpr) * 8;
+        const float *src = x + (size_t)row * ldx + k0;
+        float f[8];
+        if (vec && k0 + 8 <= c) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(src)), b2 = __ldg(reinterpret_cast<const float4 *>(src + 4));
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b2.x; f[5] = b2.y; f[6] = b2.z; f[7] = b2.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) f[e] = k0 + e < c ? __ldg(src + e) : 0.0f;
+        }
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) split_pair(f[2 * t], f[2 * t + 1], hw[t], lw[t]);
+        const size_t off = (size_t)row * kp + k0;
+        *reinterpret_cast<uint4 *>(hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4 *>(lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+}
+
 // fused gather + concat[features, rel-xyz] + split (layers_util.py:160-165), zero-padded to kp columns.
 // One warp per output row: the source feature row is one contiguous run (coalesced 16-byte loads when c % 4 == 0),
 // the two bf16 rows are written as contiguous 8-byte pieces.
@@ -1062,6 +1089,15 @@ extern "C" int ssd3d_split_rows(long rows, int c, const float *x, int ldx, void 
     SSD3D_REQUIRE(x && hi && lo, "split_rows: null pointer");
     const long total = rows * kp;
     if (total == 0) return 0;
+    const long nchunks = total / 8;
+    if (nchunks < (1L << 31) && ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15u) == 0) {
+        const int vec = (ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) ? 1 : 0;
+        const long want = (nchunks + 255) / 256;
+        const int blocks = (int)(want < (long)kNumSMs * 16 ? want : (long)kNumSMs * 16);
+        split_rows_v8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((unsigned)nchunks, c, x, ldx, (__nv_bfloat16 *)hi,
+                                                                       (__nv_bfloat16 *)lo, kp, vec);
+        SSD3D_LAUNCH_CHECK("split_rows_v8_kernel");
+    }
     const long want = (total + 255) / 256;
     const int blocks = (int)(want < (long)kNumSMs * 16 ? want : (long)kNumSMs * 16);
     split_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rows, c, x, ldx, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, kp);

@@ -447,6 +447,20 @@ def rel_err(got, exp, rtol=1e-3, atol_frac=2e-5):
     return float(np.abs(g - e).max() / scale)
 
 
+@pytest.mark.parametrize("rows,c", [(1000, 1), (333, 3), (4096, 64), (257, 67), (129, 130), (50, 512)])
+def test_split_rows_exact(pkg, cuda, rows, c):
+    """x = hi + lo with hi = bf16(x), lo = bf16(x - hi), zero padding up to the multiple of 16 (both kernels: 16-byte path
+    for c % 4 == 0, scalar otherwise)."""
+    x = torch.from_numpy(np.random.default_rng(rows + c).standard_normal((rows, c)).astype(np.float32) * 37.0).to(cuda)
+    hi, lo = pkg.split_rows(x)
+    kp = (c + 15) // 16 * 16
+    assert hi.shape == (rows, kp) and lo.shape == (rows, kp)
+    eh = x.to(torch.bfloat16)
+    el = (x - eh.float()).to(torch.bfloat16)
+    assert torch.equal(hi[:, :c], eh) and torch.equal(lo[:, :c], el)
+    assert bool((hi[:, c:] == 0).all()) and bool((lo[:, c:] == 0).all())
+
+
 @pytest.mark.parametrize("rows,cin,cout", [(1000, 4, 16), (4096, 67, 64), (777, 131, 128), (512, 259, 256), (130, 512, 1024)])
 def test_linear_bn_relu_vs_oracle(pkg, oracle_ops, cuda, rows, cin, cout):
     rng = np.random.default_rng(rows)

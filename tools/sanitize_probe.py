@@ -125,7 +125,62 @@ def small_ops():
     pkg.tf_ops.concat_rows([xyz[:, :100].contiguous(), xyz[:, 100:300].contiguous()])
 
 
-ALL = [fps3_direct, fps3_packet, ffps_cluster, fpsdist_and_generic, ball_query, sa_fused, linear_tc, small_ops]
+def fps_bucket():                        # single-CTA D-FPS with spatial pruning, incl. a resumed launch
+    pts = synth.kitti_like(1, 2048, seed=9)[..., :3].copy()
+    exp = oops.farthest_point_sample(80, pts)
+    got = pkg.farthest_point_sample(80, T(pts), bucket_kernel=True)
+    assert np.array_equal(got.cpu().numpy(), exp)
+    buf = torch.zeros((1, 80), dtype=torch.int32, device=dev)
+    temp = torch.empty((1, pkg.tf_ops.fps_temp_elems(2048, 3, 80, bucket_kernel=True)), device=dev)
+    for j0, j1 in ((0, 30), (30, 80)):
+        pkg.farthest_point_sample(80, T(pts), out=(buf, 0), rounds=(j0, j1), temp=temp, bucket_kernel=True)
+    assert np.array_equal(buf.cpu().numpy(), exp)
+
+
+def unit_lists():                        # culled ball query emitting unit lists -> fused and layer-by-layer kernels on them
+    pts = synth.kitti_like(2, 2048, seed=10)[..., :3].copy()
+    xyz, feat = T(pts), T(np.maximum(rng.standard_normal((2, 2048, 64)), 0).astype(np.float32))
+    new_xyz = xyz[:, :96].contiguous()
+    for grid in (True, False):
+        (idx,), (cnt,), (units,) = pkg.query_ball_point_multi([0.0], [1.0], [32], xyz, new_xyz, False, grid=grid, return_units=True)
+        prm, scopes = _stack(64, [64, 64, 128])
+        pp = P.prepare(prm, dev)
+        zconv, wxs, n1s = pp.hoisted([scopes[0]], True, 64)
+        hi, lo = pkg.tf_ops.split_rows(feat)
+        z, _ = pkg.tf_ops.linear_tc(hi, lo, zconv, relu=False, want_f32=True, want_split=False)
+        hst = pp.fused_stack(scopes[1:], True, n1s[0], limit=0)
+        dense = torch.zeros((2, 96, 128), device=dev); comp = torch.zeros_like(dense); lay = torch.zeros_like(dense)
+        pkg.tf_ops.sa_mlp_fused_hoisted(xyz, z, 0, wxs[0], new_xyz, idx, cnt, hst, out_f32=(dense, 0))
+        pkg.tf_ops.sa_mlp_fused_hoisted(xyz, z, 0, wxs[0], new_xyz, idx, cnt, hst, out_f32=(comp, 0), units=units)
+        _, (h2, l2) = pkg.tf_ops.linear_tc_hoisted(xyz, z, 0, wxs[0], new_xyz, idx, pp.conv(scopes[1], True), units=units)
+        pkg.tf_ops.linear_tc(h2, l2, pp.conv(scopes[2], True), out_f32=(lay, 0), units=units, unit_pool=True)
+        eh, el = pkg.tf_ops.hoist_expand_split(xyz, z, 0, wxs[0], new_xyz, idx, units=units)
+        assert torch.equal(dense, comp) and torch.equal(dense, lay)
+        nu = int(units[0].item()) * 8
+        assert eh.shape[-1] == 64 and nu > 0
+
+
+def peer_gather():                       # exchange kernel; two simulated ranks on two streams need CONCURRENT kernels, which
+    # the sanitizer tools do not give (they serialise launches): under a tool run the one-rank form (SSD3D_PROBE_SERIAL=1)
+    world, sb = (1 if os.environ.get("SSD3D_PROBE_SERIAL") else 2), 4096
+    recv_off, flag_off, total = pkg.dist.peer_layout(world, sb)
+    sym = [torch.zeros((total,), dtype=torch.uint8, device=dev) for _ in range(world)]
+    peers = torch.tensor([t.data_ptr() for t in sym], dtype=torch.int64, device=dev)
+    send = [torch.randint(0, 255, (sb,), dtype=torch.uint8, device=dev) for _ in range(world)]
+    out = [torch.zeros((world * sb,), dtype=torch.uint8, device=dev) for _ in range(world)]
+    state = [torch.zeros((4,), dtype=torch.int32, device=dev) for _ in range(world)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    torch.cuda.synchronize()
+    for _ in range(3):
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                pkg.tf_ops.peer_allgather(send[r], peers, world, r, sb, recv_off, flag_off, state[r], out[r])
+        torch.cuda.synchronize()
+    assert all(torch.equal(o, torch.cat(send)) for o in out) and all(int(s_[2].item()) == 0 for s_ in state)
+
+
+ALL = [fps3_direct, fps3_packet, ffps_cluster, fpsdist_and_generic, ball_query, sa_fused, linear_tc, small_ops, fps_bucket,
+       unit_lists, peer_gather]
 if __name__ == "__main__":
     sel = sys.argv[1:]
     for fn in ALL:
