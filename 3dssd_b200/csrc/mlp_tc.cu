@@ -1118,7 +1118,8 @@ extern "C" int ssd3d_group_concat_split(int b, int n, int c, int m, int nsample,
     const int vec4 = (c >= 4 && c % 4 == 0 && (reinterpret_cast<uintptr_t>(points) & 15u) == 0) ? 1 : 0;
     const size_t gsm = (size_t)8 * 4 * 2 * kp * sizeof(__nv_bfloat16);
     SSD3D_REQUIRE(gsm <= 96 * 1024, "group_concat_split: kp=%d too wide", kp);
-    cudaFuncSetAttribute((const void *)group_concat_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
+    const cudaError_t ea = cudaFuncSetAttribute((const void *)group_concat_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
+    if (ea != cudaSuccess) return cuda_status(ea, "group_concat_split shared-memory opt-in");
     group_concat_split_kernel<<<blocks, 256, gsm, (cudaStream_t)stream>>>(rows, n, c, m, nsample, xyz, points, new_xyz, idx,
                                                                           (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, kp, vec4);
     SSD3D_LAUNCH_CHECK("group_concat_split_kernel");

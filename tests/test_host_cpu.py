@@ -219,6 +219,50 @@ def test_c_abi_argument_validation_needs_no_gpu(pkg):
     assert L.ssd3d_concat_rows(1, 9, one, one, 3, one, null) == -1
 
 
+def test_round2_entry_points_validate_without_a_gpu(pkg):
+    """Unit-list forms, the pruned-FPS selectors and the peer exchange answer bad arguments before any CUDA call."""
+    import ctypes
+    L = pkg.lib()
+    null, one = ctypes.c_void_p(None), ctypes.c_void_p(16)
+    err = lambda: L.ssd3d_last_error().decode()
+    # linear_tc on unit lists: pooling needs ReLU + the fp32 output only; the list itself is required
+    assert L.ssd3d_linear_tc_units(1024, 64, 32, one, one, one, one, one, one, 1, null, 0, one, 32, null, null, 0, null) == -1 and "null unit list" in err()
+    assert L.ssd3d_linear_tc_units(1024, 64, 32, one, one, one, one, one, one, 0, one, 1, one, 32, null, null, 0, null) == -1 and "post-ReLU" in err()
+    assert L.ssd3d_linear_tc_units(1021, 64, 32, one, one, one, one, one, one, 1, one, 0, one, 32, null, null, 0, null) == -1 and "multiple of 8" in err()
+    assert L.ssd3d_linear_tc_hoisted_units(1, 64, 32, 8, 12, one, one, 32, one, one, one, one, 32, one, one, one, one, 1, 0, one, 32,
+                                           null, null, 0, null) == -1 and "nsample" in err()
+    assert L.ssd3d_hoist_expand_split_units(1, 64, 32, 8, 16, one, one, 32, one, one, one, null, one, one, 32, null) == -1
+    # temp size of a resumable D-FPS: 2n floats per scene where the pruned kernel is taken, n otherwise
+    assert L.ssd3d_fps_temp_elems(16384, 3, 4096, 0) == 2 * 16384          # default route of layer 1
+    assert L.ssd3d_fps_temp_elems(16384, 3, 4096, 2) == 16384              # bit 1: pruned kernel forbidden
+    assert L.ssd3d_fps_temp_elems(4096, 3, 1024, 0) == 4096 and L.ssd3d_fps_temp_elems(4096, 3, 1024, 4) == 2 * 4096
+    assert L.ssd3d_fps_temp_elems(16384, 67, 4096, 4) == 16384             # xyz only
+    assert L.ssd3d_fps_temp_elems(20000, 3, 4096, 4) == 20000              # beyond its capacity
+    assert pkg.tf_ops.fps_temp_elems(16384, 3, 4096, bucket_kernel=False) == 16384
+    # peer exchange
+    assert L.ssd3d_peer_allgather(one, 4096, one, 0, 0, 0, 8192, 16384, 16400, one, one, null) == -1 and "world" in err()
+    assert L.ssd3d_peer_allgather(one, 4100, one, 2, 0, 0, 8200, 16400, 16416, one, one, null) == -1 and "16-byte" in err()
+    assert L.ssd3d_peer_allgather(one, 4096, null, 2, 0, 0, 8192, 16384, 16400, one, one, null) == -1 and "null" in err()
+
+
+def test_peer_layout_and_padded_slices(pkg):
+    """Byte layout of a pipeline's share of the symmetric allocation: parities and flag areas do not overlap, everything the
+    kernel copies with 16-byte accesses is 16-byte aligned, for any world size and scenes-per-rank count."""
+    D = pkg.dist
+    for world in (1, 2, 3, 8):
+        for total in (world, 8 * world, 8 * world + 3, 61):
+            g = D.DetectionGather.__new__(D.DetectionGather)            # layout arithmetic only (no device)
+            g.world, g.rank, g.total, g.max_output = world, 0, total, 100
+            g.b_max = (total + world - 1) // world
+            g.block_bytes = g.b_max * 100 * 9 * 4
+            sb = (g.block_bytes + g.b_max * 4 + 15) // 16 * 16
+            recv, flags, tot = D.peer_layout(world, sb)
+            assert sb % 16 == 0 and sb >= g.block_bytes + 4 * g.b_max
+            assert recv == (0, world * sb) and flags[0] == 2 * world * sb and flags[1] - flags[0] >= 4 * world
+            assert tot >= flags[1] + 4 * world and all(v % 16 == 0 for v in recv + flags)
+            assert D.PeerArena.share_bytes(world, sb) % 256 == 0 and D.PeerArena.share_bytes(world, sb) >= tot
+
+
 def test_library_keeps_no_state(pkg):
     """include/ssd3d.h promises a library that 'keeps no state between calls': no tuning setters in the ABI (round 1
     had process-global ssd3d_tune_set_* knobs; every such choice is now an argument of an *_ex entry point) and no
