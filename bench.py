@@ -6,12 +6,12 @@
 
 A "step" is one pass of the whole path -- backbone (layer1..layer4 of configs/kitti/3dssd/3dssd.yaml incl. the vote
 layer) + detection head + decode + BEV NMS -- over one batch of 8 synthetic KITTI-shaped scenes [8,16384,4] per GPU
-(weak scaling: the batch is sharded by scene, no data-path collective; ONE ncclAllGather of the per-scene detection
-blocks ends a step and is captured inside the step's CUDA graph).
+(weak scaling: the batch is sharded by scene, no data-path collective; ONE exchange of the per-scene detection blocks
+ends a step, inside the step's CUDA graph: this library's peer-memory kernel, `--exchange nccl` for ncclAllGather).
 
-value  : scenes/s, inputs resident in HBM.  Every step is one CUDA-graph replay; `--pipeline` (default 8) steps are in
-         flight on separate streams with their own graphs, buffers and NCCL communicators (a step chains latency-bound
-         FPS stages and throughput-bound MLP stages, so the FPS of step i+1 overlaps the MLP of step i).  Timing: after
+value  : scenes/s, inputs resident in HBM.  Every step is one CUDA-graph replay; `--pipeline` (default 24) steps are in
+         flight on separate streams with their own graphs and buffers (a step chains latency-bound sampling stages that
+         keep a few SMs busy for milliseconds and short throughput-bound stages, so steps overlap).  Timing: after
          max(W, 2*pipeline) warm-up steps, `--brackets` (5) brackets of K*reps steps each (reps chosen so a bracket lasts
          >= 0.5 s), one CUDA-event pair per bracket, barrier + synchronize on both sides, L2 flushed before every step,
          max over ranks per bracket, MEDIAN bracket reported; ms_per_step = that bracket / its steps.
