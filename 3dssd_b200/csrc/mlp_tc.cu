@@ -12,8 +12,8 @@
 // split (two bf16 matrices, row-major == K-major), so every operand tile is a plain TMA box in the 128B-swizzled
 // canonical UMMA layout and no conversion happens on the load path.
 //
-// Kernel shape: 448 threads; warp 0 = TMA producer, warp 1 = MMA issuer (whole warp runs the loop, one elect.sync lane
-// issues), warps 2-5 = operand producers of the gather modes (warp 2 also allocates TMEM), warps 6-13 = epilogue
+// Kernel shape: 576 threads; warp 0 = TMA producer, warp 1 = MMA issuer (whole warp runs the loop, one elect.sync lane
+// issues), warps 2-9 = operand producers of the gather modes (warp 2 also allocates TMEM), warps 10-17 = epilogue
 // (TMEM -> registers -> scale/shift/ReLU -> fp32 / split-bf16 through TMA tensor stores, or max-pool as a shuffle
 // reduce-and-transpose butterfly; two warps per TMEM lane quarter share the 32-column chunks).
 // Tile 128 rows x BN<=256 columns, K streamed in 64-element blocks through a multi-stage mbarrier ring;
@@ -21,6 +21,10 @@
 // Gather modes (TcParams::gather): the operand tile is not read from memory but built in shared memory by the
 // producer warps from neighbour indices (1: concat(features, xyz - centre); 2: the hoisted first conv) and kept
 // resident across the n-tiles of its m-tile (TcParams::astat).
+// Unit-list mode (TcParams::units, round 2): the grouped matrix holds only the 8-row units the ball query listed (rows
+// that repeat a group's first neighbour cannot change the max-pool); the row count comes from the list at run time, the
+// gather producers look their source up through it, and the last conv of a scale pools each unit and combines the units
+// of a group with atomicMax (pooled_units_chunk).  Same bits as the dense schedule.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdio>

@@ -18,6 +18,12 @@
 // Hoisted mode (SfParams::hoist): the scale's first conv has been moved to a per-point table z (include/ssd3d.h,
 // ssd3d_sa_mlp_fused_hoisted); the gather then builds relu(z[idx] + (xyz[idx] - centre) . Wx') and the stack starts at
 // the second conv.
+// Unit-list mode (SfParams::units, round 2): a neighbour list repeats its first hit beyond pts_cnt
+// (grouping/tf_grouping_g.cu:245-248) and the copies cannot change the max-pool, so a tile is made of 16 listed 8-row units
+// (the ball query lists ceil(cnt / 8) units per non-empty group) instead of 128 consecutive rows; each unit is pooled by the
+// shuffle butterfly and the units of a group meet through atomicMax on the non-negative fp32 result, which the caller
+// zero-fills (= the cnt == 0 mask of layers_util.py:180).  Same bits as the dense schedule, 4-8x fewer rows on KITTI-like
+// clouds.
 //
 // Precision: same bf16 hi/lo split and 3-MMA scheme as mlp_tc.cu.
 #include <cuda_bf16.h>
