@@ -1,5 +1,10 @@
-import importlib, numpy as np, sys
-sys.path.insert(0,'/root/repo')
+"""CPU simulation of the pruning rule of csrc/fps_bucket.cu: how many of the 512 buckets (32 points each) of a KITTI-like
+scene a round of D-FPS has to update when a bucket is skipped whenever its bounding box lies farther from the new sample
+than its largest running distance.  Usage: python tools/fps_bucket_sim.py [bucket_size] [morton3|morton2|kd]
+(numbers quoted in DESIGN.md section 3.1: ~6 affected buckets per round after the first thousand rounds)."""
+import importlib, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 synth = importlib.import_module("3dssd_b200.synth")
 pts = synth.kitti_like(1, 16384, seed=1000)[0,:,:3].astype(np.float32)
 n=len(pts); m=4096
