@@ -597,7 +597,7 @@ def main():
                        "global_batch": SCENES_PER_GPU * world, "points": NPOINTS, "parallelism": "scene-sharded dp%d" % world,
                        "ffps": args.ffps_mode, "mlp": args.mlp_mode, "cuda_graph": not args.no_graph,
                        "l2": "flushed (256 MiB write) before every timed step",
-                       "steps_in_flight": P, "fps_cluster": args.fps_cluster, "fps_l1_kernel": "cluster" if net.fps_bucket is False else "bucket (1 CTA per scene)", "allgather_in_graph": bool(gather_in_graph and not args.no_graph),
+                       "steps_in_flight": P, "hbm_peak_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2), "fps_cluster": args.fps_cluster, "fps_l1_kernel": "cluster" if net.fps_bucket is False else "bucket (1 CTA per scene)", "allgather_in_graph": bool(gather_in_graph and not args.no_graph),
                        "exchange": {"peer": "libssd3d peer_allgather_kernel over NVLink peer memory (symmetric buffers), inside the step graph",
                                     "nccl": "ncclAllGather, one communicator per pipeline", "none": "single GPU"}[exchange],
                        "exchange_timeouts": sum(g.timeouts() for g in gathers) if exchange == "peer" else 0,
