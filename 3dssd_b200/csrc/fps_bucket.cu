@@ -14,7 +14,9 @@
 // stays valid.  On KITTI-like scenes a round touches ~6 of the 512 buckets (tools/fps_bucket_sim.py).  A whole scene then
 // fits ONE CTA: coordinates in shared memory (SoA, 192 KiB), running distances in registers (32 per thread), no
 // cluster, no DSMEM; a round is  bucket test -> update of the (usually one) affected bucket of a warp -> one
-// __syncthreads -> 16-entry arg-max.  One SM per scene instead of 4-8, and a shorter round.
+// __syncthreads -> 16-entry arg-max.  The reductions carry (value, key) only -- the key names the winner and a
+// 32 KiB table maps its original index back to its place in bucket order -- because a ballot + find-first to track
+// lanes costs as much as the two REDUX of a stage (tools/ubench/warp_ops.cu).  One SM per scene instead of 4-8.
 //
 // Exactness.  Skipping is the only approximation-shaped step and it is one-sided: a bucket is skipped only when
 // lb * (1 - 1e-5) >= bucket max, where lb is the squared distance from the sample to the box computed in fp32; the
@@ -74,8 +76,11 @@ fps3_bucket_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
     float *xs = reinterpret_cast<float *>(fb_dyn);          // [FB_MAXN] sorted x          (first 64 KiB: sort keys during setup)
     float *ys = xs + FB_MAXN, *zs = ys + FB_MAXN;
     uint32_t *skey = reinterpret_cast<uint32_t *>(fb_dyn);
-    __shared__ __align__(16) uint4 slots[2][FB_NW];         // per round parity: (max bits, key, position) of every warp
+    __shared__ __align__(8) uint2 slots[2][FB_NW];          // per round parity: (max bits, key) of every warp's best point
     __shared__ uint32_t red[6][FB_NW];
+    __shared__ uint16_t pos_of[FB_MAXN];                    // original index -> position in bucket order (the winner's key names
+                                                            // the point; this table finds its coordinates without carrying lanes
+                                                            // and positions through the reductions: a ballot + find-first per stage)
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int scene = blockIdx.x;
@@ -165,14 +170,14 @@ fps3_bucket_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
 
     // ---- coordinates into bucket order, bucket boxes, running distances
     float bminx = 0, bminy = 0, bminz = 0, bmaxx = 0, bmaxy = 0, bmaxz = 0;   // box of the slot this lane owns
-    uint32_t bmaxu = 0u, bkey = KEY_INVALID, bposl = 0u;                      // its max (bits), arg-max key, arg-max lane
+    uint32_t bmaxu = 0u, bkey = KEY_INVALID;                                  // its max (bits) and the key of the point holding it
 #pragma unroll
     for (int i = 0; i < FB_SLOTS; i++) {
         const int p = fb_pos(w, i, lane);
         const uint32_t o = (idxp[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
         const bool valid = o != 0xffffu;
         float x = 0.0f, y = 0.0f, z = 0.0f;
-        if (valid) { x = __ldg(data + 3 * o); y = __ldg(data + 3 * o + 1); z = __ldg(data + 3 * o + 2); }
+        if (valid) { x = __ldg(data + 3 * o); y = __ldg(data + 3 * o + 1); z = __ldg(data + 3 * o + 2); pos_of[o] = (uint16_t)p; }
         xs[p] = x; ys[p] = y; zs[p] = z;
         dist[i] = valid ? (resume ? tsave[o] : 1e38f) : -1.0f;    // tf_sampling_g.cu:136
         const uint32_t mnx = __reduce_min_sync(0xffffffffu, valid ? fb_ord(x) : 0xffffffffu);
@@ -186,11 +191,10 @@ fps3_bucket_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
         const uint32_t key = valid ? fps_key((int)o) : KEY_INVALID;
         uint32_t mx, kmin;
         warp_argmax(u, key, mx, kmin);
-        const uint32_t bal = __ballot_sync(0xffffffffu, u == mx && key == kmin);
         if (lane == i) {
             bminx = fb_unord(mnx); bminy = fb_unord(mny); bminz = fb_unord(mnz);
             bmaxx = fb_unord(mxx); bmaxy = fb_unord(mxy); bmaxz = fb_unord(mxz);
-            bmaxu = mx; bkey = kmin; bposl = (uint32_t)(__ffs(bal) - 1);
+            bmaxu = mx; bkey = kmin;
         }
     }
 
@@ -199,7 +203,7 @@ fps3_bucket_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
     else if (tid == 0) idxs[0] = io.ioff;
     float sx = __ldg(data + 3 * old0), sy = __ldg(data + 3 * old0 + 1), sz = __ldg(data + 3 * old0 + 2);
     // the warp's best over its 32 slots, cached between rounds (valid while none of its buckets changes)
-    uint32_t wm = 0u, wk = KEY_INVALID, wpos = 0u;
+    uint32_t wm = 0u, wk = KEY_INVALID;
     bool wdirty = true;
     __syncthreads();                                               // xs / ys / zs complete
 
@@ -214,8 +218,8 @@ fps3_bucket_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
         uint32_t mask = __ballot_sync(0xffffffffu, !skip);
         wdirty = wdirty || mask != 0u;
         while (mask) {
-            const int i = __ffs(mask) - 1;                         // warp-uniform
-            mask &= mask - 1;
+            const int i = 31 - __clz(mask);                        // warp-uniform; any order (find-leading-one is the cheaper one)
+            mask &= ~(1u << i);
             const int p = fb_pos(w, i, lane);
             const float dx = xs[p] - sx, dy = ys[p] - sy, dz = zs[p] - sz;
             float d = __fmul_rn(dx, dx);
@@ -235,28 +239,23 @@ fps3_bucket_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
             const uint32_t key = valid ? fps_key((int)kk) : KEY_INVALID;
             uint32_t mx, kmin;
             warp_argmax(u, key, mx, kmin);
-            const uint32_t bal = __ballot_sync(0xffffffffu, u == mx && key == kmin);
-            if (lane == i) { bmaxu = mx; bkey = kmin; bposl = (uint32_t)(__ffs(bal) - 1); }
+            if (lane == i) { bmaxu = mx; bkey = kmin; }
         }
         if (wdirty) {                                              // warp-uniform
-            uint32_t mx, kmin;
-            warp_argmax(bmaxu, bkey, mx, kmin);
-            const uint32_t bal = __ballot_sync(0xffffffffu, bmaxu == mx && bkey == kmin);
-            const int L = __ffs(bal) - 1;
-            wm = mx; wk = kmin;
-            wpos = (uint32_t)fb_pos(w, L, 0) + __shfl_sync(0xffffffffu, bposl, L);
+            warp_argmax(bmaxu, bkey, wm, wk);
             wdirty = false;
         }
-        if (lane == 0) slots[par][w] = make_uint4(wm, wk, wpos, 0u);
+        if (lane == 0) slots[par][w] = make_uint2(wm, wk);
         __syncthreads();
-        // ---- scene-wide arg-max of the 16 warp candidates (every warp, redundantly: no second barrier)
-        const uint4 c = slots[par][lane & (FB_NW - 1)];
+        // ---- scene-wide arg-max of the 16 warp candidates (every warp, redundantly: no second barrier); the key names
+        // the winner, pos_of finds its coordinates
+        const uint2 c = slots[par][lane & (FB_NW - 1)];
         uint32_t m3, k3;
         warp_argmax(c.x, c.y, m3, k3);
-        const uint32_t bal = __ballot_sync(0xffffffffu, c.x == m3 && c.y == k3);
-        const int p = (int)__shfl_sync(0xffffffffu, c.z, __ffs(bal) - 1);
+        const int old = fps_key_to_k(k3);
+        const int p = (int)pos_of[old];
         sx = xs[p]; sy = ys[p]; sz = zs[p];
-        if (tid == 0) idxs[j] = fps_key_to_k(k3) + io.ioff;
+        if (tid == 0) idxs[j] = old + io.ioff;
     }
 
     if (save) {
