@@ -14,9 +14,10 @@
 // stays valid.  On KITTI-like scenes a round touches ~6 of the 512 buckets (tools/fps_bucket_sim.py).  A whole scene then
 // fits ONE CTA: coordinates in shared memory (SoA, 192 KiB), running distances in registers (32 per thread), no
 // cluster, no DSMEM; a round is  bucket test -> update of the (usually one) affected bucket of a warp -> one
-// __syncthreads -> 16-entry arg-max.  The reductions carry (value, key) only -- the key names the winner and a
-// 32 KiB table maps its original index back to its place in bucket order -- because a ballot + find-first to track
-// lanes costs as much as the two REDUX of a stage (tools/ubench/warp_ops.cu).  One SM per scene instead of 4-8.
+// __syncthreads -> 16-entry arg-max.  The reductions carry (value, key) only, and the key word holds the point's place
+// in bucket order below its tie-break fields, so the winner's coordinates are one shared-memory read away: a ballot +
+// find-first to track lanes costs as much as the two REDUX of a stage (tools/ubench/warp_ops.cu).  One SM per scene
+// instead of 4-8.
 //
 // Exactness.  Skipping is the only approximation-shaped step and it is one-sided: a bucket is skipped only when
 // lb * (1 - 1e-5) >= bucket max, where lb is the squared distance from the sample to the box computed in fp32; the
@@ -62,11 +63,17 @@ __device__ __forceinline__ uint32_t fb_spread9(uint32_t v)   // 9 bits -> every 
 // sample touches (neighbours in Morton order) are worked on in parallel
 __device__ __forceinline__ int fb_pos(int w, int i, int lane) { return ((i * FB_NW + w) << 5) + lane; }
 
+// Tie-break key of point `o` (original index, < 16384) WITH its position p in bucket order in the low bits: ordered like
+// fps_key -- (o mod 1024, o div 1024) -- because those two fields are unique per point and sit above the position.  A
+// min-reduction over these words therefore returns the reference's winner AND where its coordinates are; no lane or
+// position has to be tracked through the stages (a ballot + find-first per stage cost as much as the stage's reductions).
+__device__ __forceinline__ uint32_t fb_key(uint32_t o, uint32_t p) { return ((o & 1023u) << 21) | ((o >> 10) << 17) | p; }
+__device__ __forceinline__ int fb_key_to_k(uint32_t key) { return (int)((((key >> 17) & 15u) << 10) | (key >> 21)); }
+
 #define FB_CASE(I)                                                              \
     case I:                                                                     \
         nd = fminf(d, dist[I]);                                                 \
         dist[I] = nd;                                                           \
-        kk = (idxp[(I) >> 1] >> (((I) & 1) * 16)) & 0xffffu;                    \
         break;
 
 __global__ void __launch_bounds__(FB_T, 1)
@@ -78,9 +85,7 @@ fps3_bucket_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
     uint32_t *skey = reinterpret_cast<uint32_t *>(fb_dyn);
     __shared__ __align__(8) uint2 slots[2][FB_NW];          // per round parity: (max bits, key) of every warp's best point
     __shared__ uint32_t red[6][FB_NW];
-    __shared__ uint16_t pos_of[FB_MAXN];                    // original index -> position in bucket order (the winner's key names
-                                                            // the point; this table finds its coordinates without carrying lanes
-                                                            // and positions through the reductions: a ballot + find-first per stage)
+    __shared__ uint16_t orig_of[FB_MAXN];                   // position in bucket order -> original index (0xffff: no point)
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int scene = blockIdx.x;
@@ -91,7 +96,6 @@ fps3_bucket_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
     float *tsave = io.temp ? io.temp + (size_t)scene * 2 * n : nullptr;
     uint32_t *perm = tsave ? reinterpret_cast<uint32_t *>(tsave + n) : nullptr;
 
-    uint32_t idxp[FB_SLOTS / 2];            // original index of the thread's point of slot i, two per register
     float dist[FB_SLOTS];
 
     if (!resume) {
@@ -155,7 +159,7 @@ fps3_bucket_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
             const int p = fb_pos(w, i, lane);
             uint32_t o = 0xffffu;                                  // 0xffff marks "no point" (n <= 16384 < 0xffff)
             if (p < n) o = skey[p] & 0x3fffu;
-            if (i & 1) idxp[i >> 1] |= o << 16; else idxp[i >> 1] = o;
+            orig_of[p] = (uint16_t)o;
             if (tsave != nullptr && p < n) perm[p] = o;
         }
         __syncthreads();                                           // sort buffer consumed: xs may be overwritten
@@ -163,8 +167,7 @@ fps3_bucket_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
 #pragma unroll
         for (int i = 0; i < FB_SLOTS; i++) {
             const int p = fb_pos(w, i, lane);
-            const uint32_t o = p < n ? (perm[p] & 0xffffu) : 0xffffu;
-            if (i & 1) idxp[i >> 1] |= o << 16; else idxp[i >> 1] = o;
+            orig_of[p] = (uint16_t)(p < n ? (perm[p] & 0xffffu) : 0xffffu);
         }
     }
 
@@ -174,10 +177,10 @@ fps3_bucket_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
 #pragma unroll
     for (int i = 0; i < FB_SLOTS; i++) {
         const int p = fb_pos(w, i, lane);
-        const uint32_t o = (idxp[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+        const uint32_t o = orig_of[p];                             // written by this thread above
         const bool valid = o != 0xffffu;
         float x = 0.0f, y = 0.0f, z = 0.0f;
-        if (valid) { x = __ldg(data + 3 * o); y = __ldg(data + 3 * o + 1); z = __ldg(data + 3 * o + 2); pos_of[o] = (uint16_t)p; }
+        if (valid) { x = __ldg(data + 3 * o); y = __ldg(data + 3 * o + 1); z = __ldg(data + 3 * o + 2); }
         xs[p] = x; ys[p] = y; zs[p] = z;
         dist[i] = valid ? (resume ? tsave[o] : 1e38f) : -1.0f;    // tf_sampling_g.cu:136
         const uint32_t mnx = __reduce_min_sync(0xffffffffu, valid ? fb_ord(x) : 0xffffffffu);
@@ -188,7 +191,7 @@ fps3_bucket_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
         const uint32_t mxz = __reduce_max_sync(0xffffffffu, valid ? fb_ord(z) : 0u);
         // arg-max of the slot as it stands (a fresh start has 1e38 everywhere: every bucket is "affected" in round 1)
         const uint32_t u = valid ? __float_as_uint(fmaxf(dist[i], 0.0f)) : 0u;
-        const uint32_t key = valid ? fps_key((int)o) : KEY_INVALID;
+        const uint32_t key = valid ? fb_key(o, (uint32_t)p) : KEY_INVALID;
         uint32_t mx, kmin;
         warp_argmax(u, key, mx, kmin);
         if (lane == i) {
@@ -221,22 +224,22 @@ fps3_bucket_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
             const int i = 31 - __clz(mask);                        // warp-uniform; any order (find-leading-one is the cheaper one)
             mask &= ~(1u << i);
             const int p = fb_pos(w, i, lane);
+            const uint32_t kk = orig_of[p];
             const float dx = xs[p] - sx, dy = ys[p] - sy, dz = zs[p] - sz;
             float d = __fmul_rn(dx, dx);
             d = __fmaf_rn(dy, dy, d);
             d = __fmaf_rn(dz, dz, d);
             float nd;
-            uint32_t kk;
             switch (i) {
                 FB_CASE(0) FB_CASE(1) FB_CASE(2) FB_CASE(3) FB_CASE(4) FB_CASE(5) FB_CASE(6) FB_CASE(7)
                 FB_CASE(8) FB_CASE(9) FB_CASE(10) FB_CASE(11) FB_CASE(12) FB_CASE(13) FB_CASE(14) FB_CASE(15)
                 FB_CASE(16) FB_CASE(17) FB_CASE(18) FB_CASE(19) FB_CASE(20) FB_CASE(21) FB_CASE(22) FB_CASE(23)
                 FB_CASE(24) FB_CASE(25) FB_CASE(26) FB_CASE(27) FB_CASE(28) FB_CASE(29) FB_CASE(30)
-                default: nd = fminf(d, dist[31]); dist[31] = nd; kk = idxp[15] >> 16; break;
+                default: nd = fminf(d, dist[31]); dist[31] = nd; break;
             }
             const bool valid = kk != 0xffffu;
             const uint32_t u = valid ? __float_as_uint(fmaxf(nd, 0.0f)) : 0u;
-            const uint32_t key = valid ? fps_key((int)kk) : KEY_INVALID;
+            const uint32_t key = valid ? fb_key(kk, (uint32_t)p) : KEY_INVALID;
             uint32_t mx, kmin;
             warp_argmax(u, key, mx, kmin);
             if (lane == i) { bmaxu = mx; bkey = kmin; }
@@ -247,21 +250,20 @@ fps3_bucket_kernel(int n, int m, const float *__restrict__ inp, int *__restrict_
         }
         if (lane == 0) slots[par][w] = make_uint2(wm, wk);
         __syncthreads();
-        // ---- scene-wide arg-max of the 16 warp candidates (every warp, redundantly: no second barrier); the key names
-        // the winner, pos_of finds its coordinates
+        // ---- scene-wide arg-max of the 16 warp candidates (every warp, redundantly: no second barrier); the winning key
+        // carries the winner's place
         const uint2 c = slots[par][lane & (FB_NW - 1)];
         uint32_t m3, k3;
         warp_argmax(c.x, c.y, m3, k3);
-        const int old = fps_key_to_k(k3);
-        const int p = (int)pos_of[old];
+        const int p = (int)(k3 & 0x3fffu);
         sx = xs[p]; sy = ys[p]; sz = zs[p];
-        if (tid == 0) idxs[j] = old + io.ioff;
+        if (tid == 0) idxs[j] = fb_key_to_k(k3) + io.ioff;
     }
 
     if (save) {
 #pragma unroll
         for (int i = 0; i < FB_SLOTS; i++) {
-            const uint32_t o = (idxp[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+            const uint32_t o = orig_of[fb_pos(w, i, lane)];
             if (o != 0xffffu) tsave[o] = dist[i];
         }
     }
