@@ -21,8 +21,8 @@ _i32p = ctypes.POINTER(ctypes.c_int)
 
 def build(force=False):
     """Compile liboracle.so with gcc (seconds)."""
-    src = os.path.join(_HERE, "ssd3d_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("ssd3d_oracle.c", "fps_pruned_model.c", "Makefile"))
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
@@ -61,6 +61,31 @@ def farthest_point_sample(npoint, inp):
     temp = np.empty((b, n), np.float32)
     lib().oracle_farthest_point_sample(b, n, c, int(npoint), p, temp.ctypes.data_as(_f32p), out.ctypes.data_as(_i32p))
     return out
+
+
+def fps_pruned_model(npoint, inp, rounds=None, temp=None, out=None, idx_offset=0, contract=True):
+    """CPU model of the PRODUCT's pruned D-FPS (3dssd_b200/csrc/fps_bucket.cu, see oracle/fps_pruned_model.c): used by
+    the CPU tests to check that kernel's exactness claim against farthest_point_sample above.  rounds=(j0, j1) runs a
+    range of rounds with the resume state in temp [b, 2n] (distances in original order + bucket permutation), out is
+    the [b, npoint] index array a resumed launch continues.  Returns (indices, stats) with stats =
+    (bucket updates, rounds run per scene summed, most bucket updates in one round)."""
+    inp, p = _f(inp)
+    b, n, c = inp.shape
+    assert c == 3
+    j0, j1 = (0, int(npoint)) if rounds is None else (int(rounds[0]), int(rounds[1]))
+    if out is None:
+        out = np.zeros((b, npoint), np.int32)
+    assert out.dtype == np.int32 and out.flags.c_contiguous and out.shape == (b, npoint)
+    tp = None
+    if temp is not None:
+        assert temp.dtype == np.float32 and temp.flags.c_contiguous and temp.shape == (b, 2 * n)
+        tp = temp.ctypes.data_as(_f32p)
+    stats = np.zeros(3, np.int64)
+    rc = lib().oracle_fps_pruned_model(b, n, int(npoint), p, out.ctypes.data_as(_i32p), int(npoint), int(idx_offset), j0, j1, tp,
+                                       int(bool(contract)), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+    if rc != 0:
+        raise ValueError("fps_pruned_model: unsupported arguments (n <= 16384, temp needed for partial rounds)")
+    return out, tuple(int(v) for v in stats)
 
 
 def farthest_point_sample_with_distance(npoint, dist):
