@@ -572,6 +572,9 @@ def main():
         return float(np.mean([a.elapsed_time(b) for a, b in kev]))
     k_ms = time_fps(False)            # 8-CTA cluster kernel: the latency-mode step
     kb_ms = time_fps(True)            # single-CTA kernel with spatial pruning: the throughput step
+    # the two kernels must pick the same samples on the bench's own scenes (reported, not assumed)
+    fps_agree = bool(torch.equal(pkg.farthest_point_sample(4096, xyz, bucket_kernel=True),
+                                 pkg.farthest_point_sample(4096, xyz, bucket_kernel=False)))
 
     if world > 1:
         t = torch.tensor([k_ms, mlp_ms, latency_ms, latency_thr_ms, kb_ms], dtype=torch.float64, device=dev)
@@ -597,7 +600,7 @@ def main():
                        "global_batch": SCENES_PER_GPU * world, "points": NPOINTS, "parallelism": "scene-sharded dp%d" % world,
                        "ffps": args.ffps_mode, "mlp": args.mlp_mode, "cuda_graph": not args.no_graph,
                        "l2": "flushed (256 MiB write) before every timed step",
-                       "steps_in_flight": P, "hbm_peak_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2), "fps_cluster": args.fps_cluster, "fps_l1_kernel": "cluster" if net.fps_bucket is False else "bucket (1 CTA per scene)", "allgather_in_graph": bool(gather_in_graph and not args.no_graph),
+                       "steps_in_flight": P, "hbm_peak_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2), "fps_cluster": args.fps_cluster, "fps_l1_kernel": "cluster" if net.fps_bucket is False else "bucket (1 CTA per scene)", "fps_l1_kernels_agree": fps_agree, "allgather_in_graph": bool(gather_in_graph and not args.no_graph),
                        "exchange": {"peer": "libssd3d peer_allgather_kernel over NVLink peer memory (symmetric buffers), inside the step graph",
                                     "nccl": "ncclAllGather, one communicator per pipeline", "none": "single GPU"}[exchange],
                        "exchange_timeouts": sum(g.timeouts() for g in gathers) if exchange == "peer" else 0,
