@@ -306,3 +306,65 @@ def test_head_orchestration_dry_run_writes_into_gather_buffers(dry, oracle_ops, 
     assert rb.data_ptr() == blk.data_ptr() and torch.equal(rc, cnt)
     np.testing.assert_array_equal(rc.numpy(), ec)
     assert np.abs(rb.numpy() - eb).max() < 2e-3
+
+
+@pytest.mark.parametrize("decay", [None, 0.5])
+def test_training_mode_orchestration_dry_run_matches_oracle(dry, oracle_ops, monkeypatch, decay):
+    """is_training=True through pointnet_sa_module_msg on the CPU: the literal conv -> batch-norm -> relu
+    schedule with ssd3d_bn_train / ssd3d_rowgroup_max replaced by a few float64 lines, against the oracle's restatement of
+    tf_util.py:424-444; the moving statistics are updated in place, commit_bn() writes them back and inference then folds
+    the NEW statistics."""
+    pkg = dry
+    from oracle import layers as olayers
+    T = pkg.tf_ops
+
+    def bn_train(x, gamma, beta, moving_mean=None, moving_var=None, decay=0.9, relu=True, eps=1e-3):
+        flat = x.reshape(-1, x.shape[-1]).double()
+        mean = flat.mean(0)
+        var = ((flat - mean) ** 2).mean(0)
+        inv = gamma.double() / torch.sqrt(var + eps)
+        y = x.double() * inv + (beta.double() - mean * inv)
+        if moving_mean is not None:                                  # in place, like updates_collections=None
+            moving_mean.sub_(((moving_mean.double() - mean) * (1.0 - decay)).float())
+            moving_var.sub_(((moving_var.double() - var) * (1.0 - decay)).float())
+        return (torch.relu(y) if relu else y).float(), inv.float(), (beta.double() - mean * inv).float(), mean.float(), var.float()
+
+    def rowgroup_max(y, pool, rowmask=None):
+        out = y.max(dim=-2).values
+        return out * (rowmask > 0).unsqueeze(-1).to(out.dtype) if rowmask is not None else out
+
+    monkeypatch.setattr(T, "bn_train", bn_train)
+    monkeypatch.setattr(T, "rowgroup_max", rowgroup_max)
+    rng = np.random.default_rng(11)
+    synth = importlib.import_module("3dssd_b200.synth")
+    pts = synth.kitti_like(2, 512, seed=61)
+    pts[..., 0] *= 0.1; pts[..., 2] *= 0.1
+    xyz, feats = pts[..., :3].copy(), rng.standard_normal((2, 512, 16)).astype(np.float32)
+    arch = [[[0], [0], [0.4, 0.8], [16, 32], [[16, 16, 32], [16, 32, 48]], True, [-1], ['D-FPS'], [64],
+             -1, False, 'SA_Layer', 'trn', True, -1, 64]]
+    params = dict(pkg.params.init_params(arch, 16, seed=8, random_bias=True))
+    args = (arch[0][2], arch[0][3], arch[0][4], True, decay, True, [-1], ['D-FPS'], [64], None, False, 'trn', True)
+    params_ref = {k: np.array(v, copy=True) for k, v in params.items()}            # on the CPU torch.from_numpy ALIASES the dict's
+    pp = pkg.params.prepare(params, "cpu")                                        # arrays: the oracle gets its own copy
+    got = pkg.pointnet_sa_module_msg(torch.from_numpy(xyz), torch.from_numpy(feats), *args, aggregation_channel=64, params=pp,
+                                     return_debug=True, fps_parts=2)              # fps_parts is ignored when training
+    upd = {}
+    exp = olayers.pointnet_sa_module_msg(xyz, feats, *args, aggregation_channel=64, params=params_ref, return_debug=True, bn_updates=upd)
+    np.testing.assert_array_equal(got[2].numpy(), exp[2])
+    for a, b in zip(got[3]["idx"], exp[3]["idx"]):
+        np.testing.assert_array_equal(a.numpy(), b)
+    assert np.abs(got[1].numpy() - exp[1]).max() <= 1e-4 * np.abs(exp[1]).max()
+    assert set(upd) == {"trn/conv%d_%d" % (i, j) for i in range(2) for j in range(3)} | {"trn/ensemble"}
+    for scope, u in upd.items():
+        st = pp.bn_state(scope)
+        for k in ("moving_mean", "moving_variance"):
+            assert np.abs(st[k].numpy() - u[k]).max() <= 1e-4 * max(1e-3, np.abs(u[k]).max()), (scope, k)
+    pp.commit_bn()
+    assert not np.array_equal(params["trn/conv0_0/bn/moving_mean"], params_ref["trn/conv0_0/bn/moving_mean"])
+    for scope, u in upd.items():                                                  # the oracle's view of "after one training step"
+        for k in ("moving_mean", "moving_variance"):
+            params_ref[scope + "/bn/" + k] = u[k]
+    args_inf = args[:3] + (False,) + args[4:]
+    got_i = pkg.pointnet_sa_module_msg(torch.from_numpy(xyz), torch.from_numpy(feats), *args_inf, aggregation_channel=64, params=pp)
+    exp_i = olayers.pointnet_sa_module_msg(xyz, feats, *args_inf, aggregation_channel=64, params=params_ref)
+    assert np.abs(got_i[1].numpy() - exp_i[1]).max() <= 1e-4 * np.abs(exp_i[1]).max()
