@@ -366,3 +366,39 @@ def test_header_is_plain_c():
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", hdr])
     code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)          # declarations only, comments stripped
     assert "torch" not in code.lower() and "cudaStream_t" not in code and "#include <cuda" not in code
+
+
+def test_ctypes_signatures_match_the_header(pkg):
+    """Every argtypes list of 3dssd_b200/_lib.py is the prototype of include/ssd3d.h, argument by argument (a count or a
+    width mismatch -- long vs int, size_t vs int -- is silent in ctypes and corrupts the call): the header is parsed here
+    and each parameter's C type mapped to its ctypes class."""
+    lib_mod = __import__("importlib").import_module("3dssd_b200._lib")
+    hdr = open(os.path.join(ROOT, "include", "ssd3d.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", "", hdr)
+    protos = re.findall(r"\b([a-z_ ]+?[ \*])\s*(ssd3d_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)
+    assert len(protos) >= 50
+
+    def ctype(decl):
+        decl = decl.strip()
+        if decl in ("void", ""):
+            return None
+        if "*" in decl or decl.startswith("ssd3d_stream_t"):
+            return ctypes.c_void_p
+        base = re.sub(r"\b(const|unsigned)\b", "", decl)
+        base = " ".join(base.split()[:-1]) if len(base.split()) > 1 else base.strip()     # drop the parameter name
+        return {"int": ctypes.c_int, "long": ctypes.c_long, "long long": ctypes.c_longlong, "size_t": ctypes.c_size_t,
+                "float": ctypes.c_float}[base.strip()]
+
+    seen = set()
+    for ret, name, args in protos:
+        if name == "ssd3d_last_error":
+            continue
+        want = [t for t in (ctype(a) for a in args.split(",")) if t is not None]
+        got = lib_mod._SIGNATURES[name]
+        assert len(got) == len(want), "%s: %d argtypes, the header declares %d parameters" % (name, len(got), len(want))
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert ctypes.sizeof(g) == ctypes.sizeof(w) and (g is ctypes.c_float) == (w is ctypes.c_float) and \
+                (g is ctypes.c_void_p) == (w is ctypes.c_void_p), "%s: parameter %d is %s in the header, %s in _lib.py" % (name, i, w, g)
+        seen.add(name)
+    assert seen == set(lib_mod._SIGNATURES), seen ^ set(lib_mod._SIGNATURES)
