@@ -19,7 +19,8 @@ def _scenes(kind, b, n, seed):
     rng = np.random.default_rng(seed)
     if kind == "kitti":
         pts = synth.kitti_like(b, n, seed=seed)[..., :3].copy()
-        pts[:, n // 2: n // 2 + 40] = pts[:, 3:43]                       # exact duplicates (the loader pads with them)
+        if n >= 100:
+            pts[:, n // 2: n // 2 + 40] = pts[:, 3:43]                   # exact duplicates (the loader pads with them)
     elif kind == "uniform":
         pts = rng.uniform(-40, 40, (b, n, 3)).astype(np.float32)
     elif kind == "lattice":                                              # many exactly equal distances: the tie-break decides
@@ -99,3 +100,18 @@ def test_pruned_fps_key_orders_like_the_reference_and_carries_the_place():
     np.testing.assert_array_equal(np.argsort(key, kind="stable"), ref_order)
     np.testing.assert_array_equal((((key >> 17) & 15) << 10) | (key >> 21), o)
     np.testing.assert_array_equal(key & 0x3FFF, p)
+
+
+def test_pruned_fps_model_randomised_sweep():
+    """120 seeded random scenes of mixed kinds and sizes (n 1..3000, any m <= n + 5: sampling more points than there are
+    distinct locations ends in all-zero distances, where only the tie-break decides), both roundings of the bound."""
+    rng = np.random.default_rng(2024)
+    kinds = ["kitti", "uniform", "lattice", "line", "point", "far", "tiny", "clusters"]
+    for t in range(120):
+        kind = kinds[t % len(kinds)]
+        n = int(rng.integers(1, 3000))
+        m = int(rng.integers(1, min(n + 5, 600) + 1))
+        pts = _scenes(kind, 1, n, seed=10_000 + t)
+        exp = oracle_ops.farthest_point_sample(m, pts)
+        got, _ = oracle_ops.fps_pruned_model(m, pts, contract=bool(t & 1))
+        np.testing.assert_array_equal(got, exp, err_msg="kind %s n %d m %d (case %d)" % (kind, n, m, t))
