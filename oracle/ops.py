@@ -21,7 +21,7 @@ _i32p = ctypes.POINTER(ctypes.c_int)
 
 def build(force=False):
     """Compile liboracle.so with gcc (seconds)."""
-    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("ssd3d_oracle.c", "fps_pruned_model.c", "Makefile"))
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("ssd3d_oracle.c", "fps_pruned_model.c", "bq_grid_model.c", "Makefile"))
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -131,6 +131,31 @@ def query_ball_point_dilated(min_radius, max_radius, nsample, xyz1, xyz2):
     lib().oracle_query_ball_point_dilated(b, n, m, ctypes.c_float(min_radius), ctypes.c_float(max_radius),
                                           int(nsample), p1, p2, idx.ctypes.data_as(_i32p), cnt.ctypes.data_as(_i32p))
     return idx, cnt
+
+
+def query_ball_point_grid_model(min_radius_list, max_radius_list, nsample_list, xyz1, xyz2, dilated):
+    """CPU model of the PRODUCT's culled ball query (3dssd_b200/csrc/ball_query_grid.cu, see oracle/bq_grid_model.c): all
+    shells of a layer in one call.  Returns (idx_list, cnt_list, units_list, stats) with units as the kernel lists them
+    (int32 [1 + b*m*ceil(k/8)], [0] = count, then group << 4 | j) and stats = (queries on the dense path, candidates
+    streamed by the sparse path)."""
+    xyz1, p1 = _f(xyz1)
+    xyz2, p2 = _f(xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    nq = len(max_radius_list)
+    lo = (ctypes.c_float * nq)(*[float(v) for v in min_radius_list])
+    hi = (ctypes.c_float * nq)(*[float(v) for v in max_radius_list])
+    ks = (ctypes.c_int * nq)(*[int(v) for v in nsample_list])
+    idx = [np.full((b, m, int(k)), -9, np.int32) for k in nsample_list]
+    cnt = [np.full((b, m), -9, np.int32) for _ in nsample_list]
+    units = [np.full((1 + b * m * ((int(k) + 7) // 8),), -1, np.int32) for k in nsample_list]
+    arr = lambda ts: (ctypes.c_void_p * nq)(*[t.ctypes.data for t in ts])
+    stats = np.zeros(2, np.int64)
+    rc = lib().oracle_bq_grid_model(b, n, m, nq, 1 if dilated else 0, lo, hi, ks, p1, p2, arr(idx), arr(cnt), arr(units),
+                                    stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+    if rc != 0:
+        raise ValueError("bq_grid_model: unsupported arguments (n <= 16384, 1..4 shells)")
+    return idx, cnt, units, tuple(int(v) for v in stats)
 
 
 def group_point(points, idx):
