@@ -69,11 +69,28 @@ int main(int argc, char **argv)
             cudaMemcpy(got.data(), d_out, sizeof(int) * (size_t)b * m, cudaMemcpyDeviceToHost);
             ok[variant] = rc[variant] == 0 && memcmp(got.data(), expect, sizeof(int) * (size_t)b * m) == 0;
         }
+        // round time of the pruned kernel without its per-scene setup: the first m/2 samples are a prefix of the m samples, so
+        // (time of m rounds - time of m/2 rounds) / (m - m/2) is the cost of a late round; best of 5 launches each
+        float best_full = 1e30f, best_half = 1e30f;
+        for (int rep = 0; rep < 5 && m >= 512; rep++) {
+            for (int half = 0; half < 2; half++) {
+                const int mm = half ? m / 2 : m;
+                cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+                cudaEventRecord(e0, st);
+                ssd3d_farthest_point_sample_ex(b, n, 3, mm, d_pts, (long long)n * 3, d_temp, d_out, m, 0, 0, mm, 0, 4, st);
+                cudaEventRecord(e1, st);
+                cudaStreamSynchronize(st);
+                float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+                if (half) best_half = ms < best_half ? ms : best_half; else best_full = ms < best_full ? ms : best_full;
+            }
+        }
+        const float late_round_ns = m >= 512 ? 1e6f * (best_full - best_half) / (float)(m - m / 2) : 0.0f;
         all_ok = all_ok && ok[0] && ok[1] && ok[2];
         printf("%s{\"b\": %d, \"n\": %d, \"m\": %d, \"pruned_equals_oracle\": %s, \"cluster_equals_oracle\": %s, \"pruned_resumed_equals_oracle\": %s, "
-               "\"rc\": [%d, %d, %d], \"pruned_ms\": %.4f, \"cluster_ms\": %.4f, \"pruned_ns_per_round\": %.1f, \"last_error\": \"%s\"}",
+               "\"rc\": [%d, %d, %d], \"pruned_ms\": %.4f, \"cluster_ms\": %.4f, \"pruned_ns_per_round\": %.1f, \"pruned_best_ms\": %.4f, \"pruned_half_best_ms\": %.4f, "
+               "\"pruned_late_round_ns\": %.1f, \"last_error\": \"%s\"}",
                ci ? ", " : "", b, n, m, ok[0] ? "true" : "false", ok[1] ? "true" : "false", ok[2] ? "true" : "false", rc[0], rc[1], rc[2],
-               ms_bucket, ms_cluster, 1e6 * ms_bucket / (m > 1 ? m - 1 : 1), (rc[0] | rc[1] | rc[2]) ? ssd3d_last_error() : "");
+               ms_bucket, ms_cluster, 1e6 * ms_bucket / (m > 1 ? m - 1 : 1), best_full, best_half, late_round_ns, (rc[0] | rc[1] | rc[2]) ? ssd3d_last_error() : "");
         cudaFree(d_pts); cudaFree(d_temp); cudaFree(d_out);
     }
     cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
